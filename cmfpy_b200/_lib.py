@@ -1,0 +1,117 @@
+"""ctypes binding of libcmf_b200.so (the C ABI declared in include/cmf_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no sm_100 GPU is
+visible, solver construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libcmf_b200.so")
+
+CMF_F32, CMF_F64 = 0, 1
+CMF_HOST, CMF_DEVICE = 0, 1
+CMF_PREC_FP32, CMF_PREC_TF32 = 0, 1
+PRECISIONS = {"fp32": CMF_PREC_FP32, "tf32": CMF_PREC_TF32}
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("n_features", C.c_int), ("n_components", C.c_int), ("maxlag", C.c_int),
+        ("t_local", C.c_longlong), ("t_global", C.c_longlong), ("t_offset", C.c_longlong),
+        ("device", C.c_int), ("precision", C.c_int), ("stream", C.c_void_p),
+    ]
+
+
+_H = C.c_void_p
+_SIGNATURES = {
+    "cmf_abi_version": (C.c_int, []),
+    "cmf_last_error": (C.c_char_p, []),
+    "cmf_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "cmf_precision_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cmf_mu_create": (C.c_int, [C.POINTER(_H), C.POINTER(Params)]),
+    "cmf_mu_destroy": (C.c_int, [_H]),
+    "cmf_mu_set_data": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_longlong]),
+    "cmf_mu_data_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "cmf_mu_set_norm_x": (C.c_int, [_H, C.c_double]),
+    "cmf_mu_set_factors": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong]),
+    "cmf_mu_init_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cmf_mu_scale_factors": (C.c_int, [_H, C.c_double, C.c_double]),
+    "cmf_mu_halo_width": (C.c_int, [_H, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cmf_mu_halo_export": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "cmf_mu_halo_import": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "cmf_mu_recon": (C.c_int, [_H]),
+    "cmf_mu_w_terms": (C.c_int, [_H]),
+    "cmf_mu_w_terms_buffer": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]),
+    "cmf_mu_w_apply": (C.c_int, [_H]),
+    "cmf_mu_h_step": (C.c_int, [_H]),
+    "cmf_mu_resid_sumsq": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "cmf_mu_loss": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "cmf_mu_step": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "cmf_mu_get_W": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
+    "cmf_mu_get_H": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_longlong]),
+    "cmf_mu_get_est": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_longlong]),
+    "cmf_mu_h_terms": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int]),
+    "cmf_mu_get_w_terms": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int]),
+    "cmf_mu_launch_count": (C.c_int, [_H, C.POINTER(C.c_longlong)]),
+    "cmf_mu_path_name": (C.c_char_p, [_H]),
+    "cmf_mu_kernel_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "cmf_mu_set_profiling": (C.c_int, [_H, C.c_int]),
+    "cmf_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
+                              C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cmf_tensor_transconv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names the header declares (used by the CPU-side ABI test)."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Loads the shared library once; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "cmfpy_b200: %s is missing - build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn.restype, fn.argtypes = res, args
+    if lib.cmf_abi_version() != 1:
+        raise RuntimeError("cmfpy_b200: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    """Turns a non-zero status into the Python exception the reference would
+    raise (ValueError for argument errors, RuntimeError for CUDA failures)."""
+    if rc == 0:
+        return
+    msg = load().cmf_last_error().decode("utf-8", "replace")
+    if rc == 2:
+        raise ValueError(msg)
+    raise RuntimeError("cmfpy_b200: " + msg)
+
+
+def np_dtype_code(a):
+    if a.dtype == np.float32:
+        return CMF_F32
+    if a.dtype == np.float64:
+        return CMF_F64
+    raise TypeError("expected float32 or float64, got %s" % a.dtype)
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = load().cmf_device_count(C.byref(n))
+    return n.value if rc == 0 else 0

@@ -1,0 +1,165 @@
+"""Host-side solver base: the duck type `CMF.fit` drives.
+
+Mirrors the interface of reference cmfpy/algs/base.py:12-97 (constructor
+signature, `update`, `converged`, `loss`, `W`, `H`, `X`, `normX`, `est`,
+`resids`, dimension attributes) on top of the C ABI.  All state lives on the
+GPU; `W`, `H`, `est`, `resids` materialise fresh float64 NumPy arrays on access.
+"""
+import ctypes as C
+from numbers import Integral
+
+import numpy as np
+
+from .. import _lib
+
+
+def _as_host_matrix(a, name):
+    if not isinstance(a, np.ndarray):
+        a = np.asarray(a)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    if not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class DeviceOptimizer:
+    """Common plumbing for solvers that live behind libcmf_b200."""
+
+    def __init__(self, data, model_dimensions, initW=None, initH=None,
+                 tol=1e-5, patience=3, precision="fp32", device=0, seed=None):
+        # reference base.py:20-21
+        if patience < 1 or not isinstance(patience, Integral):
+            raise ValueError("Patience must be a positive integer.")
+        if precision not in _lib.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.patience = patience
+        self.tol = tol
+        self.precision = precision
+        self.device = device
+
+        # reference base.py:33-34: copy the model dimensions onto the solver
+        for k, v in model_dimensions:
+            setattr(self, k, v)
+        N, T, K, L = self.n_features, self.n_timepoints, self.n_components, self.maxlag
+
+        X = _as_host_matrix(data, "data")
+        if X.shape != (N, T):
+            raise ValueError("data has shape %s, dimensions say %s" % (X.shape, (N, T)))
+        self._X = X
+
+        p = _lib.Params(n_features=N, n_components=K, maxlag=L, t_local=T, t_global=T,
+                        t_offset=0, device=device, precision=_lib.PRECISIONS[precision],
+                        stream=None)
+        _lib.check(self._lib.cmf_mu_create(C.byref(self._h), C.byref(p)))
+        _lib.check(self._lib.cmf_mu_set_data(self._h, X.ctypes.data, _lib.np_dtype_code(X),
+                                             _lib.CMF_HOST, T, T))
+        ss, neg = C.c_double(0), C.c_int(0)
+        _lib.check(self._lib.cmf_mu_data_stats(self._h, C.byref(ss), C.byref(neg)))
+        self.normX = float(np.sqrt(ss.value))               # base.py:25
+        self.has_negative = bool(neg.value)
+
+        # reference base.py:37-41
+        if initW is None or initH is None:
+            initW, initH = self.initialize(seed)
+        W0, H0 = _as_host_matrix(initW, "initW"), _as_host_matrix(initH, "initH")
+        if W0.shape != (L, N, K) or H0.shape != (K, T):
+            raise ValueError("initW/initH must have shapes %s and %s" % ((L, N, K), (K, T)))
+        if W0.dtype != H0.dtype:
+            H0 = H0.astype(W0.dtype)
+        _lib.check(self._lib.cmf_mu_set_factors(self._h, W0.ctypes.data, H0.ctypes.data,
+                                                _lib.np_dtype_code(W0), _lib.CMF_HOST, T))
+        self.cache_resids()
+
+    # -- lifecycle ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.cmf_mu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference interface -----------------------------------------------
+    def update(self):
+        raise NotImplementedError("Base class must override update(...)")
+
+    def initialize(self, seed=None):
+        return self.rand_init(seed)
+
+    def rand_init(self, seed=None):
+        """reference base.py:78-88: U[0,1) factors rescaled by sqrt(alpha),
+        alpha = <X, est> / ||est||^2; the reconstruction and both reductions
+        run on the device (the reference draws from the global unseeded numpy
+        RNG; here the generator is seedable)."""
+        rng = np.random.default_rng(seed)
+        N, T, K, L = self.n_features, self.n_timepoints, self.n_components, self.maxlag
+        W = rng.random((L, N, K), dtype=np.float32)
+        H = rng.random((K, T), dtype=np.float32)
+        _lib.check(self._lib.cmf_mu_set_factors(self._h, W.ctypes.data, H.ctypes.data,
+                                                _lib.CMF_F32, _lib.CMF_HOST, T))
+        xe, ee = C.c_double(0), C.c_double(0)
+        _lib.check(self._lib.cmf_mu_init_stats(self._h, C.byref(xe), C.byref(ee)))
+        s = np.float32(np.sqrt(xe.value / ee.value))
+        return s * W, s * H
+
+    def cache_resids(self):
+        """reference base.py:57-62: refresh est (device) and the residual norm."""
+        _lib.check(self._lib.cmf_mu_recon(self._h))
+
+    def converged(self, loss_hist):
+        """reference base.py:64-76."""
+        d_loss = np.diff(loss_hist[-self.patience:])
+        return bool(np.all(np.abs(d_loss) < self.tol))
+
+    @property
+    def loss(self):
+        """reference base.py:90-97: ||resids||_F / ||X||_F."""
+        out = C.c_double(0)
+        _lib.check(self._lib.cmf_mu_loss(self._h, C.byref(out)))
+        return float(out.value)
+
+    @property
+    def X(self):
+        return self._X
+
+    @property
+    def W(self):
+        L, N, K = self.maxlag, self.n_features, self.n_components
+        out = np.empty((L, N, K), dtype=np.float64)
+        _lib.check(self._lib.cmf_mu_get_W(self._h, out.ctypes.data, _lib.CMF_F64, _lib.CMF_HOST))
+        return out
+
+    @property
+    def H(self):
+        K, T = self.n_components, self.n_timepoints
+        out = np.empty((K, T), dtype=np.float64)
+        _lib.check(self._lib.cmf_mu_get_H(self._h, out.ctypes.data, _lib.CMF_F64, _lib.CMF_HOST, T))
+        return out
+
+    @property
+    def est(self):
+        N, T = self.n_features, self.n_timepoints
+        out = np.empty((N, T), dtype=np.float64)
+        _lib.check(self._lib.cmf_mu_get_est(self._h, out.ctypes.data, _lib.CMF_F64, _lib.CMF_HOST, T))
+        return out
+
+    @property
+    def resids(self):
+        return self.est - self._X
+
+    # -- extras --------------------------------------------------------------
+    @property
+    def path_name(self):
+        return self._lib.cmf_mu_path_name(self._h).decode()
+
+    @property
+    def launch_count(self):
+        n = C.c_longlong(0)
+        _lib.check(self._lib.cmf_mu_launch_count(self._h, C.byref(n)))
+        return n.value

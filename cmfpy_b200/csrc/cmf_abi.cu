@@ -1,0 +1,881 @@
+// C ABI of the cmf_b200 library (see include/cmf_b200.h for the contract and the
+// reference interfaces each entry point replaces).
+//
+// Device data layout (all fp32, all "time-major": the time index is the slow
+// axis, so a lag is a whole-row offset and every shifted operand window of the
+// three contractions is 16-byte aligned):
+//   Xt, Et : RT x Np          row tau = local time, tau in [0, RT)
+//   Ht     : (h + RT) x Kp    row tau + h, h = L-1 zero/halo rows in front
+//   W      : L x Np x Kp      (the reference's own order, padded)
+// Np = N rounded up to 4, Kp = K rounded up to 8.  Rows past the valid data
+// are zeros: the reference's "drop terms that fall off the matrix"
+// (common.py:24-27, :83-84) becomes "read a zero".
+#include "../../include/cmf_b200.h"
+
+#include <cstdarg>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "ew_kernels.cuh"
+#include "simt_gemm.cuh"
+#include "tc_path.cuh"
+
+namespace cmf {
+
+std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+}
+
+}  // namespace cmf
+
+using namespace cmf;
+
+struct cmf_mu_s {
+  cmf_mu_params p{};
+  int N = 0, K = 0, L = 0, Np = 0, Kp = 0, h = 0;
+  long long Tloc = 0, TO = 0, RT = 0, RH = 0, t_valid = 0;
+  int dev = 0, num_sms = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int precision = CMF_PREC_FP32;
+  int round_ops = 0;                 // store operands pre-rounded to TF32
+  bool use_tc = false;
+
+  float *Xt = nullptr, *Et = nullptr, *Ht = nullptr, *W = nullptr;
+  float *numden = nullptr, *wpart = nullptr, *hterms = nullptr;
+  long long wcount = 0;              // L * Np * Kp
+  int wsplits = 1;
+  long long wchunk = 0;
+
+  double *loss_partials = nullptr, *d_sumsq = nullptr, *d_ring = nullptr, *d_xpart = nullptr;
+  long long n_loss_partials = 0;
+  int ring_cap = 0;
+  int* d_neg = nullptr;
+
+  double sumsq_x = 0.0, norm_x = 0.0;
+  int has_neg = 0;
+  bool have_data = false, have_factors = false, est_valid = false, wterms_valid = false;
+
+  long long launches = 0;
+  int profiling = 0;
+  float kernel_ms[4] = {0, 0, 0, 0};
+  std::vector<cudaEvent_t> ev_pool;
+
+  tc::TcState tcs;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+#define CMF_ENTER(hh)                                              \
+  CMF_CHECK((hh) != nullptr, "null solver handle");                \
+  DeviceGuard _guard((hh)->dev);                                   \
+  CMF_CHECK(_guard.ok, "cannot select CUDA device %d", (hh)->dev)
+
+inline int ew_grid(const cmf_mu_s* h, long long n_items) {
+  long long blocks = ceil_div_ll(n_items, 256);
+  long long cap = (long long)h->num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+template <class T> int dmalloc(T** p, long long count) {
+  CMF_CUDA(cudaMalloc((void**)p, (size_t)(count > 0 ? count : 1) * sizeof(T)));
+  return 0;
+}
+
+int launch_check(cmf_mu_s* h, const char* what) {
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+// ---- contraction launches (fp32 FFMA path) ------------------------------
+int simt_recon(cmf_mu_s* h) {
+  simt::ReconA a{h->Ht, h->Kp, h->h};
+  simt::ReconB b{h->W, h->Np, h->Kp};
+  simt::ReconEpi e{h->Et, h->Xt, h->loss_partials, h->Np, h->Tloc, h->t_valid, h->round_ops};
+  const long long R = (long long)h->L * h->Kp;
+  long long nblocks;
+  if (h->Np > 64) {
+    dim3 grid((unsigned)(h->RT / 128), (unsigned)ceil_div_ll(h->Np, 128), 1);
+    nblocks = (long long)grid.x * grid.y;
+    simt::shift_gemm_kernel<128, 128, 16, 8, 8><<<grid, 256, 0, h->stream>>>(a, b, e, R, R, 1);
+  } else {
+    dim3 grid((unsigned)(h->RT / 128), 1, 1);
+    nblocks = grid.x;
+    simt::shift_gemm_kernel<128, 64, 16, 8, 4><<<grid, 256, 0, h->stream>>>(a, b, e, R, R, 1);
+  }
+  CMF_TRY(launch_check(h, "recon"));
+  ew::sum_doubles_kernel<<<1, 1024, 0, h->stream>>>(h->loss_partials, nblocks, h->d_sumsq);
+  return launch_check(h, "loss_sum");
+}
+
+int simt_w_terms(cmf_mu_s* h) {
+  const int LKp = h->L * h->Kp;
+  simt::WTermsA a{h->Xt, h->Et, h->Np};
+  simt::WTermsB b{h->Ht, h->Kp, h->h, LKp};
+  float* part = (h->wsplits == 1) ? h->numden : h->wpart;
+  simt::WTermsEpi e{part, h->Np, h->Kp, LKp, h->wcount};
+  dim3 grid((unsigned)ceil_div_ll(h->Np, 128), (unsigned)ceil_div_ll(LKp, 128), (unsigned)(h->wsplits * 2));
+  simt::shift_gemm_kernel<128, 128, 16, 8, 8><<<grid, 256, 0, h->stream>>>(a, b, e, h->Tloc, h->wchunk, 2);
+  CMF_TRY(launch_check(h, "w_terms"));
+  if (h->wsplits > 1) {
+    const long long n4 = 2 * h->wcount / 4;
+    ew::sum_splits_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>(
+        (float4*)h->numden, (const float4*)h->wpart, n4, n4, h->wsplits);
+    CMF_TRY(launch_check(h, "w_terms_sum"));
+  }
+  return 0;
+}
+
+int simt_h_terms(cmf_mu_s* h) {
+  simt::HTermsA a{h->Xt, h->Et, h->Np};
+  simt::HTermsB b{h->W, h->Kp};
+  simt::HTermsEpi e{h->hterms, h->Kp, h->TO * h->Kp};
+  const long long R = (long long)h->L * h->Np;
+  if (h->Kp <= 16) {
+    dim3 grid((unsigned)(h->TO / 256), 1, 2);
+    simt::shift_gemm_kernel<256, 16, 16, 4, 4><<<grid, 256, 0, h->stream>>>(a, b, e, R, R, 2);
+  } else if (h->Kp <= 32) {
+    dim3 grid((unsigned)(h->TO / 256), 1, 2);
+    simt::shift_gemm_kernel<256, 32, 16, 8, 4><<<grid, 256, 0, h->stream>>>(a, b, e, R, R, 2);
+  } else if (h->Kp <= 64) {
+    dim3 grid((unsigned)(h->TO / 128), 1, 2);
+    simt::shift_gemm_kernel<128, 64, 16, 8, 4><<<grid, 256, 0, h->stream>>>(a, b, e, R, R, 2);
+  } else {
+    dim3 grid((unsigned)(h->TO / 128), (unsigned)ceil_div_ll(h->Kp, 128), 2);
+    simt::shift_gemm_kernel<128, 128, 16, 8, 8><<<grid, 256, 0, h->stream>>>(a, b, e, R, R, 2);
+  }
+  return launch_check(h, "h_terms");
+}
+
+// ---- phase dispatch -----------------------------------------------------
+int do_recon(cmf_mu_s* h) {
+  CMF_CHECK(h->have_data && h->have_factors, "recon before data/factors were set");
+  if (h->use_tc) {
+    CMF_TRY(tc::recon(h->tcs, h->stream));
+    h->launches += tc::kReconLaunches;
+  } else {
+    CMF_TRY(simt_recon(h));
+  }
+  h->est_valid = true;
+  return 0;
+}
+int do_w_terms(cmf_mu_s* h) {
+  CMF_CHECK(h->est_valid, "w_terms needs a current reconstruction (call cmf_mu_recon)");
+  if (h->use_tc) {
+    CMF_TRY(tc::w_terms(h->tcs, h->stream));
+    h->launches += tc::kWTermsLaunches;
+  } else {
+    CMF_TRY(simt_w_terms(h));
+  }
+  h->wterms_valid = true;
+  return 0;
+}
+int do_w_apply(cmf_mu_s* h) {
+  CMF_CHECK(h->wterms_valid, "w_apply before w_terms");
+  const long long n4 = h->wcount / 4;
+  ew::mu_update_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>(
+      (float4*)h->W, (const float4*)h->numden, (const float4*)(h->numden + h->wcount), n4, h->round_ops);
+  CMF_TRY(launch_check(h, "w_update"));
+  h->wterms_valid = false;
+  h->est_valid = false;
+  return 0;
+}
+int do_h_terms(cmf_mu_s* h) {
+  CMF_CHECK(h->est_valid, "h terms need a current reconstruction (call cmf_mu_recon)");
+  if (h->use_tc) {
+    CMF_TRY(tc::h_terms(h->tcs, h->stream));
+    h->launches += tc::kHTermsLaunches;
+    return 0;
+  }
+  return simt_h_terms(h);
+}
+int do_h_apply(cmf_mu_s* h) {
+  const long long n4 = h->Tloc * h->Kp / 4;
+  ew::mu_update_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>(
+      (float4*)(h->Ht + (long long)h->h * h->Kp), (const float4*)h->hterms,
+      (const float4*)(h->hterms + h->TO * h->Kp), n4, h->round_ops);
+  CMF_TRY(launch_check(h, "h_update"));
+  h->est_valid = false;
+  return 0;
+}
+
+cudaEvent_t get_event(cmf_mu_s* h, size_t i) {
+  while (h->ev_pool.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[i];
+}
+
+// staging copy of a host/device 2-D block (rows x cols elements of es bytes)
+// into a dense device buffer
+int stage_block(const void* src, int mem, long long ld, long long rows, long long cols,
+                size_t es, void* dst, cudaStream_t s) {
+  CMF_CUDA(cudaMemcpy2DAsync(dst, (size_t)cols * es, src, (size_t)ld * es, (size_t)cols * es,
+                             (size_t)rows, mem == CMF_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+template <class TI>
+int load_transposed(cmf_mu_s* h, const TI* src, int mem, long long ld, long long rows, long long cols,
+                    float* dst, long long ldd) {
+  // dst[c][r] = src[r][c]; host sources go through a bounded device staging buffer
+  if (rows == 0 || cols == 0) return 0;
+  if (mem == CMF_DEVICE) {
+    dim3 grid((unsigned)ceil_div_ll(cols, 32), (unsigned)ceil_div_ll(rows, 32));
+    CMF_CHECK(grid.y <= 65535, "too many rows for the transpose grid");
+    ew::transpose_convert_kernel<TI, float><<<grid, 256, 0, h->stream>>>(src, ld, dst, ldd, rows, cols, h->round_ops);
+    return launch_check(h, "transpose_in");
+  }
+  const long long budget = 256ll << 20;
+  long long ch = budget / (long long)(rows * sizeof(TI));
+  ch = (ch / 32) * 32;
+  if (ch < 32) ch = 32;
+  if (ch > cols) ch = cols;
+  TI* stg = nullptr;
+  CMF_TRY(dmalloc(&stg, rows * ch));
+  int rc = 0;
+  for (long long c0 = 0; c0 < cols && rc == 0; c0 += ch) {
+    const long long w = (cols - c0 < ch) ? cols - c0 : ch;
+    rc = stage_block(src + c0, CMF_HOST, ld, rows, w, sizeof(TI), stg, h->stream);
+    if (rc) break;
+    dim3 grid((unsigned)ceil_div_ll(w, 32), (unsigned)ceil_div_ll(rows, 32));
+    ew::transpose_convert_kernel<TI, float><<<grid, 256, 0, h->stream>>>(stg, w, dst + c0 * ldd, ldd, rows, w, h->round_ops);
+    rc = launch_check(h, "transpose_in");
+    // the staging buffer is reused by the next chunk
+    if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) { set_error("sync failed in load_transposed"); rc = 1; }
+  }
+  cudaFree(stg);
+  return rc;
+}
+
+template <class TO>
+int store_transposed(cmf_mu_s* h, const float* src, long long lds, long long rows_out, long long cols_out,
+                     TO* dst, int mem, long long ldd) {
+  // dst[r][c] = src[c][r], dst is rows_out x cols_out (ld ldd); src is cols_out x lds
+  if (rows_out == 0 || cols_out == 0) return 0;
+  if (mem == CMF_DEVICE) {
+    dim3 grid((unsigned)ceil_div_ll(rows_out, 32), (unsigned)ceil_div_ll(cols_out, 32));
+    CMF_CHECK(grid.y <= 65535 * 32ll, "too many columns");
+    // source viewed as (cols_out x rows_out); grid.x walks its columns (= rows_out)
+    if (grid.y > 65535) {
+      // walk in slabs of 65535*32 source rows
+      const long long slab = 65535ll * 32;
+      for (long long c0 = 0; c0 < cols_out; c0 += slab) {
+        const long long w = (cols_out - c0 < slab) ? cols_out - c0 : slab;
+        dim3 g((unsigned)ceil_div_ll(rows_out, 32), (unsigned)ceil_div_ll(w, 32));
+        ew::transpose_convert_kernel<float, TO><<<g, 256, 0, h->stream>>>(src + c0 * lds, lds, dst + c0, ldd, w, rows_out, 0);
+        CMF_TRY(launch_check(h, "transpose_out"));
+      }
+      return 0;
+    }
+    ew::transpose_convert_kernel<float, TO><<<grid, 256, 0, h->stream>>>(src, lds, dst, ldd, cols_out, rows_out, 0);
+    return launch_check(h, "transpose_out");
+  }
+  const long long budget = 256ll << 20;
+  long long ch = budget / (long long)(rows_out * sizeof(TO));
+  ch = (ch / 32) * 32;
+  if (ch < 32) ch = 32;
+  if (ch > cols_out) ch = cols_out;
+  TO* stg = nullptr;
+  CMF_TRY(dmalloc(&stg, rows_out * ch));
+  int rc = 0;
+  for (long long c0 = 0; c0 < cols_out && rc == 0; c0 += ch) {
+    const long long w = (cols_out - c0 < ch) ? cols_out - c0 : ch;
+    dim3 grid((unsigned)ceil_div_ll(rows_out, 32), (unsigned)ceil_div_ll(w, 32));
+    ew::transpose_convert_kernel<float, TO><<<grid, 256, 0, h->stream>>>(src + c0 * lds, lds, stg, w, w, rows_out, 0);
+    rc = launch_check(h, "transpose_out");
+    if (rc) break;
+    if (cudaMemcpy2DAsync(dst + c0, (size_t)ldd * sizeof(TO), stg, (size_t)w * sizeof(TO), (size_t)w * sizeof(TO),
+                          (size_t)rows_out, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) {
+      set_error("device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = 1;
+    }
+  }
+  cudaFree(stg);
+  return rc;
+}
+
+void free_all(cmf_mu_s* h) {
+  tc::destroy(h->tcs);
+  cudaFree(h->Xt); cudaFree(h->Et); cudaFree(h->Ht); cudaFree(h->W);
+  cudaFree(h->numden); cudaFree(h->wpart); cudaFree(h->hterms);
+  cudaFree(h->loss_partials); cudaFree(h->d_sumsq); cudaFree(h->d_ring); cudaFree(h->d_xpart);
+  cudaFree(h->d_neg);
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+}
+
+}  // namespace
+
+// ==========================================================================
+extern "C" {
+
+int cmf_abi_version(void) { return CMF_B200_ABI_VERSION; }
+
+const char* cmf_last_error(void) { return last_error().c_str(); }
+
+int cmf_device_count(int* count) {
+  CMF_CHECK(count != nullptr, "null argument");
+  *count = 0;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return 1;
+  }
+  return 0;
+}
+
+int cmf_precision_supported(int precision, int n_features, int n_components, int maxlag) {
+  if (precision == CMF_PREC_FP32) return 1;
+  if (precision == CMF_PREC_TF32) return tc::shape_supported(n_features, n_components, maxlag) ? 1 : 0;
+  return 0;
+}
+
+int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
+  CMF_CHECK(out != nullptr && p != nullptr, "null argument");
+  *out = nullptr;
+  CMF_CHECK(p->n_features >= 1 && p->n_components >= 1 && p->maxlag >= 1, "dimensions must be positive");
+  CMF_CHECK(p->t_local >= 1 && p->t_global >= p->t_local && p->t_offset >= 0 &&
+                p->t_offset + p->t_local <= p->t_global,
+            "inconsistent time range: t_local=%lld t_offset=%lld t_global=%lld", p->t_local, p->t_offset, p->t_global);
+  CMF_CHECK(p->precision == CMF_PREC_FP32 || p->precision == CMF_PREC_TF32, "unknown precision %d", p->precision);
+  CMF_CHECK(p->t_local == p->t_global || p->t_local >= p->maxlag - 1,
+            "a time shard must hold at least L-1 columns (t_local=%lld, L=%d)", p->t_local, p->maxlag);
+  int ndev = 0;
+  CMF_CUDA(cudaGetDeviceCount(&ndev));
+  CMF_CHECK(p->device >= 0 && p->device < ndev, "device %d out of range (%d visible)", p->device, ndev);
+
+  cmf_mu_s* h = new cmf_mu_s();
+  h->p = *p;
+  h->dev = p->device;
+  DeviceGuard guard(h->dev);
+  if (!guard.ok) { delete h; set_error("cannot select CUDA device %d", p->device); return 1; }
+
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, h->dev) != cudaSuccess) { delete h; set_error("cudaGetDeviceProperties failed"); return 1; }
+  if (prop.major != 10) {
+    delete h;
+    set_error("cmf_b200 is built for sm_100a only; device %d is sm_%d%d", p->device, prop.major, prop.minor);
+    return 3;
+  }
+  h->num_sms = prop.multiProcessorCount;
+
+  h->N = p->n_features; h->K = p->n_components; h->L = p->maxlag;
+  h->Np = round_up(h->N, 4); h->Kp = round_up(h->K, 8); h->h = h->L - 1;
+  h->Tloc = p->t_local;
+  h->TO = round_up_ll(h->Tloc, 256);
+  h->RT = round_up_ll(h->TO + h->h, 256);
+  h->RH = h->h + h->RT;
+  {
+    long long remaining = p->t_global - p->t_offset;       // columns that exist from t_offset on
+    long long want = h->Tloc + h->h;
+    h->t_valid = remaining < want ? remaining : want;
+  }
+  h->precision = p->precision;
+  h->use_tc = (p->precision == CMF_PREC_TF32);
+  h->round_ops = h->use_tc ? 1 : 0;
+  if (h->use_tc && !tc::shape_supported(h->N, h->K, h->L)) {
+    delete h;
+    set_error("precision tf32 has no tensor-core kernel for N=%d K=%d L=%d; use fp32", p->n_features, p->n_components, p->maxlag);
+    return 2;
+  }
+
+  if (p->stream) {
+    h->stream = (cudaStream_t)p->stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete h; set_error("cudaStreamCreate failed"); return 1;
+    }
+    h->own_stream = true;
+  }
+
+  h->wcount = (long long)h->L * h->Np * h->Kp;
+  // split the W-term reduction over time so that the grid fills the machine
+  {
+    long long tiles = ceil_div_ll(h->Np, 128) * ceil_div_ll((long long)h->L * h->Kp, 128) * 2;
+    long long want = ceil_div_ll(2ll * h->num_sms, tiles);
+    long long max_by_len = h->Tloc / 512; if (max_by_len < 1) max_by_len = 1;
+    long long max_by_mem = (1ll << 30) / (2 * h->wcount * 4); if (max_by_mem < 1) max_by_mem = 1;
+    long long s = want;
+    if (s > max_by_len) s = max_by_len;
+    if (s > max_by_mem) s = max_by_mem;
+    if (s > 4096) s = 4096;
+    if (s < 1) s = 1;
+    h->wchunk = round_up_ll(ceil_div_ll(h->Tloc, s), 16);
+    h->wsplits = (int)ceil_div_ll(h->Tloc, h->wchunk);
+  }
+
+  int rc = 0;
+  auto A = [&](int r) { if (rc == 0) rc = r; };
+  A(dmalloc(&h->Xt, h->RT * h->Np));
+  A(dmalloc(&h->Et, h->RT * h->Np));
+  A(dmalloc(&h->Ht, h->RH * h->Kp));
+  A(dmalloc(&h->W, h->wcount));
+  A(dmalloc(&h->numden, 2 * h->wcount));
+  if (h->wsplits > 1) A(dmalloc(&h->wpart, 2 * h->wcount * h->wsplits));
+  A(dmalloc(&h->hterms, 2 * h->TO * h->Kp));
+  h->n_loss_partials = (h->RT / 128) * ceil_div_ll(h->Np, 64) + 1024;
+  A(dmalloc(&h->loss_partials, h->n_loss_partials));
+  A(dmalloc(&h->d_sumsq, 1));
+  h->ring_cap = 1024;
+  A(dmalloc(&h->d_ring, h->ring_cap));
+  A(dmalloc(&h->d_xpart, (long long)h->num_sms * 8));
+  A(dmalloc(&h->d_neg, 1));
+  if (rc == 0) {
+    cudaError_t e = cudaSuccess;
+    auto Z = [&](void* ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMemsetAsync(ptr, 0, bytes, h->stream); };
+    Z(h->Xt, (size_t)h->RT * h->Np * 4);
+    Z(h->Et, (size_t)h->RT * h->Np * 4);
+    Z(h->Ht, (size_t)h->RH * h->Kp * 4);
+    Z(h->W, (size_t)h->wcount * 4);
+    Z(h->numden, (size_t)2 * h->wcount * 4);
+    Z(h->hterms, (size_t)2 * h->TO * h->Kp * 4);
+    Z(h->d_sumsq, 8);
+    Z(h->d_neg, 4);
+    if (e != cudaSuccess) { set_error("cudaMemset failed: %s", cudaGetErrorString(e)); rc = 1; }
+  }
+  if (rc == 0 && h->use_tc) {
+    tc::Dims d{h->N, h->K, h->L, h->Np, h->Kp, h->h, h->Tloc, h->TO, h->RT, h->RH, h->t_valid, h->num_sms};
+    rc = tc::init(h->tcs, d, h->Xt, h->Et, h->Ht, h->W, h->numden, h->hterms, h->loss_partials,
+                  h->n_loss_partials, h->d_sumsq, h->stream);
+  }
+  if (rc != 0) {
+    free_all(h);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int cmf_mu_destroy(cmf_mu_t* h) {
+  if (!h) return 0;
+  DeviceGuard guard(h->dev);
+  cudaStreamSynchronize(h->stream);
+  free_all(h);
+  delete h;
+  return 0;
+}
+
+int cmf_mu_set_data(cmf_mu_t* h, const void* X, int dtype, int mem, long long ld, long long ncols) {
+  CMF_ENTER(h);
+  CMF_CHECK(X != nullptr, "null data pointer");
+  CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
+  CMF_CHECK(mem == CMF_HOST || mem == CMF_DEVICE, "unknown memory space %d", mem);
+  CMF_CHECK(ncols >= h->Tloc && ncols <= h->Tloc + h->h, "ncols=%lld must lie in [t_local, t_local+L-1] = [%lld, %lld]",
+            ncols, h->Tloc, h->Tloc + h->h);
+  CMF_CHECK(ld >= ncols, "leading dimension %lld < ncols %lld", ld, ncols);
+  if (ncols > h->t_valid) ncols = h->t_valid;    // nothing exists past the global end
+  CMF_CUDA(cudaMemsetAsync(h->Xt, 0, (size_t)h->RT * h->Np * 4, h->stream));
+  if (dtype == CMF_F32) CMF_TRY(load_transposed<float>(h, (const float*)X, mem, ld, h->N, ncols, h->Xt, h->Np));
+  else CMF_TRY(load_transposed<double>(h, (const double*)X, mem, ld, h->N, ncols, h->Xt, h->Np));
+  // local ||X||^2 over owned columns and the negativity flag
+  const long long n4 = h->Tloc * h->Np / 4;
+  const int grid = ew_grid(h, n4);
+  CMF_CUDA(cudaMemsetAsync(h->d_neg, 0, 4, h->stream));
+  ew::sumsq_neg_kernel<<<grid, 256, 0, h->stream>>>((const float4*)h->Xt, n4, h->d_xpart, h->d_neg);
+  CMF_TRY(launch_check(h, "sumsq_x"));
+  ew::sum_doubles_kernel<<<1, 1024, 0, h->stream>>>(h->d_xpart, grid, h->d_sumsq);
+  CMF_TRY(launch_check(h, "sumsq_x_final"));
+  CMF_CUDA(cudaMemcpyAsync(&h->sumsq_x, h->d_sumsq, 8, cudaMemcpyDeviceToHost, h->stream));
+  CMF_CUDA(cudaMemcpyAsync(&h->has_neg, h->d_neg, 4, cudaMemcpyDeviceToHost, h->stream));
+  CMF_CUDA(cudaStreamSynchronize(h->stream));
+  h->norm_x = std::sqrt(h->sumsq_x);
+  h->have_data = true;
+  h->est_valid = false;
+  return 0;
+}
+
+int cmf_mu_data_stats(cmf_mu_t* h, double* sumsq, int* has_negative) {
+  CMF_ENTER(h);
+  CMF_CHECK(h->have_data, "no data set");
+  if (sumsq) *sumsq = h->sumsq_x;
+  if (has_negative) *has_negative = h->has_neg;
+  return 0;
+}
+
+int cmf_mu_set_norm_x(cmf_mu_t* h, double norm_x) {
+  CMF_ENTER(h);
+  CMF_CHECK(norm_x >= 0.0, "norm_x must be non-negative");
+  h->norm_x = norm_x;
+  return 0;
+}
+
+int cmf_mu_set_factors(cmf_mu_t* h, const void* W0, const void* H0, int dtype, int mem, long long ldh) {
+  CMF_ENTER(h);
+  CMF_CHECK(W0 != nullptr && H0 != nullptr, "W or H not initalized.");   // base.py:59-60
+  CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
+  CMF_CHECK(mem == CMF_HOST || mem == CMF_DEVICE, "unknown memory space %d", mem);
+  CMF_CHECK(ldh >= h->Tloc, "leading dimension of H %lld < t_local %lld", ldh, h->Tloc);
+  const long long wn = (long long)h->L * h->N * h->K;
+  const size_t es = dtype == CMF_F32 ? 4 : 8;
+  const void* wsrc = W0;
+  void* wstage = nullptr;
+  if (mem == CMF_HOST) {
+    CMF_CUDA(cudaMalloc(&wstage, (size_t)wn * es));
+    if (cudaMemcpyAsync(wstage, W0, (size_t)wn * es, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+      cudaFree(wstage); set_error("H2D copy of W failed"); return 1;
+    }
+    wsrc = wstage;
+  }
+  const int grid = ew_grid(h, h->wcount);
+  if (dtype == CMF_F32)
+    ew::w_pad_in_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)wsrc, h->W, h->L, h->N, h->K, h->Np, h->Kp, h->round_ops);
+  else
+    ew::w_pad_in_kernel<double><<<grid, 256, 0, h->stream>>>((const double*)wsrc, h->W, h->L, h->N, h->K, h->Np, h->Kp, h->round_ops);
+  int rc = launch_check(h, "w_pad_in");
+  if (rc == 0 && cudaMemsetAsync(h->Ht, 0, (size_t)h->RH * h->Kp * 4, h->stream) != cudaSuccess) { set_error("memset failed"); rc = 1; }
+  if (rc == 0) {
+    float* dst = h->Ht + (long long)h->h * h->Kp;
+    if (dtype == CMF_F32) rc = load_transposed<float>(h, (const float*)H0, mem, ldh, h->K, h->Tloc, dst, h->Kp);
+    else rc = load_transposed<double>(h, (const double*)H0, mem, ldh, h->K, h->Tloc, dst, h->Kp);
+  }
+  if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) { set_error("sync failed in set_factors"); rc = 1; }
+  if (wstage) cudaFree(wstage);
+  if (rc) return rc;
+  h->have_factors = true;
+  h->est_valid = false;
+  h->wterms_valid = false;
+  return 0;
+}
+
+int cmf_mu_init_stats(cmf_mu_t* h, double* x_dot_est, double* est_sumsq) {
+  CMF_ENTER(h);
+  CMF_CHECK(x_dot_est != nullptr && est_sumsq != nullptr, "null argument");
+  CMF_CHECK(h->have_data && h->have_factors, "init stats before data/factors were set");
+  if (!h->est_valid) CMF_TRY(do_recon(h));
+  const long long n4 = h->Tloc * h->Np / 4;
+  int grid = ew_grid(h, n4);
+  if (grid > h->num_sms * 4) grid = h->num_sms * 4;      // d_xpart holds 8*num_sms doubles
+  ew::dot_sumsq_kernel<<<grid, 256, 0, h->stream>>>((const float4*)h->Xt, (const float4*)h->Et, n4, h->d_xpart);
+  CMF_TRY(launch_check(h, "dot_sumsq"));
+  std::vector<double> host((size_t)grid * 2);
+  CMF_CUDA(cudaMemcpyAsync(host.data(), h->d_xpart, host.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  CMF_CUDA(cudaStreamSynchronize(h->stream));
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < grid; ++i) { a += host[2 * i]; b += host[2 * i + 1]; }
+  *x_dot_est = a;
+  *est_sumsq = b;
+  return 0;
+}
+
+int cmf_mu_scale_factors(cmf_mu_t* h, double scale_w, double scale_h) {
+  CMF_ENTER(h);
+  CMF_CHECK(h->have_factors, "W or H not initalized.");
+  ew::scale_kernel<<<ew_grid(h, h->wcount / 4), 256, 0, h->stream>>>((float4*)h->W, h->wcount / 4, (float)scale_w, h->round_ops);
+  CMF_TRY(launch_check(h, "scale_w"));
+  const long long n4 = h->RH * h->Kp / 4;
+  ew::scale_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>((float4*)h->Ht, n4, (float)scale_h, h->round_ops);
+  CMF_TRY(launch_check(h, "scale_h"));
+  h->est_valid = false;
+  h->wterms_valid = false;
+  return 0;
+}
+
+int cmf_mu_halo_width(cmf_mu_t* h, int* n_cols, int* halo_ld) {
+  CMF_ENTER(h);
+  if (n_cols) *n_cols = h->h;
+  if (halo_ld) *halo_ld = h->Kp;
+  return 0;
+}
+
+int cmf_mu_halo_export(cmf_mu_t* h, float* left_edge, float* right_edge) {
+  CMF_ENTER(h);
+  CMF_CHECK(h->have_factors, "no factors set");
+  const size_t bytes = (size_t)h->h * h->Kp * 4;
+  if (bytes == 0) return 0;
+  CMF_CHECK(h->Tloc >= h->h, "shard shorter than the halo");
+  if (left_edge)
+    CMF_CUDA(cudaMemcpyAsync(left_edge, h->Ht + (long long)h->h * h->Kp, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  if (right_edge)
+    CMF_CUDA(cudaMemcpyAsync(right_edge, h->Ht + (long long)(h->h + h->Tloc - h->h) * h->Kp, bytes,
+                             cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
+int cmf_mu_halo_import(cmf_mu_t* h, const float* left_halo, const float* right_halo) {
+  CMF_ENTER(h);
+  const size_t bytes = (size_t)h->h * h->Kp * 4;
+  if (bytes == 0) return 0;
+  if (left_halo) CMF_CUDA(cudaMemcpyAsync(h->Ht, left_halo, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  else CMF_CUDA(cudaMemsetAsync(h->Ht, 0, bytes, h->stream));
+  float* r = h->Ht + (long long)(h->h + h->Tloc) * h->Kp;
+  if (right_halo) CMF_CUDA(cudaMemcpyAsync(r, right_halo, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  else CMF_CUDA(cudaMemsetAsync(r, 0, bytes, h->stream));
+  h->est_valid = false;
+  return 0;
+}
+
+int cmf_mu_recon(cmf_mu_t* h) { CMF_ENTER(h); return do_recon(h); }
+int cmf_mu_w_terms(cmf_mu_t* h) { CMF_ENTER(h); return do_w_terms(h); }
+
+int cmf_mu_w_terms_buffer(cmf_mu_t* h, float** dev_ptr, long long* count) {
+  CMF_ENTER(h);
+  if (dev_ptr) *dev_ptr = h->numden;
+  if (count) *count = h->wcount;
+  return 0;
+}
+
+int cmf_mu_w_apply(cmf_mu_t* h) { CMF_ENTER(h); return do_w_apply(h); }
+
+int cmf_mu_h_step(cmf_mu_t* h) {
+  CMF_ENTER(h);
+  CMF_TRY(do_h_terms(h));
+  return do_h_apply(h);
+}
+
+int cmf_mu_resid_sumsq(cmf_mu_t* h, double* sumsq) {
+  CMF_ENTER(h);
+  CMF_CHECK(sumsq != nullptr, "null argument");
+  CMF_CHECK(h->est_valid, "Residuals not initialized.");                // base.py:95-96
+  CMF_CUDA(cudaMemcpyAsync(sumsq, h->d_sumsq, 8, cudaMemcpyDeviceToHost, h->stream));
+  CMF_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cmf_mu_loss(cmf_mu_t* h, double* loss) {
+  double s = 0.0;
+  CMF_TRY(cmf_mu_resid_sumsq(h, &s));
+  *loss = std::sqrt(s) / h->norm_x;
+  return 0;
+}
+
+int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
+  CMF_ENTER(h);
+  CMF_CHECK(n_steps >= 0, "n_steps must be >= 0");
+  CMF_CHECK(h->have_data && h->have_factors, "step before data/factors were set");
+  if (n_steps == 0) return 0;
+  if (!h->est_valid) CMF_TRY(do_recon(h));
+  for (int k = 0; k < 4; ++k) h->kernel_ms[k] = 0.f;
+  int done = 0;
+  while (done < n_steps) {
+    const int chunk = (n_steps - done < h->ring_cap) ? n_steps - done : h->ring_cap;
+    size_t ne = 0;
+    const bool prof = h->profiling != 0;
+    for (int i = 0; i < chunk; ++i) {
+      if (ms_out) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      CMF_TRY(do_w_terms(h));
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      CMF_TRY(do_w_apply(h));
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      CMF_TRY(do_recon(h));
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      CMF_TRY(do_h_terms(h));
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      CMF_TRY(do_h_apply(h));
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      CMF_TRY(do_recon(h));
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      ew::loss_from_sumsq_kernel<<<1, 1, 0, h->stream>>>(h->d_sumsq, h->norm_x, h->d_ring, i);
+      CMF_TRY(launch_check(h, "loss"));
+    }
+    if (ms_out) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+    if (loss_out)
+      CMF_CUDA(cudaMemcpyAsync(loss_out + done, h->d_ring, (size_t)chunk * 8, cudaMemcpyDeviceToHost, h->stream));
+    CMF_CUDA(cudaStreamSynchronize(h->stream));
+    // unpack event timings
+    const int per = (ms_out ? 1 : 0) + (prof ? 7 : 0);
+    for (int i = 0; i < chunk; ++i) {
+      const size_t b = (size_t)i * per;
+      if (ms_out) {
+        const size_t nxt = (i + 1 < chunk) ? (size_t)(i + 1) * per : ne - 1;
+        CMF_CUDA(cudaEventElapsedTime(ms_out + done + i, h->ev_pool[b], h->ev_pool[nxt]));
+      }
+      if (prof) {
+        const size_t e0 = b + (ms_out ? 1 : 0);
+        float t[6];
+        for (int k = 0; k < 6; ++k) CMF_CUDA(cudaEventElapsedTime(&t[k], h->ev_pool[e0 + k], h->ev_pool[e0 + k + 1]));
+        h->kernel_ms[1] += t[0];            // w_terms
+        h->kernel_ms[3] += t[1] + t[4];     // elementwise updates
+        h->kernel_ms[0] += t[2] + t[5];     // two reconstructions (+ loss)
+        h->kernel_ms[2] += t[3];            // h_terms
+      }
+    }
+    done += chunk;
+  }
+  return 0;
+}
+
+int cmf_mu_get_W(cmf_mu_t* h, void* W_out, int dtype, int mem) {
+  CMF_ENTER(h);
+  CMF_CHECK(W_out != nullptr, "null argument");
+  CMF_CHECK(h->have_factors, "W or H not initalized.");
+  CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
+  const long long wn = (long long)h->L * h->N * h->K;
+  const size_t es = dtype == CMF_F32 ? 4 : 8;
+  void* dst = W_out;
+  void* stage = nullptr;
+  if (mem == CMF_HOST) { CMF_CUDA(cudaMalloc(&stage, (size_t)wn * es)); dst = stage; }
+  const int grid = ew_grid(h, wn);
+  if (dtype == CMF_F32) ew::w_pad_out_kernel<float><<<grid, 256, 0, h->stream>>>(h->W, (float*)dst, h->L, h->N, h->K, h->Np, h->Kp);
+  else ew::w_pad_out_kernel<double><<<grid, 256, 0, h->stream>>>(h->W, (double*)dst, h->L, h->N, h->K, h->Np, h->Kp);
+  int rc = launch_check(h, "w_pad_out");
+  if (rc == 0 && mem == CMF_HOST &&
+      cudaMemcpyAsync(W_out, stage, (size_t)wn * es, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { set_error("D2H copy of W failed"); rc = 1; }
+  if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) { set_error("sync failed: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
+  if (stage) cudaFree(stage);
+  return rc;
+}
+
+int cmf_mu_get_H(cmf_mu_t* h, void* H_out, int dtype, int mem, long long ldh) {
+  CMF_ENTER(h);
+  CMF_CHECK(H_out != nullptr, "null argument");
+  CMF_CHECK(h->have_factors, "W or H not initalized.");
+  CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
+  CMF_CHECK(ldh >= h->Tloc, "leading dimension too small");
+  const float* src = h->Ht + (long long)h->h * h->Kp;
+  int rc;
+  if (dtype == CMF_F32) rc = store_transposed<float>(h, src, h->Kp, h->K, h->Tloc, (float*)H_out, mem, ldh);
+  else rc = store_transposed<double>(h, src, h->Kp, h->K, h->Tloc, (double*)H_out, mem, ldh);
+  if (rc == 0) CMF_CUDA(cudaStreamSynchronize(h->stream));
+  return rc;
+}
+
+int cmf_mu_get_est(cmf_mu_t* h, void* est_out, int dtype, int mem, long long ld) {
+  CMF_ENTER(h);
+  CMF_CHECK(est_out != nullptr, "null argument");
+  CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
+  CMF_CHECK(ld >= h->Tloc, "leading dimension too small");
+  if (!h->est_valid) CMF_TRY(do_recon(h));
+  int rc;
+  if (dtype == CMF_F32) rc = store_transposed<float>(h, h->Et, h->Np, h->N, h->Tloc, (float*)est_out, mem, ld);
+  else rc = store_transposed<double>(h, h->Et, h->Np, h->N, h->Tloc, (double*)est_out, mem, ld);
+  if (rc == 0) CMF_CUDA(cudaStreamSynchronize(h->stream));
+  return rc;
+}
+
+int cmf_mu_h_terms(cmf_mu_t* h, void* num_out, void* den_out, int dtype) {
+  CMF_ENTER(h);
+  CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
+  if (!h->est_valid) CMF_TRY(do_recon(h));
+  CMF_TRY(do_h_terms(h));
+  for (int s = 0; s < 2; ++s) {
+    void* out = s ? den_out : num_out;
+    if (!out) continue;
+    const float* src = h->hterms + (long long)s * h->TO * h->Kp;
+    if (dtype == CMF_F32) CMF_TRY(store_transposed<float>(h, src, h->Kp, h->K, h->Tloc, (float*)out, CMF_HOST, h->Tloc));
+    else CMF_TRY(store_transposed<double>(h, src, h->Kp, h->K, h->Tloc, (double*)out, CMF_HOST, h->Tloc));
+  }
+  CMF_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cmf_mu_get_w_terms(cmf_mu_t* h, void* num_out, void* den_out, int dtype) {
+  CMF_ENTER(h);
+  CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
+  CMF_CHECK(h->wterms_valid, "no W terms computed (call cmf_mu_w_terms)");
+  const long long wn = (long long)h->L * h->N * h->K;
+  const size_t es = dtype == CMF_F32 ? 4 : 8;
+  void* stage = nullptr;
+  CMF_CUDA(cudaMalloc(&stage, (size_t)wn * es));
+  int rc = 0;
+  for (int s = 0; s < 2 && rc == 0; ++s) {
+    void* out = s ? den_out : num_out;
+    if (!out) continue;
+    const float* src = h->numden + (long long)s * h->wcount;
+    const int grid = ew_grid(h, wn);
+    if (dtype == CMF_F32) ew::w_pad_out_kernel<float><<<grid, 256, 0, h->stream>>>(src, (float*)stage, h->L, h->N, h->K, h->Np, h->Kp);
+    else ew::w_pad_out_kernel<double><<<grid, 256, 0, h->stream>>>(src, (double*)stage, h->L, h->N, h->K, h->Np, h->Kp);
+    rc = launch_check(h, "w_pad_out");
+    if (rc == 0 && (cudaMemcpyAsync(out, stage, (size_t)wn * es, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(h->stream) != cudaSuccess)) { set_error("D2H copy failed"); rc = 1; }
+  }
+  cudaFree(stage);
+  return rc;
+}
+
+int cmf_mu_launch_count(cmf_mu_t* h, long long* count) {
+  CMF_CHECK(h != nullptr && count != nullptr, "null argument");
+  *count = h->launches;
+  return 0;
+}
+
+const char* cmf_mu_path_name(cmf_mu_t* h) {
+  if (!h) return "none";
+  return h->use_tc ? "tcgen05-tf32" : "ffma-fp32";
+}
+
+int cmf_mu_kernel_ms(cmf_mu_t* h, float out[4]) {
+  CMF_CHECK(h != nullptr && out != nullptr, "null argument");
+  for (int k = 0; k < 4; ++k) out[k] = h->kernel_ms[k];
+  return 0;
+}
+
+int cmf_mu_set_profiling(cmf_mu_t* h, int on) {
+  CMF_CHECK(h != nullptr, "null solver handle");
+  h->profiling = on ? 1 : 0;
+  return 0;
+}
+
+// ---- stateless primitives ------------------------------------------------
+static int make_tmp(cmf_mu_t** h, int N, long long T, int K, int L, int device, int precision) {
+  cmf_mu_params p{};
+  p.n_features = N; p.n_components = K; p.maxlag = L;
+  p.t_local = T; p.t_global = T; p.t_offset = 0;
+  p.device = device; p.precision = precision; p.stream = nullptr;
+  return cmf_mu_create(h, &p);
+}
+
+int cmf_predict(const void* W, const void* H, void* est_out, int dtype, int n_features,
+                long long n_timepoints, int n_components, int maxlag, int device, int precision) {
+  cmf_mu_t* h = nullptr;
+  CMF_TRY(make_tmp(&h, n_features, n_timepoints, n_components, maxlag, device, precision));
+  h->have_data = true;   // X stays zero; only the reconstruction is wanted
+  int rc = cmf_mu_set_factors(h, W, H, dtype, CMF_HOST, n_timepoints);
+  if (rc == 0) rc = cmf_mu_get_est(h, est_out, dtype, CMF_HOST, n_timepoints);
+  cmf_mu_destroy(h);
+  return rc;
+}
+
+int cmf_tensor_transconv(const void* W, const void* X, void* out, int dtype, int n_features,
+                         long long n_timepoints, int n_components, int maxlag, int device, int precision) {
+  cmf_mu_t* h = nullptr;
+  CMF_TRY(make_tmp(&h, n_features, n_timepoints, n_components, maxlag, device, precision));
+  int rc = cmf_mu_set_data(h, X, dtype, CMF_HOST, n_timepoints, n_timepoints);
+  // any H works: only the numerator (the transposed convolution of X) is read back
+  std::vector<double> zeros;
+  if (rc == 0) {
+    zeros.assign((size_t)n_components * (size_t)n_timepoints, 0.0);
+    rc = cmf_mu_set_factors(h, W, zeros.data(), dtype, CMF_HOST, n_timepoints);
+  }
+  if (rc == 0) rc = cmf_mu_h_terms(h, out, nullptr, dtype);
+  cmf_mu_destroy(h);
+  return rc;
+}
+
+}  // extern "C"

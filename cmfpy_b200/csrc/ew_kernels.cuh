@@ -1,0 +1,200 @@
+// HBM-bound kernels of the MU iteration: the multiplicative update itself,
+// split-sum reduction, loss finalisation, layout/dtype conversion at the ABI
+// boundary.  All are coalesced, 128-bit vectorised where the layout allows,
+// warp-shuffle reduced, and launched on grids that are multiples of the SM
+// count (grid-stride loops).
+#pragma once
+#include "common.cuh"
+
+namespace cmf {
+namespace ew {
+
+// P <- P * num / (den + eps)   (reference cmfpy/algs/mult.py:18 and :22)
+// n4 = number of float4 elements.  Optionally rounds the result to TF32 so the
+// tensor-core path consumes exactly what is stored.
+// Algorithmic bytes: 16 per element (3 reads + 1 write).
+__global__ void __launch_bounds__(256)
+mu_update_kernel(float4* __restrict__ P, const float4* __restrict__ num,
+                 const float4* __restrict__ den, long long n4, int round_out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 p = P[i];
+    const float4 a = __ldcs(num + i), d = __ldcs(den + i);
+    p.x = p.x * a.x / (d.x + kEpsilon);
+    p.y = p.y * a.y / (d.y + kEpsilon);
+    p.z = p.z * a.z / (d.z + kEpsilon);
+    p.w = p.w * a.w / (d.w + kEpsilon);
+    if (round_out) { p.x = round_tf32(p.x); p.y = round_tf32(p.y); p.z = round_tf32(p.z); p.w = round_tf32(p.w); }
+    P[i] = p;
+  }
+}
+
+// out[i] = sum_s part[s * stride_s + i]   (deterministic split-K reduction)
+__global__ void __launch_bounds__(256)
+sum_splits_kernel(float4* __restrict__ out, const float4* __restrict__ part,
+                  long long n4, long long stride4, int nsplit) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 s = __ldcs(part + i);
+    for (int k = 1; k < nsplit; ++k) {
+      const float4 v = __ldcs(part + (long long)k * stride4 + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    out[i] = s;
+  }
+}
+
+// sum of n doubles -> out[0]  (one block; fixed order => deterministic)
+__global__ void __launch_bounds__(1024)
+sum_doubles_kernel(const double* __restrict__ in, long long n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += in[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = v;
+  }
+}
+
+// loss_out[slot] = sqrt(sumsq[0]) / norm_x    (reference base.py:90-97)
+__global__ void loss_from_sumsq_kernel(const double* sumsq, double norm_x, double* loss_out, int slot) {
+  loss_out[slot] = sqrt(sumsq[0]) / norm_x;
+}
+
+// sum of squares + any-negative flag over n floats, per-block partials
+// (reference base.py:25 la.norm(data); model.py:138 (data < 0).any())
+__global__ void __launch_bounds__(256)
+sumsq_neg_kernel(const float4* __restrict__ x, long long n4, double* __restrict__ partial,
+                 int* __restrict__ neg_flag) {
+  __shared__ double red[8];
+  double s = 0.0;
+  bool neg = false;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = x[i];
+    s += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+    neg |= (v.x < 0.f) | (v.y < 0.f) | (v.z < 0.f) | (v.w < 0.f);
+  }
+  if (__any_sync(0xffffffffu, neg) && (threadIdx.x & 31) == 0) atomicOr(neg_flag, 1);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < 8) ? red[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  }
+}
+
+// per-block partials of <x, e> and <e, e> (reference rand_init alpha,
+// cmfpy/algs/base.py:86-87); partial[2*b] and partial[2*b+1]
+__global__ void __launch_bounds__(256)
+dot_sumsq_kernel(const float4* __restrict__ x, const float4* __restrict__ e, long long n4,
+                 double* __restrict__ partial) {
+  __shared__ double red[2][8];
+  double sxe = 0.0, see = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = x[i], b = e[i];
+    sxe += (double)(a.x * b.x + a.y * b.y) + (double)(a.z * b.z + a.w * b.w);
+    see += (double)(b.x * b.x + b.y * b.y) + (double)(b.z * b.z + b.w * b.w);
+  }
+  sxe = warp_sum(sxe);
+  see = warp_sum(see);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sxe; red[1][threadIdx.x >> 5] = see; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double a = (threadIdx.x < 8) ? red[0][threadIdx.x] : 0.0;
+    double b = (threadIdx.x < 8) ? red[1][threadIdx.x] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = a; partial[2 * blockIdx.x + 1] = b; }
+  }
+}
+
+// p[i] *= s  (rescale of the random initialisation, base.py:88)
+__global__ void __launch_bounds__(256)
+scale_kernel(float4* __restrict__ p, long long n4, float s, int round_out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = p[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    p[i] = v;
+  }
+}
+
+// dst[c][r] = (float) src[r][c]  for r < rows, c < cols; 32x32 smem tiles.
+// src: rows x cols, leading dimension lds.  dst: cols x ldd.
+// Used for X (N x T -> T x Np) and H (K x T -> T x Kp) on the way in, and the
+// reverse on the way out.  round_out rounds to TF32 on the way in.
+template <class TI, class TO>
+__global__ void __launch_bounds__(256)
+transpose_convert_kernel(const TI* __restrict__ src, long long lds, TO* __restrict__ dst,
+                         long long ldd, long long rows, long long cols, int round_out) {
+  __shared__ float tile[32][33];
+  const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const long long r = r0 + ty + j, c = c0 + tx;
+    tile[ty + j][tx] = (r < rows && c < cols) ? (float)src[r * lds + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const long long c = c0 + ty + j, r = r0 + tx;
+    if (c < cols && r < rows) {
+      float v = tile[tx][ty + j];
+      if (round_out) v = round_tf32(v);
+      dst[c * ldd + r] = (TO)v;
+    }
+  }
+}
+
+// W between the reference layout L x N x K (dtype TI) and the padded device
+// layout L x Np x Kp (fp32).  One thread per padded element.
+template <class TI>
+__global__ void __launch_bounds__(256)
+w_pad_in_kernel(const TI* __restrict__ src, float* __restrict__ dst, int L, int N, int K,
+                int Np, int Kp, int round_out) {
+  const long long total = (long long)L * Np * Kp;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int k = (int)(i % Kp);
+    const int n = (int)((i / Kp) % Np);
+    const int l = (int)(i / ((long long)Kp * Np));
+    float v = (k < K && n < N) ? (float)src[((long long)l * N + n) * K + k] : 0.f;
+    if (round_out) v = round_tf32(v);
+    dst[i] = v;
+  }
+}
+template <class TO>
+__global__ void __launch_bounds__(256)
+w_pad_out_kernel(const float* __restrict__ src, TO* __restrict__ dst, int L, int N, int K,
+                 int Np, int Kp) {
+  const long long total = (long long)L * N * K;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int k = (int)(i % K);
+    const int n = (int)((i / K) % N);
+    const int l = (int)(i / ((long long)K * N));
+    dst[i] = (TO)src[((long long)l * Np + n) * Kp + k];
+  }
+}
+
+// elementwise dtype conversion (staging of float64 host data)
+template <class TI, class TO>
+__global__ void __launch_bounds__(256)
+convert_kernel(const TI* __restrict__ src, TO* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = (TO)src[i];
+}
+
+}  // namespace ew
+}  // namespace cmf

@@ -1,0 +1,300 @@
+// Exact-fp32 shift-GEMM on the FFMA pipe.
+//
+// One register-tiled, double-buffered SGEMM skeleton, C[m][c] = sum_r A(m,r)*B(r,c),
+// whose operands are *functors*: the three contractions of the MU iteration
+// (reconstruction, W terms, H terms) differ only in how (row, reduction index)
+// maps to an address in the time-major device arrays, and a lag is just an
+// offset in that mapping - no shifted copy of H, X or est is ever materialised.
+//
+// This is the CMF_PREC_FP32 path, and the general-shape path (any N, K, L, T).
+// The tcgen05 path in tc_*.cuh replaces it for CMF_PREC_TF32.
+#pragma once
+#include "common.cuh"
+
+namespace cmf {
+namespace simt {
+
+// Operand functor concept
+//   static constexpr bool kAlongR;
+//       true : the 4 elements (i, r..r+3) are contiguous in memory
+//       false: the 4 elements (i..i+3, r) are contiguous in memory
+//   __device__ const float* ptr(long long i, long long r, int src) const;
+//       address of element (i, r) - 16-byte aligned, 4 valid floats - or
+//       nullptr when the quad lies outside the operand (reads as zeros).
+// Epilogue functor concept
+//   static constexpr bool kReduce;
+//   __device__ float store(long long m, long long c, float4 v, int split, int src) const;
+//   __device__ void  block_sum(double s, long long block_linear) const;   (if kReduce)
+
+template <int BM, int BN, int BK, int TM, int TN, class AOp, class BOp, class Epi>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+shift_gemm_kernel(const AOp a, const BOp b, const Epi epi, long long R, long long r_chunk, int nsrc) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int TXN = BN / TN;          // threads along the column dimension
+  constexpr int NV = TN / 4;            // float4 vectors per thread row
+  constexpr int MV = TM / 4;
+  constexpr int LDA = BM + 4, LDB = BN + 4;
+  static_assert(TM % 4 == 0 && TN % 4 == 0 && BK % 4 == 0, "tile shape");
+  constexpr int QA = (BM * BK / 4 + NT - 1) / NT;
+  constexpr int QB = (BN * BK / 4 + NT - 1) / NT;
+
+  __shared__ __align__(16) float As[2][BK][LDA];
+  __shared__ __align__(16) float Bs[2][BK][LDB];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TXN, ty = tid / TXN;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const long long c0 = (long long)blockIdx.y * BN;
+  const int split = blockIdx.z / nsrc, src = blockIdx.z % nsrc;
+  const long long r_begin = (long long)split * r_chunk;
+  const long long r_end = min(R, r_begin + r_chunk);
+  const int ntiles = (int)((r_end - r_begin + BK - 1) / BK);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 ra[QA], rb[QB];
+
+  auto fetch = [&](int t) {
+    const long long r0 = r_begin + (long long)t * BK;
+#pragma unroll
+    for (int it = 0; it < QA; ++it) {
+      const int q = tid + it * NT;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < BM * BK / 4) {
+        const float* p;
+        if (AOp::kAlongR) {
+          const int i = q / (BK / 4), rq = q % (BK / 4);
+          const long long r = r0 + rq * 4;
+          p = (r < r_end) ? a.ptr(m0 + i, r, src) : nullptr;
+        } else {
+          const int r = q / (BM / 4), iq = q % (BM / 4);
+          p = (r0 + r < r_end) ? a.ptr(m0 + iq * 4, r0 + r, src) : nullptr;
+        }
+        if (p) v = __ldg(reinterpret_cast<const float4*>(p));
+      }
+      ra[it] = v;
+    }
+#pragma unroll
+    for (int it = 0; it < QB; ++it) {
+      const int q = tid + it * NT;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < BN * BK / 4) {
+        const float* p;
+        if (BOp::kAlongR) {
+          const int i = q / (BK / 4), rq = q % (BK / 4);
+          const long long r = r0 + rq * 4;
+          p = (r < r_end) ? b.ptr(c0 + i, r, src) : nullptr;
+        } else {
+          const int r = q / (BN / 4), iq = q % (BN / 4);
+          p = (r0 + r < r_end) ? b.ptr(c0 + iq * 4, r0 + r, src) : nullptr;
+        }
+        if (p) v = __ldg(reinterpret_cast<const float4*>(p));
+      }
+      rb[it] = v;
+    }
+  };
+
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int it = 0; it < QA; ++it) {
+      const int q = tid + it * NT;
+      if (q < BM * BK / 4) {
+        if (AOp::kAlongR) {
+          const int i = q / (BK / 4), rq = q % (BK / 4);
+          As[buf][rq * 4 + 0][i] = ra[it].x;
+          As[buf][rq * 4 + 1][i] = ra[it].y;
+          As[buf][rq * 4 + 2][i] = ra[it].z;
+          As[buf][rq * 4 + 3][i] = ra[it].w;
+        } else {
+          const int r = q / (BM / 4), iq = q % (BM / 4);
+          *reinterpret_cast<float4*>(&As[buf][r][iq * 4]) = ra[it];
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < QB; ++it) {
+      const int q = tid + it * NT;
+      if (q < BN * BK / 4) {
+        if (BOp::kAlongR) {
+          const int i = q / (BK / 4), rq = q % (BK / 4);
+          Bs[buf][rq * 4 + 0][i] = rb[it].x;
+          Bs[buf][rq * 4 + 1][i] = rb[it].y;
+          Bs[buf][rq * 4 + 2][i] = rb[it].z;
+          Bs[buf][rq * 4 + 3][i] = rb[it].w;
+        } else {
+          const int r = q / (BN / 4), iq = q % (BN / 4);
+          *reinterpret_cast<float4*>(&Bs[buf][r][iq * 4]) = rb[it];
+        }
+      }
+    }
+  };
+
+  if (ntiles > 0) {
+    fetch(0);
+    stash(0);
+  }
+  __syncthreads();
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) fetch(t + 1);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float af[TM], bf[TN];
+#pragma unroll
+      for (int v = 0; v < MV; ++v) {
+        const float4 x = *reinterpret_cast<const float4*>(&As[buf][kk][ty * TM + v * 4]);
+        af[v * 4 + 0] = x.x; af[v * 4 + 1] = x.y; af[v * 4 + 2] = x.z; af[v * 4 + 3] = x.w;
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const float4 x = *reinterpret_cast<const float4*>(&Bs[buf][kk][v * (BN / NV) + tx * 4]);
+        bf[v * 4 + 0] = x.x; bf[v * 4 + 1] = x.y; bf[v * 4 + 2] = x.z; bf[v * 4 + 3] = x.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
+    }
+    if (t + 1 < ntiles) stash(buf ^ 1);
+    __syncthreads();
+  }
+
+  float part = 0.f;
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const float4 o = make_float4(acc[i][v * 4], acc[i][v * 4 + 1], acc[i][v * 4 + 2], acc[i][v * 4 + 3]);
+      part += epi.store(m0 + ty * TM + i, c0 + v * (BN / NV) + tx * 4, o, split, src);
+    }
+
+  if (Epi::kReduce) {
+    __shared__ double red[NT / 32];
+    double s = warp_sum((double)part);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid < 32) {
+      double v = (tid < NT / 32) ? red[tid] : 0.0;
+      v = warp_sum(v);
+      if (tid == 0)
+        epi.block_sum(v, ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------
+// Operand / epilogue functors over the time-major device arrays
+//   Ht : (h + RT) x Kp, row index tau + h      (tau = local time, h = L-1)
+//   Xt, Et : RT x Np
+//   W  : L x Np x Kp
+// ------------------------------------------------------------------------
+
+// K1 reconstruction  Et[tau][n] = sum_{l,k} Ht[tau-l][k] * W[l][n][k]
+// (reference cmf_predict, cmfpy/common.py:50-58; r = l*Kp + k)
+struct ReconA {
+  static constexpr bool kAlongR = true;
+  const float* Ht; int Kp, h;
+  __device__ const float* ptr(long long tau, long long r, int) const {
+    const int l = (int)(r / Kp), k = (int)(r % Kp);
+    return Ht + (tau - l + h) * Kp + k;
+  }
+};
+struct ReconB {
+  static constexpr bool kAlongR = true;
+  const float* W; int Np, Kp;
+  __device__ const float* ptr(long long n, long long r, int) const {
+    if (n >= Np) return nullptr;
+    const int l = (int)(r / Kp), k = (int)(r % Kp);
+    return W + ((long long)l * Np + n) * Kp + k;
+  }
+};
+// writes est (zero past the valid range) and accumulates sum (est - X)^2 over
+// owned rows (reference cache_resids + loss, cmfpy/algs/base.py:57-62, 90-97)
+struct ReconEpi {
+  static constexpr bool kReduce = true;
+  float* Et; const float* Xt; double* block_partials;
+  int Np; long long t_own, t_valid; int round_out;
+  __device__ float store(long long tau, long long n, float4 v, int, int) const {
+    if (n >= Np) return 0.f;
+    if (tau >= t_valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float s = 0.f;
+    if (tau < t_own) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(Xt + tau * Np + n));
+      const float d0 = v.x - x.x, d1 = v.y - x.y, d2 = v.z - x.z, d3 = v.w - x.w;
+      s = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    *reinterpret_cast<float4*>(Et + tau * Np + n) = v;
+    return s;
+  }
+  __device__ void block_sum(double s, long long b) const { block_partials[b] = s; }
+};
+
+// K2 W terms  out[src][l][n][k] = sum_tau S[tau][n] * Ht[tau-l][k],  S = Xt | Et
+// (reference _compute_mult_W, cmfpy/algs/mult.py:27-40; c = l*Kp + k)
+struct WTermsA {
+  static constexpr bool kAlongR = false;
+  const float* Xt; const float* Et; int Np;
+  __device__ const float* ptr(long long n, long long tau, int src) const {
+    if (n >= Np) return nullptr;
+    return (src ? Et : Xt) + tau * Np + n;
+  }
+};
+struct WTermsB {
+  static constexpr bool kAlongR = false;
+  const float* Ht; int Kp, h, LKp;
+  __device__ const float* ptr(long long c, long long tau, int) const {
+    if (c >= LKp) return nullptr;
+    const int l = (int)(c / Kp), k = (int)(c % Kp);
+    return Ht + (tau - l + h) * Kp + k;
+  }
+};
+struct WTermsEpi {
+  static constexpr bool kReduce = false;
+  float* part; int Np, Kp, LKp; long long per_src;   // per_src = L*Np*Kp
+  __device__ float store(long long n, long long c, float4 v, int split, int src) const {
+    if (n >= Np || c >= LKp) return 0.f;
+    const int l = (int)(c / Kp), k = (int)(c % Kp);
+    float* o = part + ((long long)split * 2 + src) * per_src + ((long long)l * Np + n) * Kp + k;
+    *reinterpret_cast<float4*>(o) = v;
+    return 0.f;
+  }
+  __device__ void block_sum(double, long long) const {}
+};
+
+// K3 H terms  out[src][tau][k] = sum_{l,n} S[tau+l][n] * W[l][n][k],  S = Xt | Et
+// (reference tensor_transconv, cmfpy/common.py:61-86; r = l*Np + n)
+struct HTermsA {
+  static constexpr bool kAlongR = true;
+  const float* Xt; const float* Et; int Np;
+  __device__ const float* ptr(long long tau, long long r, int src) const {
+    const int l = (int)(r / Np), n = (int)(r % Np);
+    return (src ? Et : Xt) + (tau + l) * Np + n;
+  }
+};
+struct HTermsB {
+  static constexpr bool kAlongR = false;
+  const float* W; int Kp;
+  __device__ const float* ptr(long long k, long long r, int) const {
+    if (k >= Kp) return nullptr;
+    return W + r * Kp + k;
+  }
+};
+struct HTermsEpi {
+  static constexpr bool kReduce = false;
+  float* out; int Kp; long long per_src;              // per_src = TO*Kp
+  __device__ float store(long long tau, long long k, float4 v, int, int src) const {
+    if (k >= Kp) return 0.f;
+    *reinterpret_cast<float4*>(out + (long long)src * per_src + tau * Kp + k) = v;
+    return 0.f;
+  }
+  __device__ void block_sum(double, long long) const {}
+};
+
+}  // namespace simt
+}  // namespace cmf

@@ -1,0 +1,153 @@
+"""CMF model object with the reference's API (reference cmfpy/model.py:24-245),
+driving the GPU multiplicative-update solver.
+
+Kept from the reference: constructor arguments, `fit`, `predict`, `score`,
+`motifs` (W: L x N x K), `factors` (H: K x T), `n_features`, `n_timesteps`,
+`loss_hist`, `time_hist`, `argsort_units`, the error types.  Out of scope
+(SURVEY.md section 2): plotting, HDF5 loading and the helpers that are broken in
+the reference itself.
+"""
+import time
+
+import numpy as np
+
+from .algs import ALGORITHMS
+from .common import cmf_predict
+
+NOT_FITTED_ERROR = ValueError(
+    "This CMF instance is not fitted yet. Call 'fit' with appropriate"
+    "arguments before using this method."
+)
+
+
+class ModelDimensions:
+    """Holds dimensions of a CMF model (reference model.py:24-69)."""
+
+    def __init__(self, data=None, n_features=None, n_timepoints=None,
+                 maxlag=None, n_components=None):
+        if data is None:
+            if (n_features is None) or (n_timepoints is None):
+                raise ValueError("Must either specify 'data' or ('n_features' "
+                                 "and 'n_timepoints').")
+        else:
+            n_features, n_timepoints = data.shape
+        if maxlag is None:
+            raise ValueError("Must specify 'n_lags'.")
+        if n_components is None:
+            raise ValueError("Must specify 'n_components'.")
+        self.n_features = n_features
+        self.n_timepoints = n_timepoints
+        self.maxlag = maxlag
+        self.n_components = n_components
+
+    def __iter__(self):
+        yield from self.__dict__.items()
+
+
+class CMF(object):
+    """Convolutive matrix factorization: X ~ sum_l W[l] @ shift(H, l)."""
+
+    def __init__(self, n_components, maxlag, n_iter_max=100,
+                 l1_W=0.0, l1_H=0.0, verbose=True, alg_name='mult',
+                 **alg_opts):
+        """Same parameters as reference model.py:80-120.  `l1_W`/`l1_H` are
+        stored and, as in the reference, not used by any solver.  Solver options
+        (`tol`, `patience`, `initW`, `initH`, and the device-side `precision`,
+        `device`, `seed`) travel through **alg_opts."""
+        self.n_components = n_components
+        self.maxlag = maxlag
+        self.n_iter_max = n_iter_max
+        self.l1_W = l1_W
+        self.l1_H = l1_H
+        self.alg_name = alg_name
+        self.alg_opts = alg_opts
+        self.verbose = verbose
+
+    def fit(self, data):
+        """Fits the model (reference model.py:122-176): negativity check, one
+        solver object, `loss_hist = [loss0, loss1, ...]`, cumulative
+        `time_hist`, early stop through `converged`.
+
+        `time_hist` holds device time measured with CUDA events (a host clock
+        around an asynchronous launch would measure nothing).  When `tol == 0`
+        the convergence test can never fire (strict `<`, base.py:73), so the
+        iterations are submitted in one batch with a single synchronisation."""
+        data = np.asarray(data)
+        if (data < 0).any():
+            raise ValueError('Negative values in data to fit')
+
+        dims = ModelDimensions(data, maxlag=self.maxlag, n_components=self.n_components)
+        if self.alg_name not in ALGORITHMS:
+            raise KeyError("alg_name %r is not provided by cmfpy_b200 (available: %s)"
+                           % (self.alg_name, sorted(ALGORITHMS)))
+        algorithm = ALGORITHMS[self.alg_name](data, dims, **self.alg_opts)
+
+        self.loss_hist = [algorithm.loss]
+        self.time_hist = [0.0]
+
+        if algorithm.tol == 0 and not self.verbose and self.n_iter_max > 0:
+            losses, secs = algorithm.update_many(self.n_iter_max, return_times=True)
+            for loss, dur in zip(losses, secs):
+                self.time_hist.append(self.time_hist[-1] + dur)
+                self.loss_hist.append(loss)
+        else:
+            iterations = range(self.n_iter_max)
+            if self.verbose:
+                try:
+                    from tqdm import trange
+                    iterations = trange(self.n_iter_max)
+                except ImportError:
+                    pass
+            for itr in iterations:
+                losses, secs = algorithm.update_many(1, return_times=True)
+                self.time_hist.append(self.time_hist[-1] + secs[0])
+                self.loss_hist.append(losses[0])
+                if algorithm.converged(self.loss_hist):
+                    break
+
+        self._W = algorithm.W
+        self._H = algorithm.H
+        self._precision = algorithm.precision
+        self._device = algorithm.device
+        algorithm.close()
+
+    def predict(self):
+        """Low-rank reconstruction, N x T (reference model.py:191-200)."""
+        return cmf_predict(self.motifs, self.factors,
+                           precision="fp32", device=getattr(self, "_device", 0))
+
+    def score(self, data):
+        """R^2 = 1 - ||predict - data||^2 / ||data||^2 (reference model.py:202-221)."""
+        error = self.predict() - data
+        return 1 - (np.linalg.norm(error) ** 2 / np.linalg.norm(data) ** 2)
+
+    @property
+    def motifs(self):
+        """W (lags x features x components)."""
+        try:
+            return self._W
+        except AttributeError:
+            raise NOT_FITTED_ERROR
+
+    @property
+    def factors(self):
+        """H (components x timebins)."""
+        try:
+            return self._H
+        except AttributeError:
+            raise NOT_FITTED_ERROR
+
+    @property
+    def n_features(self):
+        return self.motifs.shape[1]
+
+    @property
+    def n_timesteps(self):
+        return self.factors.shape[1]
+
+    def argsort_units(self):
+        """Units ordered by dominant component then peak lag (reference model.py:247-259)."""
+        W = self.motifs
+        top = np.argmax(W.sum(axis=0), axis=-1)
+        peak = np.argmax(W[:, np.arange(self.n_features), top], axis=0)
+        return np.lexsort((peak, top))

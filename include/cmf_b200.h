@@ -1,0 +1,175 @@
+/*
+ * cmf_b200.h - C ABI of the B200-native convolutive-NMF multiplicative-update engine.
+ *
+ * This is the drop-in boundary for the hot path of degleris1/cmfpy: the solver
+ * object that `CMF.fit` builds at reference cmfpy/model.py:146
+ * (`ALGORITHMS[alg_name](data, dims, **alg_opts)`) and drives through
+ * `.update()` / `.loss` / `.W` / `.H` (model.py:149-176).  The reference has no
+ * FFI of its own (it is pure Python + NumPy); each entry point below names the
+ * reference interface it replaces.  A reference maintainer binds these with
+ * ctypes - see INTEGRATION.md and cmfpy_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, non-zero on
+ *     failure, and never throws.  cmf_last_error() describes the last failure
+ *     on the calling thread.
+ *   - host-side array arguments use the REFERENCE layouts (row-major):
+ *       X  : N x T        (features x time)        model.py:127-128
+ *       W  : L x N x K    (lags x features x comps) model.py:223-229
+ *       H  : K x T                                   model.py:239-245
+ *   - `dtype` is CMF_F32 or CMF_F64 (the reference works in float64; the
+ *     device computes in fp32 / tf32 and converts at the boundary).
+ *   - `mem` is CMF_HOST (pageable or pinned host pointer) or CMF_DEVICE
+ *     (pointer valid on the solver's device, e.g. a torch tensor's data_ptr()).
+ *   - a handle is not thread-safe; one host thread drives one handle.
+ *
+ * Time sharding: a handle owns the global columns
+ * [t_offset, t_offset + t_local) of a problem with t_global columns.  A
+ * single-GPU solve is the case t_offset = 0, t_local = t_global.  The phase
+ * calls (cmf_mu_w_terms ... cmf_mu_recon) plus the halo import/export and the
+ * exposed W-term buffer are what a multi-GPU driver strings together with an
+ * all-reduce and a neighbour exchange; cmf_mu_step() is the fused single-GPU
+ * iteration.
+ */
+#ifndef CMF_B200_H
+#define CMF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMF_B200_ABI_VERSION 1
+
+enum { CMF_F32 = 0, CMF_F64 = 1 };
+enum { CMF_HOST = 0, CMF_DEVICE = 1 };
+/* CMF_PREC_FP32: exact fp32 FFMA contractions.
+ * CMF_PREC_TF32: tcgen05 tensor-core contractions, operands rounded (RN) to
+ *                TF32, fp32 accumulation in tensor memory.                  */
+enum { CMF_PREC_FP32 = 0, CMF_PREC_TF32 = 1 };
+
+typedef struct cmf_mu_s cmf_mu_t;
+
+typedef struct cmf_mu_params {
+  int n_features;        /* N   (ModelDimensions.n_features,   model.py:62) */
+  int n_components;      /* K   (ModelDimensions.n_components, model.py:65) */
+  int maxlag;            /* L   (ModelDimensions.maxlag,       model.py:64) */
+  long long t_local;     /* columns owned by this handle                    */
+  long long t_global;    /* T   (ModelDimensions.n_timepoints, model.py:63) */
+  long long t_offset;    /* global index of the first owned column          */
+  int device;            /* CUDA device ordinal                             */
+  int precision;         /* CMF_PREC_*                                      */
+  void* stream;          /* cudaStream_t to run on, or NULL for an own one  */
+} cmf_mu_params;
+
+/* ---- library ---------------------------------------------------------- */
+int         cmf_abi_version(void);
+const char* cmf_last_error(void);
+int         cmf_device_count(int* count);
+/* 1 if `precision` has a kernel path for this shape on this build.         */
+int         cmf_precision_supported(int precision, int n_features,
+                                    int n_components, int maxlag);
+
+/* ---- solver lifecycle: AbstractOptimizer.__init__, algs/base.py:15-43 -- */
+int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* params);
+int cmf_mu_destroy(cmf_mu_t* h);
+
+/* self.X = data (base.py:24).  X: N x ncols row-major with leading dimension
+ * ld (elements); ncols in [t_local, t_local + L - 1]: the columns past
+ * t_local are the static right halo a shard needs for the H step (zero when
+ * absent or past t_global).  Also accumulates the local sum of squares used
+ * for normX (base.py:25) and flags negative entries (model.py:138).         */
+int cmf_mu_set_data(cmf_mu_t* h, const void* X, int dtype, int mem,
+                    long long ld, long long ncols);
+/* Local sum over owned columns of X^2 and whether any entry was negative.   */
+int cmf_mu_data_stats(cmf_mu_t* h, double* sumsq, int* has_negative);
+/* normX = ||X||_F of the GLOBAL matrix (base.py:25).  Defaults to the local
+ * value; a sharded driver sets the all-reduced one.                          */
+int cmf_mu_set_norm_x(cmf_mu_t* h, double norm_x);
+
+/* self.W, self.H = initW, initH (base.py:40-41).  W0: L x N x K,
+ * H0: K x t_local (owned columns only, leading dimension ldh).  Copies; the
+ * caller's arrays are never written (MU rebinds W/H, mult.py:18,22).         */
+int cmf_mu_set_factors(cmf_mu_t* h, const void* W0, const void* H0, int dtype,
+                       int mem, long long ldh);
+
+/* rand_init (base.py:78-88): with random W, H already set, the two local
+ * reductions behind alpha = <X, est> / ||est||^2 over owned columns, and the
+ * in-place rescale W *= scale_w, H *= scale_h (base.py:88: both sqrt(alpha)). */
+int cmf_mu_init_stats(cmf_mu_t* h, double* x_dot_est, double* est_sumsq);
+int cmf_mu_scale_factors(cmf_mu_t* h, double scale_w, double scale_h);
+
+/* ---- halo plumbing for time sharding (no reference counterpart) --------- */
+/* Edges to send: left_edge = first L-1 owned columns, right_edge = last L-1
+ * owned columns of H, each as (L-1) x halo_ld fp32, time-major, DEVICE.     */
+int cmf_mu_halo_width(cmf_mu_t* h, int* n_cols, int* halo_ld);
+int cmf_mu_halo_export(cmf_mu_t* h, float* left_edge, float* right_edge);
+/* Halos received: left_halo = the L-1 columns before t_offset (from rank-1's
+ * right_edge), right_halo = the L-1 columns after the owned range (from
+ * rank+1's left_edge).  NULL means zeros (global boundary).                  */
+int cmf_mu_halo_import(cmf_mu_t* h, const float* left_halo, const float* right_halo);
+
+/* ---- phases of MultUpdate.update(), algs/mult.py:15-25 ------------------ */
+/* est = cmf_predict(W, H) (common.py:50-58) on owned + right-halo columns,
+ * and the local sum of squared residuals (cache_resids, base.py:57-62).      */
+int cmf_mu_recon(cmf_mu_t* h);
+/* num/denom of the W step (_compute_mult_W, mult.py:27-40) from the cached
+ * est; local partial sums over owned columns.  The result lives in one
+ * DEVICE buffer [num | den], 2 * count fp32, exposed for an in-place
+ * all-reduce.                                                                */
+int cmf_mu_w_terms(cmf_mu_t* h);
+int cmf_mu_w_terms_buffer(cmf_mu_t* h, float** dev_ptr, long long* count);
+/* W <- W * num / (den + EPSILON)  (mult.py:18).                             */
+int cmf_mu_w_apply(cmf_mu_t* h);
+/* num/denom of the H step (_compute_mult_H, mult.py:42-48; tensor_transconv,
+ * common.py:61-86) from the cached est, then H <- H * num / (den + EPSILON)
+ * (mult.py:22) on owned columns.                                             */
+int cmf_mu_h_step(cmf_mu_t* h);
+/* Local sum of squared residuals of the last cmf_mu_recon (device -> host). */
+int cmf_mu_resid_sumsq(cmf_mu_t* h, double* sumsq);
+/* loss = ||resids||_F / normX (base.py:90-97) from the local residual; only
+ * meaningful unsharded or after the driver reduced it itself.               */
+int cmf_mu_loss(cmf_mu_t* h, double* loss);
+
+/* ---- the fused single-GPU iteration ------------------------------------ */
+/* n_steps x MultUpdate.update() (mult.py:15-25): W terms, W update, recon,
+ * H terms, H update, recon + loss.  loss_out[i] = loss after step i
+ * (what update() returns, mult.py:25); ms_out[i] = device time of step i
+ * (CUDA events; may be NULL).  One host sync at the end.                     */
+int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out);
+
+/* ---- read-back: algorithm.W / algorithm.H (model.py:175-176) ------------ */
+int cmf_mu_get_W(cmf_mu_t* h, void* W_out, int dtype, int mem);
+int cmf_mu_get_H(cmf_mu_t* h, void* H_out, int dtype, int mem, long long ldh);
+/* self.est (base.py:61) / CMF.predict (model.py:191-200): N x t_local.      */
+int cmf_mu_get_est(cmf_mu_t* h, void* est_out, int dtype, int mem, long long ld);
+/* Debug / kernel-level parity: the H-step terms without applying them,
+ * each K x t_local row-major, HOST.                                          */
+int cmf_mu_h_terms(cmf_mu_t* h, void* num_out, void* den_out, int dtype);
+/* Debug / kernel-level parity: W-step terms, each L x N x K row-major, HOST.*/
+int cmf_mu_get_w_terms(cmf_mu_t* h, void* num_out, void* den_out, int dtype);
+
+/* Number of kernels this handle has launched since creation (bench
+ * `gpu_launches`) and the name of the contraction path in use.              */
+int         cmf_mu_launch_count(cmf_mu_t* h, long long* count);
+const char* cmf_mu_path_name(cmf_mu_t* h);
+/* Device time (ms) spent in each contraction kernel during the last
+ * cmf_mu_step call: [recon, w_terms, h_terms, elementwise], summed over
+ * steps (CUDA events on the solver's stream).                               */
+int cmf_mu_kernel_ms(cmf_mu_t* h, float out[4]);
+/* Toggle per-kernel event timing inside cmf_mu_step (off by default).       */
+int cmf_mu_set_profiling(cmf_mu_t* h, int on);
+
+/* ---- stateless primitives (cmfpy/common.py) ----------------------------- */
+/* cmf_predict(W, H) -> est, N x T (common.py:50-58).  Host pointers.        */
+int cmf_predict(const void* W, const void* H, void* est_out, int dtype,
+                int n_features, long long n_timepoints, int n_components,
+                int maxlag, int device, int precision);
+/* tensor_transconv(W, X) -> K x T (common.py:61-86).  Host pointers.        */
+int cmf_tensor_transconv(const void* W, const void* X, void* out, int dtype,
+                         int n_features, long long n_timepoints,
+                         int n_components, int maxlag, int device, int precision);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMF_B200_H */

@@ -1,0 +1,239 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the golden
+fixtures generated from the unmodified reference and against the CPU oracle on
+the same seeded inputs.
+
+Tolerances (stated once, used everywhere):
+  * loss trajectory: max_i |loss_gpu[i] - loss_ref[i]| / loss_ref[i] <= 1e-4
+    over all recorded iterations (BASELINE.json north_star), float64 reference;
+  * single contraction, fp32 path: rtol 2e-5 of the largest entry;
+  * single contraction, tf32 path: rtol 2e-3 of the largest entry (10-bit
+    mantissa operands, fp32 accumulation).
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+from oracle import cmf_oracle as o
+from tests.cases import CASES, case_inputs, make_inputs
+from tests.conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+TRAJ_TOL = 1e-4
+FULL_CASES = [n for n, c in CASES.items() if c[6]]
+ALL_CASES = list(CASES)
+
+
+def _supported(precision, N, K, L):
+    from cmfpy_b200 import _lib
+    return bool(_lib.load().cmf_precision_supported(_lib.PRECISIONS[precision], N, K, L))
+
+
+def _inputs(name):
+    g = golden(name)
+    if "X" in g.files:
+        return g, g["X"], g["W0"], g["H0"]
+    X, W0, H0 = case_inputs(name)
+    return g, X, W0, H0
+
+
+def _solver(X, W0, H0, L, K, precision):
+    from cmfpy_b200.algs.mult import MultUpdate
+    from cmfpy_b200.model import ModelDimensions
+    return MultUpdate(X, ModelDimensions(X, maxlag=L, n_components=K), initW=W0, initH=H0,
+                      tol=0, precision=precision)
+
+
+def _close(a, b, rel):
+    scale = np.abs(b).max() + 1e-30
+    assert np.abs(a - b).max() <= rel * scale, "max abs err %.3e vs scale %.3e" % (np.abs(a - b).max(), scale)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_single_step_kernels(built_lib, name, precision):
+    """est, W terms, W update, H terms, H update of iteration 1, one kernel at a
+    time, against the reference's own intermediates."""
+    g, X, W0, H0 = _inputs(name)
+    N, T, K, L = (int(v) for v in g["shape"])
+    if not _supported(precision, N, K, L):
+        pytest.skip("no %s kernel for this shape" % precision)
+    rel = 2e-5 if precision == "fp32" else 2e-3
+    alg = _solver(X, W0, H0, L, K, precision)
+    _close(alg.est, g["est0"], rel)
+    numW, denW = alg._compute_mult_W()
+    _close(numW, g["numW"], rel)
+    _close(denW, g["denW"], rel)
+    alg2 = _solver(X, g["W1"].astype(np.float32), H0, L, K, precision)
+    numH, denH = alg2._compute_mult_H()
+    _close(numH, g["numH"], rel)
+    _close(denH, g["denH"], rel)
+    loss1 = alg.update()
+    assert abs(loss1 - g["loss_hist"][1]) / g["loss_hist"][1] < TRAJ_TOL
+    _close(alg.W, g["W1"], 10 * rel)
+    _close(alg.H, g["H1"], 10 * rel)
+    # zeros stay exactly zero under MU (0 * num / (den + eps) == 0)
+    assert np.all(alg.W[g["W1"] == 0] == 0)
+    assert np.all(alg.H[g["H1"] == 0] == 0)
+    assert (alg.W >= 0).all() and (alg.H >= 0).all()
+    alg.close(); alg2.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_loss_trajectory(built_lib, name, precision):
+    g, X, W0, H0 = _inputs(name)
+    N, T, K, L = (int(v) for v in g["shape"])
+    if not _supported(precision, N, K, L):
+        pytest.skip("no %s kernel for this shape" % precision)
+    n_iter = int(g["n_iter"])
+    alg = _solver(X, W0, H0, L, K, precision)
+    hist = np.array([alg.loss] + alg.update_many(n_iter))
+    ref = g["loss_hist"]
+    rel = np.abs(hist - ref) / ref
+    print("%s/%s: max rel loss err %.3e (final %.6f vs %.6f)" % (name, precision, rel.max(), hist[-1], ref[-1]))
+    assert rel.max() <= TRAJ_TOL
+    Wg, Hg = alg.W, alg.H
+    if "W_final" in g.files:
+        ftol = 5e-3 if precision == "fp32" else 5e-2
+        _close(Wg, g["W_final"], ftol)
+        _close(Hg, g["H_final"], ftol)
+    else:
+        assert abs(Wg.sum() - g["W_sum"]) / g["W_sum"] < 1e-3
+        assert abs(Hg.sum() - g["H_sum"]) / g["H_sum"] < 1e-3
+    alg.close()
+
+
+def test_update_one_by_one_equals_batched(built_lib):
+    g, X, W0, H0 = _inputs("odd_k5")
+    N, T, K, L = (int(v) for v in g["shape"])
+    a = _solver(X, W0, H0, L, K, "fp32")
+    b = _solver(X, W0, H0, L, K, "fp32")
+    la = [a.update() for _ in range(6)]
+    lb = b.update_many(6)
+    assert la == lb                      # same kernels, same order: bit-identical
+    assert np.array_equal(a.W, b.W) and np.array_equal(a.H, b.H)
+    a.close(); b.close()
+
+
+def test_caller_arrays_are_not_mutated(built_lib):
+    """MU rebinds W/H (reference mult.py:18,22); initW/initH/data stay untouched."""
+    g, X, W0, H0 = _inputs("k1")
+    N, T, K, L = (int(v) for v in g["shape"])
+    Xc, Wc, Hc = X.copy(), W0.copy(), H0.copy()
+    alg = _solver(X, W0, H0, L, K, "fp32")
+    alg.update_many(3)
+    assert np.array_equal(X, Xc) and np.array_equal(W0, Wc) and np.array_equal(H0, Hc)
+    alg.close()
+
+
+# ---- the reference's own unit tests, run through the GPU primitives -------
+def test_reference_sdot_vectors_on_gpu(built_lib):
+    from cmfpy_b200.common import s_dot
+    from tests.test_oracle import OV, B_SDOT, SDOT_EXPECT
+    for s, exp in SDOT_EXPECT.items():
+        assert_allclose(s_dot(OV, B_SDOT, s), [exp], rtol=1e-6)
+
+
+def test_reference_sTdot_vectors_on_gpu(built_lib):
+    from cmfpy_b200.common import s_T_dot
+    from tests.test_oracle import OV, B_STDOT, STDOT_EXPECT
+    for s, exp in STDOT_EXPECT.items():
+        assert_allclose(s_T_dot(OV, B_STDOT, s), [exp], rtol=1e-6)
+
+
+def test_primitives_against_oracle(built_lib):
+    from cmfpy_b200.common import cmf_predict, tensor_transconv
+    rng = np.random.default_rng(3)
+    for (N, T, K, L) in [(5, 33, 2, 4), (130, 700, 9, 17), (64, 257, 16, 1)]:
+        W, H, X = rng.random((L, N, K)), rng.random((K, T)), rng.random((N, T))
+        _close(cmf_predict(W, H), o.cmf_predict(W, H), 2e-6)
+        _close(tensor_transconv(W, X), o.tensor_transconv(W, X), 2e-6)
+
+
+# ---- model API --------------------------------------------------------------
+def test_cmf_fit_predict_score(built_lib):
+    from cmfpy_b200 import CMF
+    g, X, W0, H0 = _inputs("A")
+    model = CMF(3, 20, n_iter_max=100, verbose=False, tol=0, initW=W0, initH=H0)
+    assert model.fit(X) is None                      # reference fit returns None
+    assert len(model.loss_hist) == 101 and len(model.time_hist) == 101
+    assert model.time_hist[0] == 0.0 and np.all(np.diff(model.time_hist) > 0)
+    rel = np.abs(np.array(model.loss_hist) - g["loss_hist"]) / g["loss_hist"]
+    assert rel.max() <= TRAJ_TOL
+    assert model.motifs.shape == (20, 100, 3) and model.factors.shape == (3, 250)
+    assert model.n_features == 100 and model.n_timesteps == 250
+    est = model.predict()
+    assert est.shape == (100, 250)
+    _close(est, o.cmf_predict(model.motifs, model.factors), 2e-6)
+    r2 = model.score(X)
+    assert abs((1 - r2) - model.loss_hist[-1] ** 2) < 1e-5
+    assert sorted(model.argsort_units()) == list(range(100))
+
+
+def test_cmf_early_stopping_and_random_init(built_lib):
+    from cmfpy_b200 import CMF
+    X, _, _ = make_inputs(20, 120, 3, 5, "planted", seed=9)
+    model = CMF(3, 5, n_iter_max=100000, verbose=False, tol=1e-3, seed=0)
+    model.fit(X)
+    assert 3 < len(model.loss_hist) < 2000           # converged() fired
+    d = np.abs(np.diff(model.loss_hist[-3:]))
+    assert np.all(d < 1e-3)
+    # the alpha rescale of rand_init makes <X, est0> = ||est0||^2
+    from cmfpy_b200.algs.mult import MultUpdate
+    from cmfpy_b200.model import ModelDimensions
+    alg = MultUpdate(X, ModelDimensions(X, maxlag=5, n_components=3), seed=1)
+    est = alg.est
+    assert abs((X * est).sum() / (est ** 2).sum() - 1.0) < 1e-4
+    alg.close()
+
+
+def test_errors_match_reference(built_lib):
+    from cmfpy_b200 import CMF
+    from cmfpy_b200.algs.mult import MultUpdate
+    from cmfpy_b200.model import ModelDimensions
+    X = np.random.default_rng(0).random((6, 50)).astype(np.float32)
+    with pytest.raises(ValueError):
+        CMF(2, 3, verbose=False).fit(-X)
+    with pytest.raises(ValueError):
+        MultUpdate(X, ModelDimensions(X, maxlag=3, n_components=2), patience=0)
+    with pytest.raises(ValueError):
+        MultUpdate(X, ModelDimensions(X, maxlag=3, n_components=2), patience=2.5)
+    with pytest.raises(ValueError):
+        MultUpdate(X, ModelDimensions(X, maxlag=3, n_components=2), initW=np.ones((3, 6, 3)), initH=np.ones((2, 50)))
+
+
+# ---- size-independent properties at a larger size -----------------------------
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_properties_large(built_lib, precision):
+    N, T, K, L = 1024, 1 << 15, 32, 64        # config C at T/32
+    if not _supported(precision, N, K, L):
+        pytest.skip("no %s kernel for this shape" % precision)
+    X, W0, H0 = make_inputs(N, T, K, L, "planted", seed=42)
+    alg = _solver(X, W0, H0, L, K, precision)
+    l0 = alg.loss
+    hist = alg.update_many(4)
+    assert np.all(np.diff([l0] + hist) < 0), "MU must decrease the loss here"
+    W, H = alg.W, alg.H
+    assert np.isfinite(W).all() and np.isfinite(H).all() and (W >= 0).all() and (H >= 0).all()
+    # linearity of the reconstruction: recon(2W, H) = 2 recon(W, H)
+    from cmfpy_b200.common import cmf_predict
+    Ws, Hs = W[:, :64].astype(np.float32), H[:, :4096].astype(np.float32)
+    e1, e2 = cmf_predict(Ws, Hs, precision=precision), cmf_predict(2 * Ws, Hs, precision=precision)
+    assert_allclose(e2, 2 * e1, rtol=1e-6, atol=1e-6)
+    # the loss the solver reports equals the loss of what it returns
+    est = alg.est
+    loss = np.linalg.norm(est - X) / np.linalg.norm(X)
+    assert abs(loss - hist[-1]) / hist[-1] < 1e-4
+    alg.close()
+
+
+def test_fp32_and_tf32_agree_large(built_lib):
+    N, T, K, L = 512, 1 << 14, 16, 32
+    if not _supported("tf32", N, K, L):
+        pytest.skip("no tf32 kernel for this shape")
+    X, W0, H0 = make_inputs(N, T, K, L, "planted", seed=17)
+    a, b = _solver(X, W0, H0, L, K, "fp32"), _solver(X, W0, H0, L, K, "tf32")
+    ha, hb = np.array(a.update_many(10)), np.array(b.update_many(10))
+    assert (np.abs(ha - hb) / ha).max() < TRAJ_TOL
+    a.close(); b.close()
