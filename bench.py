@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the MU hot path: MU iterations/second on BASELINE.json config 3
+(N=1024, T=2^20, K=32, L=64), T-sharded over --gpus GPUs of one box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--precision tf32|fp32] [--config C|B|D|E|A] [--t-scale S]
+
+One "step" = one MultUpdate.update() (W terms, W update, reconstruction,
+H terms, H update, reconstruction + loss).  Prints ONE JSON line (rank 0).
+See DESIGN.md "Measurement" for how every field is derived.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tests.cases import FULL, make_inputs  # noqa: E402
+
+METRIC = "mu_iterations_per_second"
+UNIT = "it/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("CMF_BENCH_PRECISION", "auto"),
+                    choices=["auto", "tf32", "fp32"])
+    ap.add_argument("--config", default="C", choices=sorted(FULL))
+    ap.add_argument("--t-scale", type=float, default=1.0,
+                    help="shrink T (debug only; the line is then labelled reduced)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "power_w_max": float(max(pw)) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def algorithmic_flops(N, T, K, L):
+    """six shift-contractions of 2 N K L T flops per iteration."""
+    return 12.0 * N * K * L * T
+
+
+def reference_iteration_seconds(N, T, K, L, n_iter, seed=0):
+    """Times the oracle port of the reference's MU update (float64, per-lag
+    NumPy/BLAS GEMMs, three reconstructions per iteration as the reference
+    does) on this box's host cores."""
+    from oracle import cmf_oracle
+    X, W0, H0 = make_inputs(N, T, K, L, "uniform", seed)
+    alg = cmf_oracle.MultUpdateOracle(X.astype(np.float64), L, K, initW=W0.astype(np.float64),
+                                      initH=H0.astype(np.float64), tol=0, reuse_est=False)
+    alg.update()                                   # warm-up (BLAS threads, page faults)
+    t0 = time.perf_counter()
+    for _ in range(n_iter):
+        alg.update()
+    return (time.perf_counter() - t0) / n_iter
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 0) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+def cpu_baseline(N, T, K, L, budget_iters=2):
+    """Bounded sample: the reference update at T_s = min(T, 4096) columns with
+    identical N, K, L, extrapolated linearly in T (the reference's cost is
+    linear in N*T*L)."""
+    Ts = int(min(T, 4096))
+    sec = reference_iteration_seconds(N, Ts, K, L, budget_iters)
+    sec_full = sec * (T / Ts)
+    return {"value": 1.0 / sec_full, "unit": UNIT, "cores": int(blas_threads()), "kind": "port",
+            "sample": "oracle port of reference MultUpdate.update (float64 NumPy/BLAS), %d iterations at "
+                      "N=%d T=%d K=%d L=%d (%.3f s/it), extrapolated linearly in T to T=%d"
+                      % (budget_iters, N, Ts, K, L, sec, T)}
+
+
+# --------------------------------------------------------------------------
+# reference arm
+# --------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, T, K, L = FULL[args.config]
+    T = int(T * args.t_scale)
+    Ts = int(min(T, 4096))
+    total = max(1, args.steps)
+    # warm-up + timed steps, each a bounded sample of the workload
+    from oracle import cmf_oracle
+    X, W0, H0 = make_inputs(N, Ts, K, L, "uniform", 0)
+    alg = cmf_oracle.MultUpdateOracle(X.astype(np.float64), L, K, initW=W0.astype(np.float64),
+                                      initH=H0.astype(np.float64), tol=0, reuse_est=False)
+    for _ in range(max(1, min(args.warmup, 2))):
+        alg.update()
+    t0 = time.perf_counter()
+    for _ in range(total):
+        alg.update()
+    sec = (time.perf_counter() - t0) / total
+    sec_full = sec * (T / Ts)
+    value = 1.0 / sec_full
+    cores = int(blas_threads())
+    sample = ("oracle port of reference MultUpdate.update (float64 NumPy/BLAS, %d BLAS threads), %d timed "
+              "iterations at N=%d T=%d K=%d L=%d (%.3f s/it), extrapolated linearly in T to T=%d"
+              % (cores, total, N, Ts, K, L, sec, T))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_full * 1e3,
+            "higher_is_better": True, "scaling": "weak" if False else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config %s: N=%d T=%d K=%d L=%d MU" % (args.config, N, T, K, L)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import __graft_entry__ as g
+    g.build()
+    from cmfpy_b200 import _lib
+    lib = _lib.load()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, T, K, L = FULL[args.config]
+    T = int(T * args.t_scale)
+    assert T % world == 0
+    Tloc = T // world
+    precision = args.precision
+    if precision == "auto":
+        precision = "tf32" if lib.cmf_precision_supported(_lib.CMF_PREC_TF32, N, K, L) else "fp32"
+
+    from cmfpy_b200.dist import ShardedMultUpdate
+    # synthetic inputs generated on the device, identical for any world size:
+    # global column t of X / H0 depends only on (seed, t)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234)
+    W0 = torch.rand((L, N, K), generator=gen, device=dev, dtype=torch.float32)
+    chunk = 1 << 14
+    X = torch.empty((N, Tloc + L - 1), device=dev, dtype=torch.float32)
+    H0 = torch.empty((K, Tloc), device=dev, dtype=torch.float32)
+    t_begin = rank * Tloc
+    ncols_x = min(Tloc + L - 1, T - t_begin)
+    for c0 in range(0, T, chunk):
+        # every rank walks the same global stream so that shards agree
+        xb = torch.rand((N, chunk), generator=gen, device=dev, dtype=torch.float32)
+        hb = torch.rand((K, chunk), generator=gen, device=dev, dtype=torch.float32)
+        lo, hi = max(c0, t_begin), min(c0 + chunk, t_begin + ncols_x)
+        if lo < hi:
+            X[:, lo - t_begin:hi - t_begin] = xb[:, lo - c0:hi - c0]
+        lo, hi = max(c0, t_begin), min(c0 + chunk, t_begin + Tloc)
+        if lo < hi:
+            H0[:, lo - t_begin:hi - t_begin] = hb[:, lo - c0:hi - c0]
+    del xb, hb
+    # scale the init like rand_init does, cheaply: E[X]=0.5, E[est]=L*K/4
+    s = float(np.sqrt(0.5 / (L * K / 4.0)))
+    W0 *= s
+    H0 *= s
+
+    alg = ShardedMultUpdate(X[:, :ncols_x], N, T, K, L, t_offset=t_begin, t_local=Tloc,
+                            initW=W0, initH=H0, precision=precision, device=local_rank,
+                            group=dist.group.WORLD if dist else None)
+    del X, H0
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    alg.update_many(args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = alg.launch_count
+    alg.set_profiling(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = alg.torch_stream
+    barrier()
+    ev0.record(stream)
+    losses = alg.update_many(args.steps)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    kms = alg.kernel_ms()
+    alg.set_profiling(False)
+    launches = alg.launch_count - launches0
+    if dist:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the public host API (pinned host buffers) -------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, N, T, K, L, Tloc, rank, world, local_rank, precision, dist)
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    peaks, peaks_src = measured_peaks()
+    flops_iter = algorithmic_flops(N, T, K, L)
+    recon_launches = 2 * args.steps
+    recon_ms = kms["recon"] / recon_launches
+    recon_flops = 2.0 * N * K * L * Tloc            # per launch, per GPU
+    achieved = recon_flops / (recon_ms * 1e-3) / 1e12
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+    roofline = {
+        "bound": "tensor", "kernel": "recon (shift-GEMM, %s)" % alg.path_name,
+        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+        "traffic": None,
+        "peak_source": "%s bf16_tflops_sustained / 2 (TF32 dense = half of bf16; not separately measured)" % peaks_src,
+        "whole_iteration_tflops": flops_iter / world / (ms_per_step * 1e-3) / 1e12,
+        "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
+        "hbm_update_kernels": {
+            "h_update_gbs": None, "peak_gbs": peaks["hbm_gbs"]},
+    }
+    cb = None
+    if not args.no_cpu_baseline:
+        cb = cpu_baseline(N, T, K, L)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "tf32" if precision == "tf32" else "f32", "data": "synthetic",
+        "config": {"workload": "config %s: N=%d T=%d K=%d L=%d MU%s" %
+                   (args.config, N, T, K, L, "" if args.t_scale == 1.0 else " (T reduced: debug)"),
+                   "sharding": "time axis, %d x %d columns, halo %d" % (world, Tloc, L - 1),
+                   "l2": "inputs_exceed_l2 (X and est are %.1f GiB each per GPU)" % (N * Tloc * 4 / 2**30),
+                   "precision": precision, "path": alg.path_name},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cb,
+        "final_loss": losses[-1],
+    }
+    print(json.dumps(line), flush=True)
+    alg.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, N, T, K, L, Tloc, rank, world, local_rank, precision, dist):
+    """The call a user makes: solver built from HOST arrays (pinned), every
+    update() returns its loss to the host, W and H read back at the end.  The
+    timed region holds all host<->device traffic."""
+    from cmfpy_b200.dist import ShardedMultUpdate
+    dev = torch.device("cuda", local_rank)
+    t_begin = rank * Tloc
+    ncols_x = min(Tloc + L - 1, T - t_begin)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    Xh = torch.empty((N, ncols_x), dtype=torch.float32, pin_memory=True)
+    Xh.copy_(torch.rand((N, ncols_x), generator=gen, device=dev))
+    s = float(np.sqrt(0.5 / (L * K / 4.0)))
+    gen.manual_seed(7)
+    W0h = torch.empty((L, N, K), dtype=torch.float32, pin_memory=True)
+    W0h.copy_(torch.rand((L, N, K), generator=gen, device=dev) * s)
+    gen.manual_seed(99 + rank)
+    H0h = torch.empty((K, Tloc), dtype=torch.float32, pin_memory=True)
+    H0h.copy_(torch.rand((K, Tloc), generator=gen, device=dev) * s)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    alg = ShardedMultUpdate(Xh.numpy(), N, T, K, L, t_offset=t_begin, t_local=Tloc,
+                            initW=W0h.numpy(), initH=H0h.numpy(), precision=precision,
+                            device=local_rank, group=dist.group.WORLD if dist else None)
+    last = None
+    for _ in range(args.steps):
+        last = alg.update()                       # host float every step (D2H + sync)
+    W = alg.W_host()
+    H = alg.H_local_host()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sec = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([sec], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    h2d = (Xh.numel() + W0h.numel() + H0h.numel()) * 4
+    d2h = (W.size + H.size) * 4 + 8 * args.steps
+    alg.close()
+    return {"value": args.steps / sec, "unit": UNIT,
+            "h2d_bytes_per_step": int(h2d * world / args.steps),
+            "d2h_bytes_per_step": int(d2h * world / args.steps),
+            "seconds_total": sec, "final_loss": last,
+            "what": "solver built from pinned host X/W0/H0 (H2D inside the timed region), %d update() calls each "
+                    "returning the loss to the host, W and H copied back" % args.steps}
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

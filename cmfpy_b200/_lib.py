@@ -48,6 +48,7 @@ _SIGNATURES = {
     "cmf_mu_w_apply": (C.c_int, [_H]),
     "cmf_mu_h_step": (C.c_int, [_H]),
     "cmf_mu_resid_sumsq": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "cmf_mu_resid_sumsq_buffer": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "cmf_mu_loss": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "cmf_mu_step": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "cmf_mu_get_W": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),

@@ -667,6 +667,12 @@ int cmf_mu_resid_sumsq(cmf_mu_t* h, double* sumsq) {
   return 0;
 }
 
+int cmf_mu_resid_sumsq_buffer(cmf_mu_t* h, double** dev_ptr) {
+  CMF_CHECK(h != nullptr && dev_ptr != nullptr, "null argument");
+  *dev_ptr = h->d_sumsq;
+  return 0;
+}
+
 int cmf_mu_loss(cmf_mu_t* h, double* loss) {
   double s = 0.0;
   CMF_TRY(cmf_mu_resid_sumsq(h, &s));

@@ -126,6 +126,9 @@ int cmf_mu_w_apply(cmf_mu_t* h);
 int cmf_mu_h_step(cmf_mu_t* h);
 /* Local sum of squared residuals of the last cmf_mu_recon (device -> host). */
 int cmf_mu_resid_sumsq(cmf_mu_t* h, double* sumsq);
+/* DEVICE address of that double, so a sharded driver can all-reduce it
+ * without a host round trip.                                                */
+int cmf_mu_resid_sumsq_buffer(cmf_mu_t* h, double** dev_ptr);
 /* loss = ||resids||_F / normX (base.py:90-97) from the local residual; only
  * meaningful unsharded or after the driver reduced it itself.               */
 int cmf_mu_loss(cmf_mu_t* h, double* loss);
