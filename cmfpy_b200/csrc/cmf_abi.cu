@@ -179,7 +179,7 @@ int simt_h_terms(cmf_mu_s* h) {
 // ---- phase dispatch -----------------------------------------------------
 int do_recon(cmf_mu_s* h) {
   CMF_CHECK(h->have_data && h->have_factors, "recon before data/factors were set");
-  if (h->use_tc) {
+  if (h->use_tc && (h->tcs.mask & 1)) {
     CMF_TRY(tc::recon(h->tcs, h->stream));
     h->launches += tc::kReconLaunches;
   } else {
@@ -190,7 +190,7 @@ int do_recon(cmf_mu_s* h) {
 }
 int do_w_terms(cmf_mu_s* h) {
   CMF_CHECK(h->est_valid, "w_terms needs a current reconstruction (call cmf_mu_recon)");
-  if (h->use_tc) {
+  if (h->use_tc && (h->tcs.mask & 2)) {
     CMF_TRY(tc::w_terms(h->tcs, h->stream));
     h->launches += tc::kWTermsLaunches;
   } else {
@@ -211,7 +211,7 @@ int do_w_apply(cmf_mu_s* h) {
 }
 int do_h_terms(cmf_mu_s* h) {
   CMF_CHECK(h->est_valid, "h terms need a current reconstruction (call cmf_mu_recon)");
-  if (h->use_tc) {
+  if (h->use_tc && (h->tcs.mask & 4)) {
     CMF_TRY(tc::h_terms(h->tcs, h->stream));
     h->launches += tc::kHTermsLaunches;
     return 0;
@@ -664,6 +664,7 @@ int cmf_mu_resid_sumsq(cmf_mu_t* h, double* sumsq) {
   CMF_CHECK(h->est_valid, "Residuals not initialized.");                // base.py:95-96
   CMF_CUDA(cudaMemcpyAsync(sumsq, h->d_sumsq, 8, cudaMemcpyDeviceToHost, h->stream));
   CMF_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->use_tc) CMF_TRY(tc::check(h->tcs, h->stream));
   return 0;
 }
 
@@ -714,6 +715,7 @@ int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
     if (loss_out)
       CMF_CUDA(cudaMemcpyAsync(loss_out + done, h->d_ring, (size_t)chunk * 8, cudaMemcpyDeviceToHost, h->stream));
     CMF_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->use_tc) CMF_TRY(tc::check(h->tcs, h->stream));
     // unpack event timings
     const int per = (ms_out ? 1 : 0) + (prof ? 7 : 0);
     for (int i = 0; i < chunk; ++i) {
@@ -833,7 +835,8 @@ int cmf_mu_launch_count(cmf_mu_t* h, long long* count) {
 
 const char* cmf_mu_path_name(cmf_mu_t* h) {
   if (!h) return "none";
-  return h->use_tc ? "tcgen05-tf32" : "ffma-fp32";
+  if (!h->use_tc) return "ffma-fp32";
+  return h->tcs.mask == 7 ? "tcgen05-tf32" : "tcgen05-tf32(partial)";
 }
 
 int cmf_mu_kernel_ms(cmf_mu_t* h, float out[4]) {

@@ -1,0 +1,577 @@
+// tcgen05 / TMEM / TMA shift-GEMM kernels (CMF_PREC_TF32), sm_100a.
+//
+// All three contractions of the MU iteration run as warp-specialised persistent
+// kernels: one TMA producer warp, one MMA-issuing warp (a single elected thread
+// issues tcgen05.mma), four epilogue warps draining tensor memory.  A lag is
+// never materialised: it is a row offset of a shared-memory operand window
+//   * K-major no-swizzle "panels"  [k-chunk][row][16 B]  (row pitch 16 B: any
+//     row shift is a legal descriptor start address), or
+//   * MN-major SWIZZLE_128B_BASE32B rows of 128 B where the N-direction atom
+//     stride is ONE ROW (overlapping atoms: lag a+1 is lag a moved by a row).
+// Both were validated on hardware with tools/umma_probe.py (profiles/r01_umma_probe.log):
+// swizzles are functions of the absolute shared-memory address, so shifted
+// windows read what TMA wrote, and every layout used here sustains the full
+// 128 cycles per 128x256x8 MMA.
+//
+// This file is specialised for Kp == 32 (K in 25..32: one 128-byte row of H^T).
+#pragma once
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace cmf {
+namespace tc {
+
+using namespace ptx;
+
+constexpr int kKp = 32;              // padded component count this file handles
+constexpr uint32_t kTimeoutCycles = 2000000000u;   // ~1 s: a pipeline bug must never hang the GPU
+
+// error codes written to *err (0 = fine)
+enum { kErrTimeout = 1 };
+
+struct Abort {
+  volatile int* flag;     // shared memory
+  int* global_err;
+  __device__ __forceinline__ bool wait(uint64_t* bar, uint32_t parity) const {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (true) {
+#pragma unroll 1
+      for (int i = 0; i < 64; ++i)
+        if (mbar_try_wait(bar, parity)) return true;
+      if (*flag) return false;
+      if ((unsigned long long)(clock64() - t0) > kTimeoutCycles) {
+        *flag = 1;
+        atomicExch(global_err, kErrTimeout);
+        return false;
+      }
+    }
+  }
+};
+
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int nstages) {
+    if (++stage == nstages) { stage = 0; phase ^= 1; }
+  }
+};
+
+// ==========================================================================
+// K1  reconstruction + loss
+//   est^T[tau][n] = sum_l sum_k W[l][n][k] * H^T[tau-l][k]
+//   (reference cmf_predict, cmfpy/common.py:50-58, and cache_resids / loss,
+//    cmfpy/algs/base.py:57-62, 90-97)
+// UMMA view per tile: D[128 n][256 tau] += A_l[128 n][32 k] * B_l[256 tau][32 k]^T
+//   A_l = W[l][n0..n0+128][:]  K-major SWIZZLE_128B, streamed through a ring
+//   B_l = rows (L-1-l) .. of the H^T window, K-major no-swizzle panels
+// Two TMEM accumulators (2 x 256 columns) ping-pong so the epilogue of tile i
+// (TMEM -> registers -> est^T, fused loss against X^T) overlaps the MMAs of
+// tile i+1.
+// ==========================================================================
+struct ReconParams {
+  int Np, L, n_tiles_n, wrows;
+  long long n_tiles;               // n_tiles_n * (RT / 256)
+  long long t_own, t_valid;
+  float* Et;
+  const float* Xt;
+  double* loss_partials;           // one per CTA
+  int round_out;
+  int* err;
+};
+
+constexpr int kReconStages = 6;
+constexpr int kReconThreads = 192;
+constexpr int kReconABytes = 128 * kKp * 4;       // 16 KB per lag
+
+__host__ __device__ inline size_t recon_smem_bytes(int wrows) {
+  return 1024 + (size_t)kReconStages * kReconABytes + 2 * (size_t)wrows * kKp * 4 + 256;
+}
+
+__global__ void __launch_bounds__(kReconThreads, 1)
+tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
+                const ReconParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* As = smem;                                           // [stages][16 KB]
+  uint8_t* Hs = As + kReconStages * kReconABytes;               // [2][wrows * 128]
+  const uint32_t hbytes = (uint32_t)p.wrows * kKp * 4;
+  uint64_t* bars = (uint64_t*)(Hs + 2 * hbytes);
+  uint64_t* full = bars;                                        // [stages]
+  uint64_t* empty = bars + kReconStages;                        // [stages]
+  uint64_t* hfull = bars + 2 * kReconStages;                    // [2]
+  uint64_t* hempty = hfull + 2;                                 // [2]
+  uint64_t* tfull = hempty + 2;                                 // [2]
+  uint64_t* tempty = tfull + 2;                                 // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
+  __shared__ double red[4];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kReconStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1);
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4);
+    }
+    *abort_flag = 0;
+    fence_mbar_init();
+    prefetch_tmap(&tmW);
+    prefetch_tmap(&tmH);
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const Abort ab{abort_flag, p.err};
+  const int L = p.L, wrows = p.wrows;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      PipeState ps;
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int nt = (int)(tile % p.n_tiles_n);
+        const long long tt = tile / p.n_tiles_n;
+        const int hb = it & 1;
+        if (!ab.wait(&hempty[hb], ((it >> 1) & 1) ^ 1)) break;
+        mbar_arrive_expect_tx(&hfull[hb], hbytes);
+        uint8_t* hdst = Hs + (size_t)hb * hbytes;
+        for (int kc = 0; kc < kKp / 4; ++kc)
+          for (int rb = 0; rb < wrows / 64; ++rb)
+            tma_load_2d(hdst + ((size_t)kc * wrows + rb * 64) * 16, &tmH, &hfull[hb], kc * 4,
+                        (int)(tt * 256 + rb * 64));
+        bool ok = true;
+        for (int l = 0; l < L; ++l) {
+          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+          mbar_arrive_expect_tx(&full[ps.stage], kReconABytes);
+          tma_load_2d(As + (size_t)ps.stage * kReconABytes, &tmW, &full[ps.stage], 0, l * p.Np + nt * 128);
+          ps.advance(kReconStages);
+        }
+        if (!ok) break;
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, 256, 0, 0);
+      PipeState ps;
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t par = (it >> 1) & 1;
+        if (!ab.wait(&tempty[b], par ^ 1)) break;
+        if (!ab.wait(&hfull[b], par)) break;
+        tc_fence_after();
+        const uint32_t hbase = smem_u32(Hs + (size_t)b * hbytes);
+        const uint32_t dtm = tmem + (uint32_t)b * 256;
+        bool ok = true;
+        for (int l = 0; l < L; ++l) {
+          if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t abase = smem_u32(As + (size_t)ps.stage * kReconABytes);
+#pragma unroll
+          for (int ks = 0; ks < kKp / 8; ++ks) {
+            const uint64_t ad = make_smem_desc(abase + ks * 32, 16, 1024, kSwz128);
+            const uint64_t bd = make_smem_desc(hbase + (uint32_t)(ks * 2 * wrows + (L - 1 - l)) * 16,
+                                               (uint32_t)wrows * 16, 128, kSwzNone);
+            mma_tf32_ss(dtm, ad, bd, idesc, (l | ks) != 0 ? 1u : 0u);
+          }
+          mma_commit(&empty[ps.stage]);
+          ps.advance(kReconStages);
+        }
+        if (!ok) break;
+        mma_commit(&tfull[b]);
+        mma_commit(&hempty[b]);
+      }
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> est^T, fused loss ----------------
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    double loss_acc = 0.0;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int nt = (int)(tile % p.n_tiles_n);
+      const long long tt = tile / p.n_tiles_n;
+      const int b = it & 1;
+      if (!ab.wait(&tfull[b], (it >> 1) & 1)) break;
+      tc_fence_after();
+      const int n = nt * 128 + q * 32 + lane;
+      const bool n_ok = n < p.Np;
+      float tile_loss = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + c * 32), r);
+        tmem_ld_wait();
+        const long long tau0 = tt * 256 + c * 32;
+        if (n_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long tau = tau0 + j;
+            float v = __uint_as_float(r[j]);
+            if (tau >= p.t_valid) v = 0.f;
+            const size_t off = (size_t)tau * p.Np + n;
+            if (tau < p.t_own) {
+              const float d = v - __ldg(p.Xt + off);
+              tile_loss = fmaf(d, d, tile_loss);
+            }
+            if (p.round_out) v = round_tf32(v);
+            p.Et[off] = v;
+          }
+        }
+      }
+      loss_acc += (double)tile_loss;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[b]);
+    }
+    // block partial of the loss (epilogue warps only)
+    loss_acc = warp_sum(loss_acc);
+    if (lane == 0) red[q] = loss_acc;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 2 && lane == 0) p.loss_partials[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ==========================================================================
+// K2  W terms
+//   out[src][l][n][k] = sum_tau S^T[tau][n] * H^T[tau-l][k],  S = X | est
+//   (reference _compute_mult_W, cmfpy/algs/mult.py:27-40)
+// UMMA view per work item (128 n, 16 lags, one source, a chunk of time):
+//   D[128 n][2 x (8 lags x 32 k)] += A[128 n][8 tau]^T-major * B[(lag,k)][8 tau]
+//   A = S^T rows, MN-major SWIZZLE_128B_BASE32B (4 regions of 32 n)
+//   B = H^T rows, MN-major SWIZZLE_128B_BASE32B, N-atom stride = one row:
+//       atom a of MMA g is lag  l0 + 8g + 7 - a
+// Partial sums per time chunk go to a scratch buffer and are reduced in a fixed
+// order by sum_splits_kernel (deterministic; no float atomics).
+// ==========================================================================
+struct WTermsParams {
+  int Np, L, n_tiles_n, n_lag_groups, n_chunks, h;
+  long long n_items;              // n_tiles_n * n_lag_groups * 2 * n_chunks
+  long long stages_total;         // ceil(t_own / 32)
+  float* part;                    // [chunk][src][L][Np][Kp]
+  long long per_src;              // L * Np * Kp
+  int* err;
+};
+
+constexpr int kWtStages = 6;
+constexpr int kWtThreads = 192;
+constexpr int kWtABytes = 4 * 32 * 128;           // 128 n x 32 tau
+constexpr int kWtBRows = 48;                      // 32 tau + 15 lags, padded
+constexpr int kWtBBytes = kWtBRows * 128;
+constexpr int kWtStageBytes = kWtABytes + kWtBBytes;
+
+__host__ __device__ inline size_t wterms_smem_bytes() { return 1024 + (size_t)kWtStages * kWtStageBytes + 256; }
+
+__global__ void __launch_bounds__(kWtThreads, 1)
+tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmE,
+                 const __grid_constant__ CUtensorMap tmH, const WTermsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* St = smem;                                            // [stages][A 16 KB | B 6 KB]
+  uint64_t* bars = (uint64_t*)(St + kWtStages * kWtStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWtStages;
+  uint64_t* tfull = bars + 2 * kWtStages;                        // [1]
+  uint64_t* tempty = tfull + 1;                                  // [1]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
+  volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kWtStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    *abort_flag = 0;
+    fence_mbar_init();
+    prefetch_tmap(&tmX); prefetch_tmap(&tmE); prefetch_tmap(&tmH);
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const Abort ab{abort_flag, p.err};
+
+  // item -> (chunk, n tile, src, lag group); lag group fastest so that the CTAs
+  // that stream the same S^T rows run at the same time (L2 reuse)
+  auto decode = [&](long long item, int& lg, int& src, int& nt, int& ch) {
+    lg = (int)(item % p.n_lag_groups); item /= p.n_lag_groups;
+    src = (int)(item % 2); item /= 2;
+    nt = (int)(item % p.n_tiles_n); item /= p.n_tiles_n;
+    ch = (int)item;
+  };
+  auto chunk_range = [&](int ch, long long& s0, long long& s1) {
+    const long long base = p.stages_total / p.n_chunks, rem = p.stages_total % p.n_chunks;
+    s0 = ch * base + (ch < rem ? ch : rem);
+    s1 = s0 + base + (ch < rem ? 1 : 0);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps;
+      bool ok = true;
+      for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+        int lg, src, nt, ch;
+        decode(item, lg, src, nt, ch);
+        long long s0, s1;
+        chunk_range(ch, s0, s1);
+        const CUtensorMap* tmS = src ? &tmE : &tmX;
+        for (long long s = s0; s < s1; ++s) {
+          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+          uint8_t* dst = St + (size_t)ps.stage * kWtStageBytes;
+          mbar_arrive_expect_tx(&full[ps.stage], kWtStageBytes);
+          const int tau0 = (int)(s * 32);
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            tma_load_2d(dst + r * 4096, tmS, &full[ps.stage], nt * 128 + r * 32, tau0);
+          // H^T rows tau0 - (l0+15) .. tau0 + 32; row index in Ht is tau + h
+          tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], 0, tau0 - (lg * 16 + 15) + p.h);
+          ps.advance(kWtStages);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, 256, 1, 1);
+      PipeState ps;
+      int it = 0;
+      bool ok = true;
+      for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x, ++it) {
+        int lg, src, nt, ch;
+        decode(item, lg, src, nt, ch);
+        long long s0, s1;
+        chunk_range(ch, s0, s1);
+        if (!ab.wait(tempty, (it & 1) ^ 1)) break;
+        tc_fence_after();
+        for (long long s = s0; s < s1; ++s) {
+          if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t abase = smem_u32(St + (size_t)ps.stage * kWtStageBytes);
+          const uint32_t bbase = abase + kWtABytes;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint64_t bd = make_smem_desc(bbase + (uint32_t)((8 - 8 * g) + ks * 8) * 128, 128, 512, 1);
+              mma_tf32_ss(tmem + g * 256, ad, bd, idesc, (s > s0 || ks > 0) ? 1u : 0u);
+            }
+          }
+          mma_commit(&empty[ps.stage]);
+          ps.advance(kWtStages);
+        }
+        if (!ok) break;
+        mma_commit(tfull);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int it = 0;
+    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      int lg, src, nt, ch;
+      decode(item, lg, src, nt, ch);
+      if (!ab.wait(tfull, it & 1)) break;
+      tc_fence_after();
+      const int n = nt * 128 + q * 32 + lane;
+      float* obase = p.part + ((long long)ch * 2 + src) * p.per_src;
+#pragma unroll 1
+      for (int c = 0; c < 16; ++c) {            // 16 column blocks of 32 = (g, a): one lag each
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        const int g = c >> 3, a = c & 7;
+        const int l = lg * 16 + 8 * g + 7 - a;
+        if (n < p.Np && l < p.L) {
+          float4* o = reinterpret_cast<float4*>(obase + ((long long)l * p.Np + n) * kKp);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ==========================================================================
+// K3  H terms
+//   out[src][tau][k] = sum_l sum_n W[l][n][k] * S^T[tau+l][n],  S = X | est
+//   (reference tensor_transconv, cmfpy/common.py:61-86, via mult.py:42-48)
+// The output has only K rows, so four lag groups share the 128 MMA rows:
+//   row (g,k) of D accumulates lags l = j + J*g (J = Lp/4, j = 0..J-1):
+//   D[(g,k)][c] += W[j+J*g][n][k] * S^T[base + c + j][n]      (M=128, N=256)
+//   => D[(g,k)][c] is the group-g part of out[k][base + c - J*g].
+//   A = W rows of 4 lags, MN-major SWIZZLE_128B_BASE32B (4 regions: one per g)
+//   B = S^T window, K-major no-swizzle panels, row shift j
+// Two accumulators: X (numerator) and est (denominator) share every A stage.
+// The epilogue adds D into a zeroed out[src] with red.global.add.f32 (at most
+// two CTAs touch an address, so the sum is order-independent).
+// ==========================================================================
+struct HTermsParams {
+  int Np, J, n_chunks_n, wrows;    // n chunks of 32 features; window rows >= 256 + J - 1
+  long long n_tiles;               // TO / 256
+  long long t_rows;                // rows of out (TO)
+  float* out;                      // [2][TO][Kp], zeroed before launch
+  int* err;
+};
+
+constexpr int kHtStages = 4;
+constexpr int kHtThreads = 192;
+constexpr int kHtABytes = 4 * 32 * 128;            // 4 lag groups x 32 n x 32 k
+
+__host__ __device__ inline size_t hterms_smem_bytes(int wrows) {
+  return 1024 + (size_t)kHtStages * kHtABytes + 2 * 2 * (size_t)wrows * 128 + 256;
+}
+
+__global__ void __launch_bounds__(kHtThreads, 1)
+tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                 const __grid_constant__ CUtensorMap tmE, const HTermsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* As = smem;                                             // [stages][16 KB]
+  const uint32_t wbytes = (uint32_t)p.wrows * 128;                // one source, one 32-feature chunk
+  uint8_t* Ws = As + kHtStages * kHtABytes;                       // [2 buffers][2 sources][wbytes]
+  uint64_t* bars = (uint64_t*)(Ws + 4 * (size_t)wbytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kHtStages;
+  uint64_t* wfull = bars + 2 * kHtStages;                         // [2]
+  uint64_t* wempty = wfull + 2;                                   // [2]
+  uint64_t* tfull = wempty + 2;                                   // [1]
+  uint64_t* tempty = tfull + 1;                                   // [1]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
+  volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kHtStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    *abort_flag = 0;
+    fence_mbar_init();
+    prefetch_tmap(&tmW); prefetch_tmap(&tmX); prefetch_tmap(&tmE);
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const Abort ab{abort_flag, p.err};
+  const int J = p.J, wrows = p.wrows;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps;
+      long long wcount = 0;                 // window loads issued so far
+      bool ok = true;
+      for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+        const int base = (int)(tile * 256);
+        for (int nc = 0; nc < p.n_chunks_n && ok; ++nc, ++wcount) {
+          const int wb = (int)(wcount & 1);
+          if (!ab.wait(&wempty[wb], (uint32_t)((wcount >> 1) & 1) ^ 1)) { ok = false; break; }
+          mbar_arrive_expect_tx(&wfull[wb], 2 * wbytes);
+          for (int src = 0; src < 2; ++src) {
+            uint8_t* wdst = Ws + ((size_t)wb * 2 + src) * wbytes;
+            const CUtensorMap* tmS = src ? &tmE : &tmX;
+            for (int kc = 0; kc < 8; ++kc)
+              for (int rb = 0; rb < wrows / 32; ++rb)
+                tma_load_2d(wdst + ((size_t)kc * wrows + rb * 32) * 16, tmS, &wfull[wb], nc * 32 + kc * 4,
+                            base + rb * 32);
+          }
+          for (int j = 0; j < J; ++j) {
+            if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+            uint8_t* dst = As + (size_t)ps.stage * kHtABytes;
+            mbar_arrive_expect_tx(&full[ps.stage], kHtABytes);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              tma_load_2d(dst + g * 4096, &tmW, &full[ps.stage], 0, (j + J * g) * p.Np + nc * 32);
+            ps.advance(kHtStages);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, 256, 1, 0);
+      PipeState ps;
+      long long wcount = 0;
+      int it = 0;
+      bool ok = true;
+      for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x, ++it) {
+        if (!ab.wait(tempty, (it & 1) ^ 1)) break;
+        tc_fence_after();
+        for (int nc = 0; nc < p.n_chunks_n && ok; ++nc, ++wcount) {
+          const int wb = (int)(wcount & 1);
+          if (!ab.wait(&wfull[wb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t wbase = smem_u32(Ws + (size_t)wb * 2 * wbytes);
+          for (int j = 0; j < J; ++j) {
+            if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+            tc_fence_after();
+            const uint32_t abase = smem_u32(As + (size_t)ps.stage * kHtABytes);
+#pragma unroll
+            for (int src = 0; src < 2; ++src) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
+                const uint64_t bd = make_smem_desc(wbase + src * wbytes + (uint32_t)(ks * 2 * wrows + j) * 16,
+                                                   (uint32_t)wrows * 16, 128, kSwzNone);
+                mma_tf32_ss(tmem + src * 256, ad, bd, idesc, (nc | j | ks) != 0 ? 1u : 0u);
+              }
+            }
+            mma_commit(&empty[ps.stage]);
+            ps.advance(kHtStages);
+          }
+          if (!ok) break;
+          mma_commit(&wempty[wb]);
+        }
+        if (!ok) break;
+        mma_commit(tfull);
+      }
+    }
+  } else {
+    const int q = warp & 3;                 // lag group g of this warp's 32 TMEM lanes; lane = k
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      if (!ab.wait(tfull, it & 1)) break;
+      tc_fence_after();
+      const long long base = tile * 256 - (long long)J * q;       // out row of column 0
+#pragma unroll 1
+      for (int c = 0; c < 16; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        const int src = c >> 3;
+        float* o = p.out + (size_t)src * p.t_rows * kKp;
+        const long long t0 = base + (c & 7) * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const long long t = t0 + j;
+          if (t >= 0) atomicAdd(o + t * kKp + lane, __uint_as_float(r[j]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tc
+}  // namespace cmf

@@ -23,6 +23,12 @@ CASES = {
     "k1":       (16, 128, 1, 9, "planted", 30, True),
     "n1":       (1, 96, 2, 5, "uniform", 20, True),
     "zeros":    (24, 160, 3, 6, "zeros_rows", 20, True),
+    # shapes the tensor-core path accepts (25 <= K <= 32), with edge cases:
+    # N not a multiple of 32, L not a multiple of 4/16, L = 1, L > 64
+    "tc_k32":   (96, 700, 32, 12, "planted", 30, True),
+    "tc_k27":   (130, 1000, 27, 5, "planted", 30, True),
+    "tc_l1":    (64, 512, 32, 1, "uniform", 20, True),
+    "tc_l70":   (40, 600, 30, 70, "planted", 20, True),
     "mid":      (128, 2048, 8, 16, "planted", 100, False),
     # BASELINE config 2 at full size
     "B":        (256, 65536, 8, 32, "planted", 100, False),
