@@ -51,7 +51,9 @@ struct cmf_mu_s {
   int round_ops = 0;                 // store operands pre-rounded to TF32
   bool use_tc = false;
 
-  float *Xt = nullptr, *Et = nullptr, *Ht = nullptr, *W = nullptr;
+  float *Xt = nullptr, *Et = nullptr, *Ht = nullptr, *W = nullptr;   // Ht, W: fp32 masters
+  float *Ht_op = nullptr, *W_op = nullptr;   // TF32-rounded operand copies (tensor-core path only)
+  float *Htc = nullptr, *Wc = nullptr;       // what the contractions read: *_op if present, else masters
   float *numden = nullptr, *wpart = nullptr, *hterms = nullptr;
   long long wcount = 0;              // L * Np * Kp
   int wsplits = 1;
@@ -118,8 +120,8 @@ int launch_check(cmf_mu_s* h, const char* what) {
 
 // ---- contraction launches (fp32 FFMA path) ------------------------------
 int simt_recon(cmf_mu_s* h) {
-  simt::ReconA a{h->Ht, h->Kp, h->h};
-  simt::ReconB b{h->W, h->Np, h->Kp};
+  simt::ReconA a{h->Htc, h->Kp, h->h};
+  simt::ReconB b{h->Wc, h->Np, h->Kp};
   simt::ReconEpi e{h->Et, h->Xt, h->loss_partials, h->Np, h->Tloc, h->t_valid, h->round_ops};
   const long long R = (long long)h->L * h->Kp;
   long long nblocks;
@@ -140,7 +142,7 @@ int simt_recon(cmf_mu_s* h) {
 int simt_w_terms(cmf_mu_s* h) {
   const int LKp = h->L * h->Kp;
   simt::WTermsA a{h->Xt, h->Et, h->Np};
-  simt::WTermsB b{h->Ht, h->Kp, h->h, LKp};
+  simt::WTermsB b{h->Htc, h->Kp, h->h, LKp};
   float* part = (h->wsplits == 1) ? h->numden : h->wpart;
   simt::WTermsEpi e{part, h->Np, h->Kp, LKp, h->wcount};
   dim3 grid((unsigned)ceil_div_ll(h->Np, 128), (unsigned)ceil_div_ll(LKp, 128), (unsigned)(h->wsplits * 2));
@@ -157,7 +159,7 @@ int simt_w_terms(cmf_mu_s* h) {
 
 int simt_h_terms(cmf_mu_s* h) {
   simt::HTermsA a{h->Xt, h->Et, h->Np};
-  simt::HTermsB b{h->W, h->Kp};
+  simt::HTermsB b{h->Wc, h->Kp};
   simt::HTermsEpi e{h->hterms, h->Kp, h->TO * h->Kp};
   const long long R = (long long)h->L * h->Np;
   if (h->Kp <= 16) {
@@ -203,7 +205,7 @@ int do_w_apply(cmf_mu_s* h) {
   CMF_CHECK(h->wterms_valid, "w_apply before w_terms");
   const long long n4 = h->wcount / 4;
   ew::mu_update_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>(
-      (float4*)h->W, (const float4*)h->numden, (const float4*)(h->numden + h->wcount), n4, h->round_ops);
+      (float4*)h->W, (const float4*)h->numden, (const float4*)(h->numden + h->wcount), n4, (float4*)h->W_op);
   CMF_TRY(launch_check(h, "w_update"));
   h->wterms_valid = false;
   h->est_valid = false;
@@ -222,10 +224,25 @@ int do_h_apply(cmf_mu_s* h) {
   const long long n4 = h->Tloc * h->Kp / 4;
   ew::mu_update_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>(
       (float4*)(h->Ht + (long long)h->h * h->Kp), (const float4*)h->hterms,
-      (const float4*)(h->hterms + h->TO * h->Kp), n4, h->round_ops);
+      (const float4*)(h->hterms + h->TO * h->Kp), n4,
+      h->Ht_op ? (float4*)(h->Ht_op + (long long)h->h * h->Kp) : nullptr);
   CMF_TRY(launch_check(h, "h_update"));
   h->est_valid = false;
   return 0;
+}
+
+// refresh the TF32 operand copies from the fp32 masters (no-op on the fp32 path)
+int sync_ops_W(cmf_mu_s* h) {
+  if (!h->W_op) return 0;
+  ew::round_copy_kernel<<<ew_grid(h, h->wcount / 4), 256, 0, h->stream>>>((float4*)h->W_op, (const float4*)h->W, h->wcount / 4);
+  return launch_check(h, "round_w");
+}
+int sync_ops_H(cmf_mu_s* h, long long row0, long long nrows) {
+  if (!h->Ht_op || nrows <= 0) return 0;
+  const long long n4 = nrows * h->Kp / 4;
+  ew::round_copy_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>((float4*)(h->Ht_op + row0 * h->Kp),
+                                                               (const float4*)(h->Ht + row0 * h->Kp), n4);
+  return launch_check(h, "round_h");
 }
 
 cudaEvent_t get_event(cmf_mu_s* h, size_t i) {
@@ -248,13 +265,13 @@ int stage_block(const void* src, int mem, long long ld, long long rows, long lon
 
 template <class TI>
 int load_transposed(cmf_mu_s* h, const TI* src, int mem, long long ld, long long rows, long long cols,
-                    float* dst, long long ldd) {
+                    float* dst, long long ldd, int round_in) {
   // dst[c][r] = src[r][c]; host sources go through a bounded device staging buffer
   if (rows == 0 || cols == 0) return 0;
   if (mem == CMF_DEVICE) {
     dim3 grid((unsigned)ceil_div_ll(cols, 32), (unsigned)ceil_div_ll(rows, 32));
     CMF_CHECK(grid.y <= 65535, "too many rows for the transpose grid");
-    ew::transpose_convert_kernel<TI, float><<<grid, 256, 0, h->stream>>>(src, ld, dst, ldd, rows, cols, h->round_ops);
+    ew::transpose_convert_kernel<TI, float><<<grid, 256, 0, h->stream>>>(src, ld, dst, ldd, rows, cols, round_in);
     return launch_check(h, "transpose_in");
   }
   const long long budget = 256ll << 20;
@@ -270,7 +287,7 @@ int load_transposed(cmf_mu_s* h, const TI* src, int mem, long long ld, long long
     rc = stage_block(src + c0, CMF_HOST, ld, rows, w, sizeof(TI), stg, h->stream);
     if (rc) break;
     dim3 grid((unsigned)ceil_div_ll(w, 32), (unsigned)ceil_div_ll(rows, 32));
-    ew::transpose_convert_kernel<TI, float><<<grid, 256, 0, h->stream>>>(stg, w, dst + c0 * ldd, ldd, rows, w, h->round_ops);
+    ew::transpose_convert_kernel<TI, float><<<grid, 256, 0, h->stream>>>(stg, w, dst + c0 * ldd, ldd, rows, w, round_in);
     rc = launch_check(h, "transpose_in");
     // the staging buffer is reused by the next chunk
     if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) { set_error("sync failed in load_transposed"); rc = 1; }
@@ -329,7 +346,7 @@ int store_transposed(cmf_mu_s* h, const float* src, long long lds, long long row
 
 void free_all(cmf_mu_s* h) {
   tc::destroy(h->tcs);
-  cudaFree(h->Xt); cudaFree(h->Et); cudaFree(h->Ht); cudaFree(h->W);
+  cudaFree(h->Xt); cudaFree(h->Et); cudaFree(h->Ht); cudaFree(h->W); cudaFree(h->Ht_op); cudaFree(h->W_op);
   cudaFree(h->numden); cudaFree(h->wpart); cudaFree(h->hterms);
   cudaFree(h->loss_partials); cudaFree(h->d_sumsq); cudaFree(h->d_ring); cudaFree(h->d_xpart);
   cudaFree(h->d_neg);
@@ -445,6 +462,7 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
   A(dmalloc(&h->Et, h->RT * h->Np));
   A(dmalloc(&h->Ht, h->RH * h->Kp));
   A(dmalloc(&h->W, h->wcount));
+  if (h->round_ops) { A(dmalloc(&h->Ht_op, h->RH * h->Kp)); A(dmalloc(&h->W_op, h->wcount)); }
   A(dmalloc(&h->numden, 2 * h->wcount));
   if (h->wsplits > 1) A(dmalloc(&h->wpart, 2 * h->wcount * h->wsplits));
   A(dmalloc(&h->hterms, 2 * h->TO * h->Kp));
@@ -462,15 +480,18 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
     Z(h->Et, (size_t)h->RT * h->Np * 4);
     Z(h->Ht, (size_t)h->RH * h->Kp * 4);
     Z(h->W, (size_t)h->wcount * 4);
+    if (h->Ht_op) { Z(h->Ht_op, (size_t)h->RH * h->Kp * 4); Z(h->W_op, (size_t)h->wcount * 4); }
     Z(h->numden, (size_t)2 * h->wcount * 4);
     Z(h->hterms, (size_t)2 * h->TO * h->Kp * 4);
     Z(h->d_sumsq, 8);
     Z(h->d_neg, 4);
     if (e != cudaSuccess) { set_error("cudaMemset failed: %s", cudaGetErrorString(e)); rc = 1; }
   }
+  h->Htc = h->Ht_op ? h->Ht_op : h->Ht;
+  h->Wc = h->W_op ? h->W_op : h->W;
   if (rc == 0 && h->use_tc) {
     tc::Dims d{h->N, h->K, h->L, h->Np, h->Kp, h->h, h->Tloc, h->TO, h->RT, h->RH, h->t_valid, h->num_sms};
-    rc = tc::init(h->tcs, d, h->Xt, h->Et, h->Ht, h->W, h->numden, h->hterms, h->loss_partials,
+    rc = tc::init(h->tcs, d, h->Xt, h->Et, h->Htc, h->Wc, h->numden, h->hterms, h->loss_partials,
                   h->n_loss_partials, h->d_sumsq, h->stream);
   }
   if (rc != 0) {
@@ -501,8 +522,8 @@ int cmf_mu_set_data(cmf_mu_t* h, const void* X, int dtype, int mem, long long ld
   CMF_CHECK(ld >= ncols, "leading dimension %lld < ncols %lld", ld, ncols);
   if (ncols > h->t_valid) ncols = h->t_valid;    // nothing exists past the global end
   CMF_CUDA(cudaMemsetAsync(h->Xt, 0, (size_t)h->RT * h->Np * 4, h->stream));
-  if (dtype == CMF_F32) CMF_TRY(load_transposed<float>(h, (const float*)X, mem, ld, h->N, ncols, h->Xt, h->Np));
-  else CMF_TRY(load_transposed<double>(h, (const double*)X, mem, ld, h->N, ncols, h->Xt, h->Np));
+  if (dtype == CMF_F32) CMF_TRY(load_transposed<float>(h, (const float*)X, mem, ld, h->N, ncols, h->Xt, h->Np, h->round_ops));
+  else CMF_TRY(load_transposed<double>(h, (const double*)X, mem, ld, h->N, ncols, h->Xt, h->Np, h->round_ops));
   // local ||X||^2 over owned columns and the negativity flag
   const long long n4 = h->Tloc * h->Np / 4;
   const int grid = ew_grid(h, n4);
@@ -554,16 +575,18 @@ int cmf_mu_set_factors(cmf_mu_t* h, const void* W0, const void* H0, int dtype, i
   }
   const int grid = ew_grid(h, h->wcount);
   if (dtype == CMF_F32)
-    ew::w_pad_in_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)wsrc, h->W, h->L, h->N, h->K, h->Np, h->Kp, h->round_ops);
+    ew::w_pad_in_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)wsrc, h->W, h->L, h->N, h->K, h->Np, h->Kp, 0);
   else
-    ew::w_pad_in_kernel<double><<<grid, 256, 0, h->stream>>>((const double*)wsrc, h->W, h->L, h->N, h->K, h->Np, h->Kp, h->round_ops);
+    ew::w_pad_in_kernel<double><<<grid, 256, 0, h->stream>>>((const double*)wsrc, h->W, h->L, h->N, h->K, h->Np, h->Kp, 0);
   int rc = launch_check(h, "w_pad_in");
   if (rc == 0 && cudaMemsetAsync(h->Ht, 0, (size_t)h->RH * h->Kp * 4, h->stream) != cudaSuccess) { set_error("memset failed"); rc = 1; }
   if (rc == 0) {
     float* dst = h->Ht + (long long)h->h * h->Kp;
-    if (dtype == CMF_F32) rc = load_transposed<float>(h, (const float*)H0, mem, ldh, h->K, h->Tloc, dst, h->Kp);
-    else rc = load_transposed<double>(h, (const double*)H0, mem, ldh, h->K, h->Tloc, dst, h->Kp);
+    if (dtype == CMF_F32) rc = load_transposed<float>(h, (const float*)H0, mem, ldh, h->K, h->Tloc, dst, h->Kp, 0);
+    else rc = load_transposed<double>(h, (const double*)H0, mem, ldh, h->K, h->Tloc, dst, h->Kp, 0);
   }
+  if (rc == 0) rc = sync_ops_W(h);
+  if (rc == 0) rc = sync_ops_H(h, 0, h->RH);
   if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) { set_error("sync failed in set_factors"); rc = 1; }
   if (wstage) cudaFree(wstage);
   if (rc) return rc;
@@ -596,11 +619,13 @@ int cmf_mu_init_stats(cmf_mu_t* h, double* x_dot_est, double* est_sumsq) {
 int cmf_mu_scale_factors(cmf_mu_t* h, double scale_w, double scale_h) {
   CMF_ENTER(h);
   CMF_CHECK(h->have_factors, "W or H not initalized.");
-  ew::scale_kernel<<<ew_grid(h, h->wcount / 4), 256, 0, h->stream>>>((float4*)h->W, h->wcount / 4, (float)scale_w, h->round_ops);
+  ew::scale_kernel<<<ew_grid(h, h->wcount / 4), 256, 0, h->stream>>>((float4*)h->W, h->wcount / 4, (float)scale_w, 0);
   CMF_TRY(launch_check(h, "scale_w"));
   const long long n4 = h->RH * h->Kp / 4;
-  ew::scale_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>((float4*)h->Ht, n4, (float)scale_h, h->round_ops);
+  ew::scale_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>((float4*)h->Ht, n4, (float)scale_h, 0);
   CMF_TRY(launch_check(h, "scale_h"));
+  CMF_TRY(sync_ops_W(h));
+  CMF_TRY(sync_ops_H(h, 0, h->RH));
   h->est_valid = false;
   h->wterms_valid = false;
   return 0;
@@ -636,6 +661,8 @@ int cmf_mu_halo_import(cmf_mu_t* h, const float* left_halo, const float* right_h
   float* r = h->Ht + (long long)(h->h + h->Tloc) * h->Kp;
   if (right_halo) CMF_CUDA(cudaMemcpyAsync(r, right_halo, bytes, cudaMemcpyDeviceToDevice, h->stream));
   else CMF_CUDA(cudaMemsetAsync(r, 0, bytes, h->stream));
+  CMF_TRY(sync_ops_H(h, 0, h->h));
+  CMF_TRY(sync_ops_H(h, h->h + h->Tloc, h->h));
   h->est_valid = false;
   return 0;
 }

@@ -13,9 +13,12 @@ namespace ew {
 // n4 = number of float4 elements.  Optionally rounds the result to TF32 so the
 // tensor-core path consumes exactly what is stored.
 // Algorithmic bytes: 16 per element (3 reads + 1 write).
+// P_op (optional) receives the TF32-rounded copy the tensor-core kernels read;
+// the fp32 master P keeps full precision so rounding never accumulates in the state.
+// Algorithmic bytes: 16 per element (3 reads + 1 write), +4 with P_op.
 __global__ void __launch_bounds__(256)
 mu_update_kernel(float4* __restrict__ P, const float4* __restrict__ num,
-                 const float4* __restrict__ den, long long n4, int round_out) {
+                 const float4* __restrict__ den, long long n4, float4* __restrict__ P_op) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 p = P[i];
@@ -24,8 +27,22 @@ mu_update_kernel(float4* __restrict__ P, const float4* __restrict__ num,
     p.y = p.y * a.y / (d.y + kEpsilon);
     p.z = p.z * a.z / (d.z + kEpsilon);
     p.w = p.w * a.w / (d.w + kEpsilon);
-    if (round_out) { p.x = round_tf32(p.x); p.y = round_tf32(p.y); p.z = round_tf32(p.z); p.w = round_tf32(p.w); }
     P[i] = p;
+    if (P_op) {
+      p.x = round_tf32(p.x); p.y = round_tf32(p.y); p.z = round_tf32(p.z); p.w = round_tf32(p.w);
+      P_op[i] = p;
+    }
+  }
+}
+
+// dst = round_tf32(src)
+__global__ void __launch_bounds__(256)
+round_copy_kernel(float4* __restrict__ dst, const float4* __restrict__ src, long long n4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 p = src[i];
+    p.x = round_tf32(p.x); p.y = round_tf32(p.y); p.z = round_tf32(p.z); p.w = round_tf32(p.w);
+    dst[i] = p;
   }
 }
 

@@ -560,7 +560,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const long long t = t0 + j;
-          if (t >= 0) atomicAdd(o + t * kKp + lane, __uint_as_float(r[j]));
+          if (t >= 0 && t < p.t_rows) atomicAdd(o + t * kKp + lane, __uint_as_float(r[j]));
         }
       }
       tc_fence_before();

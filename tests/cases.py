@@ -34,6 +34,7 @@ CASES = {
     "B":        (256, 65536, 8, 32, "planted", 100, False),
     # configs 3..5 at reduced T (identical N, K, L), few iterations
     "C_small":  (1024, 4096, 32, 64, "planted", 3, False),
+    "C_mid":    (1024, 8192, 32, 64, "planted", 25, False),
     "D_small":  (512, 2048, 16, 256, "planted", 3, False),
     "E_small":  (2048, 2048, 128, 16, "planted", 3, False),
 }
