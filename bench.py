@@ -31,7 +31,7 @@ UNIT = "it/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CMF_BENCH_PRECISION", "auto"),
@@ -55,26 +55,37 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.proc, self.lines = index, None, []
+        self.t_begin = self.t_end = None
 
     def start(self):
+        """Launch nvidia-smi and wait until it is actually sampling."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._pump, daemon=True)
             self.thr.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -82,7 +93,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for (ts, ln) in self.lines
+                  if self.t_begin is None or (self.t_begin <= ts <= (self.t_end or ts) + 0.06)]
+        if not inside:                        # region shorter than one sampling period
+            inside = [ln for (_, ln) in self.lines[-3:]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -105,6 +120,26 @@ def measured_peaks():
         d = json.load(open(path))
         return d, "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def cublas_tf32_tflops(torch, dev, n=8192, iters=10):
+    """cuBLAS TF32 GEMM rate measured here and now (context for the roofline:
+    MEASURED_PEAKS.json holds bf16 only).  Best of `iters`, CUDA events."""
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn((n, n), device=dev, dtype=torch.float32)
+        b = torch.randn((n, n), device=dev, dtype=torch.float32)
+        torch.matmul(a, b)
+        best = 1e30
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        torch.backends.cuda.matmul.allow_tf32 = old
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
 
 
 def algorithmic_flops(N, T, K, L):
@@ -267,10 +302,12 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stream = alg.torch_stream
     barrier()
+    sampler.mark_begin()
     ev0.record(stream)
     losses = alg.update_many(args.steps)
     ev1.record(stream)
     barrier()
+    sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     kms = alg.kernel_ms()
@@ -294,6 +331,7 @@ def run_b200(args):
         return
 
     peaks, peaks_src = measured_peaks()
+    tf32_live = cublas_tf32_tflops(torch, dev)
     flops_iter = algorithmic_flops(N, T, K, L)
     recon_launches = 2 * args.steps
     recon_ms = kms["recon"] / recon_launches
@@ -305,10 +343,15 @@ def run_b200(args):
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
         "traffic": None,
         "peak_source": "%s bf16_tflops_sustained / 2 (TF32 dense = half of bf16; not separately measured)" % peaks_src,
+        "cublas_tf32_tflops_live": tf32_live,
         "whole_iteration_tflops": flops_iter / world / (ms_per_step * 1e-3) / 1e12,
         "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
         "hbm_update_kernels": {
-            "h_update_gbs": None, "peak_gbs": peaks["hbm_gbs"]},
+            # W and H multiplicative updates: 16 B/element algorithmic (+4 B for the TF32 operand copy)
+            "bytes_per_step": (20 if precision == "tf32" else 16) * (L * N * K + K * Tloc),
+            "achieved_gbs": (20 if precision == "tf32" else 16) * (L * N * K + K * Tloc) /
+                            max(kms["elementwise"] / args.steps * 1e-3, 1e-12) / 1e9,
+            "peak_gbs": peaks["hbm_gbs"]},
     }
     cb = None
     if not args.no_cpu_baseline:

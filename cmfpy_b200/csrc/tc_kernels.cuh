@@ -64,7 +64,9 @@ struct PipeState {
 //    cmfpy/algs/base.py:57-62, 90-97)
 // UMMA view per tile: D[128 n][256 tau] += A_l[128 n][32 k] * B_l[256 tau][32 k]^T
 //   A_l = W[l][n0..n0+128][:]  K-major SWIZZLE_128B, streamed through a ring
-//   B_l = rows (L-1-l) .. of the H^T window, K-major no-swizzle panels
+//   B_l = rows (L-1-l) .. of the H^T window: K-major SWIZZLE_128B rows of 128 B,
+//         a lag is +128 B on the descriptor start address (swizzle is a function
+//         of the absolute smem address, so shifted reads see what TMA wrote)
 // Two TMEM accumulators (2 x 256 columns) ping-pong so the epilogue of tile i
 // (TMEM -> registers -> est^T, fused loss against X^T) overlaps the MMAs of
 // tile i+1.
@@ -139,10 +141,8 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (!ab.wait(&hempty[hb], ((it >> 1) & 1) ^ 1)) break;
         mbar_arrive_expect_tx(&hfull[hb], hbytes);
         uint8_t* hdst = Hs + (size_t)hb * hbytes;
-        for (int kc = 0; kc < kKp / 4; ++kc)
-          for (int rb = 0; rb < wrows / 64; ++rb)
-            tma_load_2d(hdst + ((size_t)kc * wrows + rb * 64) * 16, &tmH, &hfull[hb], kc * 4,
-                        (int)(tt * 256 + rb * 64));
+        for (int rb = 0; rb < wrows / 64; ++rb)
+          tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], 0, (int)(tt * 256 + rb * 64));
         bool ok = true;
         for (int l = 0; l < L; ++l) {
           if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
@@ -175,8 +175,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
           for (int ks = 0; ks < kKp / 8; ++ks) {
             const uint64_t ad = make_smem_desc(abase + ks * 32, 16, 1024, kSwz128);
-            const uint64_t bd = make_smem_desc(hbase + (uint32_t)(ks * 2 * wrows + (L - 1 - l)) * 16,
-                                               (uint32_t)wrows * 16, 128, kSwzNone);
+            const uint64_t bd = make_smem_desc(hbase + (uint32_t)(L - 1 - l) * 128 + ks * 32, 16, 1024, kSwz128);
             mma_tf32_ss(dtm, ad, bd, idesc, (l | ks) != 0 ? 1u : 0u);
           }
           mma_commit(&empty[ps.stage]);
@@ -201,25 +200,34 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       const int n = nt * 128 + q * 32 + lane;
       const bool n_ok = n < p.Np;
       float tile_loss = 0.f;
+      const float* __restrict__ Xt = p.Xt;
+      float* __restrict__ Et = p.Et;
+      const size_t np = (size_t)p.Np;
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         uint32_t r[32];
+        float x[32];
         tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + c * 32), r);
-        tmem_ld_wait();
         const long long tau0 = tt * 256 + c * 32;
+        const size_t off0 = (size_t)tau0 * np + n;
+        // all 32 X loads are issued before anything depends on them
+        if (n_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = (tau0 + j < p.t_own) ? __ldcs(Xt + off0 + (size_t)j * np) : 0.f;
+        }
+        tmem_ld_wait();
         if (n_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const long long tau = tau0 + j;
             float v = __uint_as_float(r[j]);
             if (tau >= p.t_valid) v = 0.f;
-            const size_t off = (size_t)tau * p.Np + n;
             if (tau < p.t_own) {
-              const float d = v - __ldg(p.Xt + off);
+              const float d = v - x[j];
               tile_loss = fmaf(d, d, tile_loss);
             }
             if (p.round_out) v = round_tf32(v);
-            p.Et[off] = v;
+            Et[off0 + (size_t)j * np] = v;
           }
         }
       }
@@ -415,16 +423,18 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 //   D[(g,k)][c] += W[j+J*g][n][k] * S^T[base + c + j][n]      (M=128, N=256)
 //   => D[(g,k)][c] is the group-g part of out[k][base + c - J*g].
 //   A = W rows of 4 lags, MN-major SWIZZLE_128B_BASE32B (4 regions: one per g)
-//   B = S^T window, K-major no-swizzle panels, row shift j
+//   B = S^T window, K-major SWIZZLE_128B rows of 32 features, row shift j = +128 B
 // Two accumulators: X (numerator) and est (denominator) share every A stage.
-// The epilogue adds D into a zeroed out[src] with red.global.add.f32 (at most
-// two CTAs touch an address, so the sum is order-independent).
+// The epilogue stores the four group partials as they are (plain 16-byte
+// stores, time-contiguous): scratch[src][g][k][base + c]; combine_groups_kernel
+// then forms out[src][t][k] = sum_g scratch[src][g][k][t + J*g].  No atomics,
+// deterministic.
 // ==========================================================================
 struct HTermsParams {
   int Np, J, n_chunks_n, wrows;    // n chunks of 32 features; window rows >= 256 + J - 1
-  long long n_tiles;               // TO / 256
-  long long t_rows;                // rows of out (TO)
-  float* out;                      // [2][TO][Kp], zeroed before launch
+  long long n_tiles;               // TO / 256 + 1
+  long long ts;                    // scratch row length (TO + 256)
+  float* scratch;                  // [2][4][Kp][ts]
   int* err;
 };
 
@@ -486,10 +496,8 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           for (int src = 0; src < 2; ++src) {
             uint8_t* wdst = Ws + ((size_t)wb * 2 + src) * wbytes;
             const CUtensorMap* tmS = src ? &tmE : &tmX;
-            for (int kc = 0; kc < 8; ++kc)
-              for (int rb = 0; rb < wrows / 32; ++rb)
-                tma_load_2d(wdst + ((size_t)kc * wrows + rb * 32) * 16, tmS, &wfull[wb], nc * 32 + kc * 4,
-                            base + rb * 32);
+            for (int rb = 0; rb < wrows / 32; ++rb)
+              tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], nc * 32, base + rb * 32);
           }
           for (int j = 0; j < J; ++j) {
             if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
@@ -527,8 +535,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
-                const uint64_t bd = make_smem_desc(wbase + src * wbytes + (uint32_t)(ks * 2 * wrows + j) * 16,
-                                                   (uint32_t)wrows * 16, 128, kSwzNone);
+                const uint64_t bd = make_smem_desc(wbase + src * wbytes + (uint32_t)j * 128 + ks * 32, 16, 1024, kSwz128);
                 mma_tf32_ss(tmem + src * 256, ad, bd, idesc, (nc | j | ks) != 0 ? 1u : 0u);
               }
             }
@@ -548,20 +555,18 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       if (!ab.wait(tfull, it & 1)) break;
       tc_fence_after();
-      const long long base = tile * 256 - (long long)J * q;       // out row of column 0
 #pragma unroll 1
       for (int c = 0; c < 16; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
         tmem_ld_wait();
         const int src = c >> 3;
-        float* o = p.out + (size_t)src * p.t_rows * kKp;
-        const long long t0 = base + (c & 7) * 32;
+        float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)(src * 4 + q) * kKp + lane) * p.ts +
+                                              tile * 256 + (c & 7) * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const long long t = t0 + j;
-          if (t >= 0 && t < p.t_rows) atomicAdd(o + t * kKp + lane, __uint_as_float(r[j]));
-        }
+        for (int j = 0; j < 8; ++j)
+          o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
       }
       tc_fence_before();
       __syncwarp();
@@ -571,6 +576,33 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// out[src][t][k] = sum_g scratch[src][g][k][t + J*g]   (t < t_rows; 32 x 32 tiles through smem
+// so that both the time-contiguous reads and the k-contiguous writes coalesce)
+__global__ void __launch_bounds__(256)
+combine_groups_kernel(const float* __restrict__ scratch, float* __restrict__ out, long long ts, long long t_rows, int J) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long t0 = (long long)blockIdx.x * 32;
+  for (int src = 0; src < 2; ++src) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = ty + 8 * i;
+      float acc = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        acc += __ldcs(scratch + ((size_t)(src * 4 + g) * kKp + k) * ts + t0 + tx + (long long)J * g);
+      tile[k][tx] = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long t = t0 + ty + 8 * i;
+      if (t < t_rows) out[((size_t)src * t_rows + t) * kKp + tx] = tile[tx][ty + 8 * i];
+    }
+    __syncthreads();
+  }
 }
 
 }  // namespace tc

@@ -23,6 +23,7 @@ struct TcState {
   float *Xt = nullptr, *Et = nullptr, *Ht = nullptr, *W = nullptr, *numden = nullptr, *hterms = nullptr;
   double *loss_partials = nullptr, *d_sumsq = nullptr;
   float* wpart = nullptr;
+  float* hscratch = nullptr;        // [2][4][Kp][TO + 256] lag-group partials of the H terms
   int* d_err = nullptr;
   int n_chunks = 1, n_lag_groups = 1, J = 1;
   int recon_wrows = 320, hterms_wrows = 288;
@@ -31,7 +32,7 @@ struct TcState {
   CUtensorMap tmW_k1, tmH_k1, tmX_k2, tmE_k2, tmH_k2, tmW_k3, tmX_k3, tmE_k3;
 };
 
-constexpr int kReconLaunches = 2, kWTermsLaunches = 2, kHTermsLaunches = 2;
+constexpr int kReconLaunches = 2, kWTermsLaunches = 2, kHTermsLaunches = 2;   // kernels per phase
 
 // The tensor-core kernels in tc_kernels.cuh are specialised for one 128-byte
 // row of H^T (25 <= K <= 32) and lag windows that fit shared memory.
@@ -72,6 +73,8 @@ inline int make_map(CUtensorMap* m, const float* base, long long rows, long long
 
 inline void destroy(TcState& s) {
   cudaFree(s.wpart);
+  cudaFree(s.hscratch);
+  s.hscratch = nullptr;
   cudaFree(s.d_err);
   s.wpart = nullptr;
   s.d_err = nullptr;
@@ -98,7 +101,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     s.recon_grid = (int)(tiles < d.num_sms ? tiles : d.num_sms);
   }
   CMF_TRY(make_map(&s.tmW_k1, W, (long long)d.L * d.Np, d.Kp, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
-  CMF_TRY(make_map(&s.tmH_k1, Ht, d.RH, d.Kp, 4, 64, CU_TENSOR_MAP_SWIZZLE_NONE));
+  CMF_TRY(make_map(&s.tmH_k1, Ht, d.RH, d.Kp, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
   CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)recon_smem_bytes(s.recon_wrows)));
 
@@ -138,8 +141,10 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     s.hterms_grid = (int)(tiles < d.num_sms ? tiles : d.num_sms);
   }
   CMF_TRY(make_map(&s.tmW_k3, W, (long long)d.L * d.Np, d.Kp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  CMF_TRY(make_map(&s.tmX_k3, Xt, d.RT, d.Np, 4, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
-  CMF_TRY(make_map(&s.tmE_k3, Et, d.RT, d.Np, 4, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  CMF_TRY(make_map(&s.tmX_k3, Xt, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  CMF_TRY(make_map(&s.tmE_k3, Et, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  CMF_CUDA(cudaMalloc((void**)&s.hscratch, (size_t)2 * 4 * kKp * (d.TO + 256) * 4));
+  CMF_CUDA(cudaMemsetAsync(s.hscratch, 0, (size_t)2 * 4 * kKp * (d.TO + 256) * 4, stream));
   CMF_CUDA(cudaFuncSetAttribute(tc_hterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)hterms_smem_bytes(s.hterms_wrows)));
   s.ready = true;
@@ -193,10 +198,11 @@ inline int h_terms(TcState& s, cudaStream_t stream) {
   const Dims& d = s.d;
   HTermsParams p;
   p.Np = d.Np; p.J = s.J; p.n_chunks_n = (int)ceil_div_ll(d.Np, 32); p.wrows = s.hterms_wrows;
-  p.n_tiles = d.TO / 256 + 1; p.t_rows = d.TO; p.out = s.hterms; p.err = s.d_err;
-  CMF_CUDA(cudaMemsetAsync(s.hterms, 0, (size_t)2 * d.TO * d.Kp * 4, stream));
+  p.n_tiles = d.TO / 256 + 1; p.ts = d.TO + 256; p.scratch = s.hscratch; p.err = s.d_err;
   tc_hterms_kernel<<<s.hterms_grid, kHtThreads, hterms_smem_bytes(s.hterms_wrows), stream>>>(s.tmW_k3, s.tmX_k3, s.tmE_k3, p);
-  return launch_ok("tc_hterms");
+  CMF_TRY(launch_ok("tc_hterms"));
+  combine_groups_kernel<<<(unsigned)(d.TO / 32), 256, 0, stream>>>(s.hscratch, s.hterms, p.ts, d.TO, s.J);
+  return launch_ok("combine_groups");
 }
 
 // Device-side pipeline errors (bounded waits that expired) surface here.
