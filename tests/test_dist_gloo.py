@@ -1,0 +1,93 @@
+"""World-size-2 (and 3) tests of the time-sharded driver on CPU with the gloo
+backend: the orchestration of cmfpy_b200.dist.ShardedMultUpdate (halo exchange
+order, W-term all-reduce, loss reduction, boundary zeros) must reproduce the
+unsharded reference algorithm."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import cmf_oracle as o
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, shape, n_iter, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cmfpy_b200.dist import ShardedMultUpdate
+        from tests.numpy_shard import NumpyShard
+        N, T, K, L = shape
+        rng = np.random.default_rng(0)
+        X, W0, H0 = rng.random((N, T)), rng.random((L, N, K)), rng.random((K, T))
+        Tl = T // world
+        t0 = rank * Tl
+        ncols = min(Tl + L - 1, T - t0)
+        eng = NumpyShard(X[:, t0:t0 + ncols], N, T, K, L, t0, Tl)
+        alg = ShardedMultUpdate(None, N, T, K, L, t_offset=t0, t_local=Tl, initW=W0, initH=H0[:, t0:t0 + Tl],
+                                group=dist.group.WORLD, engine=eng, tol=0)
+        l0 = alg.loss
+        losses = alg.update_many(n_iter - 1) + [alg.update()]
+        H = alg.H_local_host()
+        W = alg.W_host()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (H, W, [l0] + losses))
+        if rank == 0:
+            out.put(gathered)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape", [(2, (6, 64, 3, 5)), (3, (5, 90, 2, 9)), (2, (4, 40, 2, 1))])
+def test_sharded_driver_matches_unsharded_oracle(world, shape):
+    n_iter = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, n_iter, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    N, T, K, L = shape
+    rng = np.random.default_rng(0)
+    X, W0, H0 = rng.random((N, T)), rng.random((L, N, K)), rng.random((K, T))
+    ref = o.MultUpdateOracle(X, L, K, initW=W0, initH=H0, tol=0)
+    ref_hist = [ref.loss] + [ref.update() for _ in range(n_iter)]
+    H = np.concatenate([g[0] for g in gathered], axis=1)
+    for g in gathered:                       # W is replicated and identical on every rank
+        np.testing.assert_allclose(g[1], ref.W, rtol=2e-5)
+        np.testing.assert_allclose(g[2], ref_hist, rtol=1e-6)
+    np.testing.assert_allclose(H, ref.H, rtol=2e-5)
+
+
+def test_single_rank_uses_fused_step():
+    from cmfpy_b200.dist import ShardedMultUpdate
+    from tests.numpy_shard import NumpyShard
+    rng = np.random.default_rng(1)
+    N, T, K, L = 5, 50, 2, 4
+    X, W0, H0 = rng.random((N, T)), rng.random((L, N, K)), rng.random((K, T))
+    alg = ShardedMultUpdate(None, N, T, K, L, 0, T, W0, H0, engine=NumpyShard(X, N, T, K, L, 0, T), tol=0)
+    ref = o.MultUpdateOracle(X, L, K, initW=W0, initH=H0, tol=0)
+    assert alg.loss == pytest.approx(ref.loss, rel=1e-12)
+    got = alg.update_many(3)
+    exp = [ref.update() for _ in range(3)]
+    np.testing.assert_allclose(got, exp, rtol=1e-6)
+    assert not alg.converged([1.0, 0.5, 0.5])              # tol = 0: strict "<" never fires
+    alg.tol = 1e-5
+    assert not alg.converged([1.0, 0.5, 0.4])
+    assert alg.converged([1.0, 0.5, 0.5 + 1e-9, 0.5 + 2e-9])
