@@ -212,12 +212,14 @@ class ShardedMultUpdate:
         if self.world > 1:
             t = self._host_scalar(ss)
             self._all_reduce(t)
-            ss = float(t.item())
+            ss = float(self._to_host(t).item())
         self.normX = float(np.sqrt(ss))
         eng.set_norm_x(self.normX)
         eng.set_factors(initW, initH)
         if self.world > 1:
             self._sl, self._sr, self._rl, self._rr = eng.halo_buffers()
+            if self.torch_stream is not None:       # buffers were zero-filled on torch's current stream
+                torch.cuda.current_stream(self.torch_stream.device).synchronize()
             self._exchange_halos()
         eng.recon()
         self._loss = None
@@ -237,6 +239,15 @@ class ShardedMultUpdate:
     def _all_reduce(self, t):
         with self._stream_ctx():
             self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+
+    def _to_host(self, t):
+        """Device -> host on the solver's stream (a .item() on another stream
+        would race with the collective that produced `t`)."""
+        with self._stream_ctx():
+            out = t.cpu()
+        if self.torch_stream is not None:
+            self.torch_stream.synchronize()
+        return out
 
     def _exchange_halos(self):
         """Send my first/last L-1 H columns to the left/right neighbour and
@@ -300,7 +311,8 @@ class ShardedMultUpdate:
             self._all_reduce(s)
             sums.append(s)
         with self._stream_ctx():
-            allsums = torch.cat(sums).cpu()
+            cat = torch.cat(sums)
+        allsums = self._to_host(cat)
         losses = [float(np.sqrt(v) / self.normX) for v in allsums.tolist()]
         self._loss = losses[-1]
         if marks:
@@ -324,7 +336,7 @@ class ShardedMultUpdate:
                 s = self.engine.resid_sumsq_tensor().clone()
             if self.world > 1:
                 self._all_reduce(s)
-            self._loss = float(np.sqrt(float(s.cpu().item())) / self.normX)
+            self._loss = float(np.sqrt(float(self._to_host(s).item())) / self.normX)
         return self._loss
 
     def converged(self, loss_hist):
