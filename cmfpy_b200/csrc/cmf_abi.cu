@@ -51,9 +51,8 @@ struct cmf_mu_s {
   int round_ops = 0;                 // store operands pre-rounded to TF32
   bool use_tc = false;
 
-  float *Xt = nullptr, *Et = nullptr, *Ht = nullptr, *W = nullptr;   // Ht, W: fp32 masters
-  float *Ht_op = nullptr, *W_op = nullptr;   // TF32-rounded operand copies (tensor-core path only)
-  float *Htc = nullptr, *Wc = nullptr;       // what the contractions read: *_op if present, else masters
+  float *Xt = nullptr, *Et = nullptr, *Ht = nullptr, *W = nullptr;   // Ht, W: fp32 masters (the TF32 operand
+                                                                     // copies of the tcgen05 path live in tcs)
   float *numden = nullptr, *wpart = nullptr, *hterms = nullptr;
   long long wcount = 0;              // L * Np * Kp
   int wsplits = 1;
@@ -120,8 +119,8 @@ int launch_check(cmf_mu_s* h, const char* what) {
 
 // ---- contraction launches (fp32 FFMA path) ------------------------------
 int simt_recon(cmf_mu_s* h) {
-  simt::ReconA a{h->Htc, h->Kp, h->h};
-  simt::ReconB b{h->Wc, h->Np, h->Kp};
+  simt::ReconA a{h->Ht, h->Kp, h->h};
+  simt::ReconB b{h->W, h->Np, h->Kp};
   simt::ReconEpi e{h->Et, h->Xt, h->loss_partials, h->Np, h->Tloc, h->t_valid, h->round_ops};
   const long long R = (long long)h->L * h->Kp;
   long long nblocks;
@@ -142,7 +141,7 @@ int simt_recon(cmf_mu_s* h) {
 int simt_w_terms(cmf_mu_s* h) {
   const int LKp = h->L * h->Kp;
   simt::WTermsA a{h->Xt, h->Et, h->Np};
-  simt::WTermsB b{h->Htc, h->Kp, h->h, LKp};
+  simt::WTermsB b{h->Ht, h->Kp, h->h, LKp};
   float* part = (h->wsplits == 1) ? h->numden : h->wpart;
   simt::WTermsEpi e{part, h->Np, h->Kp, LKp, h->wcount};
   dim3 grid((unsigned)ceil_div_ll(h->Np, 128), (unsigned)ceil_div_ll(LKp, 128), (unsigned)(h->wsplits * 2));
@@ -159,7 +158,7 @@ int simt_w_terms(cmf_mu_s* h) {
 
 int simt_h_terms(cmf_mu_s* h) {
   simt::HTermsA a{h->Xt, h->Et, h->Np};
-  simt::HTermsB b{h->Wc, h->Kp};
+  simt::HTermsB b{h->W, h->Kp};
   simt::HTermsEpi e{h->hterms, h->Kp, h->TO * h->Kp};
   const long long R = (long long)h->L * h->Np;
   if (h->Kp <= 16) {
@@ -205,8 +204,10 @@ int do_w_apply(cmf_mu_s* h) {
   CMF_CHECK(h->wterms_valid, "w_apply before w_terms");
   const long long n4 = h->wcount / 4;
   ew::mu_update_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>(
-      (float4*)h->W, (const float4*)h->numden, (const float4*)(h->numden + h->wcount), n4, (float4*)h->W_op);
+      (float4*)h->W, (const float4*)h->numden, (const float4*)(h->numden + h->wcount), n4,
+      (float4*)tc::fused_w_op(h->tcs));
   CMF_TRY(launch_check(h, "w_update"));
+  CMF_TRY(tc::refresh_w(h->tcs, h->stream, true));
   h->wterms_valid = false;
   h->est_valid = false;
   return 0;
@@ -225,25 +226,16 @@ int do_h_apply(cmf_mu_s* h) {
   ew::mu_update_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>(
       (float4*)(h->Ht + (long long)h->h * h->Kp), (const float4*)h->hterms,
       (const float4*)(h->hterms + h->TO * h->Kp), n4,
-      h->Ht_op ? (float4*)(h->Ht_op + (long long)h->h * h->Kp) : nullptr);
+      tc::fused_h_op(h->tcs) ? (float4*)(tc::fused_h_op(h->tcs) + (long long)h->h * h->Kp) : nullptr);
   CMF_TRY(launch_check(h, "h_update"));
+  CMF_TRY(tc::refresh_h(h->tcs, h->stream, h->h, h->Tloc, true));
   h->est_valid = false;
   return 0;
 }
 
 // refresh the TF32 operand copies from the fp32 masters (no-op on the fp32 path)
-int sync_ops_W(cmf_mu_s* h) {
-  if (!h->W_op) return 0;
-  ew::round_copy_kernel<<<ew_grid(h, h->wcount / 4), 256, 0, h->stream>>>((float4*)h->W_op, (const float4*)h->W, h->wcount / 4);
-  return launch_check(h, "round_w");
-}
-int sync_ops_H(cmf_mu_s* h, long long row0, long long nrows) {
-  if (!h->Ht_op || nrows <= 0) return 0;
-  const long long n4 = nrows * h->Kp / 4;
-  ew::round_copy_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>((float4*)(h->Ht_op + row0 * h->Kp),
-                                                               (const float4*)(h->Ht + row0 * h->Kp), n4);
-  return launch_check(h, "round_h");
-}
+int sync_ops_W(cmf_mu_s* h) { return tc::refresh_w(h->tcs, h->stream); }
+int sync_ops_H(cmf_mu_s* h, long long row0, long long nrows) { return tc::refresh_h(h->tcs, h->stream, row0, nrows); }
 
 cudaEvent_t get_event(cmf_mu_s* h, size_t i) {
   while (h->ev_pool.size() <= i) {
@@ -346,7 +338,7 @@ int store_transposed(cmf_mu_s* h, const float* src, long long lds, long long row
 
 void free_all(cmf_mu_s* h) {
   tc::destroy(h->tcs);
-  cudaFree(h->Xt); cudaFree(h->Et); cudaFree(h->Ht); cudaFree(h->W); cudaFree(h->Ht_op); cudaFree(h->W_op);
+  cudaFree(h->Xt); cudaFree(h->Et); cudaFree(h->Ht); cudaFree(h->W);
   cudaFree(h->numden); cudaFree(h->wpart); cudaFree(h->hterms);
   cudaFree(h->loss_partials); cudaFree(h->d_sumsq); cudaFree(h->d_ring); cudaFree(h->d_xpart);
   cudaFree(h->d_neg);
@@ -412,7 +404,14 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
   h->num_sms = prop.multiProcessorCount;
 
   h->N = p->n_features; h->K = p->n_components; h->L = p->maxlag;
-  h->Np = round_up(h->N, 4); h->Kp = round_up(h->K, 8); h->h = h->L - 1;
+  h->use_tc = (p->precision == CMF_PREC_TF32);
+  if (h->use_tc && !tc::shape_supported(h->N, h->K, h->L)) {
+    delete h;
+    set_error("precision tf32 has no tensor-core kernel for N=%d K=%d L=%d; use fp32", p->n_features, p->n_components, p->maxlag);
+    return 2;
+  }
+  h->Np = round_up(h->N, 4); h->h = h->L - 1;
+  h->Kp = h->use_tc ? tc::padded_k(h->K) : round_up(h->K, 8);
   h->Tloc = p->t_local;
   h->TO = round_up_ll(h->Tloc, 256);
   h->RT = round_up_ll(h->TO + h->h, 256);
@@ -423,13 +422,7 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
     h->t_valid = remaining < want ? remaining : want;
   }
   h->precision = p->precision;
-  h->use_tc = (p->precision == CMF_PREC_TF32);
   h->round_ops = h->use_tc ? 1 : 0;
-  if (h->use_tc && !tc::shape_supported(h->N, h->K, h->L)) {
-    delete h;
-    set_error("precision tf32 has no tensor-core kernel for N=%d K=%d L=%d; use fp32", p->n_features, p->n_components, p->maxlag);
-    return 2;
-  }
 
   if (p->stream) {
     h->stream = (cudaStream_t)p->stream;
@@ -462,7 +455,6 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
   A(dmalloc(&h->Et, h->RT * h->Np));
   A(dmalloc(&h->Ht, h->RH * h->Kp));
   A(dmalloc(&h->W, h->wcount));
-  if (h->round_ops) { A(dmalloc(&h->Ht_op, h->RH * h->Kp)); A(dmalloc(&h->W_op, h->wcount)); }
   A(dmalloc(&h->numden, 2 * h->wcount));
   if (h->wsplits > 1) A(dmalloc(&h->wpart, 2 * h->wcount * h->wsplits));
   A(dmalloc(&h->hterms, 2 * h->TO * h->Kp));
@@ -480,18 +472,15 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
     Z(h->Et, (size_t)h->RT * h->Np * 4);
     Z(h->Ht, (size_t)h->RH * h->Kp * 4);
     Z(h->W, (size_t)h->wcount * 4);
-    if (h->Ht_op) { Z(h->Ht_op, (size_t)h->RH * h->Kp * 4); Z(h->W_op, (size_t)h->wcount * 4); }
     Z(h->numden, (size_t)2 * h->wcount * 4);
     Z(h->hterms, (size_t)2 * h->TO * h->Kp * 4);
     Z(h->d_sumsq, 8);
     Z(h->d_neg, 4);
     if (e != cudaSuccess) { set_error("cudaMemset failed: %s", cudaGetErrorString(e)); rc = 1; }
   }
-  h->Htc = h->Ht_op ? h->Ht_op : h->Ht;
-  h->Wc = h->W_op ? h->W_op : h->W;
   if (rc == 0 && h->use_tc) {
     tc::Dims d{h->N, h->K, h->L, h->Np, h->Kp, h->h, h->Tloc, h->TO, h->RT, h->RH, h->t_valid, h->num_sms};
-    rc = tc::init(h->tcs, d, h->Xt, h->Et, h->Htc, h->Wc, h->numden, h->hterms, h->loss_partials,
+    rc = tc::init(h->tcs, d, h->Xt, h->Et, h->Ht, h->W, h->numden, h->hterms, h->loss_partials,
                   h->n_loss_partials, h->d_sumsq, h->stream);
   }
   if (rc != 0) {

@@ -50,11 +50,16 @@ shift_gemm_kernel(const AOp a, const BOp b, const Epi epi, long long R, long lon
   const long long r_end = min(R, r_begin + r_chunk);
   const int ntiles = (int)((r_end - r_begin + BK - 1) / BK);
 
-  float acc[TM][TN];
+  // Two-level accumulation: `acc` collects kFlush reduction tiles, then is
+  // folded into `tot`.  Keeps the fp32 rounding error of a length-R sum near
+  // sqrt(kFlush*BK) + sqrt(R/(kFlush*BK)) ulps instead of sqrt(R) (the reference
+  // sums in float64; this is what holds the fp32 path inside the 1e-4 bar with margin).
+  constexpr int kFlush = 8;
+  float acc[TM][TN], tot[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
 
   float4 ra[QA], rb[QB];
 
@@ -161,8 +166,18 @@ shift_gemm_kernel(const AOp a, const BOp b, const Epi epi, long long R, long lon
         for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
     }
     if (t + 1 < ntiles) stash(buf ^ 1);
+    if ((t % kFlush) == kFlush - 1) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+    }
     __syncthreads();
   }
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] += tot[i][j];
 
   float part = 0.f;
 #pragma unroll

@@ -13,7 +13,14 @@
 // windows read what TMA wrote, and every layout used here sustains the full
 // 128 cycles per 128x256x8 MMA.
 //
-// This file is specialised for Kp == 32 (K in 25..32: one 128-byte row of H^T).
+// Every operand row is 128 bytes (32 floats).  The padded component count
+// Kp in {8, 16, 32, 64, 128} is brought to that width by
+//   * folding s = 32/Kp consecutive lags into "virtual components" when Kp < 32
+//     (virtual lag l' covers real lags s*l' .. s*l'+s-1; its row shift is s*l'):
+//       Wv[l'][n][(dl,k)] = W[s*l'+dl][n][k],  Hv[r][(dl,k)] = H^T[r-dl][k]
+//     (fold_*_kernel below; Hv is an s-fold interleaved copy of the SMALL factor
+//     only - X and est are never copied), or
+//   * splitting into CB = Kp/32 column blocks when Kp > 32.
 #pragma once
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -23,7 +30,7 @@ namespace tc {
 
 using namespace ptx;
 
-constexpr int kKp = 32;              // padded component count this file handles
+constexpr int kKp = 32;              // operand row width in floats (virtual components per column block)
 constexpr uint32_t kTimeoutCycles = 2000000000u;   // ~1 s: a pipeline bug must never hang the GPU
 
 // error codes written to *err (0 = fine)
@@ -72,7 +79,8 @@ struct PipeState {
 // tile i+1.
 // ==========================================================================
 struct ReconParams {
-  int Np, L, n_tiles_n, wrows;
+  int Np, L, n_tiles_n, wrows;     // L = number of VIRTUAL lags
+  int s, CB, h_shift;              // lag stride in rows, column blocks, Ht row of window row 0 minus tile start
   long long n_tiles;               // n_tiles_n * (RT / 256)
   long long t_own, t_valid;
   float* Et;
@@ -133,24 +141,25 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       PipeState ps;
-      int it = 0;
-      for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      long long wcount = 0;
+      bool ok = true;
+      for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
         const int nt = (int)(tile % p.n_tiles_n);
         const long long tt = tile / p.n_tiles_n;
-        const int hb = it & 1;
-        if (!ab.wait(&hempty[hb], ((it >> 1) & 1) ^ 1)) break;
-        mbar_arrive_expect_tx(&hfull[hb], hbytes);
-        uint8_t* hdst = Hs + (size_t)hb * hbytes;
-        for (int rb = 0; rb < wrows / 64; ++rb)
-          tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], 0, (int)(tt * 256 + rb * 64));
-        bool ok = true;
-        for (int l = 0; l < L; ++l) {
-          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
-          mbar_arrive_expect_tx(&full[ps.stage], kReconABytes);
-          tma_load_2d(As + (size_t)ps.stage * kReconABytes, &tmW, &full[ps.stage], 0, l * p.Np + nt * 128);
-          ps.advance(kReconStages);
+        for (int cb = 0; cb < p.CB && ok; ++cb, ++wcount) {
+          const int hb = (int)(wcount & 1);
+          if (!ab.wait(&hempty[hb], (uint32_t)((wcount >> 1) & 1) ^ 1)) { ok = false; break; }
+          mbar_arrive_expect_tx(&hfull[hb], hbytes);
+          uint8_t* hdst = Hs + (size_t)hb * hbytes;
+          for (int rb = 0; rb < wrows / 64; ++rb)
+            tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], cb * 32, (int)(tt * 256 + p.h_shift + rb * 64));
+          for (int l = 0; l < L; ++l) {
+            if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+            mbar_arrive_expect_tx(&full[ps.stage], kReconABytes);
+            tma_load_2d(As + (size_t)ps.stage * kReconABytes, &tmW, &full[ps.stage], cb * 32, l * p.Np + nt * 128);
+            ps.advance(kReconStages);
+          }
         }
-        if (!ok) break;
       }
     }
   } else if (warp == 1) {
@@ -158,32 +167,37 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(128, 256, 0, 0);
       PipeState ps;
+      long long wcount = 0;
       int it = 0;
-      for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      bool ok = true;
+      for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x, ++it) {
         const int b = it & 1;
-        const uint32_t par = (it >> 1) & 1;
-        if (!ab.wait(&tempty[b], par ^ 1)) break;
-        if (!ab.wait(&hfull[b], par)) break;
+        if (!ab.wait(&tempty[b], (uint32_t)((it >> 1) & 1) ^ 1)) break;
         tc_fence_after();
-        const uint32_t hbase = smem_u32(Hs + (size_t)b * hbytes);
         const uint32_t dtm = tmem + (uint32_t)b * 256;
-        bool ok = true;
-        for (int l = 0; l < L; ++l) {
-          if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+        for (int cb = 0; cb < p.CB && ok; ++cb, ++wcount) {
+          const int hb = (int)(wcount & 1);
+          if (!ab.wait(&hfull[hb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
           tc_fence_after();
-          const uint32_t abase = smem_u32(As + (size_t)ps.stage * kReconABytes);
+          const uint32_t hbase = smem_u32(Hs + (size_t)hb * hbytes);
+          for (int l = 0; l < L; ++l) {
+            if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+            tc_fence_after();
+            const uint32_t abase = smem_u32(As + (size_t)ps.stage * kReconABytes);
 #pragma unroll
-          for (int ks = 0; ks < kKp / 8; ++ks) {
-            const uint64_t ad = make_smem_desc(abase + ks * 32, 16, 1024, kSwz128);
-            const uint64_t bd = make_smem_desc(hbase + (uint32_t)(L - 1 - l) * 128 + ks * 32, 16, 1024, kSwz128);
-            mma_tf32_ss(dtm, ad, bd, idesc, (l | ks) != 0 ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ad = make_smem_desc(abase + ks * 32, 16, 1024, kSwz128);
+              const uint64_t bd = make_smem_desc(hbase + (uint32_t)(p.s * (L - 1 - l)) * 128 + ks * 32, 16, 1024, kSwz128);
+              mma_tf32_ss(dtm, ad, bd, idesc, (cb | l | ks) != 0 ? 1u : 0u);
+            }
+            mma_commit(&empty[ps.stage]);
+            ps.advance(kReconStages);
           }
-          mma_commit(&empty[ps.stage]);
-          ps.advance(kReconStages);
+          if (!ok) break;
+          mma_commit(&hempty[hb]);
         }
         if (!ok) break;
         mma_commit(&tfull[b]);
-        mma_commit(&hempty[b]);
       }
     }
   } else {
@@ -260,8 +274,9 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 // order by sum_splits_kernel (deterministic; no float atomics).
 // ==========================================================================
 struct WTermsParams {
-  int Np, L, n_tiles_n, n_lag_groups, n_chunks, h;
-  long long n_items;              // n_tiles_n * n_lag_groups * 2 * n_chunks
+  int Np, L, n_tiles_n, n_lag_groups, n_chunks, h;   // L = REAL lags; lag groups hold 16 virtual lags
+  int Lv, Kp, s, CB, brows;       // virtual lags, real padded K, lag stride, column blocks, H rows per stage
+  long long n_items;              // n_tiles_n * n_lag_groups * CB * 2 * n_chunks
   long long stages_total;         // ceil(t_own / 32)
   float* part;                    // [chunk][src][L][Np][Kp]
   long long per_src;              // L * Np * Kp
@@ -271,19 +286,19 @@ struct WTermsParams {
 constexpr int kWtStages = 6;
 constexpr int kWtThreads = 192;
 constexpr int kWtABytes = 4 * 32 * 128;           // 128 n x 32 tau
-constexpr int kWtBRows = 48;                      // 32 tau + 15 lags, padded
-constexpr int kWtBBytes = kWtBRows * 128;
-constexpr int kWtStageBytes = kWtABytes + kWtBBytes;
-
-__host__ __device__ inline size_t wterms_smem_bytes() { return 1024 + (size_t)kWtStages * kWtStageBytes + 256; }
+// H rows per stage: 32 tau + 15 virtual lags of stride s, padded to 8
+__host__ __device__ inline int wterms_brows(int s) { return ((32 + 15 * s + 7) / 8) * 8; }
+__host__ __device__ inline size_t wterms_stage_bytes(int s) { return (size_t)kWtABytes + (size_t)wterms_brows(s) * 128; }
+__host__ __device__ inline size_t wterms_smem_bytes(int s) { return 1024 + (size_t)kWtStages * wterms_stage_bytes(s) + 256; }
 
 __global__ void __launch_bounds__(kWtThreads, 1)
 tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmE,
                  const __grid_constant__ CUtensorMap tmH, const WTermsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* St = smem;                                            // [stages][A 16 KB | B 6 KB]
-  uint64_t* bars = (uint64_t*)(St + kWtStages * kWtStageBytes);
+  uint8_t* St = smem;                                            // [stages][A 16 KB | B brows x 128 B]
+  const uint32_t kWtStageBytes = (uint32_t)wterms_stage_bytes(p.s);
+  uint64_t* bars = (uint64_t*)(St + (size_t)kWtStages * kWtStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kWtStages;
   uint64_t* tfull = bars + 2 * kWtStages;                        // [1]
@@ -309,8 +324,9 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
   // item -> (chunk, n tile, src, lag group); lag group fastest so that the CTAs
   // that stream the same S^T rows run at the same time (L2 reuse)
-  auto decode = [&](long long item, int& lg, int& src, int& nt, int& ch) {
+  auto decode = [&](long long item, int& lg, int& cb, int& src, int& nt, int& ch) {
     lg = (int)(item % p.n_lag_groups); item /= p.n_lag_groups;
+    cb = (int)(item % p.CB); item /= p.CB;
     src = (int)(item % 2); item /= 2;
     nt = (int)(item % p.n_tiles_n); item /= p.n_tiles_n;
     ch = (int)item;
@@ -326,8 +342,8 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       PipeState ps;
       bool ok = true;
       for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
-        int lg, src, nt, ch;
-        decode(item, lg, src, nt, ch);
+        int lg, cb, src, nt, ch;
+        decode(item, lg, cb, src, nt, ch);
         long long s0, s1;
         chunk_range(ch, s0, s1);
         const CUtensorMap* tmS = src ? &tmE : &tmX;
@@ -339,8 +355,8 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
           for (int r = 0; r < 4; ++r)
             tma_load_2d(dst + r * 4096, tmS, &full[ps.stage], nt * 128 + r * 32, tau0);
-          // H^T rows tau0 - (l0+15) .. tau0 + 32; row index in Ht is tau + h
-          tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], 0, tau0 - (lg * 16 + 15) + p.h);
+          // Hv rows tau0 - s*(l0+15) .. tau0 + 32; row index in Hv is tau + h
+          tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], cb * 32, tau0 - p.s * (lg * 16 + 15) + p.h);
           ps.advance(kWtStages);
         }
       }
@@ -352,8 +368,8 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       int it = 0;
       bool ok = true;
       for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x, ++it) {
-        int lg, src, nt, ch;
-        decode(item, lg, src, nt, ch);
+        int lg, cb, src, nt, ch;
+        decode(item, lg, cb, src, nt, ch);
         long long s0, s1;
         chunk_range(ch, s0, s1);
         if (!ab.wait(tempty, (it & 1) ^ 1)) break;
@@ -368,7 +384,8 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-              const uint64_t bd = make_smem_desc(bbase + (uint32_t)((8 - 8 * g) + ks * 8) * 128, 128, 512, 1);
+              const uint64_t bd = make_smem_desc(bbase + (uint32_t)(p.s * (8 - 8 * g) + ks * 8) * 128,
+                                                 (uint32_t)p.s * 128, 512, 1);
               mma_tf32_ss(tmem + g * 256, ad, bd, idesc, (s > s0 || ks > 0) ? 1u : 0u);
             }
           }
@@ -383,25 +400,51 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int q = warp & 3;
     int it = 0;
     for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-      int lg, src, nt, ch;
-      decode(item, lg, src, nt, ch);
+      int lg, cb, src, nt, ch;
+      decode(item, lg, cb, src, nt, ch);
       if (!ab.wait(tfull, it & 1)) break;
       tc_fence_after();
       const int n = nt * 128 + q * 32 + lane;
       float* obase = p.part + ((long long)ch * 2 + src) * p.per_src;
 #pragma unroll 1
-      for (int c = 0; c < 16; ++c) {            // 16 column blocks of 32 = (g, a): one lag each
+      for (int c = 0; c < 16; ++c) {            // 16 column blocks of 32 = (g, a): one virtual lag each
         uint32_t r[32];
         tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
         tmem_ld_wait();
         const int g = c >> 3, a = c & 7;
-        const int l = lg * 16 + 8 * g + 7 - a;
-        if (n < p.Np && l < p.L) {
-          float4* o = reinterpret_cast<float4*>(obase + ((long long)l * p.Np + n) * kKp);
+        const int lv = lg * 16 + 8 * g + 7 - a;
+        if (n < p.Np && lv < p.Lv) {
+          if (p.s == 1) {                       // 32 components of column block cb, real lag lv
+            float4* o = reinterpret_cast<float4*>(obase + ((long long)lv * p.Np + n) * p.Kp + cb * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          } else if (p.s == 2) {                // Kp = 16: two real lags of 16 components
+#pragma unroll
+            for (int dl = 0; dl < 2; ++dl) {
+              const int l = 2 * lv + dl;
+              if (l < p.L) {
+                float4* o = reinterpret_cast<float4*>(obase + ((long long)l * p.Np + n) * 16);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  o[j] = make_float4(__uint_as_float(r[16 * dl + 4 * j]), __uint_as_float(r[16 * dl + 4 * j + 1]),
+                                     __uint_as_float(r[16 * dl + 4 * j + 2]), __uint_as_float(r[16 * dl + 4 * j + 3]));
+              }
+            }
+          } else {                              // s == 4, Kp = 8: four real lags of 8 components
+#pragma unroll
+            for (int dl = 0; dl < 4; ++dl) {
+              const int l = 4 * lv + dl;
+              if (l < p.L) {
+                float4* o = reinterpret_cast<float4*>(obase + ((long long)l * p.Np + n) * 8);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  o[j] = make_float4(__uint_as_float(r[8 * dl + 4 * j]), __uint_as_float(r[8 * dl + 4 * j + 1]),
+                                     __uint_as_float(r[8 * dl + 4 * j + 2]), __uint_as_float(r[8 * dl + 4 * j + 3]));
+              }
+            }
+          }
         }
       }
       tc_fence_before();
@@ -431,7 +474,8 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 // deterministic.
 // ==========================================================================
 struct HTermsParams {
-  int Np, J, n_chunks_n, wrows;    // n chunks of 32 features; window rows >= 256 + J - 1
+  int Np, J, n_chunks_n, wrows;    // n chunks of 32 features; window rows >= 256 + s*(J-1)
+  int s, CB;                       // lag stride in rows; column blocks (regions = (4/CB lag groups) x CB)
   long long n_tiles;               // TO / 256 + 1
   long long ts;                    // scratch row length (TO + 256)
   float* scratch;                  // [2][4][Kp][ts]
@@ -504,8 +548,8 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             uint8_t* dst = As + (size_t)ps.stage * kHtABytes;
             mbar_arrive_expect_tx(&full[ps.stage], kHtABytes);
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              tma_load_2d(dst + g * 4096, &tmW, &full[ps.stage], 0, (j + J * g) * p.Np + nc * 32);
+            for (int g = 0; g < 4; ++g)      // region g = (lag group g / CB, column block g % CB)
+              tma_load_2d(dst + g * 4096, &tmW, &full[ps.stage], (g % p.CB) * 32, (j + J * (g / p.CB)) * p.Np + nc * 32);
             ps.advance(kHtStages);
           }
         }
@@ -535,7 +579,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
-                const uint64_t bd = make_smem_desc(wbase + src * wbytes + (uint32_t)j * 128 + ks * 32, 16, 1024, kSwz128);
+                const uint64_t bd = make_smem_desc(wbase + src * wbytes + (uint32_t)(p.s * j) * 128 + ks * 32, 16, 1024, kSwz128);
                 mma_tf32_ss(tmem + src * 256, ad, bd, idesc, (nc | j | ks) != 0 ? 1u : 0u);
               }
             }
@@ -578,30 +622,62 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-// out[src][t][k] = sum_g scratch[src][g][k][t + J*g]   (t < t_rows; 32 x 32 tiles through smem
-// so that both the time-contiguous reads and the k-contiguous writes coalesce)
+// out[src][t][k] = sum over lag groups g and folded lags dl of
+//     scratch[src][g*CB + cb][kk][t + dl + s*J*g]
+// with (cb, kk) = (k/32, k%32), dl = 0 when s == 1, and (0, dl*Kp + k), dl < s when s > 1.
+// 32-wide time tiles through smem so that both the time-contiguous reads and
+// the k-contiguous writes coalesce.
 __global__ void __launch_bounds__(256)
-combine_groups_kernel(const float* __restrict__ scratch, float* __restrict__ out, long long ts, long long t_rows, int J) {
-  __shared__ float tile[32][33];
+combine_groups_kernel(const float* __restrict__ scratch, float* __restrict__ out, long long ts, long long t_rows,
+                      int J, int s, int CB, int Kp) {
+  extern __shared__ float tile[];             // [Kp][33]
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long t0 = (long long)blockIdx.x * 32;
+  const int n_glag = 4 / CB;
   for (int src = 0; src < 2; ++src) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = ty + 8 * i;
+    for (int k = ty; k < Kp; k += 8) {
       float acc = 0.f;
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        acc += __ldcs(scratch + ((size_t)(src * 4 + g) * kKp + k) * ts + t0 + tx + (long long)J * g);
-      tile[k][tx] = acc;
+      for (int g = 0; g < n_glag; ++g)
+        for (int dl = 0; dl < s; ++dl) {
+          const int region = g * CB + (s == 1 ? k / 32 : 0);
+          const int kk = (s == 1) ? (k % 32) : (dl * Kp + k);
+          acc += __ldcs(scratch + ((size_t)(src * 4 + region) * kKp + kk) * ts + t0 + tx + dl + (long long)s * J * g);
+        }
+      tile[k * 33 + tx] = acc;
     }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long t = t0 + ty + 8 * i;
-      if (t < t_rows) out[((size_t)src * t_rows + t) * kKp + tx] = tile[tx][ty + 8 * i];
+    for (int idx = threadIdx.x; idx < 32 * Kp; idx += 256) {
+      const int t = idx / Kp, k = idx % Kp;
+      if (t0 + t < t_rows) out[((size_t)src * t_rows + t0 + t) * Kp + k] = tile[k * 33 + t];
     }
     __syncthreads();
+  }
+}
+
+// Hv[r][(dl,k)] = round_tf32(H^T[r - dl][k])     (s > 1; rows before 0 read as zero)
+__global__ void __launch_bounds__(256)
+fold_h_kernel(float* __restrict__ Hv, const float* __restrict__ Ht, long long row0, long long nrows, int Kp) {
+  const long long total = nrows * 32;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = row0 + i / 32;
+    const int v = (int)(i % 32), dl = v / Kp, k = v % Kp;
+    const float x = (r - dl >= 0) ? Ht[(r - dl) * Kp + k] : 0.f;
+    Hv[r * 32 + v] = round_tf32(x);
+  }
+}
+
+// Wv[l'][n][(dl,k)] = round_tf32(W[s*l' + dl][n][k])   (s > 1; lags >= L read as zero)
+__global__ void __launch_bounds__(256)
+fold_w_kernel(float* __restrict__ Wv, const float* __restrict__ W, int L, int Lv, int Np, int Kp, int s) {
+  const long long total = (long long)Lv * Np * 32;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int v = (int)(i % 32), dl = v / Kp, k = v % Kp;
+    const int n = (int)((i / 32) % Np);
+    const int lv = (int)(i / (32ll * Np));
+    const int l = s * lv + dl;
+    Wv[i] = (l < L) ? round_tf32(W[((long long)l * Np + n) * Kp + k]) : 0.f;
   }
 }
 
