@@ -36,6 +36,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CMF_BENCH_PRECISION", "auto"),
                     choices=["auto", "tf32", "fp32"])
+    ap.add_argument("--denominators", default=os.environ.get("CMF_BENCH_DENOMINATORS", "direct"),
+                    choices=["direct", "gram"])
     ap.add_argument("--config", default="C", choices=sorted(FULL))
     ap.add_argument("--t-scale", type=float, default=1.0,
                     help="shrink T (debug only; the line is then labelled reduced)")
@@ -284,7 +286,7 @@ def run_b200(args):
 
     alg = ShardedMultUpdate(X[:, :ncols_x], N, T, K, L, t_offset=t_begin, t_local=Tloc,
                             initW=W0, initH=H0, precision=precision, device=local_rank,
-                            group=dist.group.WORLD if dist else None)
+                            group=dist.group.WORLD if dist else None, denominators=args.denominators)
     del X, H0
     torch.cuda.synchronize()
 
@@ -366,7 +368,7 @@ def run_b200(args):
                    (args.config, N, T, K, L, "" if args.t_scale == 1.0 else " (T reduced: debug)"),
                    "sharding": "time axis, %d x %d columns, halo %d" % (world, Tloc, L - 1),
                    "l2": "inputs_exceed_l2 (X and est are %.1f GiB each per GPU)" % (N * Tloc * 4 / 2**30),
-                   "precision": precision, "path": alg.path_name},
+                   "precision": precision, "denominators": args.denominators, "path": alg.path_name},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cb,
         "final_loss": losses[-1],
@@ -402,7 +404,8 @@ def run_e2e(args, torch, N, T, K, L, Tloc, rank, world, local_rank, precision, d
     t0 = time.perf_counter()
     alg = ShardedMultUpdate(Xh.numpy(), N, T, K, L, t_offset=t_begin, t_local=Tloc,
                             initW=W0h.numpy(), initH=H0h.numpy(), precision=precision,
-                            device=local_rank, group=dist.group.WORLD if dist else None)
+                            device=local_rank, group=dist.group.WORLD if dist else None,
+                            denominators=args.denominators)
     last = None
     for _ in range(args.steps):
         last = alg.update()                       # host float every step (D2H + sync)

@@ -15,6 +15,8 @@ CMF_F32, CMF_F64 = 0, 1
 CMF_HOST, CMF_DEVICE = 0, 1
 CMF_PREC_FP32, CMF_PREC_TF32 = 0, 1
 PRECISIONS = {"fp32": CMF_PREC_FP32, "tf32": CMF_PREC_TF32}
+CMF_DEN_DIRECT, CMF_DEN_GRAM = 0, 1
+DENOMINATORS = {"direct": CMF_DEN_DIRECT, "gram": CMF_DEN_GRAM}
 
 
 class Params(C.Structure):
@@ -22,6 +24,7 @@ class Params(C.Structure):
         ("n_features", C.c_int), ("n_components", C.c_int), ("maxlag", C.c_int),
         ("t_local", C.c_longlong), ("t_global", C.c_longlong), ("t_offset", C.c_longlong),
         ("device", C.c_int), ("precision", C.c_int), ("stream", C.c_void_p),
+        ("denominators", C.c_int),
     ]
 
 
@@ -47,6 +50,7 @@ _SIGNATURES = {
     "cmf_mu_w_terms_buffer": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]),
     "cmf_mu_w_apply": (C.c_int, [_H]),
     "cmf_mu_h_step": (C.c_int, [_H]),
+    "cmf_mu_needs_mid_recon": (C.c_int, [_H, C.POINTER(C.c_int)]),
     "cmf_mu_resid_sumsq": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "cmf_mu_resid_sumsq_buffer": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "cmf_mu_loss": (C.c_int, [_H, C.POINTER(C.c_double)]),

@@ -27,12 +27,16 @@ class DeviceOptimizer:
     """Common plumbing for solvers that live behind libcmf_b200."""
 
     def __init__(self, data, model_dimensions, initW=None, initH=None,
-                 tol=1e-5, patience=3, precision="fp32", device=0, seed=None):
+                 tol=1e-5, patience=3, precision="fp32", device=0, seed=None,
+                 denominators="direct"):
         # reference base.py:20-21
         if patience < 1 or not isinstance(patience, Integral):
             raise ValueError("Patience must be a positive integer.")
         if precision not in _lib.PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
+        if denominators not in _lib.DENOMINATORS:
+            raise ValueError("denominators must be one of %s" % sorted(_lib.DENOMINATORS))
+        self.denominators = denominators
         self._lib = _lib.load()
         self._h = C.c_void_p()
         self.patience = patience
@@ -52,7 +56,7 @@ class DeviceOptimizer:
 
         p = _lib.Params(n_features=N, n_components=K, maxlag=L, t_local=T, t_global=T,
                         t_offset=0, device=device, precision=_lib.PRECISIONS[precision],
-                        stream=None)
+                        stream=None, denominators=_lib.DENOMINATORS[denominators])
         _lib.check(self._lib.cmf_mu_create(C.byref(self._h), C.byref(p)))
         _lib.check(self._lib.cmf_mu_set_data(self._h, X.ctypes.data, _lib.np_dtype_code(X),
                                              _lib.CMF_HOST, T, T))

@@ -189,8 +189,12 @@ int do_recon(cmf_mu_s* h) {
   h->est_valid = true;
   return 0;
 }
+bool gram_w(const cmf_mu_s* h) { return h->use_tc && (h->tcs.mask & 2) && (h->tcs.gram & 2); }
+bool gram_h(const cmf_mu_s* h) { return h->use_tc && (h->tcs.mask & 4) && (h->tcs.gram & 1); }
+
 int do_w_terms(cmf_mu_s* h) {
-  CMF_CHECK(h->est_valid, "w_terms needs a current reconstruction (call cmf_mu_recon)");
+  CMF_CHECK(h->have_data && h->have_factors, "w_terms before data/factors were set");
+  CMF_CHECK(h->est_valid || gram_w(h), "w_terms needs a current reconstruction (call cmf_mu_recon)");
   if (h->use_tc && (h->tcs.mask & 2)) {
     CMF_TRY(tc::w_terms(h->tcs, h->stream));
     h->launches += tc::kWTermsLaunches;
@@ -213,7 +217,8 @@ int do_w_apply(cmf_mu_s* h) {
   return 0;
 }
 int do_h_terms(cmf_mu_s* h) {
-  CMF_CHECK(h->est_valid, "h terms need a current reconstruction (call cmf_mu_recon)");
+  CMF_CHECK(h->have_data && h->have_factors, "h terms before data/factors were set");
+  CMF_CHECK(h->est_valid || gram_h(h), "h terms need a current reconstruction (call cmf_mu_recon)");
   if (h->use_tc && (h->tcs.mask & 4)) {
     CMF_TRY(tc::h_terms(h->tcs, h->stream));
     h->launches += tc::kHTermsLaunches;
@@ -382,6 +387,7 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
                 p->t_offset + p->t_local <= p->t_global,
             "inconsistent time range: t_local=%lld t_offset=%lld t_global=%lld", p->t_local, p->t_offset, p->t_global);
   CMF_CHECK(p->precision == CMF_PREC_FP32 || p->precision == CMF_PREC_TF32, "unknown precision %d", p->precision);
+  CMF_CHECK(p->denominators == CMF_DEN_DIRECT || p->denominators == CMF_DEN_GRAM, "unknown denominators mode %d", p->denominators);
   CMF_CHECK(p->t_local == p->t_global || p->t_local >= p->maxlag - 1,
             "a time shard must hold at least L-1 columns (t_local=%lld, L=%d)", p->t_local, p->maxlag);
   int ndev = 0;
@@ -480,6 +486,7 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
   }
   if (rc == 0 && h->use_tc) {
     tc::Dims d{h->N, h->K, h->L, h->Np, h->Kp, h->h, h->Tloc, h->TO, h->RT, h->RH, h->t_valid, h->num_sms};
+    h->tcs.gram_request = (p->denominators == CMF_DEN_GRAM) ? 3 : 0;
     rc = tc::init(h->tcs, d, h->Xt, h->Et, h->Ht, h->W, h->numden, h->hterms, h->loss_partials,
                   h->n_loss_partials, h->d_sumsq, h->stream);
   }
@@ -674,6 +681,12 @@ int cmf_mu_h_step(cmf_mu_t* h) {
   return do_h_apply(h);
 }
 
+int cmf_mu_needs_mid_recon(cmf_mu_t* h, int* needed) {
+  CMF_CHECK(h != nullptr && needed != nullptr, "null argument");
+  *needed = gram_h(h) ? 0 : 1;
+  return 0;
+}
+
 int cmf_mu_resid_sumsq(cmf_mu_t* h, double* sumsq) {
   CMF_ENTER(h);
   CMF_CHECK(sumsq != nullptr, "null argument");
@@ -716,7 +729,7 @@ int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
       if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
       CMF_TRY(do_w_apply(h));
       if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      CMF_TRY(do_recon(h));
+      if (!gram_h(h)) CMF_TRY(do_recon(h));       // the Gram H step does not read est
       if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
       CMF_TRY(do_h_terms(h));
       if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
@@ -806,7 +819,7 @@ int cmf_mu_get_est(cmf_mu_t* h, void* est_out, int dtype, int mem, long long ld)
 int cmf_mu_h_terms(cmf_mu_t* h, void* num_out, void* den_out, int dtype) {
   CMF_ENTER(h);
   CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
-  if (!h->est_valid) CMF_TRY(do_recon(h));
+  if (!h->est_valid && !gram_h(h)) CMF_TRY(do_recon(h));
   CMF_TRY(do_h_terms(h));
   for (int s = 0; s < 2; ++s) {
     void* out = s ? den_out : num_out;
@@ -852,7 +865,9 @@ int cmf_mu_launch_count(cmf_mu_t* h, long long* count) {
 const char* cmf_mu_path_name(cmf_mu_t* h) {
   if (!h) return "none";
   if (!h->use_tc) return "ffma-fp32";
-  return h->tcs.mask == 7 ? "tcgen05-tf32" : "tcgen05-tf32(partial)";
+  if (h->tcs.mask != 7) return "tcgen05-tf32(partial)";
+  if (h->tcs.gram == 3) return "tcgen05-tf32+gram";
+  return h->tcs.gram ? "tcgen05-tf32+gram(partial)" : "tcgen05-tf32";
 }
 
 int cmf_mu_kernel_ms(cmf_mu_t* h, float out[4]) {

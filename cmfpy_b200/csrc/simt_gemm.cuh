@@ -311,5 +311,83 @@ struct HTermsEpi {
   __device__ void block_sum(double, long long) const {}
 };
 
+// ---- tail corrections of the Gram route (rows of est past the end of the data) ----
+// plain store out[m][c]
+struct PlainEpi {
+  static constexpr bool kReduce = false;
+  float* out; long long ld; long long m_rows; int c_cols;
+  __device__ float store(long long m, long long c, float4 v, int, int) const {
+    if (m < m_rows && c < c_cols) *reinterpret_cast<float4*>(out + m * ld + c) = v;
+    return 0.f;
+  }
+  __device__ void block_sum(double, long long) const {}
+};
+// A(m, r=(l,n)) = Etail[m + m_off + l - t0][n] when that row exists (rows of the untruncated est at t >= t0)
+struct TailHA {
+  static constexpr bool kAlongR = true;
+  const float* Etail; int Np; long long m_off, t0, ntail;
+  __device__ const float* ptr(long long m, long long r, int) const {
+    const int l = (int)(r / Np), n = (int)(r % Np);
+    const long long row = m + m_off + l - t0;
+    if (row < 0 || row >= ntail) return nullptr;
+    return Etail + row * Np + n;
+  }
+};
+// part[split][m][c] = v   (split-K partials; summed by tail_sub_kernel)
+struct PartEpi {
+  static constexpr bool kReduce = false;
+  float* part; long long ld, m_rows; int c_cols; long long per_split;
+  __device__ float store(long long m, long long c, float4 v, int split, int) const {
+    if (m < m_rows && c < c_cols) *reinterpret_cast<float4*>(part + split * per_split + m * ld + c) = v;
+    return 0.f;
+  }
+  __device__ void block_sum(double, long long) const {}
+};
+// out[(m + m_off)][c] -= sum_split part[split][m][c]
+__global__ void __launch_bounds__(256)
+tail_sub_kernel(float* __restrict__ out, const float* __restrict__ part, int nsplit, long long per_split, long long m_rows,
+                int ld, long long m_off, long long row_end) {
+  const long long total = m_rows * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / ld;
+    const long long row = m + m_off;
+    if (row < 0 || row >= row_end) continue;
+    float acc = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) acc += part[sp * per_split + i];
+    out[row * ld + (i % ld)] -= acc;
+  }
+}
+// out[(m + m_off)][k] -= v    (rows m + m_off < row_end)
+struct SubEpi {
+  static constexpr bool kReduce = false;
+  float* out; int Kp; long long m_off, row_end;
+  __device__ float store(long long m, long long k, float4 v, int, int) const {
+    const long long row = m + m_off;
+    if (k >= Kp || row < 0 || row >= row_end) return 0.f;
+    float4* o = reinterpret_cast<float4*>(out + row * Kp + k);
+    float4 c = *o;
+    c.x -= v.x; c.y -= v.y; c.z -= v.z; c.w -= v.w;
+    *o = c;
+    return 0.f;
+  }
+  __device__ void block_sum(double, long long) const {}
+};
+
+// out[l][n][k] -= v   with c = l*Kp + k   (W-layout subtract, tail correction of the W step)
+struct SubWEpi {
+  static constexpr bool kReduce = false;
+  float* out; int Np, Kp, LKp;
+  __device__ float store(long long n, long long c, float4 v, int, int) const {
+    if (n >= Np || c >= LKp) return 0.f;
+    const int l = (int)(c / Kp), k = (int)(c % Kp);
+    float4* o = reinterpret_cast<float4*>(out + ((long long)l * Np + n) * Kp + k);
+    float4 x = *o;
+    x.x -= v.x; x.y -= v.y; x.z -= v.z; x.w -= v.w;
+    *o = x;
+    return 0.f;
+  }
+  __device__ void block_sum(double, long long) const {}
+};
+
 }  // namespace simt
 }  // namespace cmf

@@ -79,8 +79,12 @@ struct PipeState {
 // tile i+1.
 // ==========================================================================
 struct ReconParams {
-  int Np, L, n_tiles_n, wrows;     // L = number of VIRTUAL lags
-  int s, CB, h_shift;              // lag stride in rows, column blocks, Ht row of window row 0 minus tile start
+  int Np, L, n_tiles_n, wrows;     // Np = A rows per lag; L = number of VIRTUAL lags
+  int s, CB, h_shift;              // lag stride in rows, reduction blocks, B row of window row 0 minus tile start
+  int cb_cols;                     // A column blocks per lag: block cb reads lag (l + cb / cb_cols), columns (cb % cb_cols)*32
+  int n_rows, ld_out;              // valid output rows n, leading dimension of the output
+  int store_mode;                  // 0: out[tau][n] (est^T; loss, tail mask, rounding)  2: W layout out[(l*n_rows_w+n)*Kp+k], tau = l*Kp+k
+  int w_kp, w_np;                  // store_mode 2: Kp and Np of the W-layout output
   long long n_tiles;               // n_tiles_n * (RT / 256)
   long long t_own, t_valid;
   float* Et;
@@ -156,7 +160,8 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           for (int l = 0; l < L; ++l) {
             if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
             mbar_arrive_expect_tx(&full[ps.stage], kReconABytes);
-            tma_load_2d(As + (size_t)ps.stage * kReconABytes, &tmW, &full[ps.stage], cb * 32, l * p.Np + nt * 128);
+            tma_load_2d(As + (size_t)ps.stage * kReconABytes, &tmW, &full[ps.stage], (cb % p.cb_cols) * 32,
+                        (l + cb / p.cb_cols) * p.Np + nt * 128);
             ps.advance(kReconStages);
           }
         }
@@ -212,11 +217,11 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       if (!ab.wait(&tfull[b], (it >> 1) & 1)) break;
       tc_fence_after();
       const int n = nt * 128 + q * 32 + lane;
-      const bool n_ok = n < p.Np;
+      const bool n_ok = n < p.n_rows;
       float tile_loss = 0.f;
       const float* __restrict__ Xt = p.Xt;
       float* __restrict__ Et = p.Et;
-      const size_t np = (size_t)p.Np;
+      const size_t np = (size_t)p.ld_out;
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         uint32_t r[32];
@@ -230,7 +235,21 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           for (int j = 0; j < 32; ++j) x[j] = (tau0 + j < p.t_own) ? __ldcs(Xt + off0 + (size_t)j * np) : 0.f;
         }
         tmem_ld_wait();
-        if (n_ok) {
+        if (p.store_mode == 2) {
+          // tau = l*Kp + k: 32 consecutive tau are whole groups of 4 components of one lag
+          if (n_ok) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const long long tau = tau0 + 4 * j4;
+              const long long l = tau / p.w_kp;
+              const int k = (int)(tau % p.w_kp);
+              if (tau < p.t_valid)
+                *reinterpret_cast<float4*>(Et + ((size_t)l * p.w_np + n) * p.w_kp + k) =
+                    make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
+                                __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
+            }
+          }
+        } else if (n_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const long long tau = tau0 + j;
@@ -276,6 +295,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 struct WTermsParams {
   int Np, L, n_tiles_n, n_lag_groups, n_chunks, h;   // L = REAL lags; lag groups hold 16 virtual lags
   int Lv, Kp, s, CB, brows;       // virtual lags, real padded K, lag stride, column blocks, H rows per stage
+  int n_src;                      // 2: X and est; 1: the first source only
   long long n_items;              // n_tiles_n * n_lag_groups * CB * 2 * n_chunks
   long long stages_total;         // ceil(t_own / 32)
   float* part;                    // [chunk][src][L][Np][Kp]
@@ -327,7 +347,7 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   auto decode = [&](long long item, int& lg, int& cb, int& src, int& nt, int& ch) {
     lg = (int)(item % p.n_lag_groups); item /= p.n_lag_groups;
     cb = (int)(item % p.CB); item /= p.CB;
-    src = (int)(item % 2); item /= 2;
+    src = (int)(item % p.n_src); item /= p.n_src;
     nt = (int)(item % p.n_tiles_n); item /= p.n_tiles_n;
     ch = (int)item;
   };
@@ -405,7 +425,7 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       if (!ab.wait(tfull, it & 1)) break;
       tc_fence_after();
       const int n = nt * 128 + q * 32 + lane;
-      float* obase = p.part + ((long long)ch * 2 + src) * p.per_src;
+      float* obase = p.part + ((long long)ch * p.n_src + src) * p.per_src;
 #pragma unroll 1
       for (int c = 0; c < 16; ++c) {            // 16 column blocks of 32 = (g, a): one virtual lag each
         uint32_t r[32];
@@ -476,9 +496,15 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 struct HTermsParams {
   int Np, J, n_chunks_n, wrows;    // n chunks of 32 features; window rows >= 256 + s*(J-1)
   int s, CB;                       // lag stride in rows; column blocks (regions = (4/CB lag groups) x CB)
+  int n_src;                       // 2: X and est (numerator, denominator); 1: X only (denominator via Gram)
+  int pair_mode;                   // n_src == 2 with BOTH sources = X: source 1 is the next time tile (base + 256),
+                                   // so every W stage still feeds 8 MMAs when only the numerator is computed
+  long long n_time_tiles;          // time tiles (pairs in pair_mode) ; n_tiles = n_time_tiles * n_split
+  int n_split, nc_per_split;       // the feature chunks of a tile are shared by n_split work items (shorter
+                                   // accumulation chains in tensor memory; partials summed by combine_groups)
   long long n_tiles;               // TO / 256 + 1
   long long ts;                    // scratch row length (TO + 256)
-  float* scratch;                  // [2][4][Kp][ts]
+  float* scratch;                  // [n_split][2][4][32][ts]
   int* err;
 };
 
@@ -531,15 +557,18 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       PipeState ps;
       long long wcount = 0;                 // window loads issued so far
       bool ok = true;
-      for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
-        const int base = (int)(tile * 256);
-        for (int nc = 0; nc < p.n_chunks_n && ok; ++nc, ++wcount) {
+      for (long long item = blockIdx.x; item < p.n_tiles && ok; item += gridDim.x) {
+        const long long tile = item / p.n_split;
+        const int nc0 = (int)(item % p.n_split) * p.nc_per_split;
+        const int nc1 = min(nc0 + p.nc_per_split, p.n_chunks_n);
+        for (int nc = nc0; nc < nc1 && ok; ++nc, ++wcount) {
           const int wb = (int)(wcount & 1);
           if (!ab.wait(&wempty[wb], (uint32_t)((wcount >> 1) & 1) ^ 1)) { ok = false; break; }
-          mbar_arrive_expect_tx(&wfull[wb], 2 * wbytes);
-          for (int src = 0; src < 2; ++src) {
+          mbar_arrive_expect_tx(&wfull[wb], p.n_src * wbytes);
+          for (int src = 0; src < p.n_src; ++src) {
             uint8_t* wdst = Ws + ((size_t)wb * 2 + src) * wbytes;
-            const CUtensorMap* tmS = src ? &tmE : &tmX;
+            const CUtensorMap* tmS = (src && !p.pair_mode) ? &tmE : &tmX;
+            const int base = (int)((p.pair_mode ? 2 * tile + src : tile) * 256);
             for (int rb = 0; rb < wrows / 32; ++rb)
               tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], nc * 32, base + rb * 32);
           }
@@ -562,10 +591,12 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       long long wcount = 0;
       int it = 0;
       bool ok = true;
-      for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x, ++it) {
+      for (long long item = blockIdx.x; item < p.n_tiles && ok; item += gridDim.x, ++it) {
+        const int nc0 = (int)(item % p.n_split) * p.nc_per_split;
+        const int nc1 = min(nc0 + p.nc_per_split, p.n_chunks_n);
         if (!ab.wait(tempty, (it & 1) ^ 1)) break;
         tc_fence_after();
-        for (int nc = 0; nc < p.n_chunks_n && ok; ++nc, ++wcount) {
+        for (int nc = nc0; nc < nc1 && ok; ++nc, ++wcount) {
           const int wb = (int)(wcount & 1);
           if (!ab.wait(&wfull[wb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
           tc_fence_after();
@@ -576,11 +607,12 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             const uint32_t abase = smem_u32(As + (size_t)ps.stage * kHtABytes);
 #pragma unroll
             for (int src = 0; src < 2; ++src) {
+              if (src >= p.n_src) break;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
                 const uint64_t bd = make_smem_desc(wbase + src * wbytes + (uint32_t)(p.s * j) * 128 + ks * 32, 16, 1024, kSwz128);
-                mma_tf32_ss(tmem + src * 256, ad, bd, idesc, (nc | j | ks) != 0 ? 1u : 0u);
+                mma_tf32_ss(tmem + src * 256, ad, bd, idesc, ((nc - nc0) | j | ks) != 0 ? 1u : 0u);
               }
             }
             mma_commit(&empty[ps.stage]);
@@ -596,17 +628,22 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   } else {
     const int q = warp & 3;                 // lag group g of this warp's 32 TMEM lanes; lane = k
     int it = 0;
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    for (long long item = blockIdx.x; item < p.n_tiles; item += gridDim.x, ++it) {
+      const long long tile = item / p.n_split;
+      const int split = (int)(item % p.n_split);
       if (!ab.wait(tfull, it & 1)) break;
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 16; ++c) {
+      for (int c = 0; c < 8 * p.n_src; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
         tmem_ld_wait();
         const int src = c >> 3;
-        float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)(src * 4 + q) * kKp + lane) * p.ts +
-                                              tile * 256 + (c & 7) * 32);
+        const int slot = p.pair_mode ? 0 : src;                       // pair mode: both halves are numerators
+        const long long ttile = p.pair_mode ? 2 * tile + src : tile;
+        if ((ttile + 1) * 256 > p.ts) continue;                       // odd tile count: the pair's second half does not exist
+        float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)((split * 2 + slot) * 4 + q) * kKp + lane) * p.ts +
+                                              ttile * 256 + (c & 7) * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -622,33 +659,42 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-// out[src][t][k] = sum over lag groups g and folded lags dl of
-//     scratch[src][g*CB + cb][kk][t + dl + s*J*g]
+// out[src][t][k] = sum over splits sp, lag groups g and folded lags dl of
+//     scratch[sp][src][g*CB + cb][kk][t + dl + s*J*g]
 // with (cb, kk) = (k/32, k%32), dl = 0 when s == 1, and (0, dl*Kp + k), dl < s when s > 1.
-// 32-wide time tiles through smem so that both the time-contiguous reads and
-// the k-contiguous writes coalesce.
+// 128-wide time tiles through smem: the time-contiguous reads (512 B per warp row segment) and
+// the k-contiguous writes both coalesce.
 __global__ void __launch_bounds__(256)
 combine_groups_kernel(const float* __restrict__ scratch, float* __restrict__ out, long long ts, long long t_rows,
-                      int J, int s, int CB, int Kp) {
-  extern __shared__ float tile[];             // [Kp][33]
+                      int J, int s, int CB, int Kp, int n_src, int n_split) {
+  extern __shared__ float tile[];             // [Kp][129]
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const long long t0 = (long long)blockIdx.x * 32;
+  const long long t0 = (long long)blockIdx.x * 128;
   const int n_glag = 4 / CB;
-  for (int src = 0; src < 2; ++src) {
+  for (int src = 0; src < n_src; ++src) {
     for (int k = ty; k < Kp; k += 8) {
-      float acc = 0.f;
-      for (int g = 0; g < n_glag; ++g)
-        for (int dl = 0; dl < s; ++dl) {
-          const int region = g * CB + (s == 1 ? k / 32 : 0);
-          const int kk = (s == 1) ? (k % 32) : (dl * Kp + k);
-          acc += __ldcs(scratch + ((size_t)(src * 4 + region) * kKp + kk) * ts + t0 + tx + dl + (long long)s * J * g);
-        }
-      tile[k * 33 + tx] = acc;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int sp = 0; sp < n_split; ++sp)
+        for (int g = 0; g < n_glag; ++g)
+          for (int dl = 0; dl < s; ++dl) {
+            const int region = g * CB + (s == 1 ? k / 32 : 0);
+            const int kk = (s == 1) ? (k % 32) : (dl * Kp + k);
+            const long long sh = dl + (long long)s * J * g;
+            const float* row = scratch + ((size_t)((sp * 2 + src) * 4 + region) * kKp + kk) * ts + t0 + 4 * tx + sh;
+            if ((sh & 3) == 0) {
+              const float4 v = __ldcs(reinterpret_cast<const float4*>(row));
+              a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+            } else {
+              a0 += __ldcs(row); a1 += __ldcs(row + 1); a2 += __ldcs(row + 2); a3 += __ldcs(row + 3);
+            }
+          }
+      float* tk = tile + k * 129 + 4 * tx;
+      tk[0] = a0; tk[1] = a1; tk[2] = a2; tk[3] = a3;
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 32 * Kp; idx += 256) {
+    for (int idx = threadIdx.x; idx < 128 * Kp; idx += 256) {
       const int t = idx / Kp, k = idx % Kp;
-      if (t0 + t < t_rows) out[((size_t)src * t_rows + t0 + t) * Kp + k] = tile[k * 33 + t];
+      if (t0 + t < t_rows) out[((size_t)src * t_rows + t0 + t) * Kp + k] = tile[k * 129 + t];
     }
     __syncthreads();
   }
@@ -678,6 +724,80 @@ fold_w_kernel(float* __restrict__ Wv, const float* __restrict__ W, int L, int Lv
     const int lv = (int)(i / (32ll * Np));
     const int l = s * lv + dl;
     Wv[i] = (l < L) ? round_tf32(W[((long long)l * Np + n) * Kp + k]) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Gram route for the denominators (exact identities, ~K/N of the direct cost):
+//   den_H[k][t] = sum_d sum_k' R[d][k][k'] H[k'][t+d]  -  (terms of est past the end of the data)
+//   R[d][k][k'] = sum_{l-l'=d} sum_n W[l][n][k] W[l'][n][k']
+// (substitute est = sum_l' W[l'] shift(H,l') into tensor_transconv(W, est), reference common.py:61-86).
+// R comes from G = Wt Wt^T (a plain GEMM on the recon kernel) summed along its lag diagonals.
+// ---------------------------------------------------------------------------
+
+// W step:  den_W[l][n][k] = sum_{l',k'} W[l'][n][k'] A[l-l'][k'][k]  -  (terms of est past the end of the data)
+//   A[d][k'][k] = sum_u H[k'][u+d] H[k][u]  (lag autocorrelation of H) = P[d][k'][k] for d >= 0, P[-d][k][k'] for d < 0,
+//   P[d][k'][k] = sum_t H[k'][t] H[k][t-d]: the W-terms kernel run on H^T itself.
+// Mt[(l,k)][(l'v, c)] = round_tf32(A[l - l'][k'][k]) with (l', k') the real lag / component that virtual lag l'v,
+// column c of Wv holds - the K-major B operand of a plain GEMM with Wv.
+__global__ void __launch_bounds__(256)
+toeplitz_kernel(const float* __restrict__ P, float* __restrict__ Mt, int L, int Lv, int Kp, int s, int KW,
+                long long rows_alloc) {
+  const long long ld = (long long)Lv * KW;
+  const long long total = rows_alloc * ld;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long tau = i / ld;
+    const int col = (int)(i % ld);
+    const int lv = col / KW, c = col % KW;
+    const int dl = (s > 1) ? c / Kp : 0;
+    const int kq = (s > 1) ? c % Kp : c;
+    const int lp = s * lv + dl;
+    const int l = (int)(tau / Kp), k = (int)(tau % Kp);
+    float v = 0.f;
+    if (l < L && lp < L && kq < Kp) {
+      const int d = l - lp;
+      v = (d >= 0) ? P[((size_t)d * Kp + kq) * Kp + k] : P[((size_t)(-d) * Kp + k) * Kp + kq];
+    }
+    Mt[i] = round_tf32(v);
+  }
+}
+
+// Wt[(l*Kp + k)][n] = round_tf32(W[l][n][k])      (32x32 tiles through smem)
+__global__ void __launch_bounds__(256)
+transpose_round_w_kernel(const float* __restrict__ W, float* __restrict__ Wt, int Np, int Kp, long long ldt) {
+  __shared__ float tile[32][33];
+  const int l = blockIdx.z;
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int n = n0 + ty + j, k = k0 + tx;
+    tile[ty + j][tx] = (n < Np && k < Kp) ? W[((size_t)l * Np + n) * Kp + k] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int k = k0 + ty + j, n = n0 + tx;
+    if (k < Kp && n < Np) Wt[((size_t)l * Kp + k) * ldt + n] = round_tf32(tile[tx][ty + j]);
+  }
+}
+
+// Rw[j][k][k'] = R[L-1-j][k][k'] = sum_{l'} G[(l'+d)*Kp + k][l'*Kp + k'],  d = L-1-j, j in [0, 2L-1)
+// (the order the recon kernel wants its "lags": out[tau + L-1] = sum_j Rw[j] H^T[tau + L-1 - j])
+__global__ void __launch_bounds__(256)
+diag_sum_kernel(const float* __restrict__ G, long long ldg, float* __restrict__ Rw, int L, int Kp) {
+  const long long total = (long long)(2 * L - 1) * Kp * Kp;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int kq = (int)(i % Kp);
+    const int k = (int)((i / Kp) % Kp);
+    const int j = (int)(i / ((long long)Kp * Kp));
+    const int d = L - 1 - j;
+    const int lo = d < 0 ? -d : 0, hi = d > 0 ? L - d : L;     // l' range with 0 <= l'+d < L
+    float acc = 0.f;
+    for (int lp = lo; lp < hi; ++lp) acc += G[((size_t)(lp + d) * Kp + k) * ldg + (size_t)lp * Kp + kq];
+    Rw[i] = acc;
   }
 }
 

@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "ew_kernels.cuh"
+#include "simt_gemm.cuh"
 #include "tc_kernels.cuh"
 
 namespace cmf {
@@ -70,9 +71,23 @@ struct TcState {
   float* hscratch = nullptr;       // [2][4][32][TO + 256] lag-group partials of the H terms
   int* d_err = nullptr;
   int n_chunks = 1, n_lag_groups = 1;
+  int h_split = 1, h_nc_per_split = 1;   // H terms: feature-chunk splits per time tile
   int recon_grid = 1, wterms_grid = 1, hterms_grid = 1;
   long long wcount = 0, wv_count = 0, hv_count = 0;
   CUtensorMap tmW_k1, tmH_k1, tmX_k2, tmE_k2, tmH_k2, tmW_k3, tmX_k3, tmE_k3;
+
+  // ---- Gram route for the denominators (gram & 1: H step, gram & 2: W step) ----
+  int gram = 0;
+  int gram_request = 0;             // from cmf_mu_params.denominators (CMF_GRAM in the environment overrides)
+  int LK = 0, Lr = 0, Lrv = 0, dh_wrows = 0;
+  long long g_rows = 0;             // rows allocated for G (LK rounded up to 256)
+  float *Wt = nullptr, *G = nullptr, *Rw = nullptr, *Rwv = nullptr, *Etail = nullptr;
+  long long ntail = 0;              // rows of est past the end of the data that fall inside this shard's window
+  CUtensorMap tmWt_a, tmWt_b, tmRw_a;
+  // W step
+  float *P = nullptr, *Ppart = nullptr, *Mt = nullptr;
+  int p_chunks = 1, p_grid = 1;
+  CUtensorMap tmHx_k2, tmMt_b;
 };
 
 constexpr int kReconLaunches = 2, kWTermsLaunches = 2, kHTermsLaunches = 2;   // kernels per phase
@@ -93,11 +108,12 @@ inline EncodeTiledFn get_encode() {
 
 // 2-D fp32 map over a row-major [rows][cols] array (row pitch = cols floats)
 inline int make_map(CUtensorMap* m, const float* base, long long rows, long long cols, int box_cols, int box_rows,
-                    CUtensorMapSwizzle swz) {
+                    CUtensorMapSwizzle swz, long long pitch_cols = 0) {
+  if (pitch_cols <= 0) pitch_cols = cols;
   EncodeTiledFn enc = get_encode();
   CMF_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_cols * 4};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
@@ -110,6 +126,9 @@ inline int make_map(CUtensorMap* m, const float* base, long long rows, long long
 
 inline void destroy(TcState& s) {
   cudaFree(s.wpart); cudaFree(s.hscratch); cudaFree(s.d_err); cudaFree(s.Wv); cudaFree(s.Hv);
+  cudaFree(s.Wt); cudaFree(s.G); cudaFree(s.Rw); cudaFree(s.Rwv); cudaFree(s.Etail);
+  cudaFree(s.P); cudaFree(s.Ppart); cudaFree(s.Mt);
+  s.Wt = s.G = s.Rw = s.Rwv = s.Etail = s.P = s.Ppart = s.Mt = nullptr;
   s.wpart = s.hscratch = s.Wv = s.Hv = nullptr;
   s.d_err = nullptr;
   s.ready = false;
@@ -230,13 +249,149 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   CMF_TRY(make_map(&s.tmW_k3, s.Wv, (long long)f.Lv * d.Np, f.KW, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   CMF_TRY(make_map(&s.tmX_k3, Xt, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
   CMF_TRY(make_map(&s.tmE_k3, Et, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
-  CMF_CUDA(cudaMalloc((void**)&s.hscratch, (size_t)2 * 4 * kKp * (d.TO + 256) * 4));
-  CMF_CUDA(cudaMemsetAsync(s.hscratch, 0, (size_t)2 * 4 * kKp * (d.TO + 256) * 4, stream));
   CMF_CUDA(cudaFuncSetAttribute(tc_hterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)hterms_smem_bytes(f.hterms_wrows)));
-  if (d.Kp * 33 * 4 > 48 * 1024)
-    CMF_CUDA(cudaFuncSetAttribute(combine_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.Kp * 33 * 4));
+  if (d.Kp * 129 * 4 > 48 * 1024)
+    CMF_CUDA(cudaFuncSetAttribute(combine_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.Kp * 129 * 4));
+
+  // ---- Gram route ---------------------------------------------------------
+  s.gram = s.gram_request;
+  if (const char* e = getenv("CMF_GRAM")) s.gram = atoi(e);
+  s.LK = d.L * d.Kp;
+  s.Lr = 2 * d.L - 1;
+  s.Lrv = (s.Lr + f.s - 1) / f.s;
+  s.dh_wrows = round_up(256 + f.s * (s.Lrv - 1), 64);
+  s.g_rows = round_up_ll(s.LK, 256);
+  s.ntail = d.Tloc + d.h - d.t_valid;
+  if (recon_smem_bytes(s.dh_wrows) > kMaxSmem || (long long)s.g_rows * s.LK * 4 > (1ll << 30)) s.gram &= ~1;
+  if (s.gram & 1) {
+    CMF_CUDA(cudaMalloc((void**)&s.Wt, (size_t)s.LK * d.Np * 4));
+    CMF_CUDA(cudaMalloc((void**)&s.G, (size_t)s.g_rows * s.LK * 4));
+    CMF_CUDA(cudaMalloc((void**)&s.Rw, (size_t)s.Lr * d.Kp * d.Kp * 4));
+    CMF_CUDA(cudaMalloc((void**)&s.Rwv, (size_t)s.Lrv * d.Kp * f.KW * 4));
+    CMF_CUDA(cudaMemsetAsync(s.Rwv, 0, (size_t)s.Lrv * d.Kp * f.KW * 4, stream));
+    CMF_TRY(make_map(&s.tmWt_a, s.Wt, s.LK, d.Np, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+    CMF_TRY(make_map(&s.tmWt_b, s.Wt, s.LK, d.Np, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
+    CMF_TRY(make_map(&s.tmRw_a, s.Rwv, (long long)s.Lrv * d.Kp, f.KW, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+    const size_t need = recon_smem_bytes(s.dh_wrows) > recon_smem_bytes(f.recon_wrows) ? recon_smem_bytes(s.dh_wrows)
+                                                                                        : recon_smem_bytes(f.recon_wrows);
+    CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  }
+  // H terms: split the feature chunks of a tile so that the tensor-memory accumulation chain of the
+  // numerator is about as long as the one of the Gram denominator (equal truncation bias => no drift of
+  // the W/H scale split); the direct route needs no split (numerator and denominator share the chain).
+  {
+    const int n_chunks_n = (int)ceil_div_ll(d.Np, 32);
+    int Q = 1;
+    if (s.gram & 1) {
+      const double chain_num = (double)n_chunks_n * f.J * 4, chain_den = (double)s.Lrv * f.CB * 4;
+      Q = (int)(chain_num / chain_den + 0.5);
+      if (Q < 1) Q = 1;
+      if (Q > n_chunks_n) Q = n_chunks_n;
+      while (Q > 1 && (size_t)Q * 2 * 4 * kKp * (d.TO + 256) * 4 > ((size_t)6 << 30)) --Q;
+    }
+    s.h_nc_per_split = (n_chunks_n + Q - 1) / Q;
+    s.h_split = (n_chunks_n + s.h_nc_per_split - 1) / s.h_nc_per_split;
+    const size_t bytes = (size_t)s.h_split * 2 * 4 * kKp * (d.TO + 256) * 4;
+    CMF_CUDA(cudaMalloc((void**)&s.hscratch, bytes));
+    CMF_CUDA(cudaMemsetAsync(s.hscratch, 0, bytes, stream));
+    const long long tt = d.TO / 256 + 1;
+    const long long items = ((s.gram & 1) ? (tt + 1) / 2 : tt) * s.h_split;
+    s.hterms_grid = (int)(items < d.num_sms ? items : d.num_sms);
+  }
+  if ((long long)s.g_rows * f.Lv * f.KW * 4 > (1ll << 30)) s.gram &= ~2;
+  if (s.gram && s.ntail > 0) CMF_CUDA(cudaMalloc((void**)&s.Etail, (size_t)256 * d.Np * 4));
+  if (s.gram & 2) {
+    const long long pcount = (long long)d.L * d.Kp * d.Kp;
+    {   // time chunks of the autocorrelation pass: one item per SM if possible
+      const long long units = (long long)s.n_lag_groups * f.CB;
+      const long long stages_total = ceil_div_ll(d.Tloc, 32);
+      // same time chunks as the numerator pass: equal accumulation chains, equal truncation bias
+      long long c = s.n_chunks;
+      if (c > stages_total) c = stages_total;
+      if (c < 1) c = 1;
+      s.p_chunks = (int)c;
+      const long long items = units * c;
+      s.p_grid = (int)(items < d.num_sms ? items : d.num_sms);
+    }
+    CMF_CUDA(cudaMalloc((void**)&s.P, (size_t)pcount * 4));
+    CMF_CUDA(cudaMalloc((void**)&s.Ppart, (size_t)pcount * s.p_chunks * 4));
+    CMF_CUDA(cudaMalloc((void**)&s.Mt, (size_t)s.g_rows * f.Lv * f.KW * 4));
+    // H^T itself as the "data" operand: the first Kp columns of Hv are the unfolded, rounded H^T
+    CMF_TRY(make_map(&s.tmHx_k2, s.Hv + (long long)d.h * f.KW, d.Tloc, d.Kp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, f.KW));
+    CMF_TRY(make_map(&s.tmMt_b, s.Mt, s.g_rows, (long long)f.Lv * f.KW, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
+    CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(recon_smem_bytes(s.dh_wrows) <= kMaxSmem && recon_smem_bytes(s.dh_wrows) > recon_smem_bytes(f.recon_wrows)
+                                            ? recon_smem_bytes(s.dh_wrows) : recon_smem_bytes(f.recon_wrows))));
+  }
   s.ready = true;
+  return 0;
+}
+
+// untruncated est rows t_valid .. t_valid + 256 into Etail (one time tile of the recon kernel, no tail mask)
+inline int tail_est(TcState& s, cudaStream_t stream) {
+  const Dims& d = s.d;
+  const Fold& f = s.f;
+  ReconParams p{};
+  p.Np = d.Np; p.L = f.Lv; p.n_tiles_n = (int)ceil_div_ll(d.Np, 128); p.wrows = f.recon_wrows;
+  p.s = f.s; p.CB = f.CB; p.cb_cols = f.CB; p.h_shift = (int)(d.h - f.s * (f.Lv - 1) + d.t_valid);
+  p.n_rows = d.Np; p.ld_out = d.Np; p.store_mode = 0; p.w_kp = d.Kp; p.w_np = d.Np;
+  p.n_tiles = p.n_tiles_n;
+  p.t_own = 0; p.t_valid = 256;
+  p.Et = s.Etail; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
+  tc_recon_kernel<<<p.n_tiles_n, kReconThreads, recon_smem_bytes(f.recon_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
+  return launch_ok("tail_est");
+}
+
+// ---- Gram route, W step: den_W = W (*) A - tail, written into the den half of numden ----
+inline int den_w_gram(TcState& s, cudaStream_t stream) {
+  const Dims& d = s.d;
+  const Fold& f = s.f;
+  const long long pcount = (long long)d.L * d.Kp * d.Kp;
+  // (a) P[d][k'][k] = sum_t H[k'][t] H[k][t-d] over the owned columns: the W-terms kernel on H^T
+  {
+    WTermsParams p{};
+    p.Np = d.Kp; p.L = d.L; p.n_tiles_n = 1; p.n_lag_groups = s.n_lag_groups; p.n_chunks = s.p_chunks; p.h = d.h;
+    p.Lv = f.Lv; p.Kp = d.Kp; p.s = f.s; p.CB = f.CB; p.brows = wterms_brows(f.s); p.n_src = 1;
+    p.n_items = (long long)p.n_lag_groups * f.CB * p.n_chunks;
+    p.stages_total = ceil_div_ll(d.Tloc, 32);
+    p.part = (s.p_chunks == 1) ? s.P : s.Ppart;
+    p.per_src = pcount; p.err = s.d_err;
+    tc_wterms_kernel<<<s.p_grid, kWtThreads, wterms_smem_bytes(f.s), stream>>>(s.tmHx_k2, s.tmHx_k2, s.tmH_k2, p);
+    CMF_TRY(launch_ok("gram_P"));
+    if (s.p_chunks > 1) {
+      ew::sum_splits_kernel<<<ew_blocks(s, pcount / 4), 256, 0, stream>>>((float4*)s.P, (const float4*)s.Ppart, pcount / 4,
+                                                                         pcount / 4, s.p_chunks);
+      CMF_TRY(launch_ok("gram_P_sum"));
+    }
+  }
+  // (b) block-Toeplitz operand
+  toeplitz_kernel<<<ew_blocks(s, s.g_rows * f.Lv * f.KW), 256, 0, stream>>>(s.P, s.Mt, d.L, f.Lv, d.Kp, f.s, f.KW, s.g_rows);
+  CMF_TRY(launch_ok("toeplitz"));
+  // (c) den_W[n][(l,k)] = sum_{(l'v,c)} Wv[l'v][n][c] Mt[(l,k)][(l'v,c)]  (plain GEMM on the recon kernel)
+  float* den = s.numden + s.wcount;
+  {
+    ReconParams p{};
+    p.Np = d.Np; p.L = 1; p.n_tiles_n = (int)ceil_div_ll(d.Np, 128); p.wrows = 256;
+    p.s = 0; p.CB = f.Lv * f.CB; p.cb_cols = f.CB; p.h_shift = 0;
+    p.n_rows = d.Np; p.ld_out = d.Np; p.store_mode = 2; p.w_kp = d.Kp; p.w_np = d.Np;
+    p.n_tiles = (long long)p.n_tiles_n * (s.g_rows / 256);
+    p.t_own = 0; p.t_valid = s.LK;
+    p.Et = den; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
+    const int grid = (int)(p.n_tiles < d.num_sms ? p.n_tiles : d.num_sms);
+    tc_recon_kernel<<<grid, kReconThreads, recon_smem_bytes(256), stream>>>(s.tmW_k1, s.tmMt_b, p);
+    CMF_TRY(launch_ok("gram_den_w"));
+  }
+  // (d) remove the terms of est that lie past the end of the data
+  if (s.ntail > 0) {
+    CMF_TRY(tail_est(s, stream));
+    simt::WTermsA a{s.Etail, s.Etail, d.Np};
+    simt::WTermsB b{s.Ht, d.Kp, (int)(d.h + d.t_valid), d.L * d.Kp};
+    simt::SubWEpi e{den, d.Np, d.Kp, d.L * d.Kp};
+    dim3 grid((unsigned)ceil_div_ll(d.Np, 128), (unsigned)ceil_div_ll((long long)d.L * d.Kp, 128), 1);
+    simt::shift_gemm_kernel<128, 128, 16, 8, 8><<<grid, 256, 0, stream>>>(a, b, e, s.ntail, round_up_ll(s.ntail, 16), 1);
+    CMF_TRY(launch_ok("tail_den_w"));
+  }
   return 0;
 }
 
@@ -246,6 +401,7 @@ inline int recon(TcState& s, cudaStream_t stream) {
   ReconParams p;
   p.Np = d.Np; p.L = f.Lv; p.n_tiles_n = (int)ceil_div_ll(d.Np, 128); p.wrows = f.recon_wrows;
   p.s = f.s; p.CB = f.CB; p.h_shift = d.h - f.s * (f.Lv - 1);
+  p.cb_cols = f.CB; p.n_rows = d.Np; p.ld_out = d.Np; p.store_mode = 0; p.w_kp = d.Kp; p.w_np = d.Np;
   p.n_tiles = (long long)p.n_tiles_n * (d.RT / 256);
   p.t_own = d.Tloc; p.t_valid = d.t_valid;
   p.Et = s.Et; p.Xt = s.Xt; p.loss_partials = s.loss_partials; p.round_out = 1; p.err = s.d_err;
@@ -262,16 +418,96 @@ inline int w_terms(TcState& s, cudaStream_t stream) {
   p.Np = d.Np; p.L = d.L; p.n_tiles_n = (int)ceil_div_ll(d.Np, 128); p.n_lag_groups = s.n_lag_groups;
   p.n_chunks = s.n_chunks; p.h = d.h;
   p.Lv = f.Lv; p.Kp = d.Kp; p.s = f.s; p.CB = f.CB; p.brows = wterms_brows(f.s);
-  p.n_items = (long long)p.n_tiles_n * p.n_lag_groups * f.CB * 2 * p.n_chunks;
+  p.n_src = (s.gram & 2) ? 1 : 2;
+  p.n_items = (long long)p.n_tiles_n * p.n_lag_groups * f.CB * p.n_src * p.n_chunks;
   p.stages_total = ceil_div_ll(d.Tloc, 32);
   p.part = (s.n_chunks == 1) ? s.numden : s.wpart;
   p.per_src = s.wcount; p.err = s.d_err;
   tc_wterms_kernel<<<s.wterms_grid, kWtThreads, wterms_smem_bytes(f.s), stream>>>(s.tmX_k2, s.tmE_k2, s.tmH_k2, p);
   CMF_TRY(launch_ok("tc_wterms"));
   if (s.n_chunks > 1) {
-    const long long n4 = 2 * s.wcount / 4;
+    const long long n4 = p.n_src * s.wcount / 4;
     ew::sum_splits_kernel<<<ew_blocks(s, n4), 256, 0, stream>>>((float4*)s.numden, (const float4*)s.wpart, n4, n4, s.n_chunks);
     CMF_TRY(launch_ok("w_terms_sum"));
+  }
+  if (s.gram & 2) CMF_TRY(den_w_gram(s, stream));
+  return 0;
+}
+
+// ---- Gram route, H step: den_H = R (*) H - tail -------------------------------
+inline int den_h_gram(TcState& s, cudaStream_t stream) {
+  const Dims& d = s.d;
+  const Fold& f = s.f;
+  // (a) Wt = round(W)^T
+  {
+    dim3 grid((unsigned)ceil_div_ll(d.Np, 32), (unsigned)ceil_div_ll(d.Kp, 32), (unsigned)d.L);
+    transpose_round_w_kernel<<<grid, 256, 0, stream>>>(s.W, s.Wt, d.Np, d.Kp, d.Np);
+    CMF_TRY(launch_ok("transpose_round_w"));
+  }
+  // (b) G = Wt Wt^T : a plain GEMM on the recon kernel (one "lag", reduction blocks = 32-feature chunks)
+  {
+    ReconParams p{};
+    p.Np = 0; p.L = 1; p.n_tiles_n = (int)ceil_div_ll(s.LK, 128); p.wrows = 256;
+    p.s = 0; p.CB = (int)ceil_div_ll(d.Np, 32); p.h_shift = 0; p.cb_cols = p.CB;
+    p.n_rows = s.LK; p.ld_out = s.LK; p.store_mode = 0; p.w_kp = d.Kp; p.w_np = d.Np;
+    p.n_tiles = (long long)p.n_tiles_n * (s.g_rows / 256);
+    p.t_own = 0; p.t_valid = s.g_rows;
+    p.Et = s.G; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
+    const int grid = (int)(p.n_tiles < d.num_sms ? p.n_tiles : d.num_sms);
+    tc_recon_kernel<<<grid, kReconThreads, recon_smem_bytes(256), stream>>>(s.tmWt_a, s.tmWt_b, p);
+    CMF_TRY(launch_ok("gram_G"));
+  }
+  // (c) R = lag-diagonal sums of G, as a W-like operand (rounded / folded like W)
+  diag_sum_kernel<<<ew_blocks(s, (long long)s.Lr * d.Kp * d.Kp), 256, 0, stream>>>(s.G, s.LK, s.Rw, d.L, d.Kp);
+  CMF_TRY(launch_ok("diag_sum"));
+  if (f.s == 1) {
+    const long long n4 = (long long)s.Lr * d.Kp * d.Kp / 4;
+    ew::round_copy_kernel<<<ew_blocks(s, n4), 256, 0, stream>>>((float4*)s.Rwv, (const float4*)s.Rw, n4);
+  } else {
+    fold_w_kernel<<<ew_blocks(s, (long long)s.Lrv * d.Kp * 32), 256, 0, stream>>>(s.Rwv, s.Rw, s.Lr, s.Lrv, d.Kp, d.Kp, f.s);
+  }
+  CMF_TRY(launch_ok("fold_R"));
+  // (d) den_H^T[tau][k] = sum_j Rw[j][k][:] . H^T[tau + L-1 - j][:]  on the recon kernel (features := components)
+  float* den = s.hterms + d.TO * d.Kp;
+  {
+    ReconParams p{};
+    p.Np = d.Kp; p.L = s.Lrv; p.n_tiles_n = 1; p.wrows = s.dh_wrows;
+    p.s = f.s; p.CB = f.CB; p.cb_cols = f.CB; p.h_shift = d.h + (d.L - 1) - f.s * (s.Lrv - 1);
+    p.n_rows = d.Kp; p.ld_out = d.Kp; p.store_mode = 0; p.w_kp = d.Kp; p.w_np = d.Np;
+    p.n_tiles = d.TO / 256;
+    p.t_own = 0; p.t_valid = d.TO;
+    p.Et = den; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
+    const int grid = (int)(p.n_tiles < d.num_sms ? p.n_tiles : d.num_sms);
+    tc_recon_kernel<<<grid, kReconThreads, recon_smem_bytes(s.dh_wrows), stream>>>(s.tmRw_a, s.tmH_k1, p);
+    CMF_TRY(launch_ok("gram_den_h"));
+  }
+  // (e) remove the terms of est that lie past the end of the data (only the shard that sees the end)
+  if (s.ntail > 0) {
+    const long long t0 = d.t_valid;
+    CMF_TRY(tail_est(s, stream));
+    {   // den_H[tau] -= sum_{l : tau + l >= t0} W[l]^T est_ext[tau + l],  tau in [t0 - h, Tloc)
+      const long long m_off = t0 - d.h;
+      const long long rows = d.Tloc - m_off;
+      if (rows > 0) {
+        // one split per lag (the reduction (l, n) is long and the output tiny); partials live in G's buffer
+        simt::TailHA a{s.Etail, d.Np, m_off, t0, s.ntail};
+        simt::HTermsB b{s.W, d.Kp};
+        const long long per_split = round_up_ll(rows, 128) * d.Kp;
+        CMF_CHECK(per_split * d.L <= s.g_rows * s.LK, "tail scratch too small");
+        simt::PartEpi e{s.G, d.Kp, rows, d.Kp, per_split};
+        const long long R = (long long)d.L * d.Np;
+        if (d.Kp <= 64) {
+          dim3 g2((unsigned)ceil_div_ll(rows, 128), 1, (unsigned)d.L);
+          simt::shift_gemm_kernel<128, 64, 16, 8, 4><<<g2, 256, 0, stream>>>(a, b, e, R, d.Np, 1);
+        } else {
+          dim3 grid((unsigned)ceil_div_ll(rows, 128), (unsigned)ceil_div_ll(d.Kp, 128), (unsigned)d.L);
+          simt::shift_gemm_kernel<128, 128, 16, 8, 8><<<grid, 256, 0, stream>>>(a, b, e, R, d.Np, 1);
+        }
+        CMF_TRY(launch_ok("tail_den_h_parts"));
+        simt::tail_sub_kernel<<<ew_blocks(s, rows * d.Kp), 256, 0, stream>>>(den, s.G, d.L, per_split, rows, d.Kp, m_off, d.Tloc);
+        CMF_TRY(launch_ok("tail_den_h"));
+      }
+    }
   }
   return 0;
 }
@@ -282,12 +518,19 @@ inline int h_terms(TcState& s, cudaStream_t stream) {
   HTermsParams p;
   p.Np = d.Np; p.J = f.J; p.n_chunks_n = (int)ceil_div_ll(d.Np, 32); p.wrows = f.hterms_wrows;
   p.s = f.s; p.CB = f.CB;
-  p.n_tiles = d.TO / 256 + 1; p.ts = d.TO + 256; p.scratch = s.hscratch; p.err = s.d_err;
+  p.pair_mode = (s.gram & 1) ? 1 : 0;
+  p.n_src = 2;
+  p.n_split = s.h_split; p.nc_per_split = s.h_nc_per_split;
+  const long long time_tiles = d.TO / 256 + 1;
+  p.n_time_tiles = p.pair_mode ? (time_tiles + 1) / 2 : time_tiles;
+  p.n_tiles = p.n_time_tiles * s.h_split; p.ts = d.TO + 256; p.scratch = s.hscratch; p.err = s.d_err;
   tc_hterms_kernel<<<s.hterms_grid, kHtThreads, hterms_smem_bytes(f.hterms_wrows), stream>>>(s.tmW_k3, s.tmX_k3, s.tmE_k3, p);
   CMF_TRY(launch_ok("tc_hterms"));
-  combine_groups_kernel<<<(unsigned)(d.TO / 32), 256, d.Kp * 33 * 4, stream>>>(s.hscratch, s.hterms, p.ts, d.TO, f.J,
-                                                                            f.s, f.CB, d.Kp);
-  return launch_ok("combine_groups");
+  combine_groups_kernel<<<(unsigned)(d.TO / 128), 256, d.Kp * 129 * 4, stream>>>(s.hscratch, s.hterms, p.ts, d.TO, f.J,
+                                                                              f.s, f.CB, d.Kp, p.pair_mode ? 1 : 2, s.h_split);
+  CMF_TRY(launch_ok("combine_groups"));
+  if (s.gram & 1) CMF_TRY(den_h_gram(s, stream));
+  return 0;
 }
 
 // Device-side pipeline errors (bounded waits that expired) surface here.

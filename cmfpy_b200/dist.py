@@ -37,7 +37,7 @@ class _CudaView:
 class DeviceShard:
     """One time shard on one GPU, behind libcmf_b200 (the C ABI)."""
 
-    def __init__(self, X, N, T, K, L, t_offset, t_local, precision, device, stream_ptr):
+    def __init__(self, X, N, T, K, L, t_offset, t_local, precision, device, stream_ptr, denominators="direct"):
         import torch
         self._torch = torch
         self._lib = _lib.load()
@@ -46,7 +46,7 @@ class DeviceShard:
         self.t_offset, self.t_local, self.device = t_offset, t_local, device
         p = _lib.Params(n_features=N, n_components=K, maxlag=L, t_local=t_local, t_global=T,
                         t_offset=t_offset, device=device, precision=_lib.PRECISIONS[precision],
-                        stream=stream_ptr)
+                        stream=stream_ptr, denominators=_lib.DENOMINATORS[denominators])
         _lib.check(self._lib.cmf_mu_create(C.byref(self._h), C.byref(p)))
         ptr, dt, mem, ld, ncols = self._describe(X)
         if not (t_local <= ncols <= t_local + L - 1):
@@ -113,6 +113,11 @@ class DeviceShard:
 
     def h_step(self):
         _lib.check(self._lib.cmf_mu_h_step(self._h))
+
+    def needs_mid_recon(self):
+        v = C.c_int(1)
+        _lib.check(self._lib.cmf_mu_needs_mid_recon(self._h, C.byref(v)))
+        return bool(v.value)
 
     def halo_buffers(self):
         n, ld = C.c_int(0), C.c_int(0)
@@ -185,7 +190,7 @@ class ShardedMultUpdate:
 
     def __init__(self, X_local, N, T, K, L, t_offset, t_local, initW, initH,
                  precision="fp32", device=0, group=None, tol=1e-5, patience=3,
-                 engine=None):
+                 engine=None, denominators="direct"):
         import torch
         import torch.distributed as dist
         self._torch, self._dist = torch, dist
@@ -203,7 +208,7 @@ class ShardedMultUpdate:
         if engine is None:
             self.torch_stream = torch.cuda.Stream(device=device)
             self.engine = DeviceShard(X_local, N, T, K, L, t_offset, t_local, precision, device,
-                                      self.torch_stream.cuda_stream)
+                                      self.torch_stream.cuda_stream, denominators)
         else:
             self.torch_stream = None
             self.engine = engine
@@ -284,6 +289,7 @@ class ShardedMultUpdate:
         torch = self._torch
         sums = []
         marks = []
+        mid_recon = eng.needs_mid_recon() if hasattr(eng, "needs_mid_recon") else True
 
         def mark():
             if self._profiling and self.torch_stream is not None:
@@ -298,7 +304,8 @@ class ShardedMultUpdate:
             self._all_reduce(eng.w_terms_tensor())
             eng.w_apply()
             mark()
-            eng.recon()
+            if mid_recon:
+                eng.recon()
             mark()
             eng.h_step()
             mark()

@@ -46,6 +46,14 @@ enum { CMF_HOST = 0, CMF_DEVICE = 1 };
  * CMF_PREC_TF32: tcgen05 tensor-core contractions, operands rounded (RN) to
  *                TF32, fp32 accumulation in tensor memory.                  */
 enum { CMF_PREC_FP32 = 0, CMF_PREC_TF32 = 1 };
+/* How the MU denominators (the est-dependent halves of mult.py:37-38, 46) are formed on the tf32 path.
+ * CMF_DEN_DIRECT: contract est, as the reference does.
+ * CMF_DEN_GRAM  : exact identity through the small Gram operators
+ *                   den_W[l] = sum_l' W[l'] A[l-l'],   A[d] = sum_t H[:,t+d] H[:,t]^T
+ *                   den_H[:,t] = sum_d R[d] H[:,t+d],  R[d] = sum_{l-l'=d} W[l]^T W[l']
+ *                 (minus the terms of est past the end of the data); K/N of the direct cost, and est is
+ *                 then needed once per iteration (for the loss) instead of twice.  Ignored on the fp32 path. */
+enum { CMF_DEN_DIRECT = 0, CMF_DEN_GRAM = 1 };
 
 typedef struct cmf_mu_s cmf_mu_t;
 
@@ -59,6 +67,7 @@ typedef struct cmf_mu_params {
   int device;            /* CUDA device ordinal                             */
   int precision;         /* CMF_PREC_*                                      */
   void* stream;          /* cudaStream_t to run on, or NULL for an own one  */
+  int denominators;      /* CMF_DEN_*                                       */
 } cmf_mu_params;
 
 /* ---- library ---------------------------------------------------------- */
@@ -132,6 +141,11 @@ int cmf_mu_resid_sumsq_buffer(cmf_mu_t* h, double** dev_ptr);
 /* loss = ||resids||_F / normX (base.py:90-97) from the local residual; only
  * meaningful unsharded or after the driver reduced it itself.               */
 int cmf_mu_loss(cmf_mu_t* h, double* loss);
+
+/* 1 if the H step needs a reconstruction with the updated W before it (the
+ * direct denominators do; the Gram route does not).  A sharded driver skips
+ * the mid-iteration cmf_mu_recon when this returns 0.                         */
+int cmf_mu_needs_mid_recon(cmf_mu_t* h, int* needed);
 
 /* ---- the fused single-GPU iteration ------------------------------------ */
 /* n_steps x MultUpdate.update() (mult.py:15-25): W terms, W update, recon,

@@ -37,9 +37,10 @@ def _worker(rank, world, port, shape, precision, n_iter, q):
         Tl = T // world
         t0 = rank * Tl
         ncols = min(Tl + L - 1, T - t0)
+        prec, den = ("tf32", "gram") if precision == "tf32g" else (precision, "direct")
         alg = ShardedMultUpdate(np.ascontiguousarray(X[:, t0:t0 + ncols]), N, T, K, L, t_offset=t0, t_local=Tl,
-                                initW=W0, initH=np.ascontiguousarray(H0[:, t0:t0 + Tl]), precision=precision,
-                                device=rank, group=dist.group.WORLD, tol=0)
+                                initW=W0, initH=np.ascontiguousarray(H0[:, t0:t0 + Tl]), precision=prec,
+                                device=rank, group=dist.group.WORLD, tol=0, denominators=den)
         hist = [alg.loss] + alg.update_many(n_iter)
         H, W = alg.H_local_host(), alg.W_host()
         out = [None] * world
@@ -52,7 +53,9 @@ def _worker(rank, world, port, shape, precision, n_iter, q):
 
 
 @pytest.mark.parametrize("precision,shape", [("fp32", (96, 2048, 5, 12)), ("fp32", (64, 1024, 32, 33)),
-                                             ("tf32", (200, 4096, 32, 64)), ("tf32", (128, 2048, 30, 9))])
+                                             ("tf32", (200, 4096, 32, 64)), ("tf32", (128, 2048, 30, 9)),
+                                             ("tf32g", (200, 4096, 32, 64)), ("tf32g", (96, 2048, 5, 12)),
+                                             ("tf32g", (256, 2048, 128, 16))])
 def test_sharded_equals_single_gpu(built_lib, precision, shape):
     world = min(_ngpu(), 4)
     if world < 2:
@@ -74,7 +77,9 @@ def test_sharded_equals_single_gpu(built_lib, precision, shape):
         p.join(timeout=120)
         assert p.exitcode == 0
     X, W0, H0 = make_inputs(N, T, K, L, "planted", seed=5)
-    ref = MultUpdate(X, ModelDimensions(X, maxlag=L, n_components=K), initW=W0, initH=H0, tol=0, precision=precision)
+    prec, den = ("tf32", "gram") if precision == "tf32g" else (precision, "direct")
+    ref = MultUpdate(X, ModelDimensions(X, maxlag=L, n_components=K), initW=W0, initH=H0, tol=0, precision=prec,
+                     denominators=den)
     ref_hist = [ref.loss] + ref.update_many(n_iter)
     tol = 2e-5 if precision == "fp32" else 2e-4
     H = np.concatenate([o[0] for o in out], axis=1)

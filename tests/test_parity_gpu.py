@@ -30,9 +30,16 @@ FULL_CASES = [n for n, c in CASES.items() if c[6]]
 ALL_CASES = list(CASES)
 
 
+PRECISION_MODES = ["fp32", "tf32", "tf32g"]      # tf32g = tf32 with the Gram-route denominators
+
+
+def _split(precision):
+    return ("tf32", "gram") if precision == "tf32g" else (precision, "direct")
+
+
 def _supported(precision, N, K, L):
     from cmfpy_b200 import _lib
-    return bool(_lib.load().cmf_precision_supported(_lib.PRECISIONS[precision], N, K, L))
+    return bool(_lib.load().cmf_precision_supported(_lib.PRECISIONS[_split(precision)[0]], N, K, L))
 
 
 def _inputs(name):
@@ -46,8 +53,9 @@ def _inputs(name):
 def _solver(X, W0, H0, L, K, precision):
     from cmfpy_b200.algs.mult import MultUpdate
     from cmfpy_b200.model import ModelDimensions
+    prec, den = _split(precision)
     return MultUpdate(X, ModelDimensions(X, maxlag=L, n_components=K), initW=W0, initH=H0,
-                      tol=0, precision=precision)
+                      tol=0, precision=prec, denominators=den)
 
 
 def _close(a, b, rel):
@@ -55,7 +63,7 @@ def _close(a, b, rel):
     assert np.abs(a - b).max() <= rel * scale, "max abs err %.3e vs scale %.3e" % (np.abs(a - b).max(), scale)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", PRECISION_MODES)
 @pytest.mark.parametrize("name", FULL_CASES)
 def test_single_step_kernels(built_lib, name, precision):
     """est, W terms, W update, H terms, H update of iteration 1, one kernel at a
@@ -66,6 +74,8 @@ def test_single_step_kernels(built_lib, name, precision):
         pytest.skip("no %s kernel for this shape" % precision)
     rel = 2e-5 if precision == "fp32" else 2e-3
     alg = _solver(X, W0, H0, L, K, precision)
+    if precision == "tf32g":
+        assert alg.path_name == "tcgen05-tf32+gram"
     _close(alg.est, g["est0"], rel)
     numW, denW = alg._compute_mult_W()
     _close(numW, g["numW"], rel)
@@ -85,7 +95,7 @@ def test_single_step_kernels(built_lib, name, precision):
     alg.close(); alg2.close()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", PRECISION_MODES)
 @pytest.mark.parametrize("name", ALL_CASES)
 def test_loss_trajectory(built_lib, name, precision):
     g, X, W0, H0 = _inputs(name)
@@ -210,7 +220,7 @@ def test_errors_match_reference(built_lib):
 
 
 # ---- size-independent properties at a larger size -----------------------------
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", PRECISION_MODES)
 def test_properties_large(built_lib, precision):
     N, T, K, L = 1024, 1 << 15, 32, 64        # config C at T/32
     if not _supported(precision, N, K, L):
@@ -225,7 +235,7 @@ def test_properties_large(built_lib, precision):
     # linearity of the reconstruction: recon(2W, H) = 2 recon(W, H)
     from cmfpy_b200.common import cmf_predict
     Ws, Hs = W[:, :64].astype(np.float32), H[:, :4096].astype(np.float32)
-    e1, e2 = cmf_predict(Ws, Hs, precision=precision), cmf_predict(2 * Ws, Hs, precision=precision)
+    e1, e2 = cmf_predict(Ws, Hs, precision=_split(precision)[0]), cmf_predict(2 * Ws, Hs, precision=_split(precision)[0])
     assert_allclose(e2, 2 * e1, rtol=1e-6, atol=1e-6)
     # the loss the solver reports equals the loss of what it returns
     est = alg.est
@@ -234,12 +244,15 @@ def test_properties_large(built_lib, precision):
     alg.close()
 
 
-def test_fp32_and_tf32_agree_large(built_lib):
+@pytest.mark.parametrize("precision", ["tf32", "tf32g"])
+def test_fp32_and_tf32_agree_large(built_lib, precision):
     N, T, K, L = 512, 1 << 14, 16, 32
     if not _supported("tf32", N, K, L):
         pytest.skip("no tf32 kernel for this shape")
     X, W0, H0 = make_inputs(N, T, K, L, "planted", seed=17)
-    a, b = _solver(X, W0, H0, L, K, "fp32"), _solver(X, W0, H0, L, K, "tf32")
+    a, b = _solver(X, W0, H0, L, K, "fp32"), _solver(X, W0, H0, L, K, precision)
     ha, hb = np.array(a.update_many(10)), np.array(b.update_many(10))
     assert (np.abs(ha - hb) / ha).max() < TRAJ_TOL
+    # the scale split between W and H must not drift apart either
+    assert abs(a.W.sum() / b.W.sum() - 1) < 1e-3 and abs(a.H.sum() / b.H.sum() - 1) < 1e-3
     a.close(); b.close()
