@@ -36,8 +36,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CMF_BENCH_PRECISION", "auto"),
                     choices=["auto", "tf32", "fp32"])
-    ap.add_argument("--denominators", default=os.environ.get("CMF_BENCH_DENOMINATORS", "direct"),
-                    choices=["direct", "gram"])
+    ap.add_argument("--denominators", default=os.environ.get("CMF_BENCH_DENOMINATORS", "auto"),
+                    choices=["auto", "direct", "gram"])
     ap.add_argument("--config", default="C", choices=sorted(FULL))
     ap.add_argument("--t-scale", type=float, default=1.0,
                     help="shrink T (debug only; the line is then labelled reduced)")
@@ -257,6 +257,8 @@ def run_b200(args):
     if precision == "auto":
         precision = "tf32" if lib.cmf_precision_supported(_lib.CMF_PREC_TF32, N, K, L) else "fp32"
 
+    if args.denominators == "auto":
+        args.denominators = "gram" if precision == "tf32" else "direct"
     from cmfpy_b200.dist import ShardedMultUpdate
     # synthetic inputs generated on the device, identical for any world size:
     # global column t of X / H0 depends only on (seed, t)
@@ -347,7 +349,13 @@ def run_b200(args):
         "traffic": None,
         "peak_source": "%s bf16_tflops_sustained / 2 (TF32 dense = half of bf16; not separately measured)" % peaks_src,
         "cublas_tf32_tflops_live": tf32_live,
-        "whole_iteration_tflops": flops_iter / world / (ms_per_step * 1e-3) / 1e12,
+        # 12 N K L T per iteration (what the direct algorithm needs) over the measured time; with
+        # the Gram-route denominators about half of those flops are not executed at all, so this figure is a
+        # reference-equivalent rate, not a hardware utilisation
+        "reference_equivalent_tflops": flops_iter / world / (ms_per_step * 1e-3) / 1e12,
+        "executed_tflops_approx": (flops_iter * (0.5 + (2.0 * K + 4.0 * K * (2 * L - 1) / L) / (6.0 * N))
+                                   if args.denominators == "gram" and "gram" in alg.path_name else flops_iter)
+                                  / world / (ms_per_step * 1e-3) / 1e12,
         "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
         "hbm_update_kernels": {
             # W and H multiplicative updates: 16 B/element algorithmic (+4 B for the TF32 operand copy)

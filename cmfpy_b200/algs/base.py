@@ -28,14 +28,16 @@ class DeviceOptimizer:
 
     def __init__(self, data, model_dimensions, initW=None, initH=None,
                  tol=1e-5, patience=3, precision="fp32", device=0, seed=None,
-                 denominators="direct"):
+                 denominators="auto"):
         # reference base.py:20-21
         if patience < 1 or not isinstance(patience, Integral):
             raise ValueError("Patience must be a positive integer.")
         if precision not in _lib.PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
+        if denominators == "auto":      # the Gram route is the fast tensor-core path; fp32 contracts est directly
+            denominators = "gram" if precision == "tf32" else "direct"
         if denominators not in _lib.DENOMINATORS:
-            raise ValueError("denominators must be one of %s" % sorted(_lib.DENOMINATORS))
+            raise ValueError("denominators must be one of %s" % (sorted(_lib.DENOMINATORS) + ["auto"]))
         self.denominators = denominators
         self._lib = _lib.load()
         self._h = C.c_void_p()

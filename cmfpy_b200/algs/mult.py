@@ -13,6 +13,8 @@ class MultUpdate(DeviceOptimizer):
 
     Extra keyword options (all optional, passed through `CMF(**alg_opts)`):
       precision : "fp32" (exact FFMA contractions) or "tf32" (tcgen05 tensor cores)
+      denominators : "direct" (contract est, as the reference does), "gram" (exact identity
+                  through the lag Gram operators of W and H; tf32 only) or "auto"
       device    : CUDA device ordinal
       seed      : seed of the random initialisation when initW/initH are absent
     """
