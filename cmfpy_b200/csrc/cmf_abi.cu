@@ -181,8 +181,9 @@ int simt_h_terms(cmf_mu_s* h) {
 int do_recon(cmf_mu_s* h) {
   CMF_CHECK(h->have_data && h->have_factors, "recon before data/factors were set");
   if (h->use_tc && (h->tcs.mask & 1)) {
+    const long long n0 = tc::launch_counter();
     CMF_TRY(tc::recon(h->tcs, h->stream));
-    h->launches += tc::kReconLaunches;
+    h->launches += tc::launch_counter() - n0;
   } else {
     CMF_TRY(simt_recon(h));
   }
@@ -196,8 +197,9 @@ int do_w_terms(cmf_mu_s* h) {
   CMF_CHECK(h->have_data && h->have_factors, "w_terms before data/factors were set");
   CMF_CHECK(h->est_valid || gram_w(h), "w_terms needs a current reconstruction (call cmf_mu_recon)");
   if (h->use_tc && (h->tcs.mask & 2)) {
+    const long long n0 = tc::launch_counter();
     CMF_TRY(tc::w_terms(h->tcs, h->stream));
-    h->launches += tc::kWTermsLaunches;
+    h->launches += tc::launch_counter() - n0;
   } else {
     CMF_TRY(simt_w_terms(h));
   }
@@ -211,7 +213,11 @@ int do_w_apply(cmf_mu_s* h) {
       (float4*)h->W, (const float4*)h->numden, (const float4*)(h->numden + h->wcount), n4,
       (float4*)tc::fused_w_op(h->tcs));
   CMF_TRY(launch_check(h, "w_update"));
-  CMF_TRY(tc::refresh_w(h->tcs, h->stream, true));
+  {
+    const long long n0 = tc::launch_counter();
+    CMF_TRY(tc::refresh_w(h->tcs, h->stream, true));
+    h->launches += tc::launch_counter() - n0;
+  }
   h->wterms_valid = false;
   h->est_valid = false;
   return 0;
@@ -220,8 +226,9 @@ int do_h_terms(cmf_mu_s* h) {
   CMF_CHECK(h->have_data && h->have_factors, "h terms before data/factors were set");
   CMF_CHECK(h->est_valid || gram_h(h), "h terms need a current reconstruction (call cmf_mu_recon)");
   if (h->use_tc && (h->tcs.mask & 4)) {
+    const long long n0 = tc::launch_counter();
     CMF_TRY(tc::h_terms(h->tcs, h->stream));
-    h->launches += tc::kHTermsLaunches;
+    h->launches += tc::launch_counter() - n0;
     return 0;
   }
   return simt_h_terms(h);
@@ -233,14 +240,28 @@ int do_h_apply(cmf_mu_s* h) {
       (const float4*)(h->hterms + h->TO * h->Kp), n4,
       tc::fused_h_op(h->tcs) ? (float4*)(tc::fused_h_op(h->tcs) + (long long)h->h * h->Kp) : nullptr);
   CMF_TRY(launch_check(h, "h_update"));
-  CMF_TRY(tc::refresh_h(h->tcs, h->stream, h->h, h->Tloc, true));
+  {
+    const long long n0 = tc::launch_counter();
+    CMF_TRY(tc::refresh_h(h->tcs, h->stream, h->h, h->Tloc, true));
+    h->launches += tc::launch_counter() - n0;
+  }
   h->est_valid = false;
   return 0;
 }
 
 // refresh the TF32 operand copies from the fp32 masters (no-op on the fp32 path)
-int sync_ops_W(cmf_mu_s* h) { return tc::refresh_w(h->tcs, h->stream); }
-int sync_ops_H(cmf_mu_s* h, long long row0, long long nrows) { return tc::refresh_h(h->tcs, h->stream, row0, nrows); }
+int sync_ops_W(cmf_mu_s* h) {
+  const long long n0 = tc::launch_counter();
+  const int rc = tc::refresh_w(h->tcs, h->stream);
+  h->launches += tc::launch_counter() - n0;
+  return rc;
+}
+int sync_ops_H(cmf_mu_s* h, long long row0, long long nrows) {
+  const long long n0 = tc::launch_counter();
+  const int rc = tc::refresh_h(h->tcs, h->stream, row0, nrows);
+  h->launches += tc::launch_counter() - n0;
+  return rc;
+}
 
 cudaEvent_t get_event(cmf_mu_s* h, size_t i) {
   while (h->ev_pool.size() <= i) {

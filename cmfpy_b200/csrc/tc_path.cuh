@@ -90,7 +90,6 @@ struct TcState {
   CUtensorMap tmHx_k2, tmMt_b;
 };
 
-constexpr int kReconLaunches = 2, kWTermsLaunches = 2, kHTermsLaunches = 2;   // kernels per phase
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -134,7 +133,15 @@ inline void destroy(TcState& s) {
   s.ready = false;
 }
 
+// every kernel launch of this path goes through launch_ok(); the ABI reads the counter for
+// cmf_mu_launch_count()
+inline long long& launch_counter() {
+  static thread_local long long n = 0;
+  return n;
+}
+
 inline int launch_ok(const char* what) {
+  ++launch_counter();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
