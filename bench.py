@@ -257,8 +257,6 @@ def run_b200(args):
     if precision == "auto":
         precision = "tf32" if lib.cmf_precision_supported(_lib.CMF_PREC_TF32, N, K, L) else "fp32"
 
-    if args.denominators == "auto":
-        args.denominators = "gram" if precision == "tf32" else "direct"
     from cmfpy_b200.dist import ShardedMultUpdate
     # synthetic inputs generated on the device, identical for any world size:
     # global column t of X / H0 depends only on (seed, t)
@@ -356,7 +354,7 @@ def run_b200(args):
         # reference-equivalent rate, not a hardware utilisation
         "reference_equivalent_tflops": flops_iter / world / (ms_per_step * 1e-3) / 1e12,
         "executed_tflops_approx": (flops_iter * (0.5 + (2.0 * K + 4.0 * K * (2 * L - 1) / L) / (6.0 * N))
-                                   if args.denominators == "gram" and "gram" in alg.path_name else flops_iter)
+                                   if alg.path_name.endswith("+gram") else flops_iter)
                                   / world / (ms_per_step * 1e-3) / 1e12,
         "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
         "hbm_update_kernels": {

@@ -15,8 +15,8 @@ CMF_F32, CMF_F64 = 0, 1
 CMF_HOST, CMF_DEVICE = 0, 1
 CMF_PREC_FP32, CMF_PREC_TF32 = 0, 1
 PRECISIONS = {"fp32": CMF_PREC_FP32, "tf32": CMF_PREC_TF32}
-CMF_DEN_DIRECT, CMF_DEN_GRAM = 0, 1
-DENOMINATORS = {"direct": CMF_DEN_DIRECT, "gram": CMF_DEN_GRAM}
+CMF_DEN_DIRECT, CMF_DEN_GRAM, CMF_DEN_AUTO = 0, 1, 2
+DENOMINATORS = {"direct": CMF_DEN_DIRECT, "gram": CMF_DEN_GRAM, "auto": CMF_DEN_AUTO}
 
 
 class Params(C.Structure):

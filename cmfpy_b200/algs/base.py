@@ -34,10 +34,8 @@ class DeviceOptimizer:
             raise ValueError("Patience must be a positive integer.")
         if precision not in _lib.PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
-        if denominators == "auto":      # the Gram route is the fast tensor-core path; fp32 contracts est directly
-            denominators = "gram" if precision == "tf32" else "direct"
         if denominators not in _lib.DENOMINATORS:
-            raise ValueError("denominators must be one of %s" % (sorted(_lib.DENOMINATORS) + ["auto"]))
+            raise ValueError("denominators must be one of %s" % sorted(_lib.DENOMINATORS))
         self.denominators = denominators
         self._lib = _lib.load()
         self._h = C.c_void_p()

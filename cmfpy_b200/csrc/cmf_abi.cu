@@ -408,7 +408,8 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
                 p->t_offset + p->t_local <= p->t_global,
             "inconsistent time range: t_local=%lld t_offset=%lld t_global=%lld", p->t_local, p->t_offset, p->t_global);
   CMF_CHECK(p->precision == CMF_PREC_FP32 || p->precision == CMF_PREC_TF32, "unknown precision %d", p->precision);
-  CMF_CHECK(p->denominators == CMF_DEN_DIRECT || p->denominators == CMF_DEN_GRAM, "unknown denominators mode %d", p->denominators);
+  CMF_CHECK(p->denominators == CMF_DEN_DIRECT || p->denominators == CMF_DEN_GRAM || p->denominators == CMF_DEN_AUTO,
+            "unknown denominators mode %d", p->denominators);
   CMF_CHECK(p->t_local == p->t_global || p->t_local >= p->maxlag - 1,
             "a time shard must hold at least L-1 columns (t_local=%lld, L=%d)", p->t_local, p->maxlag);
   int ndev = 0;
@@ -507,7 +508,11 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
   }
   if (rc == 0 && h->use_tc) {
     tc::Dims d{h->N, h->K, h->L, h->Np, h->Kp, h->h, h->Tloc, h->TO, h->RT, h->RH, h->t_valid, h->num_sms};
-    h->tcs.gram_request = (p->denominators == CMF_DEN_GRAM) ? 3 : 0;
+    {
+      const double contraction_flops = 2.0 * h->N * h->K * (double)h->L * (double)h->Tloc;
+      const bool want = p->denominators == CMF_DEN_GRAM || (p->denominators == CMF_DEN_AUTO && contraction_flops >= 2e11);
+      h->tcs.gram_request = want ? 3 : 0;
+    }
     rc = tc::init(h->tcs, d, h->Xt, h->Et, h->Ht, h->W, h->numden, h->hterms, h->loss_partials,
                   h->n_loss_partials, h->d_sumsq, h->stream);
   }

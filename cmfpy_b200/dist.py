@@ -200,8 +200,6 @@ class ShardedMultUpdate:
         self.N, self.T, self.K, self.L = N, T, K, L
         self.t_offset, self.t_local = t_offset, t_local
         self.tol, self.patience, self.precision = tol, patience, precision
-        if denominators == "auto":
-            denominators = "gram" if precision == "tf32" else "direct"
         if self.world > 1 and t_local < L - 1:
             raise ValueError("each shard needs at least L-1 columns")
         self.profiled_ms = dict(recon=0.0, w_terms=0.0, h_terms=0.0, elementwise=0.0)

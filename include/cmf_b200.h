@@ -53,7 +53,8 @@ enum { CMF_PREC_FP32 = 0, CMF_PREC_TF32 = 1 };
  *                   den_H[:,t] = sum_d R[d] H[:,t+d],  R[d] = sum_{l-l'=d} W[l]^T W[l']
  *                 (minus the terms of est past the end of the data); K/N of the direct cost, and est is
  *                 then needed once per iteration (for the loss) instead of twice.  Ignored on the fp32 path. */
-enum { CMF_DEN_DIRECT = 0, CMF_DEN_GRAM = 1 };
+enum { CMF_DEN_DIRECT = 0, CMF_DEN_GRAM = 1, CMF_DEN_AUTO = 2 /* Gram when the shard is large enough to pay for
+                                                              its extra small kernels (2 N K L t_local >= 2e11) */ };
 
 typedef struct cmf_mu_s cmf_mu_t;
 
