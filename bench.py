@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--t-scale", type=float, default=1.0,
                     help="shrink T (debug only; the line is then labelled reduced)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-profile", action="store_true",
+                    help="no per-kernel events in the timed region (lets the iteration replay as a CUDA graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -301,7 +303,7 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = alg.launch_count
-    alg.set_profiling(True)
+    alg.set_profiling(not args.no_profile)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stream = alg.torch_stream
     barrier()
@@ -339,13 +341,14 @@ def run_b200(args):
     # reconstructions per step: two with the direct denominators, one with the Gram route (est is then
     # needed for the loss only)
     recon_launches = (1 if alg.path_name.endswith("+gram") else 2) * args.steps
-    recon_ms = kms["recon"] / recon_launches
+    recon_ms = max(kms["recon"] / recon_launches, 1e-9)
     recon_flops = 2.0 * N * K * L * Tloc            # per launch, per GPU
-    achieved = recon_flops / (recon_ms * 1e-3) / 1e12
+    achieved = recon_flops / (recon_ms * 1e-3) / 1e12 if kms["recon"] > 0 else None
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
     roofline = {
         "bound": "tensor", "kernel": "recon (shift-GEMM, %s)" % alg.path_name,
-        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+        "frac": (achieved / tf32_peak) if achieved else None,
         "traffic": None,
         "peak_source": "%s bf16_tflops_sustained / 2 (TF32 dense = half of bf16; not separately measured)" % peaks_src,
         "cublas_tf32_tflops_live": tf32_live,

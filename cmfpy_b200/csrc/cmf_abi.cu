@@ -13,6 +13,7 @@
 #include "../../include/cmf_b200.h"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 
@@ -69,6 +70,11 @@ struct cmf_mu_s {
 
   long long launches = 0;
   int profiling = 0;
+  // one MU iteration captured as a CUDA graph (launch-bound small problems; replayed by cmf_mu_step)
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_dirty = true, graph_ok = true;
+  long long graph_launches = 0;
+  int* d_counter = nullptr;
   float kernel_ms[4] = {0, 0, 0, 0};
   std::vector<cudaEvent_t> ev_pool;
 
@@ -368,6 +374,8 @@ void free_all(cmf_mu_s* h) {
   cudaFree(h->numden); cudaFree(h->wpart); cudaFree(h->hterms);
   cudaFree(h->loss_partials); cudaFree(h->d_sumsq); cudaFree(h->d_ring); cudaFree(h->d_xpart);
   cudaFree(h->d_neg);
+  cudaFree(h->d_counter);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
 }
@@ -493,6 +501,7 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
   A(dmalloc(&h->d_ring, h->ring_cap));
   A(dmalloc(&h->d_xpart, (long long)h->num_sms * 8));
   A(dmalloc(&h->d_neg, 1));
+  A(dmalloc(&h->d_counter, 1));
   if (rc == 0) {
     cudaError_t e = cudaSuccess;
     auto Z = [&](void* ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMemsetAsync(ptr, 0, bytes, h->stream); };
@@ -558,6 +567,7 @@ int cmf_mu_set_data(cmf_mu_t* h, const void* X, int dtype, int mem, long long ld
   CMF_CUDA(cudaMemcpyAsync(&h->has_neg, h->d_neg, 4, cudaMemcpyDeviceToHost, h->stream));
   CMF_CUDA(cudaStreamSynchronize(h->stream));
   h->norm_x = std::sqrt(h->sumsq_x);
+  h->graph_dirty = true;
   h->have_data = true;
   h->est_valid = false;
   return 0;
@@ -575,6 +585,7 @@ int cmf_mu_set_norm_x(cmf_mu_t* h, double norm_x) {
   CMF_ENTER(h);
   CMF_CHECK(norm_x >= 0.0, "norm_x must be non-negative");
   h->norm_x = norm_x;
+  h->graph_dirty = true;
   return 0;
 }
 
@@ -736,6 +747,53 @@ int cmf_mu_loss(cmf_mu_t* h, double* loss) {
   return 0;
 }
 
+// one MU iteration (reference MultUpdate.update, mult.py:15-25) issued on the solver's stream
+static int issue_iteration(cmf_mu_s* h, bool prof, size_t& ne, int slot) {
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  CMF_TRY(do_w_terms(h));
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  CMF_TRY(do_w_apply(h));
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  if (!gram_h(h)) CMF_TRY(do_recon(h));       // the Gram H step does not read est
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  CMF_TRY(do_h_terms(h));
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  CMF_TRY(do_h_apply(h));
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  CMF_TRY(do_recon(h));
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  if (slot >= 0) ew::loss_from_sumsq_kernel<<<1, 1, 0, h->stream>>>(h->d_sumsq, h->norm_x, h->d_ring, slot);
+  else ew::loss_from_sumsq_counter_kernel<<<1, 1, 0, h->stream>>>(h->d_sumsq, h->norm_x, h->d_ring, h->d_counter);
+  return launch_check(h, "loss");
+}
+
+// capture one iteration into h->graph_exec; on any failure fall back to plain launches for good
+static void capture_iteration(cmf_mu_s* h) {
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+  h->graph_dirty = true;
+  if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    h->graph_ok = false;
+    return;
+  }
+  const long long l0 = h->launches;
+  size_t ne = 0;
+  const int rc = issue_iteration(h, false, ne, -1);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  h->graph_launches = h->launches - l0;
+  h->launches = l0;                       // nothing ran yet; replays add graph_launches each
+  if (rc != 0 || e != cudaSuccess || graph == nullptr ||
+      cudaGraphInstantiate(&h->graph_exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    h->graph_exec = nullptr;
+    h->graph_ok = false;
+  } else {
+    h->graph_dirty = false;
+  }
+  if (graph) cudaGraphDestroy(graph);
+}
+
 int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
   CMF_ENTER(h);
   CMF_CHECK(n_steps >= 0, "n_steps must be >= 0");
@@ -743,29 +801,29 @@ int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
   if (n_steps == 0) return 0;
   if (!h->est_valid) CMF_TRY(do_recon(h));
   for (int k = 0; k < 4; ++k) h->kernel_ms[k] = 0.f;
+  const bool prof = h->profiling != 0;
+  static const bool graphs_enabled = [] { const char* e = getenv("CMF_GRAPH"); return !e || atoi(e) != 0; }();
+  bool use_graph = graphs_enabled && !prof && h->graph_ok;
+  if (use_graph && (h->graph_dirty || !h->graph_exec)) {
+    capture_iteration(h);
+    use_graph = h->graph_ok && h->graph_exec != nullptr;
+    last_error().clear();
+  }
   int done = 0;
   while (done < n_steps) {
     const int chunk = (n_steps - done < h->ring_cap) ? n_steps - done : h->ring_cap;
     size_t ne = 0;
-    const bool prof = h->profiling != 0;
+    if (use_graph) CMF_CUDA(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
     for (int i = 0; i < chunk; ++i) {
       if (ms_out) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      CMF_TRY(do_w_terms(h));
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      CMF_TRY(do_w_apply(h));
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      if (!gram_h(h)) CMF_TRY(do_recon(h));       // the Gram H step does not read est
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      CMF_TRY(do_h_terms(h));
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      CMF_TRY(do_h_apply(h));
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      CMF_TRY(do_recon(h));
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      ew::loss_from_sumsq_kernel<<<1, 1, 0, h->stream>>>(h->d_sumsq, h->norm_x, h->d_ring, i);
-      CMF_TRY(launch_check(h, "loss"));
+      if (use_graph) {
+        CMF_CUDA(cudaGraphLaunch(h->graph_exec, h->stream));
+        h->launches += h->graph_launches;
+      } else {
+        CMF_TRY(issue_iteration(h, prof, ne, i));
+      }
     }
+    if (use_graph) { h->est_valid = true; h->wterms_valid = false; }
     if (ms_out) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
     if (loss_out)
       CMF_CUDA(cudaMemcpyAsync(loss_out + done, h->d_ring, (size_t)chunk * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -785,7 +843,7 @@ int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
         for (int k = 0; k < 6; ++k) CMF_CUDA(cudaEventElapsedTime(&t[k], h->ev_pool[e0 + k], h->ev_pool[e0 + k + 1]));
         h->kernel_ms[1] += t[0];            // w_terms
         h->kernel_ms[3] += t[1] + t[4];     // elementwise updates
-        h->kernel_ms[0] += t[2] + t[5];     // two reconstructions (+ loss)
+        h->kernel_ms[0] += t[2] + t[5];     // reconstructions (+ loss)
         h->kernel_ms[2] += t[3];            // h_terms
       }
     }

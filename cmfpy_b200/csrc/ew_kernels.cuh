@@ -82,6 +82,13 @@ __global__ void loss_from_sumsq_kernel(const double* sumsq, double norm_x, doubl
   loss_out[slot] = sqrt(sumsq[0]) / norm_x;
 }
 
+// same, slot taken from (and advancing) a device counter: the form a captured CUDA graph replays
+__global__ void loss_from_sumsq_counter_kernel(const double* sumsq, double norm_x, double* loss_out, int* counter) {
+  const int slot = *counter;
+  loss_out[slot] = sqrt(sumsq[0]) / norm_x;
+  *counter = slot + 1;
+}
+
 // sum of squares + any-negative flag over n floats, per-block partials
 // (reference base.py:25 la.norm(data); model.py:138 (data < 0).any())
 __global__ void __launch_bounds__(256)
