@@ -46,6 +46,7 @@ _SIGNATURES = {
     "cmf_mu_halo_export": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "cmf_mu_halo_import": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "cmf_mu_recon": (C.c_int, [_H]),
+    "cmf_mu_recon_loss": (C.c_int, [_H]),
     "cmf_mu_w_terms": (C.c_int, [_H]),
     "cmf_mu_w_terms_buffer": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]),
     "cmf_mu_w_apply": (C.c_int, [_H]),

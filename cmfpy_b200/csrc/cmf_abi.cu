@@ -67,6 +67,7 @@ struct cmf_mu_s {
   double sumsq_x = 0.0, norm_x = 0.0;
   int has_neg = 0;
   bool have_data = false, have_factors = false, est_valid = false, wterms_valid = false;
+  bool est_stored = false;           // the est buffer holds the reconstruction (est_valid alone: only its loss is current)
 
   long long launches = 0;
   int profiling = 0;
@@ -184,24 +185,33 @@ int simt_h_terms(cmf_mu_s* h) {
 }
 
 // ---- phase dispatch -----------------------------------------------------
-int do_recon(cmf_mu_s* h) {
+bool gram_w(const cmf_mu_s* h) { return h->use_tc && (h->tcs.mask & 2) && (h->tcs.gram & 2); }
+bool gram_h(const cmf_mu_s* h) { return h->use_tc && (h->tcs.mask & 4) && (h->tcs.gram & 1); }
+
+// store_est = false: only the loss is wanted (legal when neither MU step reads est)
+int do_recon(cmf_mu_s* h, bool store_est = true) {
   CMF_CHECK(h->have_data && h->have_factors, "recon before data/factors were set");
   if (h->use_tc && (h->tcs.mask & 1)) {
     const long long n0 = tc::launch_counter();
-    CMF_TRY(tc::recon(h->tcs, h->stream));
+    CMF_TRY(tc::recon(h->tcs, h->stream, store_est));
     h->launches += tc::launch_counter() - n0;
+    h->est_stored = store_est;
   } else {
     CMF_TRY(simt_recon(h));
+    h->est_stored = true;
   }
   h->est_valid = true;
   return 0;
 }
-bool gram_w(const cmf_mu_s* h) { return h->use_tc && (h->tcs.mask & 2) && (h->tcs.gram & 2); }
-bool gram_h(const cmf_mu_s* h) { return h->use_tc && (h->tcs.mask & 4) && (h->tcs.gram & 1); }
+int ensure_est_stored(cmf_mu_s* h) {
+  if (h->est_valid && h->est_stored) return 0;
+  return do_recon(h, true);
+}
 
 int do_w_terms(cmf_mu_s* h) {
   CMF_CHECK(h->have_data && h->have_factors, "w_terms before data/factors were set");
   CMF_CHECK(h->est_valid || gram_w(h), "w_terms needs a current reconstruction (call cmf_mu_recon)");
+  if (!gram_w(h)) CMF_TRY(ensure_est_stored(h));
   if (h->use_tc && (h->tcs.mask & 2)) {
     const long long n0 = tc::launch_counter();
     CMF_TRY(tc::w_terms(h->tcs, h->stream));
@@ -231,6 +241,7 @@ int do_w_apply(cmf_mu_s* h) {
 int do_h_terms(cmf_mu_s* h) {
   CMF_CHECK(h->have_data && h->have_factors, "h terms before data/factors were set");
   CMF_CHECK(h->est_valid || gram_h(h), "h terms need a current reconstruction (call cmf_mu_recon)");
+  if (!gram_h(h)) CMF_TRY(ensure_est_stored(h));
   if (h->use_tc && (h->tcs.mask & 4)) {
     const long long n0 = tc::launch_counter();
     CMF_TRY(tc::h_terms(h->tcs, h->stream));
@@ -633,7 +644,7 @@ int cmf_mu_init_stats(cmf_mu_t* h, double* x_dot_est, double* est_sumsq) {
   CMF_ENTER(h);
   CMF_CHECK(x_dot_est != nullptr && est_sumsq != nullptr, "null argument");
   CMF_CHECK(h->have_data && h->have_factors, "init stats before data/factors were set");
-  if (!h->est_valid) CMF_TRY(do_recon(h));
+  CMF_TRY(ensure_est_stored(h));
   const long long n4 = h->Tloc * h->Np / 4;
   int grid = ew_grid(h, n4);
   if (grid > h->num_sms * 4) grid = h->num_sms * 4;      // d_xpart holds 8*num_sms doubles
@@ -701,6 +712,7 @@ int cmf_mu_halo_import(cmf_mu_t* h, const float* left_halo, const float* right_h
 }
 
 int cmf_mu_recon(cmf_mu_t* h) { CMF_ENTER(h); return do_recon(h); }
+int cmf_mu_recon_loss(cmf_mu_t* h) { CMF_ENTER(h); return do_recon(h, !(gram_w(h) && gram_h(h))); }
 int cmf_mu_w_terms(cmf_mu_t* h) { CMF_ENTER(h); return do_w_terms(h); }
 
 int cmf_mu_w_terms_buffer(cmf_mu_t* h, float** dev_ptr, long long* count) {
@@ -760,7 +772,7 @@ static int issue_iteration(cmf_mu_s* h, bool prof, size_t& ne, int slot) {
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
   CMF_TRY(do_h_apply(h));
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-  CMF_TRY(do_recon(h));
+  CMF_TRY(do_recon(h, !(gram_w(h) && gram_h(h))));   // full Gram route: est is only needed for the loss
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
   if (slot >= 0) ew::loss_from_sumsq_kernel<<<1, 1, 0, h->stream>>>(h->d_sumsq, h->norm_x, h->d_ring, slot);
   else ew::loss_from_sumsq_counter_kernel<<<1, 1, 0, h->stream>>>(h->d_sumsq, h->norm_x, h->d_ring, h->d_counter);
@@ -823,7 +835,7 @@ int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
         CMF_TRY(issue_iteration(h, prof, ne, i));
       }
     }
-    if (use_graph) { h->est_valid = true; h->wterms_valid = false; }
+    if (use_graph) { h->est_valid = true; h->est_stored = !(gram_w(h) && gram_h(h)); h->wterms_valid = false; }
     if (ms_out) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
     if (loss_out)
       CMF_CUDA(cudaMemcpyAsync(loss_out + done, h->d_ring, (size_t)chunk * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -892,7 +904,7 @@ int cmf_mu_get_est(cmf_mu_t* h, void* est_out, int dtype, int mem, long long ld)
   CMF_CHECK(est_out != nullptr, "null argument");
   CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
   CMF_CHECK(ld >= h->Tloc, "leading dimension too small");
-  if (!h->est_valid) CMF_TRY(do_recon(h));
+  CMF_TRY(ensure_est_stored(h));
   int rc;
   if (dtype == CMF_F32) rc = store_transposed<float>(h, h->Et, h->Np, h->N, h->Tloc, (float*)est_out, mem, ld);
   else rc = store_transposed<double>(h, h->Et, h->Np, h->N, h->Tloc, (double*)est_out, mem, ld);

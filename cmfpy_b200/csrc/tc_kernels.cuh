@@ -85,6 +85,8 @@ struct ReconParams {
   int n_rows, ld_out;              // valid output rows n, leading dimension of the output
   int store_mode;                  // 0: out[tau][n] (est^T; loss, tail mask, rounding)  2: W layout out[(l*n_rows_w+n)*Kp+k], tau = l*Kp+k
   int w_kp, w_np;                  // store_mode 2: Kp and Np of the W-layout output
+  int skip_store;                  // store_mode 0: accumulate the loss only, do not write est (nothing reads it
+                                   // when both denominators come from the Gram route)
   long long n_tiles;               // n_tiles_n * (RT / 256)
   long long t_own, t_valid;
   float* Et;
@@ -259,8 +261,10 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               const float d = v - x[j];
               tile_loss = fmaf(d, d, tile_loss);
             }
-            if (p.round_out) v = round_tf32(v);
-            Et[off0 + (size_t)j * np] = v;
+            if (!p.skip_store) {
+              if (p.round_out) v = round_tf32(v);
+              Et[off0 + (size_t)j * np] = v;
+            }
           }
         }
       }

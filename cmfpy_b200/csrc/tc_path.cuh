@@ -402,10 +402,11 @@ inline int den_w_gram(TcState& s, cudaStream_t stream) {
   return 0;
 }
 
-inline int recon(TcState& s, cudaStream_t stream) {
+inline int recon(TcState& s, cudaStream_t stream, bool store_est = true) {
   const Dims& d = s.d;
   const Fold& f = s.f;
-  ReconParams p;
+  ReconParams p{};
+  p.skip_store = store_est ? 0 : 1;
   p.Np = d.Np; p.L = f.Lv; p.n_tiles_n = (int)ceil_div_ll(d.Np, 128); p.wrows = f.recon_wrows;
   p.s = f.s; p.CB = f.CB; p.h_shift = d.h - f.s * (f.Lv - 1);
   p.cb_cols = f.CB; p.n_rows = d.Np; p.ld_out = d.Np; p.store_mode = 0; p.w_kp = d.Kp; p.w_np = d.Np;

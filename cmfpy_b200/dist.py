@@ -99,6 +99,9 @@ class DeviceShard:
     def recon(self):
         _lib.check(self._lib.cmf_mu_recon(self._h))
 
+    def recon_loss(self):
+        _lib.check(self._lib.cmf_mu_recon_loss(self._h))
+
     def w_terms(self):
         _lib.check(self._lib.cmf_mu_w_terms(self._h))
 
@@ -311,7 +314,7 @@ class ShardedMultUpdate:
             mark()
             self._exchange_halos()
             mark()
-            eng.recon()
+            (eng.recon_loss if hasattr(eng, "recon_loss") else eng.recon)()
             mark()
             with self._stream_ctx():
                 s = eng.resid_sumsq_tensor().clone()

@@ -122,6 +122,10 @@ int cmf_mu_halo_import(cmf_mu_t* h, const float* left_halo, const float* right_h
 /* est = cmf_predict(W, H) (common.py:50-58) on owned + right-halo columns,
  * and the local sum of squared residuals (cache_resids, base.py:57-62).      */
 int cmf_mu_recon(cmf_mu_t* h);
+/* Same, but est itself may be left unwritten when no MU step reads it (both
+ * denominators from the Gram route): only the residual sum of squares is
+ * refreshed.  cmf_mu_get_est and the direct routes recompute est on demand.   */
+int cmf_mu_recon_loss(cmf_mu_t* h);
 /* num/denom of the W step (_compute_mult_W, mult.py:27-40) from the cached
  * est; local partial sums over owned columns.  The result lives in one
  * DEVICE buffer [num | den], 2 * count fp32, exposed for an in-place
