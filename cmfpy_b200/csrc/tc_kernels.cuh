@@ -96,12 +96,14 @@ struct ReconParams {
   int* err;
 };
 
-constexpr int kReconStages = 6;
+constexpr int kReconLagsPerStage = 2;              // lags per pipeline stage: 8 MMAs per barrier round trip
+constexpr int kReconStages = 3;
 constexpr int kReconThreads = 192;
 constexpr int kReconABytes = 128 * kKp * 4;       // 16 KB per lag
+constexpr int kReconStageBytes = kReconLagsPerStage * kReconABytes;
 
 __host__ __device__ inline size_t recon_smem_bytes(int wrows) {
-  return 1024 + (size_t)kReconStages * kReconABytes + 2 * (size_t)wrows * kKp * 4 + 256;
+  return 1024 + (size_t)kReconStages * kReconStageBytes + 2 * (size_t)wrows * kKp * 4 + 256;
 }
 
 __global__ void __launch_bounds__(kReconThreads, 1)
@@ -109,8 +111,8 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 const ReconParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* As = smem;                                           // [stages][16 KB]
-  uint8_t* Hs = As + kReconStages * kReconABytes;               // [2][wrows * 128]
+  uint8_t* As = smem;                                           // [stages][2 lags x 16 KB]
+  uint8_t* Hs = As + kReconStages * kReconStageBytes;           // [2][wrows * 128]
   const uint32_t hbytes = (uint32_t)p.wrows * kKp * 4;
   uint64_t* bars = (uint64_t*)(Hs + 2 * hbytes);
   uint64_t* full = bars;                                        // [stages]
@@ -159,11 +161,13 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           uint8_t* hdst = Hs + (size_t)hb * hbytes;
           for (int rb = 0; rb < wrows / 64; ++rb)
             tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], cb * 32, (int)(tt * 256 + p.h_shift + rb * 64));
-          for (int l = 0; l < L; ++l) {
+          for (int l = 0; l < L; l += kReconLagsPerStage) {
             if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
-            mbar_arrive_expect_tx(&full[ps.stage], kReconABytes);
-            tma_load_2d(As + (size_t)ps.stage * kReconABytes, &tmW, &full[ps.stage], (cb % p.cb_cols) * 32,
-                        (l + cb / p.cb_cols) * p.Np + nt * 128);
+            const int nl = min(kReconLagsPerStage, L - l);
+            mbar_arrive_expect_tx(&full[ps.stage], nl * kReconABytes);
+            for (int u = 0; u < nl; ++u)
+              tma_load_2d(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes, &tmW, &full[ps.stage],
+                          (cb % p.cb_cols) * 32, (l + u + cb / p.cb_cols) * p.Np + nt * 128);
             ps.advance(kReconStages);
           }
         }
@@ -187,15 +191,18 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           if (!ab.wait(&hfull[hb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
           tc_fence_after();
           const uint32_t hbase = smem_u32(Hs + (size_t)hb * hbytes);
-          for (int l = 0; l < L; ++l) {
+          for (int l = 0; l < L; l += kReconLagsPerStage) {
             if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
             tc_fence_after();
-            const uint32_t abase = smem_u32(As + (size_t)ps.stage * kReconABytes);
+            const int nl = min(kReconLagsPerStage, L - l);
+            for (int u = 0; u < nl; ++u) {
+              const uint32_t abase = smem_u32(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ad = make_smem_desc(abase + ks * 32, 16, 1024, kSwz128);
-              const uint64_t bd = make_smem_desc(hbase + (uint32_t)(p.s * (L - 1 - l)) * 128 + ks * 32, 16, 1024, kSwz128);
-              mma_tf32_ss(dtm, ad, bd, idesc, (cb | l | ks) != 0 ? 1u : 0u);
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ad = make_smem_desc(abase + ks * 32, 16, 1024, kSwz128);
+                const uint64_t bd = make_smem_desc(hbase + (uint32_t)(p.s * (L - 1 - l - u)) * 128 + ks * 32, 16, 1024, kSwz128);
+                mma_tf32_ss(dtm, ad, bd, idesc, (cb | (l + u) | ks) != 0 ? 1u : 0u);
+              }
             }
             mma_commit(&empty[ps.stage]);
             ps.advance(kReconStages);
@@ -282,6 +289,192 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// --------------------------------------------------------------------------
+// K1 on a CTA pair (cta_group::2).  The single-CTA kernel above sits at the shared-memory bandwidth
+// of a 128x256x8 TF32 MMA (4 KB of A + 8 KB of B per 128 cycles, plus the TMA fills).  Two CTAs of one
+// TPC compute D[256 n][256 tau] together: each holds its own 128 rows of A and supplies HALF of the B rows
+// (its half-window of H^T), so the operand reads per SM drop from 96 to 64 B/cycle.  The leader CTA issues
+// the MMAs; TMA loads of both CTAs complete on the leader's barriers; commits are multicast to both.
+// --------------------------------------------------------------------------
+constexpr int kRecon2Stages = 8;
+
+__host__ __device__ inline size_t recon2_smem_bytes(int wrows2) {
+  return 1024 + (size_t)kRecon2Stages * kReconABytes + 2 * (size_t)wrows2 * kKp * 4 + 256;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kReconThreads, 1)
+tc_recon2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
+                 const ReconParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* As = smem;                                           // [stages][16 KB]: this CTA's 128 rows of A
+  uint8_t* Hs = As + kRecon2Stages * kReconABytes;              // [2][wrows * 128]: this CTA's half window
+  const uint32_t hbytes = (uint32_t)p.wrows * kKp * 4;
+  uint64_t* bars = (uint64_t*)(Hs + 2 * hbytes);
+  uint64_t* full = bars;                                        // used in the leader CTA
+  uint64_t* empty = bars + kRecon2Stages;                       // per CTA
+  uint64_t* hfull = bars + 2 * kRecon2Stages;                   // leader
+  uint64_t* hempty = hfull + 2;                                 // per CTA
+  uint64_t* tfull = hempty + 2;                                 // per CTA
+  uint64_t* tempty = tfull + 2;                                 // leader (count 8)
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
+  __shared__ double red[4];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (tid == 0) {
+    // full barriers live in the leader: ONE arrival (the leader's producer, which announces the bytes of
+    // both CTAs); the peer's TMA loads only complete_tx on them.  The peer cannot run a ring cycle ahead:
+    // its empty barrier flips only after the leader's MMAs consumed the stage.
+    for (int i = 0; i < kRecon2Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1);
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8);
+    }
+    *abort_flag = 0;
+    fence_mbar_init();
+    prefetch_tmap(&tmW);
+    prefetch_tmap(&tmH);
+  }
+  if (warp == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const Abort ab{abort_flag, p.err};
+  const int L = p.L, wrows = p.wrows;
+  const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ---------------- TMA producer (both CTAs) ----------------
+    if (lane == 0) {
+      PipeState ps;
+      long long wcount = 0;
+      bool ok = true;
+      for (long long tile = pair; tile < p.n_tiles && ok; tile += npairs) {
+        const int nt = (int)(tile % p.n_tiles_n);
+        const long long tt = tile / p.n_tiles_n;
+        for (int cb = 0; cb < p.CB && ok; ++cb, ++wcount) {
+          const int hb = (int)(wcount & 1);
+          if (!ab.wait(&hempty[hb], (uint32_t)((wcount >> 1) & 1) ^ 1)) { ok = false; break; }
+          const uint32_t hbar = mapa_u32(smem_u32(&hfull[hb]), 0);
+          if (leader) mbar_arrive_expect_tx(&hfull[hb], 2 * hbytes);
+          uint8_t* hdst = Hs + (size_t)hb * hbytes;
+          for (int rb = 0; rb < wrows / 64; ++rb)
+            tma_load_2d_2sm(hdst + (size_t)rb * 64 * 128, &tmH, hbar, cb * 32,
+                            (int)(tt * 256 + rank * 128 + p.h_shift + rb * 64));
+          for (int l = 0; l < L; ++l) {
+            if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+            const uint32_t fbar = mapa_u32(smem_u32(&full[ps.stage]), 0);
+            if (leader) mbar_arrive_expect_tx(&full[ps.stage], 2 * kReconABytes);
+            tma_load_2d_2sm(As + (size_t)ps.stage * kReconABytes, &tmW, fbar, (cb % p.cb_cols) * 32,
+                            (l + cb / p.cb_cols) * p.Np + nt * 256 + (int)rank * 128);
+            ps.advance(kRecon2Stages);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (leader CTA only) ----------------
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_tf32(256, 256, 0, 0);
+      PipeState ps;
+      long long wcount = 0;
+      int it = 0;
+      bool ok = true;
+      for (long long tile = pair; tile < p.n_tiles && ok; tile += npairs, ++it) {
+        const int b = it & 1;
+        if (!ab.wait(&tempty[b], (uint32_t)((it >> 1) & 1) ^ 1)) break;
+        tc_fence_after();
+        const uint32_t dtm = tmem + (uint32_t)b * 256;
+        for (int cb = 0; cb < p.CB && ok; ++cb, ++wcount) {
+          const int hb = (int)(wcount & 1);
+          if (!ab.wait(&hfull[hb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t hbase = smem_u32(Hs + (size_t)hb * hbytes);
+          for (int l = 0; l < L; ++l) {
+            if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+            tc_fence_after();
+            const uint32_t abase = smem_u32(As + (size_t)ps.stage * kReconABytes);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ad = make_smem_desc(abase + ks * 32, 16, 1024, kSwz128);
+              const uint64_t bd = make_smem_desc(hbase + (uint32_t)(p.s * (L - 1 - l)) * 128 + ks * 32, 16, 1024, kSwz128);
+              mma_tf32_ss_2sm(dtm, ad, bd, idesc, (cb | l | ks) != 0 ? 1u : 0u);
+            }
+            mma_commit_2sm(&empty[ps.stage], 3);
+            ps.advance(kRecon2Stages);
+          }
+          if (!ok) break;
+          mma_commit_2sm(&hempty[hb], 3);
+        }
+        if (!ok) break;
+        mma_commit_2sm(&tfull[b], 3);
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs): own 128 rows of the pair's tile ----------------
+    const int q = warp & 3;
+    double loss_acc = 0.0;
+    int it = 0;
+    for (long long tile = pair; tile < p.n_tiles; tile += npairs, ++it) {
+      const int nt = (int)(tile % p.n_tiles_n);
+      const long long tt = tile / p.n_tiles_n;
+      const int b = it & 1;
+      if (!ab.wait(&tfull[b], (it >> 1) & 1)) break;
+      tc_fence_after();
+      const int n = nt * 256 + (int)rank * 128 + q * 32 + lane;
+      const bool n_ok = n < p.n_rows;
+      float tile_loss = 0.f;
+      const float* __restrict__ Xt = p.Xt;
+      float* __restrict__ Et = p.Et;
+      const size_t np = (size_t)p.ld_out;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        float x[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + c * 32), r);
+        const long long tau0 = tt * 256 + c * 32;
+        const size_t off0 = (size_t)tau0 * np + n;
+        if (n_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = (tau0 + j < p.t_own) ? __ldcs(Xt + off0 + (size_t)j * np) : 0.f;
+        }
+        tmem_ld_wait();
+        if (n_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long tau = tau0 + j;
+            float v = __uint_as_float(r[j]);
+            if (tau >= p.t_valid) v = 0.f;
+            if (tau < p.t_own) {
+              const float d = v - x[j];
+              tile_loss = fmaf(d, d, tile_loss);
+            }
+            if (!p.skip_store) {
+              if (p.round_out) v = round_tf32(v);
+              Et[off0 + (size_t)j * np] = v;
+            }
+          }
+        }
+      }
+      loss_acc += (double)tile_loss;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[b]), 0));
+    }
+    loss_acc = warp_sum(loss_acc);
+    if (lane == 0) red[q] = loss_acc;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 2 && lane == 0) p.loss_partials[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_2sm(tmem, 512);
 }
 
 // ==========================================================================

@@ -77,6 +77,8 @@ struct TcState {
   CUtensorMap tmW_k1, tmH_k1, tmX_k2, tmE_k2, tmH_k2, tmW_k3, tmX_k3, tmE_k3;
 
   // ---- Gram route for the denominators (gram & 1: H step, gram & 2: W step) ----
+  int recon2 = 0;                   // 1: reconstruction on CTA pairs (cta_group::2)
+  int recon2_wrows = 192;
   int gram = 0;
   int gram_request = 0;             // from cmf_mu_params.denominators (CMF_GRAM in the environment overrides)
   int LK = 0, Lr = 0, Lrv = 0, dh_wrows = 0;
@@ -219,6 +221,14 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   CMF_TRY(make_map(&s.tmH_k1, s.Hv, d.RH, f.KW, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
   CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)recon_smem_bytes(f.recon_wrows)));
+
+  s.recon2 = 0;
+  if (const char* e = getenv("CMF_RECON2")) s.recon2 = atoi(e);
+  s.recon2_wrows = round_up(128 + f.s * (f.Lv - 1), 64);
+  if (recon2_smem_bytes(s.recon2_wrows) > kMaxSmem) s.recon2 = 0;
+  if (s.recon2)
+    CMF_CUDA(cudaFuncSetAttribute(tc_recon2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)recon2_smem_bytes(s.recon2_wrows)));
 
   // ---- K2 -------------------------------------------------------------
   s.n_lag_groups = (int)ceil_div_ll(f.Lv, 16);
@@ -413,9 +423,20 @@ inline int recon(TcState& s, cudaStream_t stream, bool store_est = true) {
   p.n_tiles = (long long)p.n_tiles_n * (d.RT / 256);
   p.t_own = d.Tloc; p.t_valid = d.t_valid;
   p.Et = s.Et; p.Xt = s.Xt; p.loss_partials = s.loss_partials; p.round_out = 1; p.err = s.d_err;
-  tc_recon_kernel<<<s.recon_grid, kReconThreads, recon_smem_bytes(f.recon_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
+  int grid = s.recon_grid;
+  if (s.recon2) {
+    p.n_tiles_n = (int)ceil_div_ll(d.Np, 256);
+    p.n_tiles = (long long)p.n_tiles_n * (d.RT / 256);
+    p.wrows = s.recon2_wrows;
+    long long g2 = 2 * p.n_tiles;
+    if (g2 > (d.num_sms & ~1)) g2 = d.num_sms & ~1;
+    grid = (int)g2;
+    tc_recon2_kernel<<<grid, kReconThreads, recon2_smem_bytes(s.recon2_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
+  } else {
+    tc_recon_kernel<<<grid, kReconThreads, recon_smem_bytes(f.recon_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
+  }
   CMF_TRY(launch_ok("tc_recon"));
-  ew::sum_doubles_kernel<<<1, 1024, 0, stream>>>(s.loss_partials, s.recon_grid, s.d_sumsq);
+  ew::sum_doubles_kernel<<<1, 1024, 0, stream>>>(s.loss_partials, grid, s.d_sumsq);
   return launch_ok("loss_sum");
 }
 
