@@ -705,12 +705,14 @@ struct HTermsParams {
   int* err;
 };
 
+constexpr int kHtLagsPerStage = 1;                 // virtual lags per pipeline stage (2 with 2 stages measured slower: 8.2 vs 8.0 ms)
 constexpr int kHtStages = 4;
 constexpr int kHtThreads = 192;
 constexpr int kHtABytes = 4 * 32 * 128;            // 4 lag groups x 32 n x 32 k
+constexpr int kHtStageBytes = kHtLagsPerStage * kHtABytes;
 
 __host__ __device__ inline size_t hterms_smem_bytes(int wrows) {
-  return 1024 + (size_t)kHtStages * kHtABytes + 2 * 2 * (size_t)wrows * 128 + 256;
+  return 1024 + (size_t)kHtStages * kHtStageBytes + 2 * 2 * (size_t)wrows * 128 + 256;
 }
 
 __global__ void __launch_bounds__(kHtThreads, 1)
@@ -720,7 +722,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* As = smem;                                             // [stages][16 KB]
   const uint32_t wbytes = (uint32_t)p.wrows * 128;                // one source, one 32-feature chunk
-  uint8_t* Ws = As + kHtStages * kHtABytes;                       // [2 buffers][2 sources][wbytes]
+  uint8_t* Ws = As + kHtStages * kHtStageBytes;                   // [2 buffers][2 sources][wbytes]
   uint64_t* bars = (uint64_t*)(Ws + 4 * (size_t)wbytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kHtStages;
@@ -769,13 +771,17 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             for (int rb = 0; rb < wrows / 32; ++rb)
               tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], nc * 32, base + rb * 32);
           }
-          for (int j = 0; j < J; ++j) {
+          for (int j = 0; j < J; j += kHtLagsPerStage) {
             if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
-            uint8_t* dst = As + (size_t)ps.stage * kHtABytes;
-            mbar_arrive_expect_tx(&full[ps.stage], kHtABytes);
+            const int nl = min(kHtLagsPerStage, J - j);
+            mbar_arrive_expect_tx(&full[ps.stage], nl * kHtABytes);
+            for (int u = 0; u < nl; ++u) {
+              uint8_t* dst = As + (size_t)ps.stage * kHtStageBytes + u * kHtABytes;
 #pragma unroll
-            for (int g = 0; g < 4; ++g)      // region g = (lag group g / CB, column block g % CB)
-              tma_load_2d(dst + g * 4096, &tmW, &full[ps.stage], (g % p.CB) * 32, (j + J * (g / p.CB)) * p.Np + nc * 32);
+              for (int g = 0; g < 4; ++g)      // region g = (lag group g / CB, column block g % CB)
+                tma_load_2d(dst + g * 4096, &tmW, &full[ps.stage], (g % p.CB) * 32,
+                            (j + u + J * (g / p.CB)) * p.Np + nc * 32);
+            }
             ps.advance(kHtStages);
           }
         }
@@ -798,18 +804,21 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           if (!ab.wait(&wfull[wb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
           tc_fence_after();
           const uint32_t wbase = smem_u32(Ws + (size_t)wb * 2 * wbytes);
-          for (int j = 0; j < J; ++j) {
+          for (int j = 0; j < J; j += kHtLagsPerStage) {
             if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
             tc_fence_after();
-            const uint32_t abase = smem_u32(As + (size_t)ps.stage * kHtABytes);
+            const int nl = min(kHtLagsPerStage, J - j);
+            for (int u = 0; u < nl; ++u) {
+              const uint32_t abase = smem_u32(As + (size_t)ps.stage * kHtStageBytes + u * kHtABytes);
 #pragma unroll
-            for (int src = 0; src < 2; ++src) {
-              if (src >= p.n_src) break;
+              for (int src = 0; src < 2; ++src) {
+                if (src >= p.n_src) break;
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
-                const uint64_t bd = make_smem_desc(wbase + src * wbytes + (uint32_t)(p.s * j) * 128 + ks * 32, 16, 1024, kSwz128);
-                mma_tf32_ss(tmem + src * 256, ad, bd, idesc, ((nc - nc0) | j | ks) != 0 ? 1u : 0u);
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
+                  const uint64_t bd = make_smem_desc(wbase + src * wbytes + (uint32_t)(p.s * (j + u)) * 128 + ks * 32, 16, 1024, kSwz128);
+                  mma_tf32_ss(tmem + src * 256, ad, bd, idesc, ((nc - nc0) | (j + u) | ks) != 0 ? 1u : 0u);
+                }
               }
             }
             mma_commit(&empty[ps.stage]);
