@@ -149,28 +149,48 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       PipeState ps;
-      long long wcount = 0;
       bool ok = true;
-      for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
-        const int nt = (int)(tile % p.n_tiles_n);
-        const long long tt = tile / p.n_tiles_n;
-        for (int cb = 0; cb < p.CB && ok; ++cb, ++wcount) {
-          const int hb = (int)(wcount & 1);
-          if (!ab.wait(&hempty[hb], (uint32_t)((wcount >> 1) & 1) ^ 1)) { ok = false; break; }
-          mbar_arrive_expect_tx(&hfull[hb], hbytes);
-          uint8_t* hdst = Hs + (size_t)hb * hbytes;
-          for (int rb = 0; rb < wrows / 64; ++rb)
-            tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], cb * 32, (int)(tt * 256 + p.h_shift + rb * 64));
-          for (int l = 0; l < L; l += kReconLagsPerStage) {
-            if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
-            const int nl = min(kReconLagsPerStage, L - l);
-            mbar_arrive_expect_tx(&full[ps.stage], nl * kReconABytes);
-            for (int u = 0; u < nl; ++u)
-              tma_load_2d(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes, &tmW, &full[ps.stage],
-                          (cb % p.cb_cols) * 32, (l + u + cb / p.cb_cols) * p.Np + nt * 128);
-            ps.advance(kReconStages);
+      // chunks = (tile, reduction block) in execution order; chunk c uses window buffer c & 1 and its
+      // window is requested while the previous chunk's W stages stream (a whole chunk of lead time)
+      struct Chunk { long long tile; int cb; bool valid; };
+      auto next_chunk = [&](Chunk c) {
+        if (++c.cb >= p.CB) { c.cb = 0; c.tile += gridDim.x; c.valid = c.tile < p.n_tiles; }
+        return c;
+      };
+      auto issue_window = [&](const Chunk& c, long long wc) -> bool {
+        const int hb = (int)(wc & 1);
+        if (!ab.wait(&hempty[hb], (uint32_t)((wc >> 1) & 1) ^ 1)) return false;
+        const long long tt = c.tile / p.n_tiles_n;
+        mbar_arrive_expect_tx(&hfull[hb], hbytes);
+        uint8_t* hdst = Hs + (size_t)hb * hbytes;
+        for (int rb = 0; rb < wrows / 64; ++rb)
+          tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], c.cb * 32, (int)(tt * 256 + p.h_shift + rb * 64));
+        return true;
+      };
+      Chunk cur{(long long)blockIdx.x, 0, (long long)blockIdx.x < p.n_tiles};
+      long long wc = 0;
+      if (cur.valid) ok = issue_window(cur, 0);
+      while (cur.valid && ok) {
+        const Chunk nxt = next_chunk(cur);
+        bool prefetched = !nxt.valid;
+        const int nt = (int)(cur.tile % p.n_tiles_n);
+        int stage_in_chunk = 0;
+        for (int l = 0; l < L; l += kReconLagsPerStage, ++stage_in_chunk) {
+          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+          const int nl = min(kReconLagsPerStage, L - l);
+          mbar_arrive_expect_tx(&full[ps.stage], nl * kReconABytes);
+          for (int u = 0; u < nl; ++u)
+            tma_load_2d(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes, &tmW, &full[ps.stage],
+                        (cur.cb % p.cb_cols) * 32, (l + u + cur.cb / p.cb_cols) * p.Np + nt * 128);
+          ps.advance(kReconStages);
+          if (!prefetched && stage_in_chunk >= 1) {
+            if (!issue_window(nxt, wc + 1)) { ok = false; break; }
+            prefetched = true;
           }
         }
+        if (ok && !prefetched) ok = issue_window(nxt, wc + 1);
+        cur = nxt;
+        ++wc;
       }
     }
   } else if (warp == 1) {
@@ -754,37 +774,64 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       PipeState ps;
-      long long wcount = 0;                 // window loads issued so far
       bool ok = true;
-      for (long long item = blockIdx.x; item < p.n_tiles && ok; item += gridDim.x) {
-        const long long tile = item / p.n_split;
-        const int nc0 = (int)(item % p.n_split) * p.nc_per_split;
-        const int nc1 = min(nc0 + p.nc_per_split, p.n_chunks_n);
-        for (int nc = nc0; nc < nc1 && ok; ++nc, ++wcount) {
-          const int wb = (int)(wcount & 1);
-          if (!ab.wait(&wempty[wb], (uint32_t)((wcount >> 1) & 1) ^ 1)) { ok = false; break; }
-          mbar_arrive_expect_tx(&wfull[wb], p.n_src * wbytes);
-          for (int src = 0; src < p.n_src; ++src) {
-            uint8_t* wdst = Ws + ((size_t)wb * 2 + src) * wbytes;
-            const CUtensorMap* tmS = (src && !p.pair_mode) ? &tmE : &tmX;
-            const int base = (int)((p.pair_mode ? 2 * tile + src : tile) * 256);
-            for (int rb = 0; rb < wrows / 32; ++rb)
-              tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], nc * 32, base + rb * 32);
-          }
-          for (int j = 0; j < J; j += kHtLagsPerStage) {
-            if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
-            const int nl = min(kHtLagsPerStage, J - j);
-            mbar_arrive_expect_tx(&full[ps.stage], nl * kHtABytes);
-            for (int u = 0; u < nl; ++u) {
-              uint8_t* dst = As + (size_t)ps.stage * kHtStageBytes + u * kHtABytes;
+      // chunks = (work item, 32-feature chunk) in execution order; chunk c uses window buffer c & 1.
+      // The window of chunk c+1 is requested while the W stages of chunk c stream, i.e. a whole chunk
+      // (J stages) before the MMAs need it - not merely the depth of the W ring ahead.
+      struct Chunk { long long item; int nc, nc1; bool valid; };
+      auto make_chunk = [&](long long item) {
+        Chunk c{item, 0, 0, item < p.n_tiles};
+        if (c.valid) {
+          c.nc = (int)(item % p.n_split) * p.nc_per_split;
+          c.nc1 = min(c.nc + p.nc_per_split, p.n_chunks_n);
+        }
+        return c;
+      };
+      auto next_chunk = [&](Chunk c) {
+        if (++c.nc >= c.nc1) c = make_chunk(c.item + gridDim.x);
+        return c;
+      };
+      auto issue_window = [&](const Chunk& c, long long wc) -> bool {
+        const int wb = (int)(wc & 1);
+        if (!ab.wait(&wempty[wb], (uint32_t)((wc >> 1) & 1) ^ 1)) return false;
+        const long long tile = c.item / p.n_split;
+        mbar_arrive_expect_tx(&wfull[wb], p.n_src * wbytes);
+        for (int src = 0; src < p.n_src; ++src) {
+          uint8_t* wdst = Ws + ((size_t)wb * 2 + src) * wbytes;
+          const CUtensorMap* tmS = (src && !p.pair_mode) ? &tmE : &tmX;
+          const int base = (int)((p.pair_mode ? 2 * tile + src : tile) * 256);
+          for (int rb = 0; rb < wrows / 32; ++rb)
+            tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], c.nc * 32, base + rb * 32);
+        }
+        return true;
+      };
+      Chunk cur = make_chunk(blockIdx.x);
+      long long wc = 0;
+      if (cur.valid) ok = issue_window(cur, 0);
+      while (cur.valid && ok) {
+        const Chunk nxt = next_chunk(cur);
+        bool prefetched = !nxt.valid;
+        int stage_in_chunk = 0;
+        for (int j = 0; j < J; j += kHtLagsPerStage, ++stage_in_chunk) {
+          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+          const int nl = min(kHtLagsPerStage, J - j);
+          mbar_arrive_expect_tx(&full[ps.stage], nl * kHtABytes);
+          for (int u = 0; u < nl; ++u) {
+            uint8_t* dst = As + (size_t)ps.stage * kHtStageBytes + u * kHtABytes;
 #pragma unroll
-              for (int g = 0; g < 4; ++g)      // region g = (lag group g / CB, column block g % CB)
-                tma_load_2d(dst + g * 4096, &tmW, &full[ps.stage], (g % p.CB) * 32,
-                            (j + u + J * (g / p.CB)) * p.Np + nc * 32);
-            }
-            ps.advance(kHtStages);
+            for (int g = 0; g < 4; ++g)      // region g = (lag group g / CB, column block g % CB)
+              tma_load_2d(dst + g * 4096, &tmW, &full[ps.stage], (g % p.CB) * 32,
+                          (j + u + J * (g / p.CB)) * p.Np + cur.nc * 32);
+          }
+          ps.advance(kHtStages);
+          if (!prefetched && stage_in_chunk >= 1) {       // by now the MMAs are inside `cur`: the other buffer is free
+            if (!issue_window(nxt, wc + 1)) { ok = false; break; }
+            prefetched = true;
           }
         }
+        if (ok && !prefetched) ok = issue_window(nxt, wc + 1);
+        cur = nxt;
+        ++wc;
       }
     }
   } else if (warp == 1) {
