@@ -349,7 +349,11 @@ def run_b200(args):
         "bound": "tensor", "kernel": "recon (shift-GEMM, %s)" % alg.path_name,
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
         "frac": (achieved / tf32_peak) if achieved else None,
-        "traffic": None,
+        # DRAM bytes per K1 launch from `ncu --set full` (profiles/r01_ncu_tc_kernels_gram.txt /
+        # _direct.txt); captured for config C on one GPU only
+        "traffic": ((4.44e9 if alg.path_name.endswith("+gram") else 8.70e9)
+                    if (args.config == "C" and world == 1 and args.t_scale == 1.0 and precision == "tf32") else None),
+        "traffic_unit": "bytes per launch (algorithmic: %.2e)" % ((4.0 if alg.path_name.endswith("+gram") else 8.0) * N * Tloc),
         "peak_source": "%s bf16_tflops_sustained / 2 (TF32 dense = half of bf16; not separately measured)" % peaks_src,
         "cublas_tf32_tflops_live": tf32_live,
         # 12 N K L T per iteration (what the direct algorithm needs) over the measured time; with

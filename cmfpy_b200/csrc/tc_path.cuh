@@ -307,6 +307,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
       if (Q > n_chunks_n) Q = n_chunks_n;
       while (Q > 1 && (size_t)Q * 2 * 4 * kKp * (d.TO + 256) * 4 > ((size_t)6 << 30)) --Q;
     }
+    if (const char* e = getenv("CMF_HSPLIT")) { Q = atoi(e); if (Q < 1) Q = 1; if (Q > n_chunks_n) Q = n_chunks_n; }
     s.h_nc_per_split = (n_chunks_n + Q - 1) / Q;
     s.h_split = (n_chunks_n + s.h_nc_per_split - 1) / s.h_nc_per_split;
     const size_t bytes = (size_t)s.h_split * 2 * 4 * kKp * (d.TO + 256) * 4;

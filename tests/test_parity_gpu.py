@@ -120,6 +120,28 @@ def test_loss_trajectory(built_lib, name, precision):
     alg.close()
 
 
+@pytest.mark.parametrize("precision", PRECISION_MODES)
+@pytest.mark.parametrize("shape", [(3, 5, 2, 8), (1, 1, 1, 1), (7, 40, 100, 3), (300, 600, 64, 5), (5, 9, 3, 9),
+                                   (130, 257, 17, 31)])
+def test_extreme_shapes_against_oracle(built_lib, shape, precision):
+    """L > T, single entries, K padded to 128 / 64 / 32, ragged everything: three MU iterations against
+    the float64 oracle on the same inputs."""
+    N, T, K, L = shape
+    if not _supported(precision, N, K, L):
+        pytest.skip("no %s kernel for this shape" % precision)
+    X, W0, H0 = make_inputs(N, T, K, L, "uniform", seed=N + T + K + L)
+    ref = o.MultUpdateOracle(X.astype(np.float64), L, K, initW=W0.astype(np.float64), initH=H0.astype(np.float64), tol=0)
+    ref_hist = [ref.loss] + [ref.update() for _ in range(3)]
+    alg = _solver(X, W0, H0, L, K, precision)
+    hist = [alg.loss] + alg.update_many(3)
+    tol = 1e-5 if precision == "fp32" else 2e-3
+    for a, b in zip(hist, ref_hist):
+        assert abs(a - b) <= tol * max(b, 0.5), (hist, ref_hist)   # (an exactly-fittable 1x1 problem has loss ~ 0)
+    _close(alg.W, ref.W, 20 * tol)
+    _close(alg.H, ref.H, 20 * tol)
+    alg.close()
+
+
 def test_update_one_by_one_equals_batched(built_lib):
     g, X, W0, H0 = _inputs("odd_k5")
     N, T, K, L = (int(v) for v in g["shape"])
