@@ -188,9 +188,19 @@ int simt_h_terms(cmf_mu_s* h) {
 bool gram_w(const cmf_mu_s* h) { return h->use_tc && (h->tcs.mask & 2) && (h->tcs.gram & 2); }
 bool gram_h(const cmf_mu_s* h) { return h->use_tc && (h->tcs.mask & 4) && (h->tcs.gram & 1); }
 
+int ensure_est_buffer(cmf_mu_s* h) {
+  if (h->Et) return 0;
+  CMF_CUDA(cudaMalloc((void**)&h->Et, (size_t)h->RT * h->Np * 4));
+  CMF_CUDA(cudaMemsetAsync(h->Et, 0, (size_t)h->RT * h->Np * 4, h->stream));
+  if (h->use_tc) CMF_TRY(tc::attach_est(h->tcs, h->Et));
+  h->graph_dirty = true;             // kernel arguments baked into a captured iteration changed
+  return 0;
+}
+
 // store_est = false: only the loss is wanted (legal when neither MU step reads est)
 int do_recon(cmf_mu_s* h, bool store_est = true) {
   CMF_CHECK(h->have_data && h->have_factors, "recon before data/factors were set");
+  if (store_est || !(h->use_tc && (h->tcs.mask & 1))) CMF_TRY(ensure_est_buffer(h));
   if (h->use_tc && (h->tcs.mask & 1)) {
     const long long n0 = tc::launch_counter();
     CMF_TRY(tc::recon(h->tcs, h->stream, store_est));
@@ -309,7 +319,7 @@ int load_transposed(cmf_mu_s* h, const TI* src, int mem, long long ld, long long
     ew::transpose_convert_kernel<TI, float><<<grid, 256, 0, h->stream>>>(src, ld, dst, ldd, rows, cols, round_in);
     return launch_check(h, "transpose_in");
   }
-  const long long budget = 256ll << 20;
+  const long long budget = 64ll << 20;
   long long ch = budget / (long long)(rows * sizeof(TI));
   ch = (ch / 32) * 32;
   if (ch < 32) ch = 32;
@@ -354,7 +364,7 @@ int store_transposed(cmf_mu_s* h, const float* src, long long lds, long long row
     ew::transpose_convert_kernel<float, TO><<<grid, 256, 0, h->stream>>>(src, lds, dst, ldd, cols_out, rows_out, 0);
     return launch_check(h, "transpose_out");
   }
-  const long long budget = 256ll << 20;
+  const long long budget = 64ll << 20;
   long long ch = budget / (long long)(rows_out * sizeof(TO));
   ch = (ch / 32) * 32;
   if (ch < 32) ch = 32;
@@ -499,7 +509,6 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
   int rc = 0;
   auto A = [&](int r) { if (rc == 0) rc = r; };
   A(dmalloc(&h->Xt, h->RT * h->Np));
-  A(dmalloc(&h->Et, h->RT * h->Np));
   A(dmalloc(&h->Ht, h->RH * h->Kp));
   A(dmalloc(&h->W, h->wcount));
   A(dmalloc(&h->numden, 2 * h->wcount));
@@ -517,7 +526,6 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
     cudaError_t e = cudaSuccess;
     auto Z = [&](void* ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMemsetAsync(ptr, 0, bytes, h->stream); };
     Z(h->Xt, (size_t)h->RT * h->Np * 4);
-    Z(h->Et, (size_t)h->RT * h->Np * 4);
     Z(h->Ht, (size_t)h->RH * h->Kp * 4);
     Z(h->W, (size_t)h->wcount * 4);
     Z(h->numden, (size_t)2 * h->wcount * 4);
@@ -533,9 +541,11 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
       const bool want = p->denominators == CMF_DEN_GRAM || (p->denominators == CMF_DEN_AUTO && contraction_flops >= 2e11);
       h->tcs.gram_request = want ? 3 : 0;
     }
-    rc = tc::init(h->tcs, d, h->Xt, h->Et, h->Ht, h->W, h->numden, h->hterms, h->loss_partials,
+    rc = tc::init(h->tcs, d, h->Xt, nullptr, h->Ht, h->W, h->numden, h->hterms, h->loss_partials,
                   h->n_loss_partials, h->d_sumsq, h->stream);
   }
+  // est^T: needed up front unless both denominators come from the Gram route (then on first demand)
+  if (rc == 0 && !(h->use_tc && h->tcs.mask == 7 && h->tcs.gram == 3)) rc = ensure_est_buffer(h);
   if (rc != 0) {
     free_all(h);
     delete h;

@@ -714,6 +714,7 @@ struct HTermsParams {
   int Np, J, n_chunks_n, wrows;    // n chunks of 32 features; window rows >= 256 + s*(J-1)
   int s, CB;                       // lag stride in rows; column blocks (regions = (4/CB lag groups) x CB)
   int n_src;                       // 2: X and est (numerator, denominator); 1: X only (denominator via Gram)
+  int n_slots;                     // scratch slots per split (2: numerator and denominator; 1 in pair mode)
   int pair_mode;                   // n_src == 2 with BOTH sources = X: source 1 is the next time tile (base + 256),
                                    // so every W stage still feeds 8 MMAs when only the numerator is computed
   long long n_time_tiles;          // time tiles (pairs in pair_mode) ; n_tiles = n_time_tiles * n_split
@@ -721,7 +722,7 @@ struct HTermsParams {
                                    // accumulation chains in tensor memory; partials summed by combine_groups)
   long long n_tiles;               // TO / 256 + 1
   long long ts;                    // scratch row length (TO + 256)
-  float* scratch;                  // [n_split][2][4][32][ts]
+  float* scratch;                  // [n_split][n_slots][4][32][ts]
   int* err;
 };
 
@@ -895,7 +896,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         const int slot = p.pair_mode ? 0 : src;                       // pair mode: both halves are numerators
         const long long ttile = p.pair_mode ? 2 * tile + src : tile;
         if ((ttile + 1) * 256 > p.ts) continue;                       // odd tile count: the pair's second half does not exist
-        float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)((split * 2 + slot) * 4 + q) * kKp + lane) * p.ts +
+        float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)((split * p.n_slots + slot) * 4 + q) * kKp + lane) * p.ts +
                                               ttile * 256 + (c & 7) * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -919,7 +920,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 // the k-contiguous writes both coalesce.
 __global__ void __launch_bounds__(256)
 combine_groups_kernel(const float* __restrict__ scratch, float* __restrict__ out, long long ts, long long t_rows,
-                      int J, int s, int CB, int Kp, int n_src, int n_split) {
+                      int J, int s, int CB, int Kp, int n_src, int n_split, int n_slots) {
   extern __shared__ float tile[];             // [Kp][129]
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long t0 = (long long)blockIdx.x * 128;
@@ -933,7 +934,7 @@ combine_groups_kernel(const float* __restrict__ scratch, float* __restrict__ out
             const int region = g * CB + (s == 1 ? k / 32 : 0);
             const int kk = (s == 1) ? (k % 32) : (dl * Kp + k);
             const long long sh = dl + (long long)s * J * g;
-            const float* row = scratch + ((size_t)((sp * 2 + src) * 4 + region) * kKp + kk) * ts + t0 + 4 * tx + sh;
+            const float* row = scratch + ((size_t)((sp * n_slots + src) * 4 + region) * kKp + kk) * ts + t0 + 4 * tx + sh;
             if ((sh & 3) == 0) {
               const float4 v = __ldcs(reinterpret_cast<const float4*>(row));
               a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;

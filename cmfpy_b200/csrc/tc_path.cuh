@@ -251,9 +251,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     const long long items = units * s.n_chunks;
     s.wterms_grid = (int)(items < d.num_sms ? items : d.num_sms);
   }
-  CMF_CUDA(cudaMalloc((void**)&s.wpart, (size_t)s.n_chunks * 2 * s.wcount * 4));
   CMF_TRY(make_map(&s.tmX_k2, Xt, d.Tloc, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  CMF_TRY(make_map(&s.tmE_k2, Et, d.Tloc, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   CMF_TRY(make_map(&s.tmH_k2, s.Hv, d.RH, f.KW, 32, wterms_brows(f.s), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   CMF_CUDA(cudaFuncSetAttribute(tc_wterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)wterms_smem_bytes(f.s)));
@@ -265,7 +263,6 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   }
   CMF_TRY(make_map(&s.tmW_k3, s.Wv, (long long)f.Lv * d.Np, f.KW, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   CMF_TRY(make_map(&s.tmX_k3, Xt, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
-  CMF_TRY(make_map(&s.tmE_k3, Et, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
   CMF_CUDA(cudaFuncSetAttribute(tc_hterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)hterms_smem_bytes(f.hterms_wrows)));
   if (d.Kp * 129 * 4 > 48 * 1024)
@@ -305,19 +302,19 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
       Q = (int)(chain_num / chain_den + 0.5);
       if (Q < 1) Q = 1;
       if (Q > n_chunks_n) Q = n_chunks_n;
-      while (Q > 1 && (size_t)Q * 2 * 4 * kKp * (d.TO + 256) * 4 > ((size_t)6 << 30)) --Q;
+      while (Q > 1 && (size_t)Q * 4 * kKp * (d.TO + 256) * 4 > ((size_t)6 << 30)) --Q;
     }
     if (const char* e = getenv("CMF_HSPLIT")) { Q = atoi(e); if (Q < 1) Q = 1; if (Q > n_chunks_n) Q = n_chunks_n; }
     s.h_nc_per_split = (n_chunks_n + Q - 1) / Q;
     s.h_split = (n_chunks_n + s.h_nc_per_split - 1) / s.h_nc_per_split;
-    const size_t bytes = (size_t)s.h_split * 2 * 4 * kKp * (d.TO + 256) * 4;
-    CMF_CUDA(cudaMalloc((void**)&s.hscratch, bytes));
-    CMF_CUDA(cudaMemsetAsync(s.hscratch, 0, bytes, stream));
+    const size_t bytes = (size_t)s.h_split * ((s.gram & 1) ? 1 : 2) * 4 * kKp * (d.TO + 256) * 4;
+    CMF_CUDA(cudaMalloc((void**)&s.hscratch, bytes));    // fully rewritten by every launch: no memset
     const long long tt = d.TO / 256 + 1;
     const long long items = ((s.gram & 1) ? (tt + 1) / 2 : tt) * s.h_split;
     s.hterms_grid = (int)(items < d.num_sms ? items : d.num_sms);
   }
   if ((long long)s.g_rows * f.Lv * f.KW * 4 > (1ll << 30)) s.gram &= ~2;
+  CMF_CUDA(cudaMalloc((void**)&s.wpart, (size_t)s.n_chunks * ((s.gram & 2) ? 1 : 2) * s.wcount * 4));
   if (s.gram && s.ntail > 0) CMF_CUDA(cudaMalloc((void**)&s.Etail, (size_t)256 * d.Np * 4));
   if (s.gram & 2) {
     const long long pcount = (long long)d.L * d.Kp * d.Kp;
@@ -343,6 +340,19 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
                                             ? recon_smem_bytes(s.dh_wrows) : recon_smem_bytes(f.recon_wrows))));
   }
   s.ready = true;
+  return 0;
+}
+
+// The est buffer is only needed when some MU step contracts est (direct routes) or est is read back;
+// with both denominators on the Gram route it is allocated on first demand (cmf_abi.cu).
+inline int attach_est(TcState& s, float* Et) {
+  const Dims& d = s.d;
+  s.Et = Et;
+  s.tmE_k2 = s.tmX_k2;
+  s.tmE_k3 = s.tmX_k3;
+  if (!Et) return 0;
+  CMF_TRY(make_map(&s.tmE_k2, Et, d.Tloc, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  CMF_TRY(make_map(&s.tmE_k3, Et, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
   return 0;
 }
 
@@ -549,6 +559,7 @@ inline int h_terms(TcState& s, cudaStream_t stream) {
   p.Np = d.Np; p.J = f.J; p.n_chunks_n = (int)ceil_div_ll(d.Np, 32); p.wrows = f.hterms_wrows;
   p.s = f.s; p.CB = f.CB;
   p.pair_mode = (s.gram & 1) ? 1 : 0;
+  p.n_slots = p.pair_mode ? 1 : 2;
   p.n_src = 2;
   p.n_split = s.h_split; p.nc_per_split = s.h_nc_per_split;
   const long long time_tiles = d.TO / 256 + 1;
@@ -557,7 +568,8 @@ inline int h_terms(TcState& s, cudaStream_t stream) {
   tc_hterms_kernel<<<s.hterms_grid, kHtThreads, hterms_smem_bytes(f.hterms_wrows), stream>>>(s.tmW_k3, s.tmX_k3, s.tmE_k3, p);
   CMF_TRY(launch_ok("tc_hterms"));
   combine_groups_kernel<<<(unsigned)(d.TO / 128), 256, d.Kp * 129 * 4, stream>>>(s.hscratch, s.hterms, p.ts, d.TO, f.J,
-                                                                              f.s, f.CB, d.Kp, p.pair_mode ? 1 : 2, s.h_split);
+                                                                              f.s, f.CB, d.Kp, p.pair_mode ? 1 : 2, s.h_split,
+                                                                              p.n_slots);
   CMF_TRY(launch_ok("combine_groups"));
   if (s.gram & 1) CMF_TRY(den_h_gram(s, stream));
   return 0;
