@@ -35,7 +35,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CMF_BENCH_PRECISION", "auto"),
-                    choices=["auto", "tf32", "fp32"])
+                    choices=["auto", "tf32", "tf32x3", "fp32"])
     ap.add_argument("--denominators", default=os.environ.get("CMF_BENCH_DENOMINATORS", "auto"),
                     choices=["auto", "direct", "gram"])
     ap.add_argument("--config", default="C", choices=sorted(FULL))
@@ -361,7 +361,8 @@ def run_b200(args):
         # reference-equivalent rate, not a hardware utilisation
         "reference_equivalent_tflops": flops_iter / world / (ms_per_step * 1e-3) / 1e12,
         "executed_tflops_approx": (flops_iter * (0.5 + (2.0 * K + 4.0 * K * (2 * L - 1) / L) / (6.0 * N))
-                                   if alg.path_name.endswith("+gram") else flops_iter)
+                                   if alg.path_name.endswith("+gram") else
+                                   (3.0 * flops_iter if precision == "tf32x3" else flops_iter))
                                   / world / (ms_per_step * 1e-3) / 1e12,
         "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
         "hbm_update_kernels": {
@@ -378,7 +379,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
-        "dtype": "tf32" if precision == "tf32" else "f32", "data": "synthetic",
+        "dtype": {"tf32": "tf32", "tf32x3": "tf32x3 (3 TF32 MMAs per product, fp32-grade)"}.get(precision, "f32"), "data": "synthetic",
         "config": {"workload": "config %s: N=%d T=%d K=%d L=%d MU%s" %
                    (args.config, N, T, K, L, "" if args.t_scale == 1.0 else " (T reduced: debug)"),
                    "sharding": "time axis, %d x %d columns, halo %d" % (world, Tloc, L - 1),

@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libcmf_b200.so")
 
 CMF_F32, CMF_F64 = 0, 1
 CMF_HOST, CMF_DEVICE = 0, 1
-CMF_PREC_FP32, CMF_PREC_TF32 = 0, 1
-PRECISIONS = {"fp32": CMF_PREC_FP32, "tf32": CMF_PREC_TF32}
+CMF_PREC_FP32, CMF_PREC_TF32, CMF_PREC_TF32X3 = 0, 1, 2
+PRECISIONS = {"fp32": CMF_PREC_FP32, "tf32": CMF_PREC_TF32, "tf32x3": CMF_PREC_TF32X3}
 CMF_DEN_DIRECT, CMF_DEN_GRAM, CMF_DEN_AUTO = 0, 1, 2
 DENOMINATORS = {"direct": CMF_DEN_DIRECT, "gram": CMF_DEN_GRAM, "auto": CMF_DEN_AUTO}
 

@@ -51,6 +51,8 @@ struct cmf_mu_s {
   int precision = CMF_PREC_FP32;
   int round_ops = 0;                 // store operands pre-rounded to TF32
   bool use_tc = false;
+  bool x3 = false;                   // CMF_PREC_TF32X3: Xt / Et hold TF32 hi halves, Xlo / Elo the lo halves
+  float *Xlo = nullptr, *Elo = nullptr;
 
   float *Xt = nullptr, *Et = nullptr, *Ht = nullptr, *W = nullptr;   // Ht, W: fp32 masters (the TF32 operand
                                                                      // copies of the tcgen05 path live in tcs)
@@ -192,7 +194,11 @@ int ensure_est_buffer(cmf_mu_s* h) {
   if (h->Et) return 0;
   CMF_CUDA(cudaMalloc((void**)&h->Et, (size_t)h->RT * h->Np * 4));
   CMF_CUDA(cudaMemsetAsync(h->Et, 0, (size_t)h->RT * h->Np * 4, h->stream));
-  if (h->use_tc) CMF_TRY(tc::attach_est(h->tcs, h->Et));
+  if (h->x3) {
+    CMF_CUDA(cudaMalloc((void**)&h->Elo, (size_t)h->RT * h->Np * 4));
+    CMF_CUDA(cudaMemsetAsync(h->Elo, 0, (size_t)h->RT * h->Np * 4, h->stream));
+  }
+  if (h->use_tc) CMF_TRY(tc::attach_est(h->tcs, h->Et, h->Elo));
   h->graph_dirty = true;             // kernel arguments baked into a captured iteration changed
   return 0;
 }
@@ -343,7 +349,8 @@ int load_transposed(cmf_mu_s* h, const TI* src, int mem, long long ld, long long
 
 template <class TO>
 int store_transposed(cmf_mu_s* h, const float* src, long long lds, long long rows_out, long long cols_out,
-                     TO* dst, int mem, long long ldd) {
+                     TO* dst, int mem, long long ldd, const float* src_lo = nullptr) {
+  // src_lo (optional): a second array of the same layout that is added on the way out (3xTF32 hi + lo)
   // dst[r][c] = src[c][r], dst is rows_out x cols_out (ld ldd); src is cols_out x lds
   if (rows_out == 0 || cols_out == 0) return 0;
   if (mem == CMF_DEVICE) {
@@ -356,12 +363,13 @@ int store_transposed(cmf_mu_s* h, const float* src, long long lds, long long row
       for (long long c0 = 0; c0 < cols_out; c0 += slab) {
         const long long w = (cols_out - c0 < slab) ? cols_out - c0 : slab;
         dim3 g((unsigned)ceil_div_ll(rows_out, 32), (unsigned)ceil_div_ll(w, 32));
-        ew::transpose_convert_kernel<float, TO><<<g, 256, 0, h->stream>>>(src + c0 * lds, lds, dst + c0, ldd, w, rows_out, 0);
+        ew::transpose_convert_kernel<float, TO><<<g, 256, 0, h->stream>>>(src + c0 * lds, lds, dst + c0, ldd, w, rows_out, 0,
+                                                                          src_lo ? src_lo + c0 * lds : nullptr);
         CMF_TRY(launch_check(h, "transpose_out"));
       }
       return 0;
     }
-    ew::transpose_convert_kernel<float, TO><<<grid, 256, 0, h->stream>>>(src, lds, dst, ldd, cols_out, rows_out, 0);
+    ew::transpose_convert_kernel<float, TO><<<grid, 256, 0, h->stream>>>(src, lds, dst, ldd, cols_out, rows_out, 0, src_lo);
     return launch_check(h, "transpose_out");
   }
   const long long budget = 64ll << 20;
@@ -375,7 +383,8 @@ int store_transposed(cmf_mu_s* h, const float* src, long long lds, long long row
   for (long long c0 = 0; c0 < cols_out && rc == 0; c0 += ch) {
     const long long w = (cols_out - c0 < ch) ? cols_out - c0 : ch;
     dim3 grid((unsigned)ceil_div_ll(rows_out, 32), (unsigned)ceil_div_ll(w, 32));
-    ew::transpose_convert_kernel<float, TO><<<grid, 256, 0, h->stream>>>(src + c0 * lds, lds, stg, w, w, rows_out, 0);
+    ew::transpose_convert_kernel<float, TO><<<grid, 256, 0, h->stream>>>(src + c0 * lds, lds, stg, w, w, rows_out, 0,
+                                                                         src_lo ? src_lo + c0 * lds : nullptr);
     rc = launch_check(h, "transpose_out");
     if (rc) break;
     if (cudaMemcpy2DAsync(dst + c0, (size_t)ldd * sizeof(TO), stg, (size_t)w * sizeof(TO), (size_t)w * sizeof(TO),
@@ -391,7 +400,7 @@ int store_transposed(cmf_mu_s* h, const float* src, long long lds, long long row
 
 void free_all(cmf_mu_s* h) {
   tc::destroy(h->tcs);
-  cudaFree(h->Xt); cudaFree(h->Et); cudaFree(h->Ht); cudaFree(h->W);
+  cudaFree(h->Xt); cudaFree(h->Et); cudaFree(h->Ht); cudaFree(h->W); cudaFree(h->Xlo); cudaFree(h->Elo);
   cudaFree(h->numden); cudaFree(h->wpart); cudaFree(h->hterms);
   cudaFree(h->loss_partials); cudaFree(h->d_sumsq); cudaFree(h->d_ring); cudaFree(h->d_xpart);
   cudaFree(h->d_neg);
@@ -425,7 +434,8 @@ int cmf_device_count(int* count) {
 
 int cmf_precision_supported(int precision, int n_features, int n_components, int maxlag) {
   if (precision == CMF_PREC_FP32) return 1;
-  if (precision == CMF_PREC_TF32) return tc::shape_supported(n_features, n_components, maxlag) ? 1 : 0;
+  if (precision == CMF_PREC_TF32 || precision == CMF_PREC_TF32X3)
+    return tc::shape_supported(n_features, n_components, maxlag) ? 1 : 0;
   return 0;
 }
 
@@ -436,7 +446,8 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
   CMF_CHECK(p->t_local >= 1 && p->t_global >= p->t_local && p->t_offset >= 0 &&
                 p->t_offset + p->t_local <= p->t_global,
             "inconsistent time range: t_local=%lld t_offset=%lld t_global=%lld", p->t_local, p->t_offset, p->t_global);
-  CMF_CHECK(p->precision == CMF_PREC_FP32 || p->precision == CMF_PREC_TF32, "unknown precision %d", p->precision);
+  CMF_CHECK(p->precision == CMF_PREC_FP32 || p->precision == CMF_PREC_TF32 || p->precision == CMF_PREC_TF32X3,
+            "unknown precision %d", p->precision);
   CMF_CHECK(p->denominators == CMF_DEN_DIRECT || p->denominators == CMF_DEN_GRAM || p->denominators == CMF_DEN_AUTO,
             "unknown denominators mode %d", p->denominators);
   CMF_CHECK(p->t_local == p->t_global || p->t_local >= p->maxlag - 1,
@@ -461,10 +472,11 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
   h->num_sms = prop.multiProcessorCount;
 
   h->N = p->n_features; h->K = p->n_components; h->L = p->maxlag;
-  h->use_tc = (p->precision == CMF_PREC_TF32);
+  h->use_tc = (p->precision != CMF_PREC_FP32);
+  h->x3 = (p->precision == CMF_PREC_TF32X3);
   if (h->use_tc && !tc::shape_supported(h->N, h->K, h->L)) {
     delete h;
-    set_error("precision tf32 has no tensor-core kernel for N=%d K=%d L=%d; use fp32", p->n_features, p->n_components, p->maxlag);
+    set_error("precision tf32 / tf32x3 has no tensor-core kernel for N=%d K=%d L=%d; use fp32", p->n_features, p->n_components, p->maxlag);
     return 2;
   }
   h->Np = round_up(h->N, 4); h->h = h->L - 1;
@@ -509,6 +521,7 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
   int rc = 0;
   auto A = [&](int r) { if (rc == 0) rc = r; };
   A(dmalloc(&h->Xt, h->RT * h->Np));
+  if (h->x3) A(dmalloc(&h->Xlo, h->RT * h->Np));
   A(dmalloc(&h->Ht, h->RH * h->Kp));
   A(dmalloc(&h->W, h->wcount));
   A(dmalloc(&h->numden, 2 * h->wcount));
@@ -526,6 +539,7 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
     cudaError_t e = cudaSuccess;
     auto Z = [&](void* ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMemsetAsync(ptr, 0, bytes, h->stream); };
     Z(h->Xt, (size_t)h->RT * h->Np * 4);
+    if (h->x3) Z(h->Xlo, (size_t)h->RT * h->Np * 4);
     Z(h->Ht, (size_t)h->RH * h->Kp * 4);
     Z(h->W, (size_t)h->wcount * 4);
     Z(h->numden, (size_t)2 * h->wcount * 4);
@@ -539,10 +553,10 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
     {
       const double contraction_flops = 2.0 * h->N * h->K * (double)h->L * (double)h->Tloc;
       const bool want = p->denominators == CMF_DEN_GRAM || (p->denominators == CMF_DEN_AUTO && contraction_flops >= 2e11);
-      h->tcs.gram_request = want ? 3 : 0;
+      h->tcs.gram_request = (want && !h->x3) ? 3 : 0;
     }
     rc = tc::init(h->tcs, d, h->Xt, nullptr, h->Ht, h->W, h->numden, h->hterms, h->loss_partials,
-                  h->n_loss_partials, h->d_sumsq, h->stream);
+                  h->n_loss_partials, h->d_sumsq, h->stream, h->Xlo);
   }
   // est^T: needed up front unless both denominators come from the Gram route (then on first demand)
   if (rc == 0 && !(h->use_tc && h->tcs.mask == 7 && h->tcs.gram == 3)) rc = ensure_est_buffer(h);
@@ -574,8 +588,9 @@ int cmf_mu_set_data(cmf_mu_t* h, const void* X, int dtype, int mem, long long ld
   CMF_CHECK(ld >= ncols, "leading dimension %lld < ncols %lld", ld, ncols);
   if (ncols > h->t_valid) ncols = h->t_valid;    // nothing exists past the global end
   CMF_CUDA(cudaMemsetAsync(h->Xt, 0, (size_t)h->RT * h->Np * 4, h->stream));
-  if (dtype == CMF_F32) CMF_TRY(load_transposed<float>(h, (const float*)X, mem, ld, h->N, ncols, h->Xt, h->Np, h->round_ops));
-  else CMF_TRY(load_transposed<double>(h, (const double*)X, mem, ld, h->N, ncols, h->Xt, h->Np, h->round_ops));
+  const int round_in = h->x3 ? 0 : h->round_ops;
+  if (dtype == CMF_F32) CMF_TRY(load_transposed<float>(h, (const float*)X, mem, ld, h->N, ncols, h->Xt, h->Np, round_in));
+  else CMF_TRY(load_transposed<double>(h, (const double*)X, mem, ld, h->N, ncols, h->Xt, h->Np, round_in));
   // local ||X||^2 over owned columns and the negativity flag
   const long long n4 = h->Tloc * h->Np / 4;
   const int grid = ew_grid(h, n4);
@@ -584,6 +599,11 @@ int cmf_mu_set_data(cmf_mu_t* h, const void* X, int dtype, int mem, long long ld
   CMF_TRY(launch_check(h, "sumsq_x"));
   ew::sum_doubles_kernel<<<1, 1024, 0, h->stream>>>(h->d_xpart, grid, h->d_sumsq);
   CMF_TRY(launch_check(h, "sumsq_x_final"));
+  if (h->x3) {
+    const long long m4 = h->RT * h->Np / 4;
+    tc::split_inplace_kernel<<<ew_grid(h, m4), 256, 0, h->stream>>>((float4*)h->Xt, (float4*)h->Xlo, m4);
+    CMF_TRY(launch_check(h, "split_x"));
+  }
   CMF_CUDA(cudaMemcpyAsync(&h->sumsq_x, h->d_sumsq, 8, cudaMemcpyDeviceToHost, h->stream));
   CMF_CUDA(cudaMemcpyAsync(&h->has_neg, h->d_neg, 4, cudaMemcpyDeviceToHost, h->stream));
   CMF_CUDA(cudaStreamSynchronize(h->stream));
@@ -658,7 +678,8 @@ int cmf_mu_init_stats(cmf_mu_t* h, double* x_dot_est, double* est_sumsq) {
   const long long n4 = h->Tloc * h->Np / 4;
   int grid = ew_grid(h, n4);
   if (grid > h->num_sms * 4) grid = h->num_sms * 4;      // d_xpart holds 8*num_sms doubles
-  ew::dot_sumsq_kernel<<<grid, 256, 0, h->stream>>>((const float4*)h->Xt, (const float4*)h->Et, n4, h->d_xpart);
+  ew::dot_sumsq_kernel<<<grid, 256, 0, h->stream>>>((const float4*)h->Xt, (const float4*)h->Et, n4, h->d_xpart,
+                                                    (const float4*)h->Xlo, (const float4*)h->Elo);
   CMF_TRY(launch_check(h, "dot_sumsq"));
   std::vector<double> host((size_t)grid * 2);
   CMF_CUDA(cudaMemcpyAsync(host.data(), h->d_xpart, host.size() * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -916,8 +937,8 @@ int cmf_mu_get_est(cmf_mu_t* h, void* est_out, int dtype, int mem, long long ld)
   CMF_CHECK(ld >= h->Tloc, "leading dimension too small");
   CMF_TRY(ensure_est_stored(h));
   int rc;
-  if (dtype == CMF_F32) rc = store_transposed<float>(h, h->Et, h->Np, h->N, h->Tloc, (float*)est_out, mem, ld);
-  else rc = store_transposed<double>(h, h->Et, h->Np, h->N, h->Tloc, (double*)est_out, mem, ld);
+  if (dtype == CMF_F32) rc = store_transposed<float>(h, h->Et, h->Np, h->N, h->Tloc, (float*)est_out, mem, ld, h->Elo);
+  else rc = store_transposed<double>(h, h->Et, h->Np, h->N, h->Tloc, (double*)est_out, mem, ld, h->Elo);
   if (rc == 0) CMF_CUDA(cudaStreamSynchronize(h->stream));
   return rc;
 }
@@ -971,6 +992,7 @@ int cmf_mu_launch_count(cmf_mu_t* h, long long* count) {
 const char* cmf_mu_path_name(cmf_mu_t* h) {
   if (!h) return "none";
   if (!h->use_tc) return "ffma-fp32";
+  if (h->x3) return "tcgen05-tf32x3";
   if (h->tcs.mask != 7) return "tcgen05-tf32(partial)";
   if (h->tcs.gram == 3) return "tcgen05-tf32+gram";
   return h->tcs.gram ? "tcgen05-tf32+gram(partial)" : "tcgen05-tf32";

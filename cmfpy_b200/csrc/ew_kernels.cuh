@@ -118,12 +118,15 @@ sumsq_neg_kernel(const float4* __restrict__ x, long long n4, double* __restrict_
 // cmfpy/algs/base.py:86-87); partial[2*b] and partial[2*b+1]
 __global__ void __launch_bounds__(256)
 dot_sumsq_kernel(const float4* __restrict__ x, const float4* __restrict__ e, long long n4,
-                 double* __restrict__ partial) {
+                 double* __restrict__ partial, const float4* __restrict__ x_lo = nullptr,
+                 const float4* __restrict__ e_lo = nullptr) {
   __shared__ double red[2][8];
   double sxe = 0.0, see = 0.0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 a = x[i], b = e[i];
+    float4 a = x[i], b = e[i];
+    if (x_lo) { const float4 t = x_lo[i]; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+    if (e_lo) { const float4 t = e_lo[i]; b.x += t.x; b.y += t.y; b.z += t.z; b.w += t.w; }
     sxe += (double)(a.x * b.x + a.y * b.y) + (double)(a.z * b.z + a.w * b.w);
     see += (double)(b.x * b.x + b.y * b.y) + (double)(b.z * b.z + b.w * b.w);
   }
@@ -159,14 +162,17 @@ scale_kernel(float4* __restrict__ p, long long n4, float s, int round_out) {
 template <class TI, class TO>
 __global__ void __launch_bounds__(256)
 transpose_convert_kernel(const TI* __restrict__ src, long long lds, TO* __restrict__ dst,
-                         long long ldd, long long rows, long long cols, int round_out) {
+                         long long ldd, long long rows, long long cols, int round_out,
+                         const TI* __restrict__ src2 = nullptr) {
   __shared__ float tile[32][33];
   const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const long long r = r0 + ty + j, c = c0 + tx;
-    tile[ty + j][tx] = (r < rows && c < cols) ? (float)src[r * lds + c] : 0.f;
+    float v = (r < rows && c < cols) ? (float)src[r * lds + c] : 0.f;
+    if (src2 && r < rows && c < cols) v += (float)src2[r * lds + c];      // hi + lo pair
+    tile[ty + j][tx] = v;
   }
   __syncthreads();
 #pragma unroll

@@ -93,8 +93,22 @@ struct ReconParams {
   const float* Xt;
   double* loss_partials;           // one per CTA
   int round_out;
+  // 3xTF32 (x3 = 1): CB counts 3 * cbx reduction blocks, combo = block / cbx selects the operand halves
+  // (0: A lo, B hi;  1: A hi, B lo;  2: A hi, B hi - the small cross terms first, while the accumulator is
+  // small and its truncation costs nothing); the lo halves sit lo_off columns to the right in both operand arrays.
+  int x3, cbx, lo_off;
+  float* Elo;                      // x3: est^T = Et (hi) + Elo
+  const float* Xlo;                // x3: X^T = Xt (hi) + Xlo
   int* err;
 };
+
+// (reduction block) -> (column block within a combo, column offsets of the A and B halves)
+struct X3Sel { int cbr, a_off, b_off; };
+__device__ __forceinline__ X3Sel x3_select(int x3, int cbx, int lo_off, int vcb) {
+  if (!x3) return X3Sel{vcb, 0, 0};
+  const int combo = vcb / cbx;
+  return X3Sel{vcb - combo * cbx, combo == 0 ? lo_off : 0, combo == 1 ? lo_off : 0};
+}
 
 constexpr int kReconLagsPerStage = 2;              // lags per pipeline stage: 8 MMAs per barrier round trip
 constexpr int kReconStages = 3;
@@ -163,8 +177,10 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const long long tt = c.tile / p.n_tiles_n;
         mbar_arrive_expect_tx(&hfull[hb], hbytes);
         uint8_t* hdst = Hs + (size_t)hb * hbytes;
+        const X3Sel sel = x3_select(p.x3, p.cbx, p.lo_off, c.cb);
         for (int rb = 0; rb < wrows / 64; ++rb)
-          tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], c.cb * 32, (int)(tt * 256 + p.h_shift + rb * 64));
+          tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], sel.cbr * 32 + sel.b_off,
+                      (int)(tt * 256 + p.h_shift + rb * 64));
         return true;
       };
       Chunk cur{(long long)blockIdx.x, 0, (long long)blockIdx.x < p.n_tiles};
@@ -174,6 +190,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const Chunk nxt = next_chunk(cur);
         bool prefetched = !nxt.valid;
         const int nt = (int)(cur.tile % p.n_tiles_n);
+        const X3Sel sel = x3_select(p.x3, p.cbx, p.lo_off, cur.cb);
         int stage_in_chunk = 0;
         for (int l = 0; l < L; l += kReconLagsPerStage, ++stage_in_chunk) {
           if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
@@ -181,7 +198,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           mbar_arrive_expect_tx(&full[ps.stage], nl * kReconABytes);
           for (int u = 0; u < nl; ++u)
             tma_load_2d(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes, &tmW, &full[ps.stage],
-                        (cur.cb % p.cb_cols) * 32, (l + u + cur.cb / p.cb_cols) * p.Np + nt * 128);
+                        (sel.cbr % p.cb_cols) * 32 + sel.a_off, (l + u + sel.cbr / p.cb_cols) * p.Np + nt * 128);
           ps.advance(kReconStages);
           if (!prefetched && stage_in_chunk >= 1) {
             if (!issue_window(nxt, wc + 1)) { ok = false; break; }
@@ -249,7 +266,9 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       const bool n_ok = n < p.n_rows;
       float tile_loss = 0.f;
       const float* __restrict__ Xt = p.Xt;
+      const float* __restrict__ Xlo = p.Xlo;
       float* __restrict__ Et = p.Et;
+      float* __restrict__ Elo = p.Elo;
       const size_t np = (size_t)p.ld_out;
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
@@ -262,6 +281,10 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (n_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = (tau0 + j < p.t_own) ? __ldcs(Xt + off0 + (size_t)j * np) : 0.f;
+          if (Xlo) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] += (tau0 + j < p.t_own) ? __ldcs(Xlo + off0 + (size_t)j * np) : 0.f;
+          }
         }
         tmem_ld_wait();
         if (p.store_mode == 2) {
@@ -289,8 +312,14 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               tile_loss = fmaf(d, d, tile_loss);
             }
             if (!p.skip_store) {
-              if (p.round_out) v = round_tf32(v);
-              Et[off0 + (size_t)j * np] = v;
+              if (Elo) {
+                const float hi = round_tf32(v);
+                Et[off0 + (size_t)j * np] = hi;
+                Elo[off0 + (size_t)j * np] = round_tf32(v - hi);
+              } else {
+                if (p.round_out) v = round_tf32(v);
+                Et[off0 + (size_t)j * np] = v;
+              }
             }
           }
         }
@@ -517,6 +546,8 @@ struct WTermsParams {
   long long stages_total;         // ceil(t_own / 32)
   float* part;                    // [chunk][src][L][Np][Kp]
   long long per_src;              // L * Np * Kp
+  int x3, lo_off;                 // 3xTF32: three passes over the item's time range - (S lo, H hi), (S hi, H lo),
+                                  // (S hi, H hi) - into one accumulator; H lo sits lo_off columns to the right
   int* err;
 };
 
@@ -530,7 +561,8 @@ __host__ __device__ inline size_t wterms_smem_bytes(int s) { return 1024 + (size
 
 __global__ void __launch_bounds__(kWtThreads, 1)
 tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmE,
-                 const __grid_constant__ CUtensorMap tmH, const WTermsParams p) {
+                 const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmXlo,
+                 const __grid_constant__ CUtensorMap tmElo, const WTermsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* St = smem;                                            // [stages][A 16 KB | B brows x 128 B]
@@ -550,7 +582,7 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     mbar_init(tempty, 4);
     *abort_flag = 0;
     fence_mbar_init();
-    prefetch_tmap(&tmX); prefetch_tmap(&tmE); prefetch_tmap(&tmH);
+    prefetch_tmap(&tmX); prefetch_tmap(&tmE); prefetch_tmap(&tmH); prefetch_tmap(&tmXlo); prefetch_tmap(&tmElo);
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
@@ -583,18 +615,21 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         decode(item, lg, cb, src, nt, ch);
         long long s0, s1;
         chunk_range(ch, s0, s1);
-        const CUtensorMap* tmS = src ? &tmE : &tmX;
-        for (long long s = s0; s < s1; ++s) {
-          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
-          uint8_t* dst = St + (size_t)ps.stage * kWtStageBytes;
-          mbar_arrive_expect_tx(&full[ps.stage], kWtStageBytes);
-          const int tau0 = (int)(s * 32);
+        for (int combo = p.x3 ? 0 : 2; combo < 3 && ok; ++combo) {
+          const CUtensorMap* tmS = combo == 0 ? (src ? &tmElo : &tmXlo) : (src ? &tmE : &tmX);
+          const int hcol = cb * 32 + (combo == 1 ? p.lo_off : 0);
+          for (long long s = s0; s < s1; ++s) {
+            if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+            uint8_t* dst = St + (size_t)ps.stage * kWtStageBytes;
+            mbar_arrive_expect_tx(&full[ps.stage], kWtStageBytes);
+            const int tau0 = (int)(s * 32);
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
-            tma_load_2d(dst + r * 4096, tmS, &full[ps.stage], nt * 128 + r * 32, tau0);
-          // Hv rows tau0 - s*(l0+15) .. tau0 + 32; row index in Hv is tau + h
-          tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], cb * 32, tau0 - p.s * (lg * 16 + 15) + p.h);
-          ps.advance(kWtStages);
+            for (int r = 0; r < 4; ++r)
+              tma_load_2d(dst + r * 4096, tmS, &full[ps.stage], nt * 128 + r * 32, tau0);
+            // Hv rows tau0 - s*(l0+15) .. tau0 + 32; row index in Hv is tau + h
+            tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], hcol, tau0 - p.s * (lg * 16 + 15) + p.h);
+            ps.advance(kWtStages);
+          }
         }
       }
     }
@@ -611,6 +646,7 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         chunk_range(ch, s0, s1);
         if (!ab.wait(tempty, (it & 1) ^ 1)) break;
         tc_fence_after();
+        if (p.x3) s1 = s0 + 3 * (s1 - s0);          // three operand passes, one accumulation
         for (long long s = s0; s < s1; ++s) {
           if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
           tc_fence_after();
@@ -723,6 +759,8 @@ struct HTermsParams {
   long long n_tiles;               // TO / 256 + 1
   long long ts;                    // scratch row length (TO + 256)
   float* scratch;                  // [n_split][n_slots][4][32][ts]
+  int x3, lo_off;                  // 3xTF32: the feature chunks of an item are walked three times - (W lo, S hi),
+                                   // (W hi, S lo), (W hi, S hi) - into the same accumulators
   int* err;
 };
 
@@ -738,7 +776,8 @@ __host__ __device__ inline size_t hterms_smem_bytes(int wrows) {
 
 __global__ void __launch_bounds__(kHtThreads, 1)
 tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
-                 const __grid_constant__ CUtensorMap tmE, const HTermsParams p) {
+                 const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmXlo,
+                 const __grid_constant__ CUtensorMap tmElo, const HTermsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* As = smem;                                             // [stages][16 KB]
@@ -762,7 +801,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     mbar_init(tempty, 4);
     *abort_flag = 0;
     fence_mbar_init();
-    prefetch_tmap(&tmW); prefetch_tmap(&tmX); prefetch_tmap(&tmE);
+    prefetch_tmap(&tmW); prefetch_tmap(&tmX); prefetch_tmap(&tmE); prefetch_tmap(&tmXlo); prefetch_tmap(&tmElo);
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
@@ -779,17 +818,20 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       // chunks = (work item, 32-feature chunk) in execution order; chunk c uses window buffer c & 1.
       // The window of chunk c+1 is requested while the W stages of chunk c stream, i.e. a whole chunk
       // (J stages) before the MMAs need it - not merely the depth of the W ring ahead.
-      struct Chunk { long long item; int nc, nc1; bool valid; };
+      struct Chunk { long long item; int nc, nc0, nc1, combo; bool valid; };
       auto make_chunk = [&](long long item) {
-        Chunk c{item, 0, 0, item < p.n_tiles};
+        Chunk c{item, 0, 0, 0, p.x3 ? 0 : 2, item < p.n_tiles};
         if (c.valid) {
-          c.nc = (int)(item % p.n_split) * p.nc_per_split;
+          c.nc0 = c.nc = (int)(item % p.n_split) * p.nc_per_split;
           c.nc1 = min(c.nc + p.nc_per_split, p.n_chunks_n);
         }
         return c;
       };
       auto next_chunk = [&](Chunk c) {
-        if (++c.nc >= c.nc1) c = make_chunk(c.item + gridDim.x);
+        if (++c.nc >= c.nc1) {
+          if (c.combo < 2) { ++c.combo; c.nc = c.nc0; }
+          else c = make_chunk(c.item + gridDim.x);
+        }
         return c;
       };
       auto issue_window = [&](const Chunk& c, long long wc) -> bool {
@@ -799,7 +841,8 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         mbar_arrive_expect_tx(&wfull[wb], p.n_src * wbytes);
         for (int src = 0; src < p.n_src; ++src) {
           uint8_t* wdst = Ws + ((size_t)wb * 2 + src) * wbytes;
-          const CUtensorMap* tmS = (src && !p.pair_mode) ? &tmE : &tmX;
+          const CUtensorMap* tmS = (src && !p.pair_mode) ? (c.combo == 1 ? &tmElo : &tmE)
+                                                         : (c.combo == 1 ? &tmXlo : &tmX);
           const int base = (int)((p.pair_mode ? 2 * tile + src : tile) * 256);
           for (int rb = 0; rb < wrows / 32; ++rb)
             tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], c.nc * 32, base + rb * 32);
@@ -821,7 +864,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             uint8_t* dst = As + (size_t)ps.stage * kHtStageBytes + u * kHtABytes;
 #pragma unroll
             for (int g = 0; g < 4; ++g)      // region g = (lag group g / CB, column block g % CB)
-              tma_load_2d(dst + g * 4096, &tmW, &full[ps.stage], (g % p.CB) * 32,
+              tma_load_2d(dst + g * 4096, &tmW, &full[ps.stage], (g % p.CB) * 32 + (cur.combo == 0 ? p.lo_off : 0),
                           (j + u + J * (g / p.CB)) * p.Np + cur.nc * 32);
           }
           ps.advance(kHtStages);
@@ -847,7 +890,8 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         const int nc1 = min(nc0 + p.nc_per_split, p.n_chunks_n);
         if (!ab.wait(tempty, (it & 1) ^ 1)) break;
         tc_fence_after();
-        for (int nc = nc0; nc < nc1 && ok; ++nc, ++wcount) {
+        const int nchunks = (p.x3 ? 3 : 1) * (nc1 - nc0);        // x3: three operand passes, one accumulation
+        for (int nc = nc0; nc < nc0 + nchunks && ok; ++nc, ++wcount) {
           const int wb = (int)(wcount & 1);
           if (!ab.wait(&wfull[wb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
           tc_fence_after();
@@ -978,6 +1022,64 @@ fold_w_kernel(float* __restrict__ Wv, const float* __restrict__ W, int L, int Lv
     const int lv = (int)(i / (32ll * Np));
     const int l = s * lv + dl;
     Wv[i] = (l < L) ? round_tf32(W[((long long)l * Np + n) * Kp + k]) : 0.f;
+  }
+}
+
+// ---- 3xTF32 operand pairs: hi = RN_tf32(x), lo = RN_tf32(x - hi)  (x - hi is exact in fp32) ----
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = round_tf32(x);
+  lo = round_tf32(x - hi);
+}
+
+// in place: hi_inout <- hi, lo_out <- lo   (X^T after it was loaded at full precision)
+__global__ void __launch_bounds__(256)
+split_inplace_kernel(float4* __restrict__ hi_inout, float4* __restrict__ lo_out, long long n4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = hi_inout[i];
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    hi_inout[i] = h;
+    lo_out[i] = l;
+  }
+}
+
+// Hv[r][c] = hi, Hv[r][KW + c] = lo of the (folded) H^T entry that column c of row r holds:
+//   s > 1: c = (dl, k), entry H^T[r - dl][k];   s == 1: entry H^T[r][c]  (KW == Kp)
+__global__ void __launch_bounds__(256)
+fold_h_x3_kernel(float* __restrict__ Hv, const float* __restrict__ Ht, long long row0, long long nrows, int Kp, int s,
+                 int KW) {
+  const long long total = nrows * KW;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = row0 + i / KW;
+    const int c = (int)(i % KW);
+    const int dl = s > 1 ? c / Kp : 0, k = s > 1 ? c % Kp : c;
+    const float x = (r - dl >= 0) ? Ht[(r - dl) * Kp + k] : 0.f;
+    float hi, lo;
+    split_tf32(x, hi, lo);
+    Hv[r * 2 * KW + c] = hi;
+    Hv[r * 2 * KW + KW + c] = lo;
+  }
+}
+
+// Wv[l'][n][c] = hi, Wv[l'][n][KW + c] = lo of W[s*l' + dl][n][k]  (lags >= L read as zero)
+__global__ void __launch_bounds__(256)
+fold_w_x3_kernel(float* __restrict__ Wv, const float* __restrict__ W, int L, int Lv, int Np, int Kp, int s, int KW) {
+  const long long total = (long long)Lv * Np * KW;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % KW);
+    const int dl = s > 1 ? c / Kp : 0, k = s > 1 ? c % Kp : c;
+    const long long row = i / KW;                    // l' * Np + n
+    const int n = (int)(row % Np);
+    const int lv = (int)(row / Np);
+    const int l = s * lv + dl;
+    const float x = (l < L) ? W[((long long)l * Np + n) * Kp + k] : 0.f;
+    float hi, lo;
+    split_tf32(x, hi, lo);
+    Wv[row * 2 * KW + c] = hi;
+    Wv[row * 2 * KW + KW + c] = lo;
   }
 }
 

@@ -66,6 +66,11 @@ struct TcState {
   int mask = 7;                    // bit0 recon, bit1 w terms, bit2 h terms run on tensor cores
   float *Xt = nullptr, *Et = nullptr, *Ht = nullptr, *W = nullptr, *numden = nullptr, *hterms = nullptr;  // masters
   float *Wv = nullptr, *Hv = nullptr;   // TF32-rounded (and, for Kp < 32, lag-folded) operand copies
+  // 3xTF32 (CMF_PREC_TF32X3): every operand is a TF32 pair.  Wv / Hv rows are [hi (KW) | lo (KW)] (KWs = 2 KW
+  // columns); Xt / Et hold the hi halves and Xlo / Elo the lo halves.
+  int x3 = 0, KWs = 32;
+  float *Xlo = nullptr, *Elo = nullptr;
+  CUtensorMap tmXlo_k2, tmElo_k2, tmXlo_k3, tmElo_k3;
   double *loss_partials = nullptr, *d_sumsq = nullptr;
   float* wpart = nullptr;
   float* hscratch = nullptr;       // [2][4][32][TO + 256] lag-group partials of the H terms
@@ -160,13 +165,17 @@ inline int ew_blocks(const TcState& s, long long items) {
 
 // When no folding is needed the MU update kernels write the rounded copy
 // themselves (fused); these return the pointers they should write, or null.
-inline float* fused_w_op(TcState& s) { return (s.ready && s.f.s == 1) ? s.Wv : nullptr; }
-inline float* fused_h_op(TcState& s) { return (s.ready && s.f.s == 1) ? s.Hv : nullptr; }
+inline float* fused_w_op(TcState& s) { return (s.ready && s.f.s == 1 && !s.x3) ? s.Wv : nullptr; }
+inline float* fused_h_op(TcState& s) { return (s.ready && s.f.s == 1 && !s.x3) ? s.Hv : nullptr; }
 
 // Rebuild the operand copies from the fp32 masters.
 inline int refresh_w(TcState& s, cudaStream_t stream, bool after_fused_update = false) {
   if (!s.ready) return 0;
   const Dims& d = s.d;
+  if (s.x3) {
+    fold_w_x3_kernel<<<ew_blocks(s, s.wv_count), 256, 0, stream>>>(s.Wv, s.W, d.L, s.f.Lv, d.Np, d.Kp, s.f.s, s.f.KW);
+    return launch_ok("split_w");
+  }
   if (s.f.s == 1) {
     if (after_fused_update) return 0;
     ew::round_copy_kernel<<<ew_blocks(s, s.wcount / 4), 256, 0, stream>>>((float4*)s.Wv, (const float4*)s.W, s.wcount / 4);
@@ -178,6 +187,12 @@ inline int refresh_w(TcState& s, cudaStream_t stream, bool after_fused_update = 
 inline int refresh_h(TcState& s, cudaStream_t stream, long long row0, long long nrows, bool after_fused_update = false) {
   if (!s.ready || nrows <= 0) return 0;
   const Dims& d = s.d;
+  if (s.x3) {
+    long long r1 = row0 + nrows + s.f.s - 1;       // a folded row depends on the s-1 rows before it
+    if (r1 > d.RH) r1 = d.RH;
+    fold_h_x3_kernel<<<ew_blocks(s, (r1 - row0) * s.f.KW), 256, 0, stream>>>(s.Hv, s.Ht, row0, r1 - row0, d.Kp, s.f.s, s.f.KW);
+    return launch_ok("split_h");
+  }
   if (s.f.s == 1) {
     if (after_fused_update) return 0;
     const long long n4 = nrows * d.Kp / 4;
@@ -192,33 +207,39 @@ inline int refresh_h(TcState& s, cudaStream_t stream, long long row0, long long 
 }
 
 inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, float* W, float* numden, float* hterms,
-                double* loss_partials, long long n_loss_partials, double* d_sumsq, cudaStream_t stream) {
+                double* loss_partials, long long n_loss_partials, double* d_sumsq, cudaStream_t stream,
+                float* Xlo = nullptr) {
   s.d = d;
   s.f = make_fold(d.Kp, d.L);
   const Fold& f = s.f;
+  s.x3 = Xlo != nullptr ? 1 : 0;
+  s.Xlo = Xlo;
+  s.KWs = (s.x3 ? 2 : 1) * f.KW;
   s.Xt = Xt; s.Et = Et; s.Ht = Ht; s.W = W; s.numden = numden; s.hterms = hterms;
   s.loss_partials = loss_partials; s.d_sumsq = d_sumsq;
   s.wcount = (long long)d.L * d.Np * d.Kp;
-  s.wv_count = (long long)f.Lv * d.Np * f.KW;
+  s.wv_count = (long long)f.Lv * d.Np * f.KW;      // per half
   s.hv_count = d.RH * f.KW;
+  const int halves = s.x3 ? 2 : 1;
   if (const char* e = getenv("CMF_TC_MASK")) s.mask = atoi(e);
+  if (s.x3) s.mask = 7;
   CMF_CHECK(d.Kp == padded_k(d.K) && shape_supported(d.N, d.K, d.L), "shape not supported by the tensor-core path");
   CMF_CHECK(n_loss_partials >= d.num_sms, "loss partial buffer too small");
 
   CMF_CUDA(cudaMalloc((void**)&s.d_err, 4));
   CMF_CUDA(cudaMemsetAsync(s.d_err, 0, 4, stream));
-  CMF_CUDA(cudaMalloc((void**)&s.Wv, (size_t)s.wv_count * 4));
-  CMF_CUDA(cudaMalloc((void**)&s.Hv, (size_t)s.hv_count * 4));
-  CMF_CUDA(cudaMemsetAsync(s.Wv, 0, (size_t)s.wv_count * 4, stream));
-  CMF_CUDA(cudaMemsetAsync(s.Hv, 0, (size_t)s.hv_count * 4, stream));
+  CMF_CUDA(cudaMalloc((void**)&s.Wv, (size_t)s.wv_count * halves * 4));
+  CMF_CUDA(cudaMalloc((void**)&s.Hv, (size_t)s.hv_count * halves * 4));
+  CMF_CUDA(cudaMemsetAsync(s.Wv, 0, (size_t)s.wv_count * halves * 4, stream));
+  CMF_CUDA(cudaMemsetAsync(s.Hv, 0, (size_t)s.hv_count * halves * 4, stream));
 
   // ---- K1 -------------------------------------------------------------
   {
     const long long tiles = ceil_div_ll(d.Np, 128) * (d.RT / 256);
     s.recon_grid = (int)(tiles < d.num_sms ? tiles : d.num_sms);
   }
-  CMF_TRY(make_map(&s.tmW_k1, s.Wv, (long long)f.Lv * d.Np, f.KW, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
-  CMF_TRY(make_map(&s.tmH_k1, s.Hv, d.RH, f.KW, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
+  CMF_TRY(make_map(&s.tmW_k1, s.Wv, (long long)f.Lv * d.Np, s.KWs, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+  CMF_TRY(make_map(&s.tmH_k1, s.Hv, d.RH, s.KWs, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
   CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)recon_smem_bytes(f.recon_wrows)));
 
@@ -248,11 +269,14 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
       if (eff > best + 1e-9) { best = eff; bestc = (int)c; }
     }
     s.n_chunks = bestc;
+    if (const char* e = getenv("CMF_WCHUNKS")) { long long c = atoll(e); s.n_chunks = (int)(c < 1 ? 1 : (c > cmax ? cmax : c)); }
     const long long items = units * s.n_chunks;
     s.wterms_grid = (int)(items < d.num_sms ? items : d.num_sms);
   }
   CMF_TRY(make_map(&s.tmX_k2, Xt, d.Tloc, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  CMF_TRY(make_map(&s.tmH_k2, s.Hv, d.RH, f.KW, 32, wterms_brows(f.s), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  s.tmXlo_k2 = s.tmX_k2;
+  if (s.x3) CMF_TRY(make_map(&s.tmXlo_k2, Xlo, d.Tloc, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  CMF_TRY(make_map(&s.tmH_k2, s.Hv, d.RH, s.KWs, 32, wterms_brows(f.s), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   CMF_CUDA(cudaFuncSetAttribute(tc_wterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)wterms_smem_bytes(f.s)));
 
@@ -261,8 +285,10 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     const long long tiles = d.TO / 256 + 1;
     s.hterms_grid = (int)(tiles < d.num_sms ? tiles : d.num_sms);
   }
-  CMF_TRY(make_map(&s.tmW_k3, s.Wv, (long long)f.Lv * d.Np, f.KW, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  CMF_TRY(make_map(&s.tmW_k3, s.Wv, (long long)f.Lv * d.Np, s.KWs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   CMF_TRY(make_map(&s.tmX_k3, Xt, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  s.tmXlo_k3 = s.tmX_k3;
+  if (s.x3) CMF_TRY(make_map(&s.tmXlo_k3, Xlo, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
   CMF_CUDA(cudaFuncSetAttribute(tc_hterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)hterms_smem_bytes(f.hterms_wrows)));
   if (d.Kp * 129 * 4 > 48 * 1024)
@@ -271,6 +297,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   // ---- Gram route ---------------------------------------------------------
   s.gram = s.gram_request;
   if (const char* e = getenv("CMF_GRAM")) s.gram = atoi(e);
+  if (s.x3) s.gram = 0;              // the Gram operators are not error-compensated: direct denominators only
   s.LK = d.L * d.Kp;
   s.Lr = 2 * d.L - 1;
   s.Lrv = (s.Lr + f.s - 1) / f.s;
@@ -345,14 +372,22 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
 
 // The est buffer is only needed when some MU step contracts est (direct routes) or est is read back;
 // with both denominators on the Gram route it is allocated on first demand (cmf_abi.cu).
-inline int attach_est(TcState& s, float* Et) {
+inline int attach_est(TcState& s, float* Et, float* Elo = nullptr) {
   const Dims& d = s.d;
   s.Et = Et;
+  s.Elo = Elo;
   s.tmE_k2 = s.tmX_k2;
   s.tmE_k3 = s.tmX_k3;
+  s.tmElo_k2 = s.tmX_k2;
+  s.tmElo_k3 = s.tmX_k3;
   if (!Et) return 0;
   CMF_TRY(make_map(&s.tmE_k2, Et, d.Tloc, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   CMF_TRY(make_map(&s.tmE_k3, Et, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  if (s.x3) {
+    CMF_CHECK(Elo != nullptr, "3xTF32 needs the lo half of est");
+    CMF_TRY(make_map(&s.tmElo_k2, Elo, d.Tloc, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    CMF_TRY(make_map(&s.tmElo_k3, Elo, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
   return 0;
 }
 
@@ -385,7 +420,8 @@ inline int den_w_gram(TcState& s, cudaStream_t stream) {
     p.stages_total = ceil_div_ll(d.Tloc, 32);
     p.part = (s.p_chunks == 1) ? s.P : s.Ppart;
     p.per_src = pcount; p.err = s.d_err;
-    tc_wterms_kernel<<<s.p_grid, kWtThreads, wterms_smem_bytes(f.s), stream>>>(s.tmHx_k2, s.tmHx_k2, s.tmH_k2, p);
+    tc_wterms_kernel<<<s.p_grid, kWtThreads, wterms_smem_bytes(f.s), stream>>>(s.tmHx_k2, s.tmHx_k2, s.tmH_k2, s.tmHx_k2,
+                                                                             s.tmHx_k2, p);
     CMF_TRY(launch_ok("gram_P"));
     if (s.p_chunks > 1) {
       ew::sum_splits_kernel<<<ew_blocks(s, pcount / 4), 256, 0, stream>>>((float4*)s.P, (const float4*)s.Ppart, pcount / 4,
@@ -434,8 +470,12 @@ inline int recon(TcState& s, cudaStream_t stream, bool store_est = true) {
   p.n_tiles = (long long)p.n_tiles_n * (d.RT / 256);
   p.t_own = d.Tloc; p.t_valid = d.t_valid;
   p.Et = s.Et; p.Xt = s.Xt; p.loss_partials = s.loss_partials; p.round_out = 1; p.err = s.d_err;
+  if (s.x3) {
+    p.x3 = 1; p.cbx = f.CB; p.CB = 3 * f.CB; p.lo_off = f.KW;
+    p.Elo = s.Elo; p.Xlo = s.Xlo;
+  }
   int grid = s.recon_grid;
-  if (s.recon2) {
+  if (s.recon2 && !s.x3) {
     p.n_tiles_n = (int)ceil_div_ll(d.Np, 256);
     p.n_tiles = (long long)p.n_tiles_n * (d.RT / 256);
     p.wrows = s.recon2_wrows;
@@ -463,7 +503,9 @@ inline int w_terms(TcState& s, cudaStream_t stream) {
   p.stages_total = ceil_div_ll(d.Tloc, 32);
   p.part = (s.n_chunks == 1) ? s.numden : s.wpart;
   p.per_src = s.wcount; p.err = s.d_err;
-  tc_wterms_kernel<<<s.wterms_grid, kWtThreads, wterms_smem_bytes(f.s), stream>>>(s.tmX_k2, s.tmE_k2, s.tmH_k2, p);
+  p.x3 = s.x3; p.lo_off = f.KW;
+  tc_wterms_kernel<<<s.wterms_grid, kWtThreads, wterms_smem_bytes(f.s), stream>>>(s.tmX_k2, s.tmE_k2, s.tmH_k2, s.tmXlo_k2,
+                                                                                  s.tmElo_k2, p);
   CMF_TRY(launch_ok("tc_wterms"));
   if (s.n_chunks > 1) {
     const long long n4 = p.n_src * s.wcount / 4;
@@ -565,7 +607,9 @@ inline int h_terms(TcState& s, cudaStream_t stream) {
   const long long time_tiles = d.TO / 256 + 1;
   p.n_time_tiles = p.pair_mode ? (time_tiles + 1) / 2 : time_tiles;
   p.n_tiles = p.n_time_tiles * s.h_split; p.ts = d.TO + 256; p.scratch = s.hscratch; p.err = s.d_err;
-  tc_hterms_kernel<<<s.hterms_grid, kHtThreads, hterms_smem_bytes(f.hterms_wrows), stream>>>(s.tmW_k3, s.tmX_k3, s.tmE_k3, p);
+  p.x3 = s.x3; p.lo_off = f.KW;
+  tc_hterms_kernel<<<s.hterms_grid, kHtThreads, hterms_smem_bytes(f.hterms_wrows), stream>>>(s.tmW_k3, s.tmX_k3, s.tmE_k3,
+                                                                                             s.tmXlo_k3, s.tmElo_k3, p);
   CMF_TRY(launch_ok("tc_hterms"));
   combine_groups_kernel<<<(unsigned)(d.TO / 128), 256, d.Kp * 129 * 4, stream>>>(s.hscratch, s.hterms, p.ts, d.TO, f.J,
                                                                               f.s, f.CB, d.Kp, p.pair_mode ? 1 : 2, s.h_split,

@@ -44,8 +44,13 @@ enum { CMF_F32 = 0, CMF_F64 = 1 };
 enum { CMF_HOST = 0, CMF_DEVICE = 1 };
 /* CMF_PREC_FP32: exact fp32 FFMA contractions.
  * CMF_PREC_TF32: tcgen05 tensor-core contractions, operands rounded (RN) to
- *                TF32, fp32 accumulation in tensor memory.                  */
-enum { CMF_PREC_FP32 = 0, CMF_PREC_TF32 = 1 };
+ *                TF32, fp32 accumulation in tensor memory.
+ * CMF_PREC_TF32X3: the same tensor-core kernels with every operand held as a
+ *                TF32 pair (hi = RN(x), lo = RN(x - hi)); each product is
+ *                a_lo b_hi + a_hi b_lo + a_hi b_hi (error-compensated "3xTF32":
+ *                ~22 mantissa bits per operand, fp32-grade results at a third
+ *                of the tf32 rate).  Direct denominators only.               */
+enum { CMF_PREC_FP32 = 0, CMF_PREC_TF32 = 1, CMF_PREC_TF32X3 = 2 };
 /* How the MU denominators (the est-dependent halves of mult.py:37-38, 46) are formed on the tf32 path.
  * CMF_DEN_DIRECT: contract est, as the reference does.
  * CMF_DEN_GRAM  : exact identity through the small Gram operators
