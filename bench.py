@@ -331,6 +331,7 @@ def run_b200(args):
         e2e = run_e2e(args, torch, N, T, K, L, Tloc, rank, world, local_rank, precision, dist)
 
     if rank != 0:
+        alg.close()
         if dist:
             dist.destroy_process_group()
         return
@@ -384,7 +385,11 @@ def run_b200(args):
                    (args.config, N, T, K, L, "" if args.t_scale == 1.0 else " (T reduced: debug)"),
                    "sharding": "time axis, %d x %d columns, halo %d" % (world, Tloc, L - 1),
                    "l2": "inputs_exceed_l2 (X and est are %.1f GiB each per GPU)" % (N * Tloc * 4 / 2**30),
-                   "precision": precision, "denominators": args.denominators, "path": alg.path_name},
+                   "precision": precision, "denominators": args.denominators, "path": alg.path_name,
+                   "collectives": ("none (1 GPU)" if world == 1 else
+                                   {"peer": "own kernels over NVLink peer memory (all-reduce fused with the W update, "
+                                            "halo pushes, loss ring)",
+                                    "nccl": "NCCL all-reduce + send/recv between the phases"}[alg.transport])},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cb,
         "final_loss": losses[-1],

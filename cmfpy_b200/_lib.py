@@ -16,6 +16,7 @@ CMF_HOST, CMF_DEVICE = 0, 1
 CMF_PREC_FP32, CMF_PREC_TF32, CMF_PREC_TF32X3 = 0, 1, 2
 PRECISIONS = {"fp32": CMF_PREC_FP32, "tf32": CMF_PREC_TF32, "tf32x3": CMF_PREC_TF32X3}
 CMF_DEN_DIRECT, CMF_DEN_GRAM, CMF_DEN_AUTO = 0, 1, 2
+CMF_PEER_BLOB_BYTES = 512
 DENOMINATORS = {"direct": CMF_DEN_DIRECT, "gram": CMF_DEN_GRAM, "auto": CMF_DEN_AUTO}
 
 
@@ -56,6 +57,10 @@ _SIGNATURES = {
     "cmf_mu_resid_sumsq_buffer": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "cmf_mu_loss": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "cmf_mu_step": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "cmf_mu_peer_export": (C.c_int, [_H, C.c_void_p]),
+    "cmf_mu_peer_attach": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
+    "cmf_mu_peer_detach": (C.c_int, [_H]),
+    "cmf_mu_step_sharded": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double)]),
     "cmf_mu_get_W": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
     "cmf_mu_get_H": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_longlong]),
     "cmf_mu_get_est": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_longlong]),

@@ -21,6 +21,7 @@
 #include "ew_kernels.cuh"
 #include "simt_gemm.cuh"
 #include "tc_path.cuh"
+#include "peer_kernels.cuh"
 
 namespace cmf {
 
@@ -82,7 +83,29 @@ struct cmf_mu_s {
   std::vector<cudaEvent_t> ev_pool;
 
   tc::TcState tcs;
+
+  // ---- peer-memory collectives of the sharded iteration (peer_kernels.cuh) ----
+  struct PeerState {
+    bool attached = false;
+    void* shared = nullptr;              // own allocation: Control | halo staging (2 x h x Kp) | ring
+    size_t shared_bytes = 0;
+    void* opened[peer::kMaxPeers][3] = {};   // IPC mappings of the peers' allocations (bases, for close)
+    peer::Peers P{};
+    uint32_t ex_epoch = 0, halo_epoch = 0, bar_epoch = 0;
+    int ring_cap = 1024;
+  } peer;
 };
+
+// what a rank publishes to its peers (cmf_mu_peer_export); plain bytes, CMF_PEER_BLOB_BYTES at most
+struct PeerBlob {
+  uint32_t magic;
+  int dev, h, Kp, ring_cap;
+  long long wcount;
+  cudaIpcMemHandle_t handle[3];          // allocations holding numden, W, the shared block
+  unsigned long long offset[3];          // of those pointers inside their allocations
+};
+static_assert(sizeof(PeerBlob) <= CMF_PEER_BLOB_BYTES, "peer blob too large");
+constexpr uint32_t kPeerMagic = 0x434d4650u;
 
 namespace {
 
@@ -398,7 +421,19 @@ int store_transposed(cmf_mu_s* h, const float* src, long long lds, long long row
   return rc;
 }
 
+int peer_detach(cmf_mu_s* h) {
+  auto& ps = h->peer;
+  if (ps.attached) cudaStreamSynchronize(h->stream);
+  for (int p = 0; p < peer::kMaxPeers; ++p)
+    for (int k = 0; k < 3; ++k)
+      if (ps.opened[p][k]) { cudaIpcCloseMemHandle(ps.opened[p][k]); ps.opened[p][k] = nullptr; }
+  ps.attached = false;
+  return 0;
+}
+
 void free_all(cmf_mu_s* h) {
+  peer_detach(h);
+  cudaFree(h->peer.shared);
   tc::destroy(h->tcs);
   cudaFree(h->Xt); cudaFree(h->Et); cudaFree(h->Ht); cudaFree(h->W); cudaFree(h->Xlo); cudaFree(h->Elo);
   cudaFree(h->numden); cudaFree(h->wpart); cudaFree(h->hterms);
@@ -1007,6 +1042,180 @@ int cmf_mu_kernel_ms(cmf_mu_t* h, float out[4]) {
 int cmf_mu_set_profiling(cmf_mu_t* h, int on) {
   CMF_CHECK(h != nullptr, "null solver handle");
   h->profiling = on ? 1 : 0;
+  return 0;
+}
+
+// ---- peer-memory collectives --------------------------------------------------
+namespace {
+typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+int allocation_base(const void* ptr, unsigned long long* offset) {
+  static GetAddressRangeFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* f = nullptr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) == cudaSuccess) fn = (GetAddressRangeFn)f;
+  }
+  CMF_CHECK(fn != nullptr, "cuMemGetAddressRange is not available from this driver");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  CMF_CHECK(fn(&base, &size, (CUdeviceptr)ptr) == CUDA_SUCCESS, "cuMemGetAddressRange failed");
+  *offset = (unsigned long long)((CUdeviceptr)ptr - base);
+  return 0;
+}
+size_t peer_halo_bytes(const cmf_mu_s* h) { return (size_t)round_up_ll(2ll * h->h * h->Kp * 4 + 16, 256); }
+}  // namespace
+
+int cmf_mu_peer_export(cmf_mu_t* h, void* blob) {
+  CMF_ENTER(h);
+  CMF_CHECK(blob != nullptr, "null argument");
+  auto& ps = h->peer;
+  if (!ps.shared) {
+    ps.shared_bytes = 256 + peer_halo_bytes(h) + (size_t)ps.ring_cap * peer::kMaxPeers * 8;
+    CMF_CUDA(cudaMalloc(&ps.shared, ps.shared_bytes));
+    CMF_CUDA(cudaMemset(ps.shared, 0, ps.shared_bytes));
+  }
+  static_assert(sizeof(peer::Control) <= 256, "control block larger than its slot");
+  PeerBlob b{};
+  b.magic = kPeerMagic; b.dev = h->dev; b.h = h->h; b.Kp = h->Kp; b.ring_cap = ps.ring_cap; b.wcount = h->wcount;
+  const void* ptrs[3] = {h->numden, h->W, ps.shared};
+  for (int k = 0; k < 3; ++k) {
+    CMF_CUDA(cudaIpcGetMemHandle(&b.handle[k], const_cast<void*>(ptrs[k])));
+    CMF_TRY(allocation_base(ptrs[k], &b.offset[k]));
+  }
+  memset(blob, 0, CMF_PEER_BLOB_BYTES);
+  memcpy(blob, &b, sizeof(b));
+  return 0;
+}
+
+int cmf_mu_peer_attach(cmf_mu_t* h, int rank, int world, const void* blobs) {
+  CMF_ENTER(h);
+  CMF_CHECK(blobs != nullptr, "null argument");
+  CMF_CHECK(world >= 1 && world <= peer::kMaxPeers && rank >= 0 && rank < world, "rank %d / world %d out of range (at most %d peers)",
+            rank, world, peer::kMaxPeers);
+  auto& ps = h->peer;
+  CMF_CHECK(ps.shared != nullptr, "cmf_mu_peer_export must be called first");
+  CMF_CHECK(!ps.attached, "peers already attached");
+  CMF_CHECK(h->wcount % 4 == 0, "W element count must be a multiple of 4");
+  peer::Peers P{};
+  P.rank = rank; P.world = world;
+  for (int p = 0; p < world; ++p) {
+    PeerBlob b;
+    memcpy(&b, (const char*)blobs + (size_t)p * CMF_PEER_BLOB_BYTES, sizeof(b));
+    CMF_CHECK(b.magic == kPeerMagic, "peer %d: not a cmf peer blob", p);
+    CMF_CHECK(b.h == h->h && b.Kp == h->Kp && b.wcount == h->wcount && b.ring_cap == ps.ring_cap,
+              "peer %d was created with different dimensions", p);
+    char* base[3];
+    if (p == rank) {
+      base[0] = (char*)h->numden; base[1] = (char*)h->W; base[2] = (char*)ps.shared;
+    } else {
+      for (int k = 0; k < 3; ++k) {
+        void* m = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&m, b.handle[k], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+          set_error("cudaIpcOpenMemHandle failed for peer %d (device %d): %s", p, b.dev, cudaGetErrorString(e));
+          cudaGetLastError();
+          peer_detach(h);
+          return 1;
+        }
+        ps.opened[p][k] = m;
+        base[k] = (char*)m + b.offset[k];
+      }
+    }
+    P.numden[p] = (float*)base[0];
+    P.W[p] = (float*)base[1];
+    P.ctl[p] = (peer::Control*)base[2];
+    P.halo_in[p] = (float*)(base[2] + 256);
+    P.ring[p] = (double*)(base[2] + 256 + peer_halo_bytes(h));
+  }
+  ps.P = P;
+  ps.attached = true;
+  return 0;
+}
+
+int cmf_mu_peer_detach(cmf_mu_t* h) {
+  CMF_ENTER(h);
+  return peer_detach(h);
+}
+
+// n_steps x MultUpdate.update() on a time shard, collectives over peer memory; every rank calls it
+// with the same n_steps.  loss_out[i] = GLOBAL loss after step i (identical on all ranks).
+int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out) {
+  CMF_ENTER(h);
+  CMF_CHECK(n_steps >= 0, "n_steps must be >= 0");
+  CMF_CHECK(h->have_data && h->have_factors, "step before data/factors were set");
+  auto& ps = h->peer;
+  CMF_CHECK(ps.attached, "cmf_mu_step_sharded needs cmf_mu_peer_attach");
+  if (n_steps == 0) return 0;
+  if (!h->est_valid) CMF_TRY(do_recon(h));
+  for (int k = 0; k < 4; ++k) h->kernel_ms[k] = 0.f;
+  const bool prof = h->profiling != 0;
+  const long long n4 = h->wcount / 4;
+  const int G = ps.P.world;
+  long long slice = ceil_div_ll(n4, G);
+  int ex_grid = (int)ceil_div_ll(slice, 256);
+  if (ex_grid > h->num_sms) ex_grid = h->num_sms;       // every block spins: all must be resident
+  if (ex_grid < 1) ex_grid = 1;
+  std::vector<double> ring((size_t)ps.ring_cap * peer::kMaxPeers);
+  int done = 0;
+  while (done < n_steps) {
+    const int chunk = (n_steps - done < ps.ring_cap) ? n_steps - done : ps.ring_cap;
+    size_t ne = 0;
+    for (int i = 0; i < chunk; ++i) {
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      CMF_TRY(do_w_terms(h));
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      // reduce-scatter of the partial W terms + W update + all-gather of W: one kernel
+      CMF_CHECK(h->wterms_valid, "w exchange before w_terms");
+      peer::wstep_exchange_kernel<<<ex_grid, 256, 0, h->stream>>>(ps.P, n4, ++ps.ex_epoch);
+      CMF_TRY(launch_check(h, "wstep_exchange"));
+      h->wterms_valid = false;
+      h->est_valid = false;
+      CMF_TRY(sync_ops_W(h));
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      if (!gram_h(h)) CMF_TRY(do_recon(h));
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      CMF_TRY(do_h_terms(h));
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      CMF_TRY(do_h_apply(h));
+      if (h->h > 0) {
+        peer::halo_exchange_kernel<<<2, 256, 0, h->stream>>>(ps.P, h->Ht, h->h, h->Kp, h->Tloc, ++ps.halo_epoch);
+        CMF_TRY(launch_check(h, "halo_exchange"));
+        CMF_TRY(sync_ops_H(h, 0, h->h));
+        CMF_TRY(sync_ops_H(h, h->h + h->Tloc, h->h));
+      }
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      CMF_TRY(do_recon(h, !(gram_w(h) && gram_h(h))));
+      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+      peer::sumsq_push_kernel<<<1, 32, 0, h->stream>>>(ps.P, h->d_sumsq, i);
+      CMF_TRY(launch_check(h, "sumsq_push"));
+    }
+    peer::barrier_kernel<<<1, 32, 0, h->stream>>>(ps.P, ++ps.bar_epoch);
+    CMF_TRY(launch_check(h, "peer_barrier"));
+    CMF_CUDA(cudaMemcpyAsync(ring.data(), ps.P.ring[ps.P.rank], (size_t)chunk * peer::kMaxPeers * 8, cudaMemcpyDeviceToHost,
+                             h->stream));
+    int perr = 0;
+    CMF_CUDA(cudaMemcpyAsync(&perr, &ps.P.ctl[ps.P.rank]->err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CMF_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->use_tc) CMF_TRY(tc::check(h->tcs, h->stream));
+    CMF_CHECK(perr == 0, "peer exchange timed out (error %d): a rank did not reach the collective", perr);
+    for (int i = 0; i < chunk; ++i) {
+      double ssum = 0.0;
+      for (int p = 0; p < G; ++p) ssum += ring[(size_t)i * peer::kMaxPeers + p];
+      if (loss_out) loss_out[done + i] = std::sqrt(ssum) / h->norm_x;
+    }
+    if (prof) {
+      for (int i = 0; i < chunk; ++i) {
+        const size_t e0 = (size_t)i * 7;
+        float t[6];
+        for (int k = 0; k < 6; ++k) CMF_CUDA(cudaEventElapsedTime(&t[k], h->ev_pool[e0 + k], h->ev_pool[e0 + k + 1]));
+        h->kernel_ms[1] += t[0];            // w_terms
+        h->kernel_ms[3] += t[1] + t[4];     // exchange + updates, halo exchange
+        h->kernel_ms[0] += t[2] + t[5];     // reconstructions (+ loss)
+        h->kernel_ms[2] += t[3];            // h_terms
+      }
+    }
+    done += chunk;
+  }
   return 0;
 }
 

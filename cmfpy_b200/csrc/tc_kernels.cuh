@@ -120,6 +120,9 @@ __host__ __device__ inline size_t recon_smem_bytes(int wrows) {
   return 1024 + (size_t)kReconStages * kReconStageBytes + 2 * (size_t)wrows * kKp * 4 + 256;
 }
 
+// kX3 = 1: the 3xTF32 instantiation (operand-half selection in the producer, hi/lo epilogue); kX3 = 0 compiles
+// to exactly the plain TF32 kernel.
+template <int kX3>
 __global__ void __launch_bounds__(kReconThreads, 1)
 tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
                 const ReconParams p) {
@@ -177,7 +180,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const long long tt = c.tile / p.n_tiles_n;
         mbar_arrive_expect_tx(&hfull[hb], hbytes);
         uint8_t* hdst = Hs + (size_t)hb * hbytes;
-        const X3Sel sel = x3_select(p.x3, p.cbx, p.lo_off, c.cb);
+        const X3Sel sel = x3_select(kX3, p.cbx, p.lo_off, c.cb);
         for (int rb = 0; rb < wrows / 64; ++rb)
           tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], sel.cbr * 32 + sel.b_off,
                       (int)(tt * 256 + p.h_shift + rb * 64));
@@ -190,7 +193,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const Chunk nxt = next_chunk(cur);
         bool prefetched = !nxt.valid;
         const int nt = (int)(cur.tile % p.n_tiles_n);
-        const X3Sel sel = x3_select(p.x3, p.cbx, p.lo_off, cur.cb);
+        const X3Sel sel = x3_select(kX3, p.cbx, p.lo_off, cur.cb);
         int stage_in_chunk = 0;
         for (int l = 0; l < L; l += kReconLagsPerStage, ++stage_in_chunk) {
           if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
@@ -281,7 +284,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (n_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = (tau0 + j < p.t_own) ? __ldcs(Xt + off0 + (size_t)j * np) : 0.f;
-          if (Xlo) {
+          if (kX3) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] += (tau0 + j < p.t_own) ? __ldcs(Xlo + off0 + (size_t)j * np) : 0.f;
           }
@@ -312,7 +315,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               tile_loss = fmaf(d, d, tile_loss);
             }
             if (!p.skip_store) {
-              if (Elo) {
+              if (kX3) {
                 const float hi = round_tf32(v);
                 Et[off0 + (size_t)j * np] = hi;
                 Elo[off0 + (size_t)j * np] = round_tf32(v - hi);
@@ -931,21 +934,28 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       const int split = (int)(item % p.n_split);
       if (!ab.wait(tfull, it & 1)) break;
       tc_fence_after();
+      // The accumulators are single-buffered (both are in use), so the MMAs of the next item wait for this
+      // drain: four tensor-memory loads are kept in flight per wait instead of one (the drain is latency-bound).
 #pragma unroll 1
-      for (int c = 0; c < 8 * p.n_src; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      for (int c0 = 0; c0 < 8 * p.n_src; c0 += 4) {
+        uint32_t r[4][32];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((c0 + u) * 32), r[u]);
         tmem_ld_wait();
-        const int src = c >> 3;
+        const int src = c0 >> 3;
         const int slot = p.pair_mode ? 0 : src;                       // pair mode: both halves are numerators
         const long long ttile = p.pair_mode ? 2 * tile + src : tile;
         if ((ttile + 1) * 256 > p.ts) continue;                       // odd tile count: the pair's second half does not exist
-        float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)((split * p.n_slots + slot) * 4 + q) * kKp + lane) * p.ts +
-                                              ttile * 256 + (c & 7) * 32);
+        float* orow = p.scratch + ((size_t)((split * p.n_slots + slot) * 4 + q) * kKp + lane) * p.ts + ttile * 256;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        for (int u = 0; u < 4; ++u) {
+          float4* o = reinterpret_cast<float4*>(orow + ((c0 + u) & 7) * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(r[u][4 * j]), __uint_as_float(r[u][4 * j + 1]),
+                               __uint_as_float(r[u][4 * j + 2]), __uint_as_float(r[u][4 * j + 3]));
+        }
       }
       tc_fence_before();
       __syncwarp();

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "ew_kernels.cuh"
@@ -240,7 +241,9 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   }
   CMF_TRY(make_map(&s.tmW_k1, s.Wv, (long long)f.Lv * d.Np, s.KWs, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
   CMF_TRY(make_map(&s.tmH_k1, s.Hv, d.RH, s.KWs, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
-  CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)recon_smem_bytes(f.recon_wrows)));
+  CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)recon_smem_bytes(f.recon_wrows)));
 
   s.recon2 = 0;
@@ -259,15 +262,24 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     long long cmax = stages_total / 4; if (cmax < 1) cmax = 1;
     const long long cmem = (2ll << 30) / (2 * s.wcount * 4); if (cmem < cmax) cmax = cmem < 1 ? 1 : cmem;
     if (cmax > 256) cmax = 256;
-    // number of time chunks: fill every SM with equal work (whole waves)
-    double best = -1.0; int bestc = 1;
+    // Number of time chunks, from a cost model of the pass (microseconds): whole waves of equally long items
+    // (a stage = 8 MMAs of 128 cycles, three passes with 3xTF32), a tensor-memory drain per item, and the
+    // write + re-read of one partial [src][L][Np][Kp] per chunk by sum_splits_kernel.  Long shards end up with
+    // the chunk count that fills the machine in whole waves (37 at config C on one GPU); short shards (T split
+    // over 8 GPUs) take fewer, larger chunks because the partial traffic no longer amortises.  Among counts
+    // within 1 % of the best the largest wins: shorter accumulation chains in tensor memory.
+    const double t_stage = 0.6 * (s.x3 ? 3.0 : 1.0), t_drain = 4.0;
+    const double t_partial = 2.0 * 2.0 * (double)s.wcount * 4.0 / 5.0e6;     // both sources; 5 TB/s
+    double best = 1e300;
+    std::vector<double> cost((size_t)cmax + 1, 1e300);
     for (long long c = 1; c <= cmax; ++c) {
-      const long long items = units * c;
-      const long long waves = ceil_div_ll(items, d.num_sms);
-      double eff = (double)items / (double)(waves * d.num_sms);
-      if (items >= 2ll * d.num_sms) eff += 1e-3;         // prefer at least two items per SM
-      if (eff > best + 1e-9) { best = eff; bestc = (int)c; }
+      const long long waves = ceil_div_ll(units * c, d.num_sms);
+      cost[c] = (double)waves * ((double)ceil_div_ll(stages_total, c) * t_stage + t_drain) + (c > 1 ? c * t_partial : 0.0);
+      if (cost[c] < best) best = cost[c];
     }
+    int bestc = 1;
+    for (long long c = 1; c <= cmax; ++c)
+      if (cost[c] <= 1.01 * best) bestc = (int)c;
     s.n_chunks = bestc;
     if (const char* e = getenv("CMF_WCHUNKS")) { long long c = atoll(e); s.n_chunks = (int)(c < 1 ? 1 : (c > cmax ? cmax : c)); }
     const long long items = units * s.n_chunks;
@@ -316,7 +328,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     CMF_TRY(make_map(&s.tmRw_a, s.Rwv, (long long)s.Lrv * d.Kp, f.KW, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
     const size_t need = recon_smem_bytes(s.dh_wrows) > recon_smem_bytes(f.recon_wrows) ? recon_smem_bytes(s.dh_wrows)
                                                                                         : recon_smem_bytes(f.recon_wrows);
-    CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   }
   // H terms: split the feature chunks of a tile so that the tensor-memory accumulation chain of the
   // numerator is about as long as the one of the Gram denominator (equal truncation bias => no drift of
@@ -362,7 +374,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     // H^T itself as the "data" operand: the first Kp columns of Hv are the unfolded, rounded H^T
     CMF_TRY(make_map(&s.tmHx_k2, s.Hv + (long long)d.h * f.KW, d.Tloc, d.Kp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, f.KW));
     CMF_TRY(make_map(&s.tmMt_b, s.Mt, s.g_rows, (long long)f.Lv * f.KW, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
-    CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(recon_smem_bytes(s.dh_wrows) <= kMaxSmem && recon_smem_bytes(s.dh_wrows) > recon_smem_bytes(f.recon_wrows)
                                             ? recon_smem_bytes(s.dh_wrows) : recon_smem_bytes(f.recon_wrows))));
   }
@@ -402,7 +414,7 @@ inline int tail_est(TcState& s, cudaStream_t stream) {
   p.n_tiles = p.n_tiles_n;
   p.t_own = 0; p.t_valid = 256;
   p.Et = s.Etail; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
-  tc_recon_kernel<<<p.n_tiles_n, kReconThreads, recon_smem_bytes(f.recon_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
+  tc_recon_kernel<0><<<p.n_tiles_n, kReconThreads, recon_smem_bytes(f.recon_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
   return launch_ok("tail_est");
 }
 
@@ -443,7 +455,7 @@ inline int den_w_gram(TcState& s, cudaStream_t stream) {
     p.t_own = 0; p.t_valid = s.LK;
     p.Et = den; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
     const int grid = (int)(p.n_tiles < d.num_sms ? p.n_tiles : d.num_sms);
-    tc_recon_kernel<<<grid, kReconThreads, recon_smem_bytes(256), stream>>>(s.tmW_k1, s.tmMt_b, p);
+    tc_recon_kernel<0><<<grid, kReconThreads, recon_smem_bytes(256), stream>>>(s.tmW_k1, s.tmMt_b, p);
     CMF_TRY(launch_ok("gram_den_w"));
   }
   // (d) remove the terms of est that lie past the end of the data
@@ -484,7 +496,8 @@ inline int recon(TcState& s, cudaStream_t stream, bool store_est = true) {
     grid = (int)g2;
     tc_recon2_kernel<<<grid, kReconThreads, recon2_smem_bytes(s.recon2_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
   } else {
-    tc_recon_kernel<<<grid, kReconThreads, recon_smem_bytes(f.recon_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
+    if (s.x3) tc_recon_kernel<1><<<grid, kReconThreads, recon_smem_bytes(f.recon_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
+    else tc_recon_kernel<0><<<grid, kReconThreads, recon_smem_bytes(f.recon_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
   }
   CMF_TRY(launch_ok("tc_recon"));
   ew::sum_doubles_kernel<<<1, 1024, 0, stream>>>(s.loss_partials, grid, s.d_sumsq);
@@ -536,7 +549,7 @@ inline int den_h_gram(TcState& s, cudaStream_t stream) {
     p.t_own = 0; p.t_valid = s.g_rows;
     p.Et = s.G; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
     const int grid = (int)(p.n_tiles < d.num_sms ? p.n_tiles : d.num_sms);
-    tc_recon_kernel<<<grid, kReconThreads, recon_smem_bytes(256), stream>>>(s.tmWt_a, s.tmWt_b, p);
+    tc_recon_kernel<0><<<grid, kReconThreads, recon_smem_bytes(256), stream>>>(s.tmWt_a, s.tmWt_b, p);
     CMF_TRY(launch_ok("gram_G"));
   }
   // (c) R = lag-diagonal sums of G, as a W-like operand (rounded / folded like W)
@@ -560,7 +573,7 @@ inline int den_h_gram(TcState& s, cudaStream_t stream) {
     p.t_own = 0; p.t_valid = d.TO;
     p.Et = den; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
     const int grid = (int)(p.n_tiles < d.num_sms ? p.n_tiles : d.num_sms);
-    tc_recon_kernel<<<grid, kReconThreads, recon_smem_bytes(s.dh_wrows), stream>>>(s.tmRw_a, s.tmH_k1, p);
+    tc_recon_kernel<0><<<grid, kReconThreads, recon_smem_bytes(s.dh_wrows), stream>>>(s.tmRw_a, s.tmH_k1, p);
     CMF_TRY(launch_ok("gram_den_h"));
   }
   // (e) remove the terms of est that lie past the end of the data (only the shard that sees the end)

@@ -148,6 +148,25 @@ class DeviceShard:
         _lib.check(self._lib.cmf_mu_step(self._h, n, losses.ctypes.data_as(C.POINTER(C.c_double)), None))
         return [float(x) for x in losses]
 
+    # -- collectives over peer memory (CUDA IPC, NVLink P2P) -----------------------
+    def peer_export(self):
+        blob = (C.c_ubyte * _lib.CMF_PEER_BLOB_BYTES)()
+        _lib.check(self._lib.cmf_mu_peer_export(self._h, blob))
+        return bytes(blob)
+
+    def peer_attach(self, rank, world, blobs):
+        buf = b"".join(blobs)
+        assert len(buf) == world * _lib.CMF_PEER_BLOB_BYTES
+        _lib.check(self._lib.cmf_mu_peer_attach(self._h, rank, world, buf))
+
+    def peer_detach(self):
+        _lib.check(self._lib.cmf_mu_peer_detach(self._h))
+
+    def step_sharded(self, n):
+        losses = np.empty(n, dtype=np.float64)
+        _lib.check(self._lib.cmf_mu_step_sharded(self._h, n, losses.ctypes.data_as(C.POINTER(C.c_double))))
+        return [float(x) for x in losses]
+
     # -- read-back --------------------------------------------------------------
     def get_W(self):
         out = np.empty((self.L, self.N, self.K), dtype=np.float32)
@@ -193,7 +212,7 @@ class ShardedMultUpdate:
 
     def __init__(self, X_local, N, T, K, L, t_offset, t_local, initW, initH,
                  precision="fp32", device=0, group=None, tol=1e-5, patience=3,
-                 engine=None, denominators="auto"):
+                 engine=None, denominators="auto", transport="auto"):
         import torch
         import torch.distributed as dist
         self._torch, self._dist = torch, dist
@@ -231,6 +250,42 @@ class ShardedMultUpdate:
             self._exchange_halos()
         eng.recon()
         self._loss = None
+        # Collectives: "peer" = the library's own kernels over NVLink peer memory (the W-term all-reduce
+        # fused with the W update, halo pushes, a loss ring; no host-side collective per iteration);
+        # "nccl" = torch.distributed collectives between the phases.  "auto" takes the peer path when
+        # the engine offers it and every rank could map its peers (CMF_TRANSPORT overrides).
+        import os
+        transport = os.environ.get("CMF_TRANSPORT", transport)
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError("transport must be auto, peer or nccl")
+        self.transport = "nccl"
+        if self.world > 1 and transport != "nccl" and hasattr(eng, "peer_export") and self.world <= 8:
+            self._attach_peers(required=(transport == "peer"))
+
+    def _attach_peers(self, required):
+        dist, eng = self._dist, self.engine
+        err = None
+        try:
+            blob = eng.peer_export()
+        except Exception as e:           # noqa: BLE001 - reported to all ranks below
+            blob, err = b"", e
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, blob, group=self.group)
+        ok = all(len(b) == _lib.CMF_PEER_BLOB_BYTES for b in blobs)
+        if ok:
+            try:
+                eng.peer_attach(self.rank, self.world, blobs)
+            except Exception as e:       # noqa: BLE001
+                ok, err = False, e
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=self.group)      # also the barrier between attach and first use
+        if all(flags):
+            self.transport = "peer"
+            return
+        if ok:
+            eng.peer_detach()
+        if required:
+            raise RuntimeError("peer-memory transport unavailable on some rank: %s" % (err,))
 
     # -- collectives ----------------------------------------------------------
     def _stream_ctx(self):
@@ -287,6 +342,10 @@ class ShardedMultUpdate:
             return []
         if self.world == 1:
             losses = eng.step_fused(n)
+            self._loss = losses[-1]
+            return losses
+        if self.transport == "peer":
+            losses = eng.step_sharded(n)
             self._loss = losses[-1]
             return losses
         torch = self._torch
@@ -378,9 +437,15 @@ class ShardedMultUpdate:
 
     def kernel_ms(self):
         """Device time per phase during the last update_many (CUDA events)."""
-        if self.world == 1:
+        if self.world == 1 or self.transport == "peer":
             return self.engine.kernel_ms()
         return dict(self.profiled_ms)
 
     def close(self):
+        if self.transport == "peer":
+            # Safe without a host barrier: when cmf_mu_step_sharded has returned here, every peer has
+            # already issued its last store into this rank's memory (the end-of-call barrier kernel is
+            # each rank's final peer access, and this rank saw all of them).
+            self.engine.peer_detach()
+            self.transport = "nccl"
         self.engine.close()

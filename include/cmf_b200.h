@@ -164,6 +164,25 @@ int cmf_mu_needs_mid_recon(cmf_mu_t* h, int* needed);
  * (CUDA events; may be NULL).  One host sync at the end.                     */
 int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out);
 
+/* ---- the sharded iteration with its collectives over peer memory --------- */
+/* One process per GPU.  Each rank publishes CMF_PEER_BLOB_BYTES (CUDA IPC
+ * handles of its W-term buffer, W and a small control block); the host layer
+ * all-gathers the blobs (any transport) and hands the world's blobs to
+ * cmf_mu_peer_attach, which maps the peers' buffers (NVLink / NVSwitch P2P).
+ * cmf_mu_step_sharded then runs n_steps x MultUpdate.update() (mult.py:15-25)
+ * with NO host-side collective: the all-reduce of the W terms is fused with the
+ * W update in one kernel (reduce-scatter -> update -> all-gather over peer
+ * loads/stores), the L-1 halo columns of H are pushed into the neighbours, and
+ * the residual sums travel through a ring in every rank's memory.  Every rank
+ * must call it with the same n_steps; loss_out[i] is the GLOBAL loss after
+ * step i, identical on all ranks.  A host barrier is required between attach
+ * and the first step, and before detach / destroy.                            */
+#define CMF_PEER_BLOB_BYTES 512
+int cmf_mu_peer_export(cmf_mu_t* h, void* blob);
+int cmf_mu_peer_attach(cmf_mu_t* h, int rank, int world, const void* blobs);
+int cmf_mu_peer_detach(cmf_mu_t* h);
+int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out);
+
 /* ---- read-back: algorithm.W / algorithm.H (model.py:175-176) ------------ */
 int cmf_mu_get_W(cmf_mu_t* h, void* W_out, int dtype, int mem);
 int cmf_mu_get_H(cmf_mu_t* h, void* H_out, int dtype, int mem, long long ldh);

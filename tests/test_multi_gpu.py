@@ -22,7 +22,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, shape, precision, n_iter, q):
+def _worker(rank, world, port, shape, precision, n_iter, q, transport="auto"):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -40,8 +40,9 @@ def _worker(rank, world, port, shape, precision, n_iter, q):
         prec, den = ("tf32", "gram") if precision == "tf32g" else (precision, "direct")
         alg = ShardedMultUpdate(np.ascontiguousarray(X[:, t0:t0 + ncols]), N, T, K, L, t_offset=t0, t_local=Tl,
                                 initW=W0, initH=np.ascontiguousarray(H0[:, t0:t0 + Tl]), precision=prec,
-                                device=rank, group=dist.group.WORLD, tol=0, denominators=den)
-        hist = [alg.loss] + alg.update_many(n_iter)
+                                device=rank, group=dist.group.WORLD, tol=0, denominators=den, transport=transport)
+        assert alg.transport == transport
+        hist = [alg.loss] + alg.update_many(n_iter // 2) + alg.update_many(n_iter - n_iter // 2)
         H, W = alg.H_local_host(), alg.W_host()
         out = [None] * world
         dist.all_gather_object(out, (H, W, hist))
@@ -52,11 +53,15 @@ def _worker(rank, world, port, shape, precision, n_iter, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("precision,shape", [("fp32", (96, 2048, 5, 12)), ("fp32", (64, 1024, 32, 33)),
                                              ("tf32", (200, 4096, 32, 64)), ("tf32", (128, 2048, 30, 9)),
                                              ("tf32g", (200, 4096, 32, 64)), ("tf32g", (96, 2048, 5, 12)),
-                                             ("tf32g", (256, 2048, 128, 16))])
-def test_sharded_equals_single_gpu(built_lib, precision, shape):
+                                             ("tf32g", (256, 2048, 128, 16)), ("tf32x3", (200, 4096, 32, 64)),
+                                             ("fp32", (40, 600, 3, 1))])
+def test_sharded_equals_single_gpu(built_lib, precision, shape, transport):
+    """transport "peer": the library's own collectives over NVLink peer memory (fused all-reduce + W update,
+    halo pushes, loss ring); "nccl": torch.distributed collectives between the phases."""
     world = min(_ngpu(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -69,7 +74,8 @@ def test_sharded_equals_single_gpu(built_lib, precision, shape):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, precision, n_iter, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, precision, n_iter, q, transport))
+             for r in range(world)]
     for p in procs:
         p.start()
     out = q.get(timeout=300)
@@ -81,7 +87,7 @@ def test_sharded_equals_single_gpu(built_lib, precision, shape):
     ref = MultUpdate(X, ModelDimensions(X, maxlag=L, n_components=K), initW=W0, initH=H0, tol=0, precision=prec,
                      denominators=den)
     ref_hist = [ref.loss] + ref.update_many(n_iter)
-    tol = 2e-5 if precision == "fp32" else 2e-4
+    tol = 2e-5 if precision in ("fp32", "tf32x3") else 2e-4
     H = np.concatenate([o[0] for o in out], axis=1)
     for o in out:
         assert np.abs(np.array(o[2]) - ref_hist).max() / ref_hist[-1] < tol
