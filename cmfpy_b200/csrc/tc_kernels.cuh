@@ -934,23 +934,223 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       const int split = (int)(item % p.n_split);
       if (!ab.wait(tfull, it & 1)) break;
       tc_fence_after();
-      // The accumulators are single-buffered (both are in use), so the MMAs of the next item wait for this
-      // drain: four tensor-memory loads are kept in flight per wait instead of one (the drain is latency-bound).
 #pragma unroll 1
-      for (int c0 = 0; c0 < 8 * p.n_src; c0 += 4) {
-        uint32_t r[4][32];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((c0 + u) * 32), r[u]);
+      for (int c = 0; c < 8 * p.n_src; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
         tmem_ld_wait();
-        const int src = c0 >> 3;
+        const int src = c >> 3;
         const int slot = p.pair_mode ? 0 : src;                       // pair mode: both halves are numerators
         const long long ttile = p.pair_mode ? 2 * tile + src : tile;
         if ((ttile + 1) * 256 > p.ts) continue;                       // odd tile count: the pair's second half does not exist
-        float* orow = p.scratch + ((size_t)((split * p.n_slots + slot) * 4 + q) * kKp + lane) * p.ts + ttile * 256;
+        float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)((split * p.n_slots + slot) * 4 + q) * kKp + lane) * p.ts +
+                                              ttile * 256 + (c & 7) * 32);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float4* o = reinterpret_cast<float4*>(orow + ((c0 + u) & 7) * 32);
+        for (int j = 0; j < 8; ++j)
+          o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// --------------------------------------------------------------------------
+// K3, ping-pong form.  One source per work item and the two 256-column accumulators ALTERNATE between
+// consecutive items, so the drain of item i (tensor memory -> scratch) overlaps the MMAs of item i+1; a stage
+// holds two lags (8 MMAs per barrier round trip, as in K1).  Needs half the window memory of the paired form
+// (wider lag ranges fit) but streams every W stage for one source only: measured 4 % (tf32 + Gram) to 30 %
+// (tf32x3, two sources) SLOWER than the paired form at config C, so it is used only where the paired form does
+// not fit shared memory (CMF_HTERMS_PP=1 forces it).
+//   item -> (time tile, source, split):  source 0 = X, 1 = est;  scratch slot = source.
+// --------------------------------------------------------------------------
+constexpr int kHpLagsPerStage = 2;
+constexpr int kHpStages = 3;
+constexpr int kHpStageBytes = kHpLagsPerStage * kHtABytes;
+
+__host__ __device__ inline size_t hterms_pp_smem_bytes(int wrows) {
+  return 1024 + (size_t)kHpStages * kHpStageBytes + 2 * (size_t)wrows * 128 + 256;
+}
+
+__global__ void __launch_bounds__(kHtThreads, 1)
+tc_hterms_pp_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                    const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmXlo,
+                    const __grid_constant__ CUtensorMap tmElo, const HTermsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* As = smem;                                             // [stages][2 lags x 16 KB]
+  const uint32_t wbytes = (uint32_t)p.wrows * 128;                // one 32-feature chunk of the window
+  uint8_t* Ws = As + kHpStages * kHpStageBytes;                   // [2 buffers][wbytes]
+  uint64_t* bars = (uint64_t*)(Ws + 2 * (size_t)wbytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kHpStages;
+  uint64_t* wfull = bars + 2 * kHpStages;                         // [2]
+  uint64_t* wempty = wfull + 2;                                   // [2]
+  uint64_t* tfull = wempty + 2;                                   // [2]
+  uint64_t* tempty = tfull + 2;                                   // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kHpStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1);
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4);
+    }
+    *abort_flag = 0;
+    fence_mbar_init();
+    prefetch_tmap(&tmW); prefetch_tmap(&tmX); prefetch_tmap(&tmE); prefetch_tmap(&tmXlo); prefetch_tmap(&tmElo);
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const Abort ab{abort_flag, p.err};
+  const int J = p.J, wrows = p.wrows;
+  const int n_pass = p.x3 ? 3 : 1;
+
+  // item -> (tile, src, split)
+  auto decode = [&](long long item, long long& tile, int& src, int& split) {
+    split = (int)(item % p.n_split); item /= p.n_split;
+    src = (int)(item % p.n_src);
+    tile = item / p.n_src;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps;
+      bool ok = true;
+      // chunks = (item, operand pass, 32-feature chunk) in execution order; chunk c uses window buffer c & 1 and
+      // its window is requested while the W stages of chunk c-1 stream
+      struct Chunk { long long item, tile; int src, nc, nc0, nc1, combo; bool valid; };
+      auto make_chunk = [&](long long item) {
+        Chunk c{item, 0, 0, 0, 0, 0, p.x3 ? 0 : 2, item < p.n_tiles};
+        if (c.valid) {
+          int split;
+          decode(item, c.tile, c.src, split);
+          c.nc0 = c.nc = split * p.nc_per_split;
+          c.nc1 = min(c.nc + p.nc_per_split, p.n_chunks_n);
+        }
+        return c;
+      };
+      auto next_chunk = [&](Chunk c) {
+        if (++c.nc >= c.nc1) {
+          if (c.combo < 2) { ++c.combo; c.nc = c.nc0; }
+          else c = make_chunk(c.item + gridDim.x);
+        }
+        return c;
+      };
+      auto issue_window = [&](const Chunk& c, long long wc) -> bool {
+        const int wb = (int)(wc & 1);
+        if (!ab.wait(&wempty[wb], (uint32_t)((wc >> 1) & 1) ^ 1)) return false;
+        mbar_arrive_expect_tx(&wfull[wb], wbytes);
+        uint8_t* wdst = Ws + (size_t)wb * wbytes;
+        const CUtensorMap* tmS = c.src ? (c.combo == 1 ? &tmElo : &tmE) : (c.combo == 1 ? &tmXlo : &tmX);
+        const int base = (int)(c.tile * 256);
+        for (int rb = 0; rb < wrows / 32; ++rb)
+          tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], c.nc * 32, base + rb * 32);
+        return true;
+      };
+      Chunk cur = make_chunk(blockIdx.x);
+      long long wc = 0;
+      if (cur.valid) ok = issue_window(cur, 0);
+      while (cur.valid && ok) {
+        const Chunk nxt = next_chunk(cur);
+        bool prefetched = !nxt.valid;
+        int stage_in_chunk = 0;
+        for (int j = 0; j < J; j += kHpLagsPerStage, ++stage_in_chunk) {
+          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+          const int nl = min(kHpLagsPerStage, J - j);
+          mbar_arrive_expect_tx(&full[ps.stage], nl * kHtABytes);
+          for (int u = 0; u < nl; ++u) {
+            uint8_t* dst = As + (size_t)ps.stage * kHpStageBytes + u * kHtABytes;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)      // region g = (lag group g / CB, column block g % CB)
+              tma_load_2d(dst + g * 4096, &tmW, &full[ps.stage], (g % p.CB) * 32 + (cur.combo == 0 ? p.lo_off : 0),
+                          (j + u + J * (g / p.CB)) * p.Np + cur.nc * 32);
+          }
+          ps.advance(kHpStages);
+          if (!prefetched && stage_in_chunk >= 1) {      // the MMAs are about to enter `cur`: the other window buffer
+            if (!issue_window(nxt, wc + 1)) { ok = false; break; }   // frees without stalling this ring
+            prefetched = true;
+          }
+        }
+        if (ok && !prefetched) ok = issue_window(nxt, wc + 1);
+        cur = nxt;
+        ++wc;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, 256, 1, 0);
+      PipeState ps;
+      long long wcount = 0;
+      int it = 0;
+      bool ok = true;
+      for (long long item = blockIdx.x; item < p.n_tiles && ok; item += gridDim.x, ++it) {
+        const int split = (int)(item % p.n_split);
+        const int nc0 = split * p.nc_per_split;
+        const int nc1 = min(nc0 + p.nc_per_split, p.n_chunks_n);
+        const int b = it & 1;
+        if (!ab.wait(&tempty[b], (uint32_t)((it >> 1) & 1) ^ 1)) break;
+        tc_fence_after();
+        const uint32_t dtm = tmem + (uint32_t)b * 256;
+        const int nchunks = n_pass * (nc1 - nc0);
+        for (int c = 0; c < nchunks && ok; ++c, ++wcount) {
+          const int wb = (int)(wcount & 1);
+          if (!ab.wait(&wfull[wb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t wbase = smem_u32(Ws + (size_t)wb * wbytes);
+          for (int j = 0; j < J; j += kHpLagsPerStage) {
+            if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+            tc_fence_after();
+            const int nl = min(kHpLagsPerStage, J - j);
+            for (int u = 0; u < nl; ++u) {
+              const uint32_t abase = smem_u32(As + (size_t)ps.stage * kHpStageBytes + u * kHtABytes);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
+                const uint64_t bd = make_smem_desc(wbase + (uint32_t)(p.s * (j + u)) * 128 + ks * 32, 16, 1024, kSwz128);
+                mma_tf32_ss(dtm, ad, bd, idesc, (c | (j + u) | ks) != 0 ? 1u : 0u);
+              }
+            }
+            mma_commit(&empty[ps.stage]);
+            ps.advance(kHpStages);
+          }
+          if (!ok) break;
+          mma_commit(&wempty[wb]);
+        }
+        if (!ok) break;
+        mma_commit(&tfull[b]);
+      }
+    }
+  } else {
+    const int q = warp & 3;                 // lag group g of this warp's 32 TMEM lanes; lane = k
+    int it = 0;
+    for (long long item = blockIdx.x; item < p.n_tiles; item += gridDim.x, ++it) {
+      long long tile; int src, split;
+      decode(item, tile, src, split);
+      const int b = it & 1;
+      if (!ab.wait(&tfull[b], (it >> 1) & 1)) break;
+      tc_fence_after();
+      float* orow = p.scratch + ((size_t)((split * p.n_slots + src) * 4 + q) * kKp + lane) * p.ts + tile * 256;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 8; c0 += 2) {
+        uint32_t r[2][32];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + (c0 + u) * 32), r[u]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float4* o = reinterpret_cast<float4*>(orow + (c0 + u) * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             o[j] = make_float4(__uint_as_float(r[u][4 * j]), __uint_as_float(r[u][4 * j + 1]),
@@ -959,7 +1159,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
+      if (lane == 0) mbar_arrive(&tempty[b]);
     }
   }
   tc_fence_before();

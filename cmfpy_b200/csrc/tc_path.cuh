@@ -56,7 +56,7 @@ inline bool shape_supported(int N, int K, int L) {
   const int Kp = padded_k(K);
   if (N < 1 || K < 1 || L < 1 || Kp == 0) return false;
   const Fold f = make_fold(Kp, L);
-  return recon_smem_bytes(f.recon_wrows) <= kMaxSmem && hterms_smem_bytes(f.hterms_wrows) <= kMaxSmem &&
+  return recon_smem_bytes(f.recon_wrows) <= kMaxSmem && hterms_pp_smem_bytes(f.hterms_wrows) <= kMaxSmem &&
          wterms_smem_bytes(f.s) <= kMaxSmem;
 }
 
@@ -78,6 +78,7 @@ struct TcState {
   int* d_err = nullptr;
   int n_chunks = 1, n_lag_groups = 1;
   int h_split = 1, h_nc_per_split = 1;   // H terms: feature-chunk splits per time tile
+  int h_pp = 0;                          // 1: ping-pong form of K3 (one source per item), 0: paired form
   int recon_grid = 1, wterms_grid = 1, hterms_grid = 1;
   long long wcount = 0, wv_count = 0, hv_count = 0;
   CUtensorMap tmW_k1, tmH_k1, tmX_k2, tmE_k2, tmH_k2, tmW_k3, tmX_k3, tmE_k3;
@@ -301,8 +302,13 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   CMF_TRY(make_map(&s.tmX_k3, Xt, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
   s.tmXlo_k3 = s.tmX_k3;
   if (s.x3) CMF_TRY(make_map(&s.tmXlo_k3, Xlo, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
-  CMF_CUDA(cudaFuncSetAttribute(tc_hterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)hterms_smem_bytes(f.hterms_wrows)));
+  if (const char* e = getenv("CMF_HTERMS_PP")) s.h_pp = atoi(e) ? 1 : 0;
+  if (hterms_smem_bytes(f.hterms_wrows) > kMaxSmem) s.h_pp = 1;
+  if (!s.h_pp)
+    CMF_CUDA(cudaFuncSetAttribute(tc_hterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)hterms_smem_bytes(f.hterms_wrows)));
+  CMF_CUDA(cudaFuncSetAttribute(tc_hterms_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)hterms_pp_smem_bytes(f.hterms_wrows)));
   if (d.Kp * 129 * 4 > 48 * 1024)
     CMF_CUDA(cudaFuncSetAttribute(combine_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.Kp * 129 * 4));
 
@@ -349,7 +355,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     const size_t bytes = (size_t)s.h_split * ((s.gram & 1) ? 1 : 2) * 4 * kKp * (d.TO + 256) * 4;
     CMF_CUDA(cudaMalloc((void**)&s.hscratch, bytes));    // fully rewritten by every launch: no memset
     const long long tt = d.TO / 256 + 1;
-    const long long items = ((s.gram & 1) ? (tt + 1) / 2 : tt) * s.h_split;
+    const long long items = s.h_pp ? tt * ((s.gram & 1) ? 1 : 2) * s.h_split : ((s.gram & 1) ? (tt + 1) / 2 : tt) * s.h_split;
     s.hterms_grid = (int)(items < d.num_sms ? items : d.num_sms);
   }
   if ((long long)s.g_rows * f.Lv * f.KW * 4 > (1ll << 30)) s.gram &= ~2;
@@ -621,6 +627,22 @@ inline int h_terms(TcState& s, cudaStream_t stream) {
   p.n_time_tiles = p.pair_mode ? (time_tiles + 1) / 2 : time_tiles;
   p.n_tiles = p.n_time_tiles * s.h_split; p.ts = d.TO + 256; p.scratch = s.hscratch; p.err = s.d_err;
   p.x3 = s.x3; p.lo_off = f.KW;
+  if (s.h_pp) {
+    // one source per item: the numerator only on the Gram route, numerator and denominator otherwise
+    const int n_slots = p.n_slots;
+    p.pair_mode = 0;
+    p.n_src = n_slots;
+    p.n_time_tiles = time_tiles;
+    p.n_tiles = time_tiles * p.n_src * s.h_split;
+    tc_hterms_pp_kernel<<<s.hterms_grid, kHtThreads, hterms_pp_smem_bytes(f.hterms_wrows), stream>>>(
+        s.tmW_k3, s.tmX_k3, s.tmE_k3, s.tmXlo_k3, s.tmElo_k3, p);
+    CMF_TRY(launch_ok("tc_hterms_pp"));
+    combine_groups_kernel<<<(unsigned)(d.TO / 128), 256, d.Kp * 129 * 4, stream>>>(s.hscratch, s.hterms, p.ts, d.TO, f.J,
+                                                                                f.s, f.CB, d.Kp, n_slots, s.h_split, n_slots);
+    CMF_TRY(launch_ok("combine_groups"));
+    if (s.gram & 1) CMF_TRY(den_h_gram(s, stream));
+    return 0;
+  }
   tc_hterms_kernel<<<s.hterms_grid, kHtThreads, hterms_smem_bytes(f.hterms_wrows), stream>>>(s.tmW_k3, s.tmX_k3, s.tmE_k3,
                                                                                              s.tmXlo_k3, s.tmElo_k3, p);
   CMF_TRY(launch_ok("tc_hterms"));
