@@ -51,6 +51,37 @@ def parse_args():
 # --------------------------------------------------------------------------
 # helpers
 # --------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Run this process on the CPUs local to GPU `index` (and so first-touch its pinned host buffers on that
+    NUMA node): host<->device copies from the far socket run at a fraction of the PCIe rate.  Returns a short
+    description for the JSON line, or None when the topology cannot be read."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if not out:
+            return None
+        bdf = out[-12:] if len(out) >= 12 else out            # 0000:xx:yy.z (nvidia-smi prints an 8-digit domain)
+        base = "/sys/bus/pci/devices/%s/" % bdf
+        with open(base + "local_cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return "all %d allowed cpus are local" % len(allowed)
+        os.sched_setaffinity(0, cpus)
+        node = open(base + "numa_node").read().strip()
+        return "numa node %s, %d cpus" % (node, len(cpus))
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -246,6 +277,7 @@ def run_b200(args):
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -390,7 +422,7 @@ def run_b200(args):
                                    {"peer": "own kernels over NVLink peer memory (all-reduce fused with the W update, "
                                             "halo pushes, loss ring)",
                                     "nccl": "NCCL all-reduce + send/recv between the phases"}[alg.transport])},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "cpu_affinity": affinity,
         "roofline": roofline, "cpu_baseline": cb,
         "final_loss": losses[-1],
     }
@@ -427,15 +459,19 @@ def run_e2e(args, torch, N, T, K, L, Tloc, rank, world, local_rank, precision, d
                             initW=W0h.numpy(), initH=H0h.numpy(), precision=precision,
                             device=local_rank, group=dist.group.WORLD if dist else None,
                             denominators=args.denominators)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
     last = None
     for _ in range(args.steps):
         last = alg.update()                       # host float every step (D2H + sync)
+    t2 = time.perf_counter()
     W = alg.W_host()
     H = alg.H_local_host()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     sec = time.perf_counter() - t0
+    parts = {"construct_h2d": t1 - t0, "steps": t2 - t1, "read_back": time.perf_counter() - t2}
     if dist:
         t = torch.tensor([sec], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -446,7 +482,7 @@ def run_e2e(args, torch, N, T, K, L, Tloc, rank, world, local_rank, precision, d
     return {"value": args.steps / sec, "unit": UNIT,
             "h2d_bytes_per_step": int(h2d * world / args.steps),
             "d2h_bytes_per_step": int(d2h * world / args.steps),
-            "seconds_total": sec, "final_loss": last,
+            "seconds_total": sec, "seconds_rank0": parts, "final_loss": last,
             "what": "solver built from pinned host X/W0/H0 (H2D inside the timed region), %d update() calls each "
                     "returning the loss to the host, W and H copied back" % args.steps}
 

@@ -72,6 +72,8 @@ _SIGNATURES = {
     "cmf_mu_set_profiling": (C.c_int, [_H, C.c_int]),
     "cmf_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
                               C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cmf_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
+                            C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "cmf_tensor_transconv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]),
 }

@@ -47,6 +47,21 @@ def tensor_transconv(W, X, precision="fp32", device=0):
     return out
 
 
+def score(W, H, X, precision="fp32", device=0):
+    """R^2 = 1 - ||cmf_predict(W, H) - X||^2 / ||X||^2 (reference model.py:202-221), reduced on the
+    device by the fused reconstruction + residual kernel: no N x T array comes back."""
+    import ctypes as C
+    W, H, X = _prep(W), _prep(H), _prep(X)
+    H, X = H.astype(W.dtype, copy=False), X.astype(W.dtype, copy=False)
+    L, N, K = W.shape
+    if H.shape[0] != K or X.shape != (N, H.shape[1]):
+        raise ValueError("W, H and X disagree on their dimensions")
+    r2 = C.c_double(0.0)
+    _lib.check(_lib.load().cmf_score(W.ctypes.data, H.ctypes.data, X.ctypes.data, _lib.np_dtype_code(W),
+                                     N, H.shape[1], K, L, device, _lib.PRECISIONS[precision], C.byref(r2)))
+    return r2.value
+
+
 def shift_cols(X, lag):
     """reference common.py:89-98 (a view; no device work)."""
     T = X.shape[1]

@@ -1255,4 +1255,21 @@ int cmf_tensor_transconv(const void* W, const void* X, void* out, int dtype, int
   return rc;
 }
 
+// CMF.score (reference model.py:202-221): 1 - ||cmf_predict(W, H) - X||^2 / ||X||^2, formed on the device by the
+// fused reconstruction + residual kernel: neither est nor the residual (N x T each) travels back to the host.
+int cmf_score(const void* W, const void* H, const void* X, int dtype, int n_features, long long n_timepoints,
+              int n_components, int maxlag, int device, int precision, double* r2_out) {
+  CMF_CHECK(r2_out != nullptr, "null argument");
+  cmf_mu_t* h = nullptr;
+  CMF_TRY(make_tmp(&h, n_features, n_timepoints, n_components, maxlag, device, precision));
+  int rc = cmf_mu_set_data(h, X, dtype, CMF_HOST, n_timepoints, n_timepoints);
+  if (rc == 0) rc = cmf_mu_set_factors(h, W, H, dtype, CMF_HOST, n_timepoints);
+  if (rc == 0) rc = cmf_mu_recon_loss(h);
+  double ss = 0.0;
+  if (rc == 0) rc = cmf_mu_resid_sumsq(h, &ss);
+  if (rc == 0) *r2_out = 1.0 - ss / h->sumsq_x;
+  cmf_mu_destroy(h);
+  return rc;
+}
+
 }  // extern "C"

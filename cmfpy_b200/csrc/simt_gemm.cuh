@@ -344,17 +344,31 @@ struct PartEpi {
   __device__ void block_sum(double, long long) const {}
 };
 // out[(m + m_off)][c] -= sum_split part[split][m][c]
+// One warp per float4 of the output: the lanes stride over the splits and a shuffle tree adds them (fixed
+// order => deterministic); a serial loop over a few hundred splits per thread was latency-bound.
 __global__ void __launch_bounds__(256)
 tail_sub_kernel(float* __restrict__ out, const float* __restrict__ part, int nsplit, long long per_split, long long m_rows,
                 int ld, long long m_off, long long row_end) {
-  const long long total = m_rows * ld;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long m = i / ld;
-    const long long row = m + m_off;
+  const long long total4 = m_rows * ld / 4;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i4 = warp0; i4 < total4; i4 += nwarps) {
+    const long long i = i4 * 4;
+    const long long row = i / ld + m_off;
     if (row < 0 || row >= row_end) continue;
-    float acc = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) acc += part[sp * per_split + i];
-    out[row * ld + (i % ld)] -= acc;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = lane; sp < nsplit; sp += 32) {
+      const float4 v = *reinterpret_cast<const float4*>(part + (size_t)sp * per_split + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+    if (lane == 0) {
+      float4* o = reinterpret_cast<float4*>(out + row * ld + (i % ld));
+      float4 c = *o;
+      c.x -= acc.x; c.y -= acc.y; c.z -= acc.z; c.w -= acc.w;
+      *o = c;
+    }
   }
 }
 // out[(m + m_off)][k] -= v    (rows m + m_off < row_end)

@@ -273,9 +273,13 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     const double t_partial = 2.0 * 2.0 * (double)s.wcount * 4.0 / 5.0e6;     // both sources; 5 TB/s
     double best = 1e300;
     std::vector<double> cost((size_t)cmax + 1, 1e300);
+    // On the Gram route the autocorrelation pass of H (den_w_gram) uses the same chunks - equal accumulation
+    // chains - but has only n_lag_groups * CB units: too few chunks would leave most SMs idle there.
+    const long long p_units = (s.gram_request & 2) && !s.x3 ? (long long)s.n_lag_groups * f.CB : 0;
     for (long long c = 1; c <= cmax; ++c) {
-      const long long waves = ceil_div_ll(units * c, d.num_sms);
-      cost[c] = (double)waves * ((double)ceil_div_ll(stages_total, c) * t_stage + t_drain) + (c > 1 ? c * t_partial : 0.0);
+      const double item = (double)ceil_div_ll(stages_total, c) * t_stage + t_drain;
+      cost[c] = (double)ceil_div_ll(units * c, d.num_sms) * item + (c > 1 ? c * t_partial : 0.0);
+      if (p_units) cost[c] += (double)ceil_div_ll(p_units * c, d.num_sms) * item;
       if (cost[c] < best) best = cost[c];
     }
     int bestc = 1;
@@ -593,19 +597,26 @@ inline int den_h_gram(TcState& s, cudaStream_t stream) {
         // one split per lag (the reduction (l, n) is long and the output tiny); partials live in G's buffer
         simt::TailHA a{s.Etail, d.Np, m_off, t0, s.ntail};
         simt::HTermsB b{s.W, d.Kp};
+        // the reduction (l, n) is long and the output tiny: split it into about two blocks per SM (this runs on
+        // ONE rank while the others wait at the next exchange); partials live in G's buffer
         const long long per_split = round_up_ll(rows, 128) * d.Kp;
-        CMF_CHECK(per_split * d.L <= s.g_rows * s.LK, "tail scratch too small");
-        simt::PartEpi e{s.G, d.Kp, rows, d.Kp, per_split};
         const long long R = (long long)d.L * d.Np;
+        const long long m_tiles = ceil_div_ll(rows, 128);
+        long long r_chunk = round_up_ll(ceil_div_ll(R * m_tiles, 2ll * d.num_sms), 16);
+        if (r_chunk < 64) r_chunk = 64;
+        long long nsplit = ceil_div_ll(R, r_chunk);
+        if (per_split * nsplit > s.g_rows * s.LK) { nsplit = (s.g_rows * s.LK) / per_split; r_chunk = round_up_ll(ceil_div_ll(R, nsplit), 16); nsplit = ceil_div_ll(R, r_chunk); }
+        CMF_CHECK(nsplit >= 1 && per_split * nsplit <= s.g_rows * s.LK, "tail scratch too small");
+        simt::PartEpi e{s.G, d.Kp, rows, d.Kp, per_split};
         if (d.Kp <= 64) {
-          dim3 g2((unsigned)ceil_div_ll(rows, 128), 1, (unsigned)d.L);
-          simt::shift_gemm_kernel<128, 64, 16, 8, 4><<<g2, 256, 0, stream>>>(a, b, e, R, d.Np, 1);
+          dim3 g2((unsigned)m_tiles, 1, (unsigned)nsplit);
+          simt::shift_gemm_kernel<128, 64, 16, 8, 4><<<g2, 256, 0, stream>>>(a, b, e, R, r_chunk, 1);
         } else {
-          dim3 grid((unsigned)ceil_div_ll(rows, 128), (unsigned)ceil_div_ll(d.Kp, 128), (unsigned)d.L);
-          simt::shift_gemm_kernel<128, 128, 16, 8, 8><<<grid, 256, 0, stream>>>(a, b, e, R, d.Np, 1);
+          dim3 grid((unsigned)m_tiles, (unsigned)ceil_div_ll(d.Kp, 128), (unsigned)nsplit);
+          simt::shift_gemm_kernel<128, 128, 16, 8, 8><<<grid, 256, 0, stream>>>(a, b, e, R, r_chunk, 1);
         }
         CMF_TRY(launch_ok("tail_den_h_parts"));
-        simt::tail_sub_kernel<<<ew_blocks(s, rows * d.Kp), 256, 0, stream>>>(den, s.G, d.L, per_split, rows, d.Kp, m_off, d.Tloc);
+        simt::tail_sub_kernel<<<ew_blocks(s, rows * d.Kp * 8), 256, 0, stream>>>(den, s.G, (int)nsplit, per_split, rows, d.Kp, m_off, d.Tloc);
         CMF_TRY(launch_ok("tail_den_h"));
       }
     }

@@ -118,8 +118,9 @@ class CMF(object):
 
     def score(self, data):
         """R^2 = 1 - ||predict - data||^2 / ||data||^2 (reference model.py:202-221)."""
-        error = self.predict() - data
-        return 1 - (np.linalg.norm(error) ** 2 / np.linalg.norm(data) ** 2)
+        from .common import score
+        return score(self.motifs, self.factors, np.asarray(data), precision="fp32",
+                     device=getattr(self, "_device", 0))
 
     @property
     def motifs(self):

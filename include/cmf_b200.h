@@ -210,6 +210,11 @@ int cmf_mu_set_profiling(cmf_mu_t* h, int on);
 int cmf_predict(const void* W, const void* H, void* est_out, int dtype,
                 int n_features, long long n_timepoints, int n_components,
                 int maxlag, int device, int precision);
+/* CMF.score(data) (model.py:202-221): R^2 = 1 - ||cmf_predict(W,H) - X||^2 /
+ * ||X||^2, reduced on the device (no N x T read-back).  Host pointers.       */
+int cmf_score(const void* W, const void* H, const void* X, int dtype,
+              int n_features, long long n_timepoints, int n_components,
+              int maxlag, int device, int precision, double* r2_out);
 /* tensor_transconv(W, X) -> K x T (common.py:61-86).  Host pointers.        */
 int cmf_tensor_transconv(const void* W, const void* X, void* out, int dtype,
                          int n_features, long long n_timepoints,

@@ -201,6 +201,18 @@ def test_primitives_against_oracle(built_lib):
         _close(tensor_transconv(W, X), o.tensor_transconv(W, X), 1e-5)
 
 
+def test_score_on_device_against_oracle(built_lib):
+    """CMF.score (reference model.py:202-221) without reading est back."""
+    from cmfpy_b200.common import score
+    rng = np.random.default_rng(11)
+    for (N, T, K, L) in [(7, 90, 2, 5), (130, 1500, 9, 17), (256, 4096, 32, 64)]:
+        W, H, X = rng.random((L, N, K)), rng.random((K, T)), rng.random((N, T)) * L * K / 4
+        ref = 1 - np.linalg.norm(o.cmf_predict(W, H) - X) ** 2 / np.linalg.norm(X) ** 2
+        assert abs(score(W, H, X) - ref) <= 1e-5 * max(1.0, abs(ref))
+        if _supported("tf32x3", N, K, L):
+            assert abs(score(W, H, X, precision="tf32x3") - ref) <= 1e-5 * max(1.0, abs(ref))
+
+
 # ---- model API --------------------------------------------------------------
 def test_cmf_fit_predict_score(built_lib):
     from cmfpy_b200 import CMF
