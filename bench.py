@@ -389,6 +389,12 @@ def run_b200(args):
         "traffic_unit": "bytes per launch (algorithmic: %.2e)" % ((4.0 if alg.path_name.endswith("+gram") else 8.0) * N * Tloc),
         "peak_source": "%s bf16_tflops_sustained / 2 (TF32 dense = half of bf16; not separately measured)" % peaks_src,
         "cublas_tf32_tflops_live": tf32_live,
+        # the tensor pipe itself: one 128x256x8 TF32 MMA (524288 flop) per 128 cycles per SM at the SM clock
+        # observed DURING the timed region (the run is power-capped well below the 1965 MHz maximum)
+        "hw_tf32_tflops_at_observed_clock": (148 * 4096.0 * clocks["sm_mhz"] * 1e6 / 1e12
+                                             if clocks and clocks.get("sm_mhz") else None),
+        "frac_of_hw_at_observed_clock": (achieved / (148 * 4096.0 * clocks["sm_mhz"] * 1e6 / 1e12)
+                                         if achieved and clocks and clocks.get("sm_mhz") else None),
         # 12 N K L T per iteration (what the direct algorithm needs) over the measured time; with
         # the Gram-route denominators about half of those flops are not executed at all, so this figure is a
         # reference-equivalent rate, not a hardware utilisation

@@ -61,6 +61,9 @@ _SIGNATURES = {
     "cmf_mu_peer_attach": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
     "cmf_mu_peer_detach": (C.c_int, [_H]),
     "cmf_mu_step_sharded": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double)]),
+    "cmf_gd_cache": (C.c_int, [_H]),
+    "cmf_gd_lipschitz_w": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "cmf_gd_step": (C.c_int, [_H, C.c_int, C.c_double, C.POINTER(C.c_double)]),
     "cmf_mu_get_W": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
     "cmf_mu_get_H": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_longlong]),
     "cmf_mu_get_est": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_longlong]),

@@ -22,6 +22,7 @@
 #include "simt_gemm.cuh"
 #include "tc_path.cuh"
 #include "peer_kernels.cuh"
+#include "gd_kernels.cuh"
 
 namespace cmf {
 
@@ -83,6 +84,15 @@ struct cmf_mu_s {
   std::vector<cudaEvent_t> ev_pool;
 
   tc::TcState tcs;
+
+  // ---- gradient solvers (gd_kernels.cuh) ----
+  struct GdState {
+    bool ready = false, cached = false;  // cached: numden / hterms hold the terms of the CURRENT W, H
+    float *P = nullptr, *Ppart = nullptr, *Pt = nullptr, *v = nullptr, *y = nullptr, *d_inv = nullptr;
+    double* d_lam = nullptr;
+    gd::PowerState* st = nullptr;
+    int max_iter = 64;
+  } gdst;
 
   // ---- peer-memory collectives of the sharded iteration (peer_kernels.cuh) ----
   struct PeerState {
@@ -434,6 +444,8 @@ int peer_detach(cmf_mu_s* h) {
 void free_all(cmf_mu_s* h) {
   peer_detach(h);
   cudaFree(h->peer.shared);
+  cudaFree(h->gdst.P); cudaFree(h->gdst.Ppart); cudaFree(h->gdst.Pt); cudaFree(h->gdst.v); cudaFree(h->gdst.y);
+  cudaFree(h->gdst.d_inv); cudaFree(h->gdst.d_lam); cudaFree(h->gdst.st);
   tc::destroy(h->tcs);
   cudaFree(h->Xt); cudaFree(h->Et); cudaFree(h->Ht); cudaFree(h->W); cudaFree(h->Xlo); cudaFree(h->Elo);
   cudaFree(h->numden); cudaFree(h->wpart); cudaFree(h->hterms);
@@ -1216,6 +1228,156 @@ int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out) {
     }
     done += chunk;
   }
+  return 0;
+}
+
+// ---- gradient descent / block coordinate descent (reference algs/gradient_descent.py) ----------
+namespace {
+int gd_ensure(cmf_mu_s* h) {
+  auto& g = h->gdst;
+  if (g.ready) return 0;
+  CMF_CHECK(!gram_w(h) && !gram_h(h), "the gradient solvers contract the residual directly: create the solver with CMF_DEN_DIRECT");
+  const long long pcount = (long long)h->L * h->Kp * h->Kp;
+  const long long n = (long long)h->L * h->Kp;
+  if (!h->use_tc) {
+    CMF_TRY(dmalloc(&g.P, pcount));
+    if (h->wsplits > 1) CMF_TRY(dmalloc(&g.Ppart, pcount * h->wsplits));
+  }
+  CMF_TRY(dmalloc(&g.Pt, pcount));
+  CMF_TRY(dmalloc(&g.v, n));
+  CMF_TRY(dmalloc(&g.y, n));
+  CMF_TRY(dmalloc(&g.d_inv, 1));
+  CMF_TRY(dmalloc(&g.d_lam, 1));
+  CMF_TRY(dmalloc(&g.st, 1));
+  CMF_CUDA(cudaMemsetAsync(g.v, 0, (size_t)n * 4, h->stream));
+  g.ready = true;
+  return 0;
+}
+
+// lambda_max of the block-Toeplitz autocorrelation matrix of H (lipschitz_W, gradient_descent.py:54-69);
+// lambda and 1 / lambda stay on the device (d_lam, d_inv)
+int gd_lipschitz(cmf_mu_s* h) {
+  CMF_TRY(gd_ensure(h));
+  auto& g = h->gdst;
+  const float* P = nullptr;
+  if (h->use_tc) {
+    const long long n0 = tc::launch_counter();
+    CMF_TRY(tc::autocorr(h->tcs, h->stream));
+    h->launches += tc::launch_counter() - n0;
+    P = h->tcs.P;
+  } else {
+    const int LKp = h->L * h->Kp;
+    const long long pcount = (long long)h->L * h->Kp * h->Kp;
+    gd::AutoA a{h->Ht + (long long)h->h * h->Kp, h->Kp};
+    simt::WTermsB b{h->Ht, h->Kp, h->h, LKp};
+    gd::AutoEpi e{h->wsplits == 1 ? g.P : g.Ppart, h->Kp, LKp, pcount};
+    dim3 grid((unsigned)ceil_div_ll(h->Kp, 128), (unsigned)ceil_div_ll(LKp, 128), (unsigned)h->wsplits);
+    simt::shift_gemm_kernel<128, 128, 16, 8, 8><<<grid, 256, 0, h->stream>>>(a, b, e, h->Tloc, h->wchunk, 1);
+    CMF_TRY(launch_check(h, "autocorr_H"));
+    if (h->wsplits > 1) {
+      ew::sum_splits_kernel<<<ew_grid(h, pcount / 4), 256, 0, h->stream>>>((float4*)g.P, (const float4*)g.Ppart, pcount / 4,
+                                                                          pcount / 4, h->wsplits);
+      CMF_TRY(launch_check(h, "autocorr_H_sum"));
+    }
+    P = g.P;
+  }
+  const int n = h->L * h->Kp;
+  gd::transpose_blocks_kernel<<<ew_grid(h, (long long)n * h->Kp), 256, 0, h->stream>>>(P, g.Pt, h->L, h->Kp);
+  CMF_TRY(launch_check(h, "autocorr_transpose"));
+  gd::power_reset_kernel<<<1, 1024, 0, h->stream>>>(g.st, g.v, n);
+  CMF_TRY(launch_check(h, "power_reset"));
+  const int mv_blocks = (int)ceil_div_ll((long long)n * 32, 256);
+  for (int it = 0; it < g.max_iter; ++it) {
+    gd::toeplitz_matvec_kernel<<<mv_blocks, 256, 0, h->stream>>>(P, g.Pt, g.v, g.y, h->L, h->Kp, g.st);
+    gd::power_normalize_kernel<<<1, 1024, 0, h->stream>>>(g.v, g.y, n, g.st, 1e-7, g.d_lam, g.d_inv);
+    h->launches += 2;
+  }
+  cudaError_t e = cudaGetLastError();
+  CMF_CHECK(e == cudaSuccess, "power iteration launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int gd_projected_step_W(cmf_mu_s* h) {
+  CMF_CHECK(h->wterms_valid, "W step before its gradient was cached");
+  const long long n4 = h->wcount / 4;
+  gd::projected_step_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>(
+      (float4*)h->W, (const float4*)h->numden, (const float4*)(h->numden + h->wcount), n4, h->gdst.d_inv, 0.f,
+      (float4*)tc::fused_w_op(h->tcs));
+  CMF_TRY(launch_check(h, "gd_w_step"));
+  {
+    const long long n0 = tc::launch_counter();
+    CMF_TRY(tc::refresh_w(h->tcs, h->stream, true));
+    h->launches += tc::launch_counter() - n0;
+  }
+  h->wterms_valid = false;
+  h->est_valid = false;
+  return 0;
+}
+
+int gd_projected_step_H(cmf_mu_s* h, double step) {
+  const long long n4 = h->Tloc * h->Kp / 4;
+  gd::projected_step_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>(
+      (float4*)(h->Ht + (long long)h->h * h->Kp), (const float4*)h->hterms, (const float4*)(h->hterms + h->TO * h->Kp), n4,
+      nullptr, (float)step,
+      tc::fused_h_op(h->tcs) ? (float4*)(tc::fused_h_op(h->tcs) + (long long)h->h * h->Kp) : nullptr);
+  CMF_TRY(launch_check(h, "gd_h_step"));
+  {
+    const long long n0 = tc::launch_counter();
+    CMF_TRY(tc::refresh_h(h->tcs, h->stream, h->h, h->Tloc, true));
+    h->launches += tc::launch_counter() - n0;
+  }
+  h->est_valid = false;
+  return 0;
+}
+}  // namespace
+
+// cache_resids + cache_gW + cache_gH (GradDescent.__init__, gradient_descent.py:36-38): afterwards the W-term and
+// H-term buffers hold num / den of the CURRENT factors, i.e. gW = den_W - num_W and gH = den_H - num_H.
+int cmf_gd_cache(cmf_mu_t* h) {
+  CMF_ENTER(h);
+  CMF_CHECK(h->have_data && h->have_factors, "gradient cache before data/factors were set");
+  CMF_CHECK(h->t_valid == h->Tloc && h->p.t_local == h->p.t_global, "the gradient solvers run on one GPU (no time sharding)");
+  CMF_TRY(gd_ensure(h));
+  CMF_TRY(do_recon(h));
+  CMF_TRY(do_w_terms(h));
+  CMF_TRY(do_h_terms(h));
+  h->gdst.cached = true;
+  return 0;
+}
+
+// lipschitz_W (gradient_descent.py:54-69)
+int cmf_gd_lipschitz_w(cmf_mu_t* h, double* lam) {
+  CMF_ENTER(h);
+  CMF_CHECK(lam != nullptr, "null argument");
+  CMF_CHECK(h->have_factors, "W or H not initalized.");
+  CMF_TRY(gd_lipschitz(h));
+  CMF_CUDA(cudaMemcpyAsync(lam, h->gdst.d_lam, 8, cudaMemcpyDeviceToHost, h->stream));
+  CMF_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->use_tc) CMF_TRY(tc::check(h->tcs, h->stream));
+  return 0;
+}
+
+// GradDescent.update (gradient_descent.py:81-92) when block_descent == 0, BlockDescent.update (:132-147) otherwise.
+// step_size_h is the caller's current H step (the reference adapts it in converged(), :94-113).
+int cmf_gd_step(cmf_mu_t* h, int block_descent, double step_size_h, double* loss_out) {
+  CMF_ENTER(h);
+  CMF_CHECK(h->gdst.cached, "cmf_gd_step before cmf_gd_cache");
+  CMF_TRY(gd_lipschitz(h));
+  CMF_TRY(gd_projected_step_W(h));
+  if (!block_descent) {
+    CMF_TRY(gd_projected_step_H(h, step_size_h));       // both steps use the gradients of the OLD factors
+    CMF_TRY(do_recon(h));
+    CMF_TRY(do_w_terms(h));
+    CMF_TRY(do_h_terms(h));
+  } else {
+    CMF_TRY(do_recon(h));                                // residuals with the new W
+    CMF_TRY(do_h_terms(h));
+    CMF_TRY(gd_projected_step_H(h, step_size_h));
+    CMF_TRY(do_recon(h));
+    CMF_TRY(do_w_terms(h));                              // gW for the next iteration; gH is recomputed there
+  }
+  if (loss_out) CMF_TRY(cmf_mu_loss(h, loss_out));
+  else CMF_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -96,7 +96,8 @@ struct TcState {
   // W step
   float *P = nullptr, *Ppart = nullptr, *Mt = nullptr;
   int p_chunks = 1, p_grid = 1;
-  CUtensorMap tmHx_k2, tmMt_b;
+  CUtensorMap tmHx_k2, tmHxlo_k2, tmMt_b;
+  bool autocorr_ready = false;
 };
 
 
@@ -206,6 +207,59 @@ inline int refresh_h(TcState& s, cudaStream_t stream, long long row0, long long 
   if (r1 > d.RH) r1 = d.RH;
   fold_h_kernel<<<ew_blocks(s, (r1 - row0) * 32), 256, 0, stream>>>(s.Hv, s.Ht, row0, r1 - row0, d.Kp);
   return launch_ok("fold_h");
+}
+
+// ---- lag autocorrelation of H:  P[d][a][b] = sum_t H[a][t] H[b][t-d]  (the W-terms kernel run on H^T itself) ----
+// Used by the Gram route (den_w_gram) and by lipschitz_W of the gradient solvers (gradient_descent.py:54-57).
+inline int ensure_autocorr(TcState& s) {
+  if (s.autocorr_ready) return 0;
+  const Dims& d = s.d;
+  const Fold& f = s.f;
+  const long long pcount = (long long)d.L * d.Kp * d.Kp;
+  {   // same time chunks as the numerator pass: equal accumulation chains, equal truncation bias
+    const long long units = (long long)s.n_lag_groups * f.CB;
+    const long long stages_total = ceil_div_ll(d.Tloc, 32);
+    long long c = s.n_chunks;
+    if (c > stages_total) c = stages_total;
+    if (c < 1) c = 1;
+    s.p_chunks = (int)c;
+    const long long items = units * c;
+    s.p_grid = (int)(items < d.num_sms ? items : d.num_sms);
+  }
+  CMF_CUDA(cudaMalloc((void**)&s.P, (size_t)pcount * 4));
+  CMF_CUDA(cudaMalloc((void**)&s.Ppart, (size_t)pcount * s.p_chunks * 4));
+  // H^T itself as the "data" operand: the first Kp columns of Hv are the unfolded, rounded H^T
+  CMF_TRY(make_map(&s.tmHx_k2, s.Hv + (long long)d.h * s.KWs, d.Tloc, d.Kp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, s.KWs));
+  s.tmHxlo_k2 = s.tmHx_k2;
+  if (s.x3)
+    CMF_TRY(make_map(&s.tmHxlo_k2, s.Hv + (long long)d.h * s.KWs + f.KW, d.Tloc, d.Kp, 32, 32,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, s.KWs));
+  s.autocorr_ready = true;
+  return 0;
+}
+
+inline int autocorr(TcState& s, cudaStream_t stream) {
+  CMF_TRY(ensure_autocorr(s));
+  const Dims& d = s.d;
+  const Fold& f = s.f;
+  const long long pcount = (long long)d.L * d.Kp * d.Kp;
+  WTermsParams p{};
+  p.Np = d.Kp; p.L = d.L; p.n_tiles_n = 1; p.n_lag_groups = s.n_lag_groups; p.n_chunks = s.p_chunks; p.h = d.h;
+  p.Lv = f.Lv; p.Kp = d.Kp; p.s = f.s; p.CB = f.CB; p.brows = wterms_brows(f.s); p.n_src = 1;
+  p.n_items = (long long)p.n_lag_groups * f.CB * p.n_chunks;
+  p.stages_total = ceil_div_ll(d.Tloc, 32);
+  p.part = (s.p_chunks == 1) ? s.P : s.Ppart;
+  p.per_src = pcount; p.err = s.d_err;
+  p.x3 = s.x3; p.lo_off = f.KW;
+  tc_wterms_kernel<<<s.p_grid, kWtThreads, wterms_smem_bytes(f.s), stream>>>(s.tmHx_k2, s.tmHx_k2, s.tmH_k2, s.tmHxlo_k2,
+                                                                           s.tmHxlo_k2, p);
+  CMF_TRY(launch_ok("autocorr_H"));
+  if (s.p_chunks > 1) {
+    ew::sum_splits_kernel<<<ew_blocks(s, pcount / 4), 256, 0, stream>>>((float4*)s.P, (const float4*)s.Ppart, pcount / 4,
+                                                                       pcount / 4, s.p_chunks);
+    CMF_TRY(launch_ok("autocorr_H_sum"));
+  }
+  return 0;
 }
 
 inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, float* W, float* numden, float* hterms,
@@ -366,23 +420,8 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   CMF_CUDA(cudaMalloc((void**)&s.wpart, (size_t)s.n_chunks * ((s.gram & 2) ? 1 : 2) * s.wcount * 4));
   if (s.gram && s.ntail > 0) CMF_CUDA(cudaMalloc((void**)&s.Etail, (size_t)256 * d.Np * 4));
   if (s.gram & 2) {
-    const long long pcount = (long long)d.L * d.Kp * d.Kp;
-    {   // time chunks of the autocorrelation pass: one item per SM if possible
-      const long long units = (long long)s.n_lag_groups * f.CB;
-      const long long stages_total = ceil_div_ll(d.Tloc, 32);
-      // same time chunks as the numerator pass: equal accumulation chains, equal truncation bias
-      long long c = s.n_chunks;
-      if (c > stages_total) c = stages_total;
-      if (c < 1) c = 1;
-      s.p_chunks = (int)c;
-      const long long items = units * c;
-      s.p_grid = (int)(items < d.num_sms ? items : d.num_sms);
-    }
-    CMF_CUDA(cudaMalloc((void**)&s.P, (size_t)pcount * 4));
-    CMF_CUDA(cudaMalloc((void**)&s.Ppart, (size_t)pcount * s.p_chunks * 4));
+    CMF_TRY(ensure_autocorr(s));
     CMF_CUDA(cudaMalloc((void**)&s.Mt, (size_t)s.g_rows * f.Lv * f.KW * 4));
-    // H^T itself as the "data" operand: the first Kp columns of Hv are the unfolded, rounded H^T
-    CMF_TRY(make_map(&s.tmHx_k2, s.Hv + (long long)d.h * f.KW, d.Tloc, d.Kp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, f.KW));
     CMF_TRY(make_map(&s.tmMt_b, s.Mt, s.g_rows, (long long)f.Lv * f.KW, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
     CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(recon_smem_bytes(s.dh_wrows) <= kMaxSmem && recon_smem_bytes(s.dh_wrows) > recon_smem_bytes(f.recon_wrows)
@@ -432,25 +471,8 @@ inline int tail_est(TcState& s, cudaStream_t stream) {
 inline int den_w_gram(TcState& s, cudaStream_t stream) {
   const Dims& d = s.d;
   const Fold& f = s.f;
-  const long long pcount = (long long)d.L * d.Kp * d.Kp;
   // (a) P[d][k'][k] = sum_t H[k'][t] H[k][t-d] over the owned columns: the W-terms kernel on H^T
-  {
-    WTermsParams p{};
-    p.Np = d.Kp; p.L = d.L; p.n_tiles_n = 1; p.n_lag_groups = s.n_lag_groups; p.n_chunks = s.p_chunks; p.h = d.h;
-    p.Lv = f.Lv; p.Kp = d.Kp; p.s = f.s; p.CB = f.CB; p.brows = wterms_brows(f.s); p.n_src = 1;
-    p.n_items = (long long)p.n_lag_groups * f.CB * p.n_chunks;
-    p.stages_total = ceil_div_ll(d.Tloc, 32);
-    p.part = (s.p_chunks == 1) ? s.P : s.Ppart;
-    p.per_src = pcount; p.err = s.d_err;
-    tc_wterms_kernel<<<s.p_grid, kWtThreads, wterms_smem_bytes(f.s), stream>>>(s.tmHx_k2, s.tmHx_k2, s.tmH_k2, s.tmHx_k2,
-                                                                             s.tmHx_k2, p);
-    CMF_TRY(launch_ok("gram_P"));
-    if (s.p_chunks > 1) {
-      ew::sum_splits_kernel<<<ew_blocks(s, pcount / 4), 256, 0, stream>>>((float4*)s.P, (const float4*)s.Ppart, pcount / 4,
-                                                                         pcount / 4, s.p_chunks);
-      CMF_TRY(launch_ok("gram_P_sum"));
-    }
-  }
+  CMF_TRY(autocorr(s, stream));
   // (b) block-Toeplitz operand
   toeplitz_kernel<<<ew_blocks(s, s.g_rows * f.Lv * f.KW), 256, 0, stream>>>(s.P, s.Mt, d.L, f.Lv, d.Kp, f.s, f.KW, s.g_rows);
   CMF_TRY(launch_ok("toeplitz"));

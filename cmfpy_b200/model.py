@@ -85,7 +85,7 @@ class CMF(object):
         self.loss_hist = [algorithm.loss]
         self.time_hist = [0.0]
 
-        if algorithm.tol == 0 and not self.verbose and self.n_iter_max > 0:
+        if algorithm.tol == 0 and not self.verbose and self.n_iter_max > 0 and getattr(algorithm, "batchable", True):
             losses, secs = algorithm.update_many(self.n_iter_max, return_times=True)
             for loss, dur in zip(losses, secs):
                 self.time_hist.append(self.time_hist[-1] + dur)

@@ -183,6 +183,22 @@ int cmf_mu_peer_attach(cmf_mu_t* h, int rank, int world, const void* blobs);
 int cmf_mu_peer_detach(cmf_mu_t* h);
 int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out);
 
+/* ---- gradient solvers: GradDescent / BlockDescent, algs/gradient_descent.py -- */
+/* Their gradients are the MU terms: gW[l] = s_T_dot(resids, H, l) = den_W - num_W
+ * (:41-45) and gH = den_H - num_H (:47-52), so the same contraction kernels serve.
+ * Single GPU, direct denominators (CMF_DEN_DIRECT).
+ * cmf_gd_cache: cache_resids + cache_gW + cache_gH (:36-38); afterwards
+ *   cmf_mu_get_w_terms / cmf_mu_h_terms return num and den of the current factors.
+ * cmf_gd_lipschitz_w: lambda_max of the (K L) x (K L) block-Toeplitz matrix of the
+ *   lag autocorrelations of H (:54-69), by power iteration on the device.
+ * cmf_gd_step: one update(); block_descent = 0: W and H steps from the cached
+ *   gradients, then residuals and both gradients (:81-92); 1: W step, residuals,
+ *   gH, H step, residuals, gW (:132-147).  x <- max(x - ss g, 0) (:148-159) with
+ *   ss = 1 / lipschitz_W for W and step_size_h for H.  Returns the loss (:120-123). */
+int cmf_gd_cache(cmf_mu_t* h);
+int cmf_gd_lipschitz_w(cmf_mu_t* h, double* lambda_max);
+int cmf_gd_step(cmf_mu_t* h, int block_descent, double step_size_h, double* loss_out);
+
 /* ---- read-back: algorithm.W / algorithm.H (model.py:175-176) ------------ */
 int cmf_mu_get_W(cmf_mu_t* h, void* W_out, int dtype, int mem);
 int cmf_mu_get_H(cmf_mu_t* h, void* H_out, int dtype, int mem, long long ldh);

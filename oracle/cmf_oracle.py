@@ -241,6 +241,78 @@ def fit(data, maxlag, n_components, n_iter_max=100, **kw):
 
 
 # --------------------------------------------------------------------------
+# Gradient solvers (reference cmfpy/algs/gradient_descent.py)
+# --------------------------------------------------------------------------
+def lipschitz_W(H, L):
+    """Largest eigenvalue of the block-Toeplitz matrix of the lag autocorrelations of H
+    (gradient_descent.py:54-69).  The reference calls ``eigh(hW, eigvals=(n-1, n-1))``, a keyword SciPy >= 1.14
+    no longer accepts; ``subset_by_index`` is its replacement and returns the same eigenvalue."""
+    from scipy.linalg import eigh
+    K = H.shape[0]
+    first_row = [s_T_dot(H, H, l) for l in range(L)]             # :56
+    hW = np.empty((K * L, K * L))
+    for i in range(L):                                           # :58-67
+        for j in range(L):
+            blk = first_row[j - i] if i <= j else first_row[i - j].T
+            hW[i * K:(i + 1) * K, j * K:(j + 1) * K] = blk
+    return float(eigh(hW, subset_by_index=[K * L - 1, K * L - 1], eigvals_only=True)[0])   # :69
+
+
+def projected_step(x, dx, ss):
+    """x <- max(x - ss dx, 0) (gradient_descent.py:148-159); returns a new array."""
+    return np.maximum(x - ss * dx, 0.0)
+
+
+class GradDescentOracle(MultUpdateOracle):
+    """Duck-type of reference ``GradDescent`` (gradient_descent.py:15-123); ``block=True`` gives ``BlockDescent``
+    (:126-147)."""
+
+    def __init__(self, data, maxlag, n_components, step_decrement=5., block=False, **kw):
+        super().__init__(data, maxlag, n_components, **kw)
+        self.W, self.H = self.W.copy(), self.H.copy()
+        self.step_size = 1e-4                                    # :29
+        self.step_decrement = step_decrement
+        self.block = block
+        self.cache_gW()                                          # :37-38
+        self.cache_gH()
+
+    def cache_gW(self):                                          # :40-45
+        self.gW = np.stack([s_T_dot(self.resids, self.H, l) for l in range(self.maxlag)])
+        return self.gW
+
+    def cache_gH(self):                                          # :47-52
+        self.gH = tensor_transconv(self.W, self.resids)
+        return self.gH
+
+    def lipschitz_W(self):
+        return lipschitz_W(self.H, self.maxlag)
+
+    def update(self):
+        if not self.block:                                       # :81-92
+            lam = self.lipschitz_W()
+            self.W = projected_step(self.W, self.gW, 1.0 / lam)
+            self.H = projected_step(self.H, self.gH, self.step_size)
+            self.cache_resids()
+            self.cache_gW()
+            self.cache_gH()
+        else:                                                    # :132-147
+            self.W = projected_step(self.W, self.gW, 1.0 / self.lipschitz_W())
+            self.cache_resids()
+            self.cache_gH()
+            self.H = projected_step(self.H, self.gH, self.step_size)
+            self.cache_resids()
+            self.cache_gW()
+        return self.loss
+
+    def converged(self, loss_hist):                              # :94-113
+        d_loss = np.diff(loss_hist[-self.patience:])
+        if d_loss[-1] > 0:
+            self.step_size /= self.step_decrement
+            return False
+        return bool(np.all(np.abs(d_loss) < self.tol))
+
+
+# --------------------------------------------------------------------------
 # T-sharded restatement (what the multi-GPU path must reproduce)
 # --------------------------------------------------------------------------
 def sharded_update(X, W, H, n_shards):
