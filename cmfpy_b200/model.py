@@ -146,9 +146,62 @@ class CMF(object):
     def n_timesteps(self):
         return self.factors.shape[1]
 
+    def sort_components(self, data):
+        """Orders the components by explanatory power (reference model.py:178-189; there `data` is an undefined
+        name - it is an argument here).  The per-component reconstructions and residual norms run on the device."""
+        ind = np.argsort(compute_loadings(data, self.motifs, self.factors, device=getattr(self, "_device", 0)))
+        self._W = self._W[:, :, ind]
+        self._H = self._H[ind, :]
+        return ind
+
     def argsort_units(self):
         """Units ordered by dominant component then peak lag (reference model.py:247-259)."""
         W = self.motifs
         top = np.argmax(W.sum(axis=0), axis=-1)
         peak = np.argmax(W[:, np.arange(self.n_features), top], axis=0)
         return np.lexsort((peak, top))
+
+
+def compute_loadings(data, W, H, device=0, precision="fp32"):
+    """||W_k (*) H_k - data||_F / (||data||_F + EPSILON) for every component k (reference model.py:278-293, which
+    calls names that do not exist there).  data is uploaded once; each component costs one fused
+    reconstruction + residual reduction on the device and nothing N x T comes back."""
+    import ctypes as C
+    from . import _lib
+    from .common import EPSILON
+    lib = _lib.load()
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    W = np.ascontiguousarray(W, dtype=np.float64)
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    L, N, K = W.shape
+    T = H.shape[1]
+    if data.shape != (N, T) or H.shape[0] != K:
+        raise ValueError("data, W and H disagree on their dimensions")
+    h = C.c_void_p()
+    p = _lib.Params(n_features=N, n_components=1, maxlag=L, t_local=T, t_global=T, t_offset=0, device=device,
+                    precision=_lib.PRECISIONS[precision], stream=None, denominators=_lib.CMF_DEN_DIRECT)
+    _lib.check(lib.cmf_mu_create(C.byref(h), C.byref(p)))
+    try:
+        _lib.check(lib.cmf_mu_set_data(h, data.ctypes.data, _lib.CMF_F64, _lib.CMF_HOST, T, T))
+        ss, neg = C.c_double(0), C.c_int(0)
+        _lib.check(lib.cmf_mu_data_stats(h, C.byref(ss), C.byref(neg)))
+        data_mag = float(np.sqrt(ss.value))
+        loadings = []
+        for k in range(K):
+            Wk = np.ascontiguousarray(W[:, :, k:k + 1])
+            Hk = np.ascontiguousarray(H[k:k + 1, :])
+            _lib.check(lib.cmf_mu_set_factors(h, Wk.ctypes.data, Hk.ctypes.data, _lib.CMF_F64, _lib.CMF_HOST, T))
+            _lib.check(lib.cmf_mu_recon_loss(h))
+            r = C.c_double(0)
+            _lib.check(lib.cmf_mu_resid_sumsq(h, C.byref(r)))
+            loadings.append(float(np.sqrt(r.value)) / (data_mag + EPSILON))
+    finally:
+        lib.cmf_mu_destroy(h)
+    return loadings
+
+
+def renormalize(W, H):
+    """Rows of H to unit energy, the scale moved into W (reference model.py:296-311); returns new arrays."""
+    from .common import EPSILON
+    row_norms = np.linalg.norm(H, axis=1) + EPSILON
+    return W * row_norms[None, None, :], H / row_norms[:, None]

@@ -215,6 +215,28 @@ def test_score_on_device_against_oracle(built_lib):
             assert abs(score(W, H, X, precision="tf32x3") - ref) <= 1e-4 * max(1.0, abs(ref))
 
 
+def test_loadings_sort_and_renormalize(built_lib):
+    """compute_loadings / sort_components / renormalize (reference model.py:178-189, 278-311)."""
+    from cmfpy_b200 import CMF
+    from cmfpy_b200.model import compute_loadings, renormalize
+    rng = np.random.default_rng(5)
+    N, T, K, L = 40, 300, 4, 7
+    W, H = rng.random((L, N, K)), rng.random((K, T))
+    W[:, :, 2] *= 3.0                                   # one dominant component
+    X = o.cmf_predict(W, H)
+    ref = [np.linalg.norm(o.cmf_predict(W[:, :, k:k + 1], H[k:k + 1]) - X) / (np.linalg.norm(X) + o.EPSILON) for k in range(K)]
+    got = compute_loadings(X, W, H)
+    assert_allclose(got, ref, rtol=1e-5)
+    model = CMF(K, L)
+    model._W, model._H = W.copy(), H.copy()
+    ind = model.sort_components(X)
+    assert list(ind) == list(np.argsort(ref)) and ind[0] == 2
+    assert np.array_equal(model.motifs, W[:, :, ind]) and np.array_equal(model.factors, H[ind])
+    W2, H2 = renormalize(W, H)
+    assert_allclose(np.linalg.norm(H2, axis=1), 1.0, rtol=1e-12)
+    assert_allclose(o.cmf_predict(W2, H2), X, rtol=1e-10)
+
+
 # ---- model API --------------------------------------------------------------
 def test_cmf_fit_predict_score(built_lib):
     from cmfpy_b200 import CMF
