@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--no-profile", action="store_true",
                     help="no per-kernel events in the timed region (lets the iteration replay as a CUDA graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32-grade", action="store_true",
+                    help="skip the short secondary measurement of the error-compensated tf32x3 mode")
     return ap.parse_args()
 
 
@@ -321,7 +323,6 @@ def run_b200(args):
     alg = ShardedMultUpdate(X[:, :ncols_x], N, T, K, L, t_offset=t_begin, t_local=Tloc,
                             initW=W0, initH=H0, precision=precision, device=local_rank,
                             group=dist.group.WORLD if dist else None, denominators=args.denominators)
-    del X, H0
     torch.cuda.synchronize()
 
     def barrier():
@@ -362,6 +363,36 @@ def run_b200(args):
     if not args.no_e2e:
         e2e = run_e2e(args, torch, N, T, K, L, Tloc, rank, world, local_rank, precision, dist)
 
+    # fp32-grade companion number (north_star: the 1e-4 parity bar is an fp32 bar, "TF32 variant reported
+    # separately"): the same workload on the error-compensated tensor-core mode, a few steps, outside the timed region
+    fp32_grade = None
+    if (precision == "tf32" and not args.no_fp32_grade and
+            lib.cmf_precision_supported(_lib.CMF_PREC_TF32X3, N, K, L)):
+        alg3 = ShardedMultUpdate(X[:, :ncols_x], N, T, K, L, t_offset=t_begin, t_local=Tloc,
+                                 initW=W0, initH=H0, precision="tf32x3", device=local_rank,
+                                 group=dist.group.WORLD if dist else None)
+        alg3.update_many(2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(alg3.torch_stream)
+        l3 = alg3.update_many(5)
+        e1.record(alg3.torch_stream)
+        torch.cuda.synchronize()
+        ms3 = e0.elapsed_time(e1)
+        if dist:
+            t3 = torch.tensor([ms3], device=dev)
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            ms3 = float(t3.item())
+        fp32_grade = {"precision": "tf32x3", "path": alg3.path_name, "value": 5 / (ms3 * 1e-3), "unit": UNIT,
+                      "steps": 5, "warmup": 2, "loss_after_7_steps": l3[-1],
+                      "what": "same workload, every product as three TF32 MMAs on hi/lo operand pairs; loss "
+                              "trajectories within 1e-4 of the float64 reference on all golden cases but config B "
+                              "(profiles/r01_trajectory_errors_tf32x3.log)"}
+        alg3.close()
+        del alg3
+    del X, H0
     if rank != 0:
         alg.close()
         if dist:
@@ -429,7 +460,7 @@ def run_b200(args):
                                             "halo pushes, loss ring)",
                                     "nccl": "NCCL all-reduce + send/recv between the phases"}[alg.transport])},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "cpu_affinity": affinity,
-        "roofline": roofline, "cpu_baseline": cb,
+        "roofline": roofline, "cpu_baseline": cb, "fp32_grade": fp32_grade,
         "final_loss": losses[-1],
     }
     print(json.dumps(line), flush=True)

@@ -600,7 +600,7 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
     {
       const double contraction_flops = 2.0 * h->N * h->K * (double)h->L * (double)h->Tloc;
       const bool want = p->denominators == CMF_DEN_GRAM || (p->denominators == CMF_DEN_AUTO && contraction_flops >= 2e11);
-      h->tcs.gram_request = (want && !h->x3) ? 3 : 0;
+      h->tcs.gram_request = want ? 3 : 0;
     }
     rc = tc::init(h->tcs, d, h->Xt, nullptr, h->Ht, h->W, h->numden, h->hterms, h->loss_partials,
                   h->n_loss_partials, h->d_sumsq, h->stream, h->Xlo);
@@ -1039,7 +1039,7 @@ int cmf_mu_launch_count(cmf_mu_t* h, long long* count) {
 const char* cmf_mu_path_name(cmf_mu_t* h) {
   if (!h) return "none";
   if (!h->use_tc) return "ffma-fp32";
-  if (h->x3) return "tcgen05-tf32x3";
+  if (h->x3) return h->tcs.gram == 3 ? "tcgen05-tf32x3+gram" : (h->tcs.gram ? "tcgen05-tf32x3+gram(partial)" : "tcgen05-tf32x3");
   if (h->tcs.mask != 7) return "tcgen05-tf32(partial)";
   if (h->tcs.gram == 3) return "tcgen05-tf32+gram";
   return h->tcs.gram ? "tcgen05-tf32+gram(partial)" : "tcgen05-tf32";

@@ -97,17 +97,18 @@ struct ReconParams {
   // (0: A lo, B hi;  1: A hi, B lo;  2: A hi, B hi - the small cross terms first, while the accumulator is
   // small and its truncation costs nothing); the lo halves sit lo_off columns to the right in both operand arrays.
   int x3, cbx, lo_off;
-  float* Elo;                      // x3: est^T = Et (hi) + Elo
+  int lo_off_b;                    // lo offset of the B operand when it differs from A's (0: same as lo_off)
+  float* Elo;                      // x3: est^T = Et (hi) + Elo; null: the result is stored unsplit
   const float* Xlo;                // x3: X^T = Xt (hi) + Xlo
   int* err;
 };
 
 // (reduction block) -> (column block within a combo, column offsets of the A and B halves)
 struct X3Sel { int cbr, a_off, b_off; };
-__device__ __forceinline__ X3Sel x3_select(int x3, int cbx, int lo_off, int vcb) {
+__device__ __forceinline__ X3Sel x3_select(int x3, int cbx, int lo_off, int lo_off_b, int vcb) {
   if (!x3) return X3Sel{vcb, 0, 0};
   const int combo = vcb / cbx;
-  return X3Sel{vcb - combo * cbx, combo == 0 ? lo_off : 0, combo == 1 ? lo_off : 0};
+  return X3Sel{vcb - combo * cbx, combo == 0 ? lo_off : 0, combo == 1 ? (lo_off_b ? lo_off_b : lo_off) : 0};
 }
 
 constexpr int kReconLagsPerStage = 2;              // lags per pipeline stage: 8 MMAs per barrier round trip
@@ -180,7 +181,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const long long tt = c.tile / p.n_tiles_n;
         mbar_arrive_expect_tx(&hfull[hb], hbytes);
         uint8_t* hdst = Hs + (size_t)hb * hbytes;
-        const X3Sel sel = x3_select(kX3, p.cbx, p.lo_off, c.cb);
+        const X3Sel sel = x3_select(kX3, p.cbx, p.lo_off, p.lo_off_b, c.cb);
         for (int rb = 0; rb < wrows / 64; ++rb)
           tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], sel.cbr * 32 + sel.b_off,
                       (int)(tt * 256 + p.h_shift + rb * 64));
@@ -193,7 +194,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const Chunk nxt = next_chunk(cur);
         bool prefetched = !nxt.valid;
         const int nt = (int)(cur.tile % p.n_tiles_n);
-        const X3Sel sel = x3_select(kX3, p.cbx, p.lo_off, cur.cb);
+        const X3Sel sel = x3_select(kX3, p.cbx, p.lo_off, p.lo_off_b, cur.cb);
         int stage_in_chunk = 0;
         for (int l = 0; l < L; l += kReconLagsPerStage, ++stage_in_chunk) {
           if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
@@ -284,7 +285,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (n_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = (tau0 + j < p.t_own) ? __ldcs(Xt + off0 + (size_t)j * np) : 0.f;
-          if (kX3) {
+          if (kX3 && Xlo) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] += (tau0 + j < p.t_own) ? __ldcs(Xlo + off0 + (size_t)j * np) : 0.f;
           }
@@ -315,7 +316,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               tile_loss = fmaf(d, d, tile_loss);
             }
             if (!p.skip_store) {
-              if (kX3) {
+              if (kX3 && Elo) {
                 const float hi = round_tf32(v);
                 Et[off0 + (size_t)j * np] = hi;
                 Elo[off0 + (size_t)j * np] = round_tf32(v - hi);
@@ -1306,9 +1307,10 @@ fold_w_x3_kernel(float* __restrict__ Wv, const float* __restrict__ W, int L, int
 //   P[d][k'][k] = sum_t H[k'][t] H[k][t-d]: the W-terms kernel run on H^T itself.
 // Mt[(l,k)][(l'v, c)] = round_tf32(A[l - l'][k'][k]) with (l', k') the real lag / component that virtual lag l'v,
 // column c of Wv holds - the K-major B operand of a plain GEMM with Wv.
+// x3: every row is [hi (Lv KW) | lo (Lv KW)].
 __global__ void __launch_bounds__(256)
 toeplitz_kernel(const float* __restrict__ P, float* __restrict__ Mt, int L, int Lv, int Kp, int s, int KW,
-                long long rows_alloc) {
+                long long rows_alloc, int x3) {
   const long long ld = (long long)Lv * KW;
   const long long total = rows_alloc * ld;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -1325,13 +1327,20 @@ toeplitz_kernel(const float* __restrict__ P, float* __restrict__ Mt, int L, int 
       const int d = l - lp;
       v = (d >= 0) ? P[((size_t)d * Kp + kq) * Kp + k] : P[((size_t)(-d) * Kp + k) * Kp + kq];
     }
-    Mt[i] = round_tf32(v);
+    if (x3) {
+      const float hi = round_tf32(v);
+      Mt[tau * 2 * ld + col] = hi;
+      Mt[tau * 2 * ld + ld + col] = round_tf32(v - hi);
+    } else {
+      Mt[i] = round_tf32(v);
+    }
   }
 }
 
 // Wt[(l*Kp + k)][n] = round_tf32(W[l][n][k])      (32x32 tiles through smem)
+// x3: rows are [hi (lo_off columns) | lo]
 __global__ void __launch_bounds__(256)
-transpose_round_w_kernel(const float* __restrict__ W, float* __restrict__ Wt, int Np, int Kp, long long ldt) {
+transpose_round_w_kernel(const float* __restrict__ W, float* __restrict__ Wt, int Np, int Kp, long long ldt, int lo_off) {
   __shared__ float tile[32][33];
   const int l = blockIdx.z;
   const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
@@ -1345,7 +1354,11 @@ transpose_round_w_kernel(const float* __restrict__ W, float* __restrict__ Wt, in
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int k = k0 + ty + j, n = n0 + tx;
-    if (k < Kp && n < Np) Wt[((size_t)l * Kp + k) * ldt + n] = round_tf32(tile[tx][ty + j]);
+    if (k < Kp && n < Np) {
+      const float v = tile[tx][ty + j], hi = round_tf32(v);
+      Wt[((size_t)l * Kp + k) * ldt + n] = hi;
+      if (lo_off) Wt[((size_t)l * Kp + k) * ldt + lo_off + n] = round_tf32(v - hi);
+    }
   }
 }
 

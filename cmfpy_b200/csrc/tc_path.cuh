@@ -89,6 +89,7 @@ struct TcState {
   int gram = 0;
   int gram_request = 0;             // from cmf_mu_params.denominators (CMF_GRAM in the environment overrides)
   int LK = 0, Lr = 0, Lrv = 0, dh_wrows = 0;
+  int NpA = 0;                      // row half-width of Wt (Np rounded up to 32: the lo half starts on a TMA box boundary)
   long long g_rows = 0;             // rows allocated for G (LK rounded up to 256)
   float *Wt = nullptr, *G = nullptr, *Rw = nullptr, *Rwv = nullptr, *Etail = nullptr;
   long long ntail = 0;              // rows of est past the end of the data that fall inside this shard's window
@@ -209,6 +210,22 @@ inline int refresh_h(TcState& s, cudaStream_t stream, long long row0, long long 
   return launch_ok("fold_h");
 }
 
+// 3xTF32 bookkeeping of a launch on the recon kernel: p.CB holds the reduction blocks of ONE operand pass on entry
+inline void set_x3(const TcState& s, ReconParams& p, int lo_a, int lo_b) {
+  if (!s.x3) return;
+  p.x3 = 1; p.cbx = p.CB; p.CB = 3 * p.cbx; p.lo_off = lo_a; p.lo_off_b = lo_b;
+}
+inline void launch_recon(const TcState& s, int grid, size_t smem, cudaStream_t stream, const CUtensorMap& a,
+                         const CUtensorMap& b, const ReconParams& p) {
+  if (s.x3) tc_recon_kernel<1><<<grid, kReconThreads, smem, stream>>>(a, b, p);
+  else tc_recon_kernel<0><<<grid, kReconThreads, smem, stream>>>(a, b, p);
+}
+inline int set_recon_smem(size_t bytes) {
+  CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
 // ---- lag autocorrelation of H:  P[d][a][b] = sum_t H[a][t] H[b][t-d]  (the W-terms kernel run on H^T itself) ----
 // Used by the Gram route (den_w_gram) and by lipschitz_W of the gradient solvers (gradient_descent.py:54-57).
 inline int ensure_autocorr(TcState& s) {
@@ -296,10 +313,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   }
   CMF_TRY(make_map(&s.tmW_k1, s.Wv, (long long)f.Lv * d.Np, s.KWs, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
   CMF_TRY(make_map(&s.tmH_k1, s.Hv, d.RH, s.KWs, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
-  CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)recon_smem_bytes(f.recon_wrows)));
-  CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)recon_smem_bytes(f.recon_wrows)));
+  CMF_TRY(set_recon_smem(recon_smem_bytes(f.recon_wrows)));
 
   s.recon2 = 0;
   if (const char* e = getenv("CMF_RECON2")) s.recon2 = atoi(e);
@@ -373,7 +387,6 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   // ---- Gram route ---------------------------------------------------------
   s.gram = s.gram_request;
   if (const char* e = getenv("CMF_GRAM")) s.gram = atoi(e);
-  if (s.x3) s.gram = 0;              // the Gram operators are not error-compensated: direct denominators only
   s.LK = d.L * d.Kp;
   s.Lr = 2 * d.L - 1;
   s.Lrv = (s.Lr + f.s - 1) / f.s;
@@ -382,17 +395,21 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   s.ntail = d.Tloc + d.h - d.t_valid;
   if (recon_smem_bytes(s.dh_wrows) > kMaxSmem || (long long)s.g_rows * s.LK * 4 > (1ll << 30)) s.gram &= ~1;
   if (s.gram & 1) {
-    CMF_CUDA(cudaMalloc((void**)&s.Wt, (size_t)s.LK * d.Np * 4));
+    // 3xTF32: Wt rows are [hi (NpA) | lo (NpA)], Rwv rows [hi (KW) | lo (KW)]
+    s.NpA = s.x3 ? round_up(d.Np, 32) : d.Np;
+    const long long wt_ld = (long long)halves * s.NpA;
+    CMF_CUDA(cudaMalloc((void**)&s.Wt, (size_t)s.LK * wt_ld * 4));
+    CMF_CUDA(cudaMemsetAsync(s.Wt, 0, (size_t)s.LK * wt_ld * 4, stream));
     CMF_CUDA(cudaMalloc((void**)&s.G, (size_t)s.g_rows * s.LK * 4));
     CMF_CUDA(cudaMalloc((void**)&s.Rw, (size_t)s.Lr * d.Kp * d.Kp * 4));
-    CMF_CUDA(cudaMalloc((void**)&s.Rwv, (size_t)s.Lrv * d.Kp * f.KW * 4));
-    CMF_CUDA(cudaMemsetAsync(s.Rwv, 0, (size_t)s.Lrv * d.Kp * f.KW * 4, stream));
-    CMF_TRY(make_map(&s.tmWt_a, s.Wt, s.LK, d.Np, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
-    CMF_TRY(make_map(&s.tmWt_b, s.Wt, s.LK, d.Np, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
-    CMF_TRY(make_map(&s.tmRw_a, s.Rwv, (long long)s.Lrv * d.Kp, f.KW, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+    CMF_CUDA(cudaMalloc((void**)&s.Rwv, (size_t)s.Lrv * d.Kp * s.KWs * 4));
+    CMF_CUDA(cudaMemsetAsync(s.Rwv, 0, (size_t)s.Lrv * d.Kp * s.KWs * 4, stream));
+    CMF_TRY(make_map(&s.tmWt_a, s.Wt, s.LK, wt_ld, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+    CMF_TRY(make_map(&s.tmWt_b, s.Wt, s.LK, wt_ld, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
+    CMF_TRY(make_map(&s.tmRw_a, s.Rwv, (long long)s.Lrv * d.Kp, s.KWs, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
     const size_t need = recon_smem_bytes(s.dh_wrows) > recon_smem_bytes(f.recon_wrows) ? recon_smem_bytes(s.dh_wrows)
                                                                                         : recon_smem_bytes(f.recon_wrows);
-    CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    CMF_TRY(set_recon_smem(need));
   }
   // H terms: split the feature chunks of a tile so that the tensor-memory accumulation chain of the
   // numerator is about as long as the one of the Gram denominator (equal truncation bias => no drift of
@@ -416,16 +433,15 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     const long long items = s.h_pp ? tt * ((s.gram & 1) ? 1 : 2) * s.h_split : ((s.gram & 1) ? (tt + 1) / 2 : tt) * s.h_split;
     s.hterms_grid = (int)(items < d.num_sms ? items : d.num_sms);
   }
-  if ((long long)s.g_rows * f.Lv * f.KW * 4 > (1ll << 30)) s.gram &= ~2;
+  if ((long long)s.g_rows * f.Lv * f.KW * halves * 4 > (1ll << 30)) s.gram &= ~2;
   CMF_CUDA(cudaMalloc((void**)&s.wpart, (size_t)s.n_chunks * ((s.gram & 2) ? 1 : 2) * s.wcount * 4));
   if (s.gram && s.ntail > 0) CMF_CUDA(cudaMalloc((void**)&s.Etail, (size_t)256 * d.Np * 4));
   if (s.gram & 2) {
     CMF_TRY(ensure_autocorr(s));
-    CMF_CUDA(cudaMalloc((void**)&s.Mt, (size_t)s.g_rows * f.Lv * f.KW * 4));
-    CMF_TRY(make_map(&s.tmMt_b, s.Mt, s.g_rows, (long long)f.Lv * f.KW, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
-    CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(recon_smem_bytes(s.dh_wrows) <= kMaxSmem && recon_smem_bytes(s.dh_wrows) > recon_smem_bytes(f.recon_wrows)
-                                            ? recon_smem_bytes(s.dh_wrows) : recon_smem_bytes(f.recon_wrows))));
+    CMF_CUDA(cudaMalloc((void**)&s.Mt, (size_t)s.g_rows * f.Lv * f.KW * halves * 4));
+    CMF_TRY(make_map(&s.tmMt_b, s.Mt, s.g_rows, (long long)f.Lv * f.KW * halves, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
+    CMF_TRY(set_recon_smem(recon_smem_bytes(s.dh_wrows) <= kMaxSmem && recon_smem_bytes(s.dh_wrows) > recon_smem_bytes(f.recon_wrows)
+                               ? recon_smem_bytes(s.dh_wrows) : recon_smem_bytes(f.recon_wrows)));
   }
   s.ready = true;
   return 0;
@@ -463,7 +479,8 @@ inline int tail_est(TcState& s, cudaStream_t stream) {
   p.n_tiles = p.n_tiles_n;
   p.t_own = 0; p.t_valid = 256;
   p.Et = s.Etail; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
-  tc_recon_kernel<0><<<p.n_tiles_n, kReconThreads, recon_smem_bytes(f.recon_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
+  set_x3(s, p, f.KW, f.KW);
+  launch_recon(s, p.n_tiles_n, recon_smem_bytes(f.recon_wrows), stream, s.tmW_k1, s.tmH_k1, p);
   return launch_ok("tail_est");
 }
 
@@ -474,7 +491,7 @@ inline int den_w_gram(TcState& s, cudaStream_t stream) {
   // (a) P[d][k'][k] = sum_t H[k'][t] H[k][t-d] over the owned columns: the W-terms kernel on H^T
   CMF_TRY(autocorr(s, stream));
   // (b) block-Toeplitz operand
-  toeplitz_kernel<<<ew_blocks(s, s.g_rows * f.Lv * f.KW), 256, 0, stream>>>(s.P, s.Mt, d.L, f.Lv, d.Kp, f.s, f.KW, s.g_rows);
+  toeplitz_kernel<<<ew_blocks(s, s.g_rows * f.Lv * f.KW), 256, 0, stream>>>(s.P, s.Mt, d.L, f.Lv, d.Kp, f.s, f.KW, s.g_rows, s.x3);
   CMF_TRY(launch_ok("toeplitz"));
   // (c) den_W[n][(l,k)] = sum_{(l'v,c)} Wv[l'v][n][c] Mt[(l,k)][(l'v,c)]  (plain GEMM on the recon kernel)
   float* den = s.numden + s.wcount;
@@ -487,7 +504,8 @@ inline int den_w_gram(TcState& s, cudaStream_t stream) {
     p.t_own = 0; p.t_valid = s.LK;
     p.Et = den; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
     const int grid = (int)(p.n_tiles < d.num_sms ? p.n_tiles : d.num_sms);
-    tc_recon_kernel<0><<<grid, kReconThreads, recon_smem_bytes(256), stream>>>(s.tmW_k1, s.tmMt_b, p);
+    set_x3(s, p, f.KW, f.Lv * f.KW);
+    launch_recon(s, grid, recon_smem_bytes(256), stream, s.tmW_k1, s.tmMt_b, p);
     CMF_TRY(launch_ok("gram_den_w"));
   }
   // (d) remove the terms of est that lie past the end of the data
@@ -568,7 +586,8 @@ inline int den_h_gram(TcState& s, cudaStream_t stream) {
   // (a) Wt = round(W)^T
   {
     dim3 grid((unsigned)ceil_div_ll(d.Np, 32), (unsigned)ceil_div_ll(d.Kp, 32), (unsigned)d.L);
-    transpose_round_w_kernel<<<grid, 256, 0, stream>>>(s.W, s.Wt, d.Np, d.Kp, d.Np);
+    transpose_round_w_kernel<<<grid, 256, 0, stream>>>(s.W, s.Wt, d.Np, d.Kp, (long long)(s.x3 ? 2 : 1) * s.NpA,
+                                                       s.x3 ? s.NpA : 0);
     CMF_TRY(launch_ok("transpose_round_w"));
   }
   // (b) G = Wt Wt^T : a plain GEMM on the recon kernel (one "lag", reduction blocks = 32-feature chunks)
@@ -581,13 +600,16 @@ inline int den_h_gram(TcState& s, cudaStream_t stream) {
     p.t_own = 0; p.t_valid = s.g_rows;
     p.Et = s.G; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
     const int grid = (int)(p.n_tiles < d.num_sms ? p.n_tiles : d.num_sms);
-    tc_recon_kernel<0><<<grid, kReconThreads, recon_smem_bytes(256), stream>>>(s.tmWt_a, s.tmWt_b, p);
+    set_x3(s, p, s.NpA, s.NpA);
+    launch_recon(s, grid, recon_smem_bytes(256), stream, s.tmWt_a, s.tmWt_b, p);
     CMF_TRY(launch_ok("gram_G"));
   }
   // (c) R = lag-diagonal sums of G, as a W-like operand (rounded / folded like W)
   diag_sum_kernel<<<ew_blocks(s, (long long)s.Lr * d.Kp * d.Kp), 256, 0, stream>>>(s.G, s.LK, s.Rw, d.L, d.Kp);
   CMF_TRY(launch_ok("diag_sum"));
-  if (f.s == 1) {
+  if (s.x3) {
+    fold_w_x3_kernel<<<ew_blocks(s, (long long)s.Lrv * d.Kp * f.KW), 256, 0, stream>>>(s.Rwv, s.Rw, s.Lr, s.Lrv, d.Kp, d.Kp, f.s, f.KW);
+  } else if (f.s == 1) {
     const long long n4 = (long long)s.Lr * d.Kp * d.Kp / 4;
     ew::round_copy_kernel<<<ew_blocks(s, n4), 256, 0, stream>>>((float4*)s.Rwv, (const float4*)s.Rw, n4);
   } else {
@@ -605,7 +627,8 @@ inline int den_h_gram(TcState& s, cudaStream_t stream) {
     p.t_own = 0; p.t_valid = d.TO;
     p.Et = den; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
     const int grid = (int)(p.n_tiles < d.num_sms ? p.n_tiles : d.num_sms);
-    tc_recon_kernel<0><<<grid, kReconThreads, recon_smem_bytes(s.dh_wrows), stream>>>(s.tmRw_a, s.tmH_k1, p);
+    set_x3(s, p, f.KW, f.KW);
+    launch_recon(s, grid, recon_smem_bytes(s.dh_wrows), stream, s.tmRw_a, s.tmH_k1, p);
     CMF_TRY(launch_ok("gram_den_h"));
   }
   // (e) remove the terms of est that lie past the end of the data (only the shard that sees the end)

@@ -35,13 +35,13 @@ FULL_CASES = [n for n, c in CASES.items() if c[6]]
 ALL_CASES = list(CASES)
 
 
-PRECISION_MODES = ["fp32", "tf32", "tf32g", "tf32x3"]   # tf32g = tf32 with the Gram-route denominators;
+PRECISION_MODES = ["fp32", "tf32", "tf32g", "tf32x3", "tf32x3g"]   # ...g = Gram-route denominators;
                                                         # tf32x3 = error-compensated tensor-core path (fp32-grade)
-EXACT_MODES = ("fp32", "tf32x3")                        # modes held to the 1e-4 parity bar
+EXACT_MODES = ("fp32", "tf32x3", "tf32x3g")             # modes held to the 1e-4 parity bar
 
 
 def _split(precision):
-    return ("tf32", "gram") if precision == "tf32g" else (precision, "direct")
+    return (precision[:-1], "gram") if precision.endswith("g") else (precision, "direct")
 
 
 def _supported(precision, N, K, L):
@@ -79,12 +79,16 @@ def test_single_step_kernels(built_lib, name, precision):
     N, T, K, L = (int(v) for v in g["shape"])
     if not _supported(precision, N, K, L):
         pytest.skip("no %s kernel for this shape" % precision)
-    rel = 2e-5 if precision in EXACT_MODES else 2e-3
+    # tf32x3: tensor memory accumulates with round-toward-zero, a relative bias of ~5.7e-8 per MMA step of the
+    # chain (measured: est at L=70, K=32 -> 280 steps -> 1.6e-5; Gram den_H, 556 steps -> 3.4e-5)
+    rel = 2e-5 if precision == "fp32" else (6e-5 if precision in EXACT_MODES else 2e-3)
     alg = _solver(X, W0, H0, L, K, precision)
     if precision == "tf32g":
         assert alg.path_name == "tcgen05-tf32+gram"
     if precision == "tf32x3":
         assert alg.path_name == "tcgen05-tf32x3"
+    if precision == "tf32x3g":
+        assert alg.path_name == "tcgen05-tf32x3+gram"
     _close(alg.est, g["est0"], rel)
     numW, denW = alg._compute_mult_W()
     _close(numW, g["numW"], rel)
@@ -118,7 +122,7 @@ def test_loss_trajectory(built_lib, name, precision):
     rel = np.abs(hist - ref) / ref
     print("%s/%s: max rel loss err %.3e (final %.6f vs %.6f)" % (name, precision, rel.max(), hist[-1], ref[-1]))
     tol = TRAJ_TOL if precision in EXACT_MODES else TRAJ_TOL_TF32
-    if precision == "tf32x3":
+    if precision.startswith("tf32x3"):
         tol = TRAJ_TOL_X3.get(name, tol)
     assert rel.max() <= tol
     Wg, Hg = alg.W, alg.H
@@ -314,7 +318,7 @@ def test_properties_large(built_lib, precision):
     alg.close()
 
 
-@pytest.mark.parametrize("precision", ["tf32", "tf32g", "tf32x3"])
+@pytest.mark.parametrize("precision", ["tf32", "tf32g", "tf32x3", "tf32x3g"])
 def test_fp32_and_tf32_agree_large(built_lib, precision):
     N, T, K, L = 512, 1 << 14, 16, 32
     if not _supported("tf32", N, K, L):
