@@ -49,7 +49,7 @@ enum { CMF_HOST = 0, CMF_DEVICE = 1 };
  *                TF32 pair (hi = RN(x), lo = RN(x - hi)); each product is
  *                a_lo b_hi + a_hi b_lo + a_hi b_hi (error-compensated "3xTF32":
  *                ~22 mantissa bits per operand, fp32-grade results at a third
- *                of the tf32 rate).  Direct denominators only.               */
+ *                of the tf32 rate), on either denominator route.             */
 enum { CMF_PREC_FP32 = 0, CMF_PREC_TF32 = 1, CMF_PREC_TF32X3 = 2 };
 /* How the MU denominators (the est-dependent halves of mult.py:37-38, 46) are formed on the tf32 path.
  * CMF_DEN_DIRECT: contract est, as the reference does.
