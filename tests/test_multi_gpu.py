@@ -37,7 +37,7 @@ def _worker(rank, world, port, shape, precision, n_iter, q, transport="auto"):
         Tl = T // world
         t0 = rank * Tl
         ncols = min(Tl + L - 1, T - t0)
-        prec, den = ("tf32", "gram") if precision == "tf32g" else (precision, "direct")
+        prec, den = (precision[:-1], "gram") if precision.endswith("g") else (precision, "direct")
         alg = ShardedMultUpdate(np.ascontiguousarray(X[:, t0:t0 + ncols]), N, T, K, L, t_offset=t0, t_local=Tl,
                                 initW=W0, initH=np.ascontiguousarray(H0[:, t0:t0 + Tl]), precision=prec,
                                 device=rank, group=dist.group.WORLD, tol=0, denominators=den, transport=transport)
@@ -58,7 +58,7 @@ def _worker(rank, world, port, shape, precision, n_iter, q, transport="auto"):
                                              ("tf32", (200, 4096, 32, 64)), ("tf32", (128, 2048, 30, 9)),
                                              ("tf32g", (200, 4096, 32, 64)), ("tf32g", (96, 2048, 5, 12)),
                                              ("tf32g", (256, 2048, 128, 16)), ("tf32x3", (200, 4096, 32, 64)),
-                                             ("fp32", (40, 600, 3, 1))])
+                                             ("tf32x3g", (200, 4096, 32, 64)), ("fp32", (40, 600, 3, 1))])
 def test_sharded_equals_single_gpu(built_lib, precision, shape, transport):
     """transport "peer": the library's own collectives over NVLink peer memory (fused all-reduce + W update,
     halo pushes, loss ring); "nccl": torch.distributed collectives between the phases."""
@@ -83,11 +83,11 @@ def test_sharded_equals_single_gpu(built_lib, precision, shape, transport):
         p.join(timeout=120)
         assert p.exitcode == 0
     X, W0, H0 = make_inputs(N, T, K, L, "planted", seed=5)
-    prec, den = ("tf32", "gram") if precision == "tf32g" else (precision, "direct")
+    prec, den = (precision[:-1], "gram") if precision.endswith("g") else (precision, "direct")
     ref = MultUpdate(X, ModelDimensions(X, maxlag=L, n_components=K), initW=W0, initH=H0, tol=0, precision=prec,
                      denominators=den)
     ref_hist = [ref.loss] + ref.update_many(n_iter)
-    tol = 2e-5 if precision in ("fp32", "tf32x3") else 2e-4
+    tol = 2e-5 if precision in ("fp32", "tf32x3", "tf32x3g") else 2e-4
     H = np.concatenate([o[0] for o in out], axis=1)
     for o in out:
         assert np.abs(np.array(o[2]) - ref_hist).max() / ref_hist[-1] < tol
