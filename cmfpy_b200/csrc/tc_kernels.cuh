@@ -765,6 +765,8 @@ struct HTermsParams {
   float* scratch;                  // [n_split][n_slots][4][32][ts]
   int x3, lo_off;                  // 3xTF32: the feature chunks of an item are walked three times - (W lo, S hi),
                                    // (W hi, S lo), (W hi, S hi) - into the same accumulators
+  int dbg;                         // timing experiments only (CMF_HT_DBG; results are then WRONG): 1 = drain without
+                                   // stores, 2 = no drain at all, 4 = every window from time tile 0 (L2-resident)
   int* err;
 };
 
@@ -847,7 +849,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           uint8_t* wdst = Ws + ((size_t)wb * 2 + src) * wbytes;
           const CUtensorMap* tmS = (src && !p.pair_mode) ? (c.combo == 1 ? &tmElo : &tmE)
                                                          : (c.combo == 1 ? &tmXlo : &tmX);
-          const int base = (int)((p.pair_mode ? 2 * tile + src : tile) * 256);
+          const int base = (p.dbg & 4) ? 0 : (int)((p.pair_mode ? 2 * tile + src : tile) * 256);
           for (int rb = 0; rb < wrows / 32; ++rb)
             tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], c.nc * 32, base + rb * 32);
         }
@@ -937,6 +939,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < 8 * p.n_src; ++c) {
+        if (p.dbg & 2) break;
         uint32_t r[32];
         tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
         tmem_ld_wait();
@@ -944,6 +947,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         const int slot = p.pair_mode ? 0 : src;                       // pair mode: both halves are numerators
         const long long ttile = p.pair_mode ? 2 * tile + src : tile;
         if ((ttile + 1) * 256 > p.ts) continue;                       // odd tile count: the pair's second half does not exist
+        if ((p.dbg & 1) && r[0] != 0x7fc00001u) continue;
         float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)((split * p.n_slots + slot) * 4 + q) * kKp + lane) * p.ts +
                                               ttile * 256 + (c & 7) * 32);
 #pragma unroll

@@ -683,6 +683,8 @@ inline int h_terms(TcState& s, cudaStream_t stream) {
   p.n_time_tiles = p.pair_mode ? (time_tiles + 1) / 2 : time_tiles;
   p.n_tiles = p.n_time_tiles * s.h_split; p.ts = d.TO + 256; p.scratch = s.hscratch; p.err = s.d_err;
   p.x3 = s.x3; p.lo_off = f.KW;
+  p.dbg = 0;
+  if (const char* e = getenv("CMF_HT_DBG")) p.dbg = atoi(e);
   if (s.h_pp) {
     // one source per item: the numerator only on the Gram route, numerator and denominator otherwise
     const int n_slots = p.n_slots;
