@@ -266,6 +266,18 @@ timing("time: A MN-SW128_32B, B K-SW128 (N=256)", img_t3, desc(0, REG, 512, SW12
 timing("time: A K-SW128, B MN-SW128_32B overlapping (N=256)", img_t5, desc(0, 16, 1024, SW128),
        desc(16384 + 3 * 128, 128, 512, SW128_32B), 2, 64, 4, idesc(128, 256, 0, 1), 256)
 
+# shifted K-major SW128 windows (what K1 and K3 read: a lag is +128 B on the start address)
+img = Image(16384 + (256 + 24) * 128)
+k_major_sw128(img, 0, A); k_major_sw128(img, 16384, Bw)
+for sh in (0, 1, 4, 5, 8):
+    timing("time: A K-SW128, B K-SW128 window shift %d (N=256)" % sh, img, desc(0, 16, 1024, SW128),
+           desc(16384 + sh * 128, 16, 1024, SW128), 2, 2, 4, idesc(128, 256, 0, 0), 256)
+img = Image(4 * REG + (256 + 24) * 128)
+mn_major_sw128_32(img, 0, Amn, REG); k_major_sw128(img, 4 * REG, Bw)
+for sh in (0, 5):
+    timing("time: A MN-SW128_32B, B K-SW128 window shift %d (N=256)" % sh, img, desc(0, REG, 512, SW128_32B),
+           desc(4 * REG + sh * 128, 16, 1024, SW128), 64, 2, 4, idesc(128, 256, 1, 0), 256)
+
 print()
 print("SUMMARY: %d/%d passed" % (sum(results.values()), len(results)))
 for k, v in results.items():
