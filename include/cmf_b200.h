@@ -28,8 +28,9 @@
  * single-GPU solve is the case t_offset = 0, t_local = t_global.  The phase
  * calls (cmf_mu_w_terms ... cmf_mu_recon) plus the halo import/export and the
  * exposed W-term buffer are what a multi-GPU driver strings together with an
- * all-reduce and a neighbour exchange; cmf_mu_step() is the fused single-GPU
- * iteration.
+ * all-reduce and a neighbour exchange of its own (NCCL, MPI); cmf_mu_step() is
+ * the fused single-GPU iteration and cmf_mu_step_sharded() the multi-GPU one,
+ * whose collectives are the library's own kernels over NVLink peer memory.
  */
 #ifndef CMF_B200_H
 #define CMF_B200_H
