@@ -98,6 +98,8 @@ struct ReconParams {
   // small and its truncation costs nothing); the lo halves sit lo_off columns to the right in both operand arrays.
   int x3, cbx, lo_off;
   int lo_off_b;                    // lo offset of the B operand when it differs from A's (0: same as lo_off)
+  int LB;                          // lags per window (0: all L).  Long lag ranges are walked in blocks of LB lags, each
+                                   // with its own window of 256 + s (LB - 1) rows, into the same accumulator
   float* Elo;                      // x3: est^T = Et (hi) + Elo; null: the result is stored unsplit
   const float* Xlo;                // x3: X^T = Xt (hi) + Xlo
   int* err;
@@ -162,6 +164,8 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   const uint32_t tmem = *tmem_slot;
   const Abort ab{abort_flag, p.err};
   const int L = p.L, wrows = p.wrows;
+  const int LB = (p.LB > 0 && p.LB < L) ? p.LB : L;             // lags per window
+  const int n_lb = (L + LB - 1) / LB;
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -170,9 +174,12 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       bool ok = true;
       // chunks = (tile, reduction block) in execution order; chunk c uses window buffer c & 1 and its
       // window is requested while the previous chunk's W stages stream (a whole chunk of lead time)
-      struct Chunk { long long tile; int cb; bool valid; };
+      struct Chunk { long long tile; int cb, lb; bool valid; };
       auto next_chunk = [&](Chunk c) {
-        if (++c.cb >= p.CB) { c.cb = 0; c.tile += gridDim.x; c.valid = c.tile < p.n_tiles; }
+        if (++c.lb >= n_lb) {
+          c.lb = 0;
+          if (++c.cb >= p.CB) { c.cb = 0; c.tile += gridDim.x; c.valid = c.tile < p.n_tiles; }
+        }
         return c;
       };
       auto issue_window = [&](const Chunk& c, long long wc) -> bool {
@@ -182,12 +189,13 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         mbar_arrive_expect_tx(&hfull[hb], hbytes);
         uint8_t* hdst = Hs + (size_t)hb * hbytes;
         const X3Sel sel = x3_select(kX3, p.cbx, p.lo_off, p.lo_off_b, c.cb);
+        const int l1 = min(L, (c.lb + 1) * LB);                 // window row 0 holds lag l1 - 1 of this block
         for (int rb = 0; rb < wrows / 64; ++rb)
           tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], sel.cbr * 32 + sel.b_off,
-                      (int)(tt * 256 + p.h_shift + rb * 64));
+                      (int)(tt * 256 + p.h_shift + p.s * (L - l1) + rb * 64));
         return true;
       };
-      Chunk cur{(long long)blockIdx.x, 0, (long long)blockIdx.x < p.n_tiles};
+      Chunk cur{(long long)blockIdx.x, 0, 0, (long long)blockIdx.x < p.n_tiles};
       long long wc = 0;
       if (cur.valid) ok = issue_window(cur, 0);
       while (cur.valid && ok) {
@@ -195,10 +203,11 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         bool prefetched = !nxt.valid;
         const int nt = (int)(cur.tile % p.n_tiles_n);
         const X3Sel sel = x3_select(kX3, p.cbx, p.lo_off, p.lo_off_b, cur.cb);
+        const int l0 = cur.lb * LB, l1 = min(L, l0 + LB);
         int stage_in_chunk = 0;
-        for (int l = 0; l < L; l += kReconLagsPerStage, ++stage_in_chunk) {
+        for (int l = l0; l < l1; l += kReconLagsPerStage, ++stage_in_chunk) {
           if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
-          const int nl = min(kReconLagsPerStage, L - l);
+          const int nl = min(kReconLagsPerStage, l1 - l);
           mbar_arrive_expect_tx(&full[ps.stage], nl * kReconABytes);
           for (int u = 0; u < nl; ++u)
             tma_load_2d(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes, &tmW, &full[ps.stage],
@@ -227,21 +236,23 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (!ab.wait(&tempty[b], (uint32_t)((it >> 1) & 1) ^ 1)) break;
         tc_fence_after();
         const uint32_t dtm = tmem + (uint32_t)b * 256;
-        for (int cb = 0; cb < p.CB && ok; ++cb, ++wcount) {
+        for (int chunk = 0; chunk < p.CB * n_lb && ok; ++chunk, ++wcount) {
+          const int cb = chunk / n_lb, lb = chunk - cb * n_lb;
+          const int l0 = lb * LB, l1 = min(L, l0 + LB);
           const int hb = (int)(wcount & 1);
           if (!ab.wait(&hfull[hb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
           tc_fence_after();
           const uint32_t hbase = smem_u32(Hs + (size_t)hb * hbytes);
-          for (int l = 0; l < L; l += kReconLagsPerStage) {
+          for (int l = l0; l < l1; l += kReconLagsPerStage) {
             if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
             tc_fence_after();
-            const int nl = min(kReconLagsPerStage, L - l);
+            const int nl = min(kReconLagsPerStage, l1 - l);
             for (int u = 0; u < nl; ++u) {
               const uint32_t abase = smem_u32(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t ad = make_smem_desc(abase + ks * 32, 16, 1024, kSwz128);
-                const uint64_t bd = make_smem_desc(hbase + (uint32_t)(p.s * (L - 1 - l - u)) * 128 + ks * 32, 16, 1024, kSwz128);
+                const uint64_t bd = make_smem_desc(hbase + (uint32_t)(p.s * (l1 - 1 - l - u)) * 128 + ks * 32, 16, 1024, kSwz128);
                 mma_tf32_ss(dtm, ad, bd, idesc, (cb | (l + u) | ks) != 0 ? 1u : 0u);
               }
             }

@@ -89,6 +89,7 @@ struct TcState {
   int gram = 0;
   int gram_request = 0;             // from cmf_mu_params.denominators (CMF_GRAM in the environment overrides)
   int LK = 0, Lr = 0, Lrv = 0, dh_wrows = 0;
+  int dh_LB = 0;                    // lags per window of R (*) H (0: one window; > 0: the 2L-1 lags are walked in blocks)
   int NpA = 0;                      // row half-width of Wt (Np rounded up to 32: the lo half starts on a TMA box boundary)
   long long g_rows = 0;             // rows allocated for G (LK rounded up to 256)
   float *Wt = nullptr, *G = nullptr, *Rw = nullptr, *Rwv = nullptr, *Etail = nullptr;
@@ -393,7 +394,14 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   s.dh_wrows = round_up(256 + f.s * (s.Lrv - 1), 64);
   s.g_rows = round_up_ll(s.LK, 256);
   s.ntail = d.Tloc + d.h - d.t_valid;
-  if (recon_smem_bytes(s.dh_wrows) > kMaxSmem || (long long)s.g_rows * s.LK * 4 > (1ll << 30)) s.gram &= ~1;
+  if (recon_smem_bytes(s.dh_wrows) > kMaxSmem) {
+    // the 2L-1 lags of R do not fit one window: blocks of LB lags, each with a window of 256 + s (LB - 1) rows
+    const int max_rows = (int)((kMaxSmem - recon_smem_bytes(0)) / (2 * kKp * 4) / 64) * 64;
+    s.dh_LB = ((max_rows - 256) / f.s + 1) & ~1;
+    if (s.dh_LB < 2) s.gram &= ~1;
+    else s.dh_wrows = round_up(256 + f.s * (s.dh_LB - 1), 64);
+  }
+  if ((long long)s.g_rows * s.LK * 4 > (1ll << 30)) s.gram &= ~1;
   if (s.gram & 1) {
     // 3xTF32: Wt rows are [hi (NpA) | lo (NpA)], Rwv rows [hi (KW) | lo (KW)]
     s.NpA = s.x3 ? round_up(d.Np, 32) : d.Np;
@@ -620,7 +628,7 @@ inline int den_h_gram(TcState& s, cudaStream_t stream) {
   float* den = s.hterms + d.TO * d.Kp;
   {
     ReconParams p{};
-    p.Np = d.Kp; p.L = s.Lrv; p.n_tiles_n = 1; p.wrows = s.dh_wrows;
+    p.Np = d.Kp; p.L = s.Lrv; p.n_tiles_n = 1; p.wrows = s.dh_wrows; p.LB = s.dh_LB;
     p.s = f.s; p.CB = f.CB; p.cb_cols = f.CB; p.h_shift = d.h + (d.L - 1) - f.s * (s.Lrv - 1);
     p.n_rows = d.Kp; p.ld_out = d.Kp; p.store_mode = 0; p.w_kp = d.Kp; p.w_np = d.Np;
     p.n_tiles = d.TO / 256;
