@@ -34,7 +34,10 @@ struct Fold {
   int Kp = 32, s = 1, CB = 1, Lv = 1, KW = 32;   // lag stride, column blocks, virtual lags, virtual row width
   int J = 1, n_glag = 4;                          // H terms: virtual lags per lag group, lag groups (4 / CB)
   int recon_wrows = 320, hterms_wrows = 288;
+  int recon_LB = 0;                               // K1: lags per window (0: all of them in one window)
 };
+
+constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
 
 inline Fold make_fold(int Kp, int L) {
   Fold f;
@@ -46,11 +49,15 @@ inline Fold make_fold(int Kp, int L) {
   f.n_glag = 4 / f.CB;
   f.J = (f.Lv + f.n_glag - 1) / f.n_glag;
   f.recon_wrows = round_up(256 + f.s * (f.Lv - 1), 64);
+  if (recon_smem_bytes(f.recon_wrows) > kMaxSmem) {
+    // the lag range does not fit one window of H^T: blocks of recon_LB lags (tc_recon_kernel, ReconParams::LB)
+    const int max_rows = (int)((kMaxSmem - recon_smem_bytes(0)) / (2 * kKp * 4) / 64) * 64;
+    f.recon_LB = ((max_rows - 256) / f.s + 1) & ~1;
+    f.recon_wrows = round_up(256 + f.s * (f.recon_LB - 1), 64);
+  }
   f.hterms_wrows = round_up(256 + f.s * (f.J - 1), 32);
   return f;
 }
-
-constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
 
 inline bool shape_supported(int N, int K, int L) {
   const int Kp = padded_k(K);
@@ -319,7 +326,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   s.recon2 = 0;
   if (const char* e = getenv("CMF_RECON2")) s.recon2 = atoi(e);
   s.recon2_wrows = round_up(128 + f.s * (f.Lv - 1), 64);
-  if (recon2_smem_bytes(s.recon2_wrows) > kMaxSmem) s.recon2 = 0;
+  if (recon2_smem_bytes(s.recon2_wrows) > kMaxSmem || f.recon_LB) s.recon2 = 0;
   if (s.recon2)
     CMF_CUDA(cudaFuncSetAttribute(tc_recon2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)recon2_smem_bytes(s.recon2_wrows)));
@@ -443,7 +450,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   }
   if ((long long)s.g_rows * f.Lv * f.KW * halves * 4 > (1ll << 30)) s.gram &= ~2;
   CMF_CUDA(cudaMalloc((void**)&s.wpart, (size_t)s.n_chunks * ((s.gram & 2) ? 1 : 2) * s.wcount * 4));
-  if (s.gram && s.ntail > 0) CMF_CUDA(cudaMalloc((void**)&s.Etail, (size_t)256 * d.Np * 4));
+  if (s.gram && s.ntail > 0) CMF_CUDA(cudaMalloc((void**)&s.Etail, (size_t)round_up_ll(s.ntail, 256) * d.Np * 4));
   if (s.gram & 2) {
     CMF_TRY(ensure_autocorr(s));
     CMF_CUDA(cudaMalloc((void**)&s.Mt, (size_t)s.g_rows * f.Lv * f.KW * halves * 4));
@@ -476,7 +483,7 @@ inline int attach_est(TcState& s, float* Et, float* Elo = nullptr) {
   return 0;
 }
 
-// untruncated est rows t_valid .. t_valid + 256 into Etail (one time tile of the recon kernel, no tail mask)
+// untruncated est rows t_valid .. t_valid + ntail into Etail (whole time tiles of the recon kernel, no tail mask)
 inline int tail_est(TcState& s, cudaStream_t stream) {
   const Dims& d = s.d;
   const Fold& f = s.f;
@@ -484,11 +491,14 @@ inline int tail_est(TcState& s, cudaStream_t stream) {
   p.Np = d.Np; p.L = f.Lv; p.n_tiles_n = (int)ceil_div_ll(d.Np, 128); p.wrows = f.recon_wrows;
   p.s = f.s; p.CB = f.CB; p.cb_cols = f.CB; p.h_shift = (int)(d.h - f.s * (f.Lv - 1) + d.t_valid);
   p.n_rows = d.Np; p.ld_out = d.Np; p.store_mode = 0; p.w_kp = d.Kp; p.w_np = d.Np;
-  p.n_tiles = p.n_tiles_n;
-  p.t_own = 0; p.t_valid = 256;
+  const long long tail_tiles = ceil_div_ll(s.ntail, 256);          // L - 1 rows of est lie past the end of the data
+  p.n_tiles = p.n_tiles_n * tail_tiles;
+  p.t_own = 0; p.t_valid = 256 * tail_tiles;
   p.Et = s.Etail; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
+  p.LB = f.recon_LB;
   set_x3(s, p, f.KW, f.KW);
-  launch_recon(s, p.n_tiles_n, recon_smem_bytes(f.recon_wrows), stream, s.tmW_k1, s.tmH_k1, p);
+  launch_recon(s, (int)(p.n_tiles < d.num_sms ? p.n_tiles : d.num_sms), recon_smem_bytes(f.recon_wrows), stream, s.tmW_k1,
+               s.tmH_k1, p);
   return launch_ok("tail_est");
 }
 
@@ -540,6 +550,7 @@ inline int recon(TcState& s, cudaStream_t stream, bool store_est = true) {
   p.n_tiles = (long long)p.n_tiles_n * (d.RT / 256);
   p.t_own = d.Tloc; p.t_valid = d.t_valid;
   p.Et = s.Et; p.Xt = s.Xt; p.loss_partials = s.loss_partials; p.round_out = 1; p.err = s.d_err;
+  p.LB = f.recon_LB;
   if (s.x3) {
     p.x3 = 1; p.cbx = f.CB; p.CB = 3 * f.CB; p.lo_off = f.KW;
     p.Elo = s.Elo; p.Xlo = s.Xlo;

@@ -138,7 +138,7 @@ def test_loss_trajectory(built_lib, name, precision):
 
 @pytest.mark.parametrize("precision", PRECISION_MODES)
 @pytest.mark.parametrize("shape", [(3, 5, 2, 8), (1, 1, 1, 1), (7, 40, 100, 3), (300, 600, 64, 5), (5, 9, 3, 9),
-                                   (130, 257, 17, 31)])
+                                   (130, 257, 17, 31), (64, 3000, 32, 300)])    # the last: lag range > one K1 window
 def test_extreme_shapes_against_oracle(built_lib, shape, precision):
     """L > T, single entries, K padded to 128 / 64 / 32, ragged everything: three MU iterations against
     the float64 oracle on the same inputs."""
@@ -151,6 +151,10 @@ def test_extreme_shapes_against_oracle(built_lib, shape, precision):
     alg = _solver(X, W0, H0, L, K, precision)
     hist = [alg.loss] + alg.update_many(3)
     tol = 1e-5 if precision in EXACT_MODES else 2e-3
+    if precision.startswith("tf32x3") and L * K >= 4096:
+        # tensor-memory accumulation (round toward zero) biases a chain by ~5.7e-8 per MMA step: the 2L-1 = 599
+        # lags of the Gram H denominator are 2396 steps -> 1.4e-4 (measured 1.55e-4); direct est: 1200 steps -> 7e-5
+        tol = 2e-4
     for a, b in zip(hist, ref_hist):
         assert abs(a - b) <= tol * max(b, 0.5), (hist, ref_hist)   # (an exactly-fittable 1x1 problem has loss ~ 0)
     _close(alg.W, ref.W, 20 * tol)
