@@ -63,14 +63,19 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ float4 ld_peer(const float4* p) { return __ldcv(p); }
 
 // spin until *flag >= epoch (wrap-safe); false on timeout
+// Once one wait has timed out (err != 0) every later wait on this rank gives up at once, so a broken exchange costs
+// one timeout, not one per kernel; the host reads err at the end of the call and raises.
 __device__ __forceinline__ bool wait_epoch(const uint32_t* flag, uint32_t epoch, int* err) {
   if ((int32_t)(ld_acquire_sys(flag) - epoch) >= 0) return true;
+  if (*reinterpret_cast<volatile int*>(err) != 0) return false;
   const long long t0 = clock64();
+  unsigned spins = 0;
   while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
     if (clock64() - t0 > kSpinTimeoutCycles) {
       atomicExch(err, kErrPeerTimeout);
       return false;
     }
+    if ((++spins & 1023u) == 0 && *reinterpret_cast<volatile int*>(err) != 0) return false;
     __nanosleep(64);
   }
   return true;
