@@ -209,10 +209,10 @@ def blas_threads():
 
 
 def cpu_baseline(N, T, K, L, budget_iters=2):
-    """Bounded sample: the reference update at T_s = min(T, 4096) columns with
+    """Bounded sample: the reference update at T_s = min(T, 16384) columns with
     identical N, K, L, extrapolated linearly in T (the reference's cost is
     linear in N*T*L)."""
-    Ts = int(min(T, 4096))
+    Ts = int(min(T, 16384))
     sec = reference_iteration_seconds(N, Ts, K, L, budget_iters)
     sec_full = sec * (T / Ts)
     return {"value": 1.0 / sec_full, "unit": UNIT, "cores": int(blas_threads()), "kind": "port",
@@ -230,10 +230,21 @@ def run_reference(args):
         return
     N, T, K, L = FULL[args.config]
     T = int(T * args.t_scale)
-    Ts = int(min(T, 4096))
     total = max(1, args.steps)
-    # warm-up + timed steps, each a bounded sample of the workload
     from oracle import cmf_oracle
+    # Sample size: as many columns as fit a ~2 minute run of `total` timed steps (longer samples are more faithful -
+    # the per-column cost of the NumPy path grows once X leaves the CPU caches), between 4096 and 16384 columns.
+    Ts = int(min(T, 4096))
+    X, W0, H0 = make_inputs(N, Ts, K, L, "uniform", 0)
+    probe = cmf_oracle.MultUpdateOracle(X.astype(np.float64), L, K, initW=W0.astype(np.float64),
+                                        initH=H0.astype(np.float64), tol=0, reuse_est=False)
+    t0 = time.perf_counter()
+    probe.update()
+    per_col = (time.perf_counter() - t0) / Ts
+    while Ts * 2 <= min(T, 16384) and 1.4 * per_col * (Ts * 2) * (total + 2) <= 120.0:
+        Ts *= 2
+    del probe
+    # warm-up + timed steps, each a bounded sample of the workload
     X, W0, H0 = make_inputs(N, Ts, K, L, "uniform", 0)
     alg = cmf_oracle.MultUpdateOracle(X.astype(np.float64), L, K, initW=W0.astype(np.float64),
                                       initH=H0.astype(np.float64), tol=0, reuse_est=False)
