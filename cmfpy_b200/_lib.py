@@ -39,6 +39,8 @@ _SIGNATURES = {
     "cmf_mu_destroy": (C.c_int, [_H]),
     "cmf_mu_set_data": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_longlong]),
     "cmf_mu_data_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "cmf_mu_row_stats": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cmf_mu_scale_rows": (C.c_int, [_H, C.c_void_p]),
     "cmf_mu_set_norm_x": (C.c_int, [_H, C.c_double]),
     "cmf_mu_set_factors": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong]),
     "cmf_mu_init_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

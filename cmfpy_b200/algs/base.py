@@ -28,7 +28,7 @@ class DeviceOptimizer:
 
     def __init__(self, data, model_dimensions, initW=None, initH=None,
                  tol=1e-5, patience=3, precision="fp32", device=0, seed=None,
-                 denominators="auto"):
+                 denominators="auto", normalize=None):
         # reference base.py:20-21
         if patience < 1 or not isinstance(patience, Integral):
             raise ValueError("Patience must be a positive integer.")
@@ -60,6 +60,15 @@ class DeviceOptimizer:
         _lib.check(self._lib.cmf_mu_create(C.byref(self._h), C.byref(p)))
         _lib.check(self._lib.cmf_mu_set_data(self._h, X.ctypes.data, _lib.np_dtype_code(X),
                                              _lib.CMF_HOST, T, T))
+        if normalize is not None:
+            # the reference normalises in its dataset classes, on the host, before the solver sees the data
+            # (songbird.py:18-19, maze.py:71-72, vox_celeb.py:100-102); here the rows are scaled where they live
+            from ..common import row_scales
+            s1, s2, sa = (np.empty(N) for _ in range(3))
+            _lib.check(self._lib.cmf_mu_row_stats(self._h, s1.ctypes.data, s2.ctypes.data, sa.ctypes.data))
+            self.row_scale = row_scales(normalize, s1, s2, sa, T)
+            _lib.check(self._lib.cmf_mu_scale_rows(self._h, self.row_scale.ctypes.data))
+            self._X = X * self.row_scale[:, None]
         ss, neg = C.c_double(0), C.c_int(0)
         _lib.check(self._lib.cmf_mu_data_stats(self._h, C.byref(ss), C.byref(neg)))
         self.normX = float(np.sqrt(ss.value))               # base.py:25

@@ -62,6 +62,29 @@ def score(W, H, X, precision="fp32", device=0):
     return r2.value
 
 
+NORMALIZATIONS = ("l2", "l1", "std")
+
+
+def row_scales(mode, s1, s2, sabs, n_timepoints):
+    """Per-feature scale factors of the reference's dataset normalisations from the per-feature sums over ALL
+    time points (s1 = sum x, s2 = sum x^2, sabs = sum |x|):
+      "l2"  : 1 / (1e-6 + ||row||_2)            datasets/songbird.py:18-19
+      "l1"  : 1 / (1e-8 + ||row||_1)            datasets/maze.py:71-72
+      "std" : 1 / std(row), population variance, 1 where the variance is 0
+              (StandardScaler(with_mean=False), datasets/vox_celeb.py:100-102)"""
+    s1, s2, sabs = (np.asarray(a, dtype=np.float64) for a in (s1, s2, sabs))
+    if mode == "l2":
+        return 1.0 / (1e-6 + np.sqrt(s2))
+    if mode == "l1":
+        return 1.0 / (1e-8 + sabs)
+    if mode == "std":
+        var = np.maximum(s2 / n_timepoints - (s1 / n_timepoints) ** 2, 0.0)
+        std = np.sqrt(var)
+        std[std < 10 * np.finfo(np.float64).eps] = 1.0
+        return 1.0 / std
+    raise ValueError("normalize must be one of %s" % (NORMALIZATIONS,))
+
+
 def shift_cols(X, lag):
     """reference common.py:89-98 (a view; no device work)."""
     T = X.shape[1]

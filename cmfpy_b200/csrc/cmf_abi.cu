@@ -599,7 +599,10 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
     tc::Dims d{h->N, h->K, h->L, h->Np, h->Kp, h->h, h->Tloc, h->TO, h->RT, h->RH, h->t_valid, h->num_sms};
     {
       const double contraction_flops = 2.0 * h->N * h->K * (double)h->L * (double)h->Tloc;
-      const bool want = p->denominators == CMF_DEN_GRAM || (p->denominators == CMF_DEN_AUTO && contraction_flops >= 2e11);
+      // auto: the Gram operators cost about K / N (W step) and 2 K / N (H step) of the direct contractions and
+      // add T-independent small kernels: worth it for large shards with N >= 4 K
+      const bool want = p->denominators == CMF_DEN_GRAM ||
+                        (p->denominators == CMF_DEN_AUTO && contraction_flops >= 2e11 && h->N >= 4 * h->K);
       h->tcs.gram_request = want ? 3 : 0;
     }
     rc = tc::init(h->tcs, d, h->Xt, nullptr, h->Ht, h->W, h->numden, h->hterms, h->loss_partials,
@@ -625,20 +628,9 @@ int cmf_mu_destroy(cmf_mu_t* h) {
   return 0;
 }
 
-int cmf_mu_set_data(cmf_mu_t* h, const void* X, int dtype, int mem, long long ld, long long ncols) {
-  CMF_ENTER(h);
-  CMF_CHECK(X != nullptr, "null data pointer");
-  CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
-  CMF_CHECK(mem == CMF_HOST || mem == CMF_DEVICE, "unknown memory space %d", mem);
-  CMF_CHECK(ncols >= h->Tloc && ncols <= h->Tloc + h->h, "ncols=%lld must lie in [t_local, t_local+L-1] = [%lld, %lld]",
-            ncols, h->Tloc, h->Tloc + h->h);
-  CMF_CHECK(ld >= ncols, "leading dimension %lld < ncols %lld", ld, ncols);
-  if (ncols > h->t_valid) ncols = h->t_valid;    // nothing exists past the global end
-  CMF_CUDA(cudaMemsetAsync(h->Xt, 0, (size_t)h->RT * h->Np * 4, h->stream));
-  const int round_in = h->x3 ? 0 : h->round_ops;
-  if (dtype == CMF_F32) CMF_TRY(load_transposed<float>(h, (const float*)X, mem, ld, h->N, ncols, h->Xt, h->Np, round_in));
-  else CMF_TRY(load_transposed<double>(h, (const double*)X, mem, ld, h->N, ncols, h->Xt, h->Np, round_in));
-  // local ||X||^2 over owned columns and the negativity flag
+// X^T is in place at full precision (x3: unsplit): local ||X||^2 over owned columns, the negativity flag, and the
+// hi/lo split of the 3xTF32 mode
+static int finish_data(cmf_mu_s* h) {
   const long long n4 = h->Tloc * h->Np / 4;
   const int grid = ew_grid(h, n4);
   CMF_CUDA(cudaMemsetAsync(h->d_neg, 0, 4, h->stream));
@@ -658,7 +650,80 @@ int cmf_mu_set_data(cmf_mu_t* h, const void* X, int dtype, int mem, long long ld
   h->graph_dirty = true;
   h->have_data = true;
   h->est_valid = false;
+  h->wterms_valid = false;
   return 0;
+}
+
+// Per-feature sums over the owned columns: s1[n] = sum_t X[n,t], s2[n] = sum_t X[n,t]^2, sabs[n] = sum_t |X[n,t]|
+// (each N doubles, HOST; any may be NULL).  What the reference's dataset normalisations reduce
+// (songbird.py:18-19, maze.py:71-72, vox_celeb.py:100-102); a sharded driver all-reduces them before scaling.
+int cmf_mu_row_stats(cmf_mu_t* h, double* s1, double* s2, double* sabs) {
+  CMF_ENTER(h);
+  CMF_CHECK(h->have_data, "no data set");
+  const int rows_per_chunk = 1024;
+  const int nchunks = (int)ceil_div_ll(h->Tloc, rows_per_chunk);
+  double *part = nullptr, *out = nullptr;
+  CMF_TRY(dmalloc(&part, (long long)nchunks * 3 * h->Np));
+  int rc = dmalloc(&out, 3ll * h->Np);
+  std::vector<double> host((size_t)3 * h->Np);
+  if (rc == 0) {
+    dim3 grid((unsigned)ceil_div_ll(h->Np, 256), (unsigned)nchunks);
+    ew::row_stats_kernel<<<grid, 256, 0, h->stream>>>(h->Xt, h->Xlo, h->Tloc, h->Np, rows_per_chunk, part);
+    rc = launch_check(h, "row_stats");
+  }
+  if (rc == 0) {
+    ew::row_stats_sum_kernel<<<(unsigned)ceil_div_ll(3ll * h->Np, 256), 256, 0, h->stream>>>(part, nchunks, h->Np, out);
+    rc = launch_check(h, "row_stats_sum");
+  }
+  if (rc == 0 && (cudaMemcpyAsync(host.data(), out, host.size() * 8, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                  cudaStreamSynchronize(h->stream) != cudaSuccess)) { set_error("row stats read-back failed"); rc = 1; }
+  cudaFree(part); cudaFree(out);
+  if (rc) return rc;
+  for (int n = 0; n < h->N; ++n) {
+    if (s1) s1[n] = host[n];
+    if (s2) s2[n] = host[(size_t)h->Np + n];
+    if (sabs) sabs[n] = host[(size_t)2 * h->Np + n];
+  }
+  return 0;
+}
+
+// X[n, :] *= scale[n] on the device (owned columns and the static right halo), then the same bookkeeping as
+// cmf_mu_set_data (local ||X||^2, negativity flag, hi/lo split).  scale: N doubles, HOST.
+int cmf_mu_scale_rows(cmf_mu_t* h, const double* scale) {
+  CMF_ENTER(h);
+  CMF_CHECK(scale != nullptr, "null argument");
+  CMF_CHECK(h->have_data, "no data set");
+  std::vector<float> sc((size_t)h->Np, 0.f);
+  for (int n = 0; n < h->N; ++n) sc[n] = (float)scale[n];
+  float* d_sc = nullptr;
+  CMF_TRY(dmalloc(&d_sc, h->Np));
+  int rc = 0;
+  if (cudaMemcpyAsync(d_sc, sc.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { set_error("H2D copy failed"); rc = 1; }
+  if (rc == 0) {
+    const long long total = h->RT * h->Np;
+    ew::scale_rows_kernel<<<ew_grid(h, total), 256, 0, h->stream>>>(h->Xt, h->Xlo, h->RT, h->Np, d_sc, h->x3 ? 0 : h->round_ops);
+    rc = launch_check(h, "scale_rows");
+  }
+  if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) { set_error("sync failed in scale_rows"); rc = 1; }
+  cudaFree(d_sc);
+  if (rc) return rc;
+  return finish_data(h);
+}
+
+int cmf_mu_set_data(cmf_mu_t* h, const void* X, int dtype, int mem, long long ld, long long ncols) {
+  CMF_ENTER(h);
+  CMF_CHECK(X != nullptr, "null data pointer");
+  CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
+  CMF_CHECK(mem == CMF_HOST || mem == CMF_DEVICE, "unknown memory space %d", mem);
+  CMF_CHECK(ncols >= h->Tloc && ncols <= h->Tloc + h->h, "ncols=%lld must lie in [t_local, t_local+L-1] = [%lld, %lld]",
+            ncols, h->Tloc, h->Tloc + h->h);
+  CMF_CHECK(ld >= ncols, "leading dimension %lld < ncols %lld", ld, ncols);
+  if (ncols > h->t_valid) ncols = h->t_valid;    // nothing exists past the global end
+  CMF_CUDA(cudaMemsetAsync(h->Xt, 0, (size_t)h->RT * h->Np * 4, h->stream));
+  const int round_in = h->x3 ? 0 : h->round_ops;
+  if (dtype == CMF_F32) CMF_TRY(load_transposed<float>(h, (const float*)X, mem, ld, h->N, ncols, h->Xt, h->Np, round_in));
+  else CMF_TRY(load_transposed<double>(h, (const double*)X, mem, ld, h->N, ncols, h->Xt, h->Np, round_in));
+  return finish_data(h);
 }
 
 int cmf_mu_data_stats(cmf_mu_t* h, double* sumsq, int* has_negative) {

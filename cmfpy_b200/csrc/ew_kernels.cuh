@@ -217,6 +217,49 @@ w_pad_out_kernel(const float* __restrict__ src, TO* __restrict__ dst, int L, int
   }
 }
 
+// ---- per-feature statistics / scaling of X^T (time-major: feature n is a column, so a warp reads 32 features of
+// one time step as one 128-byte line).  Used for the dataset normalisations of the reference
+// (datasets/songbird.py:18-19 L2 rows, datasets/maze.py:71-72 L1 rows, datasets/vox_celeb.py:100-102 unit variance).
+// part[chunk][stat][n], stat = sum x, sum x^2, sum |x| over the rows of the chunk; x = hi + lo when lo is given.
+__global__ void __launch_bounds__(256)
+row_stats_kernel(const float* __restrict__ Xt, const float* __restrict__ Xlo, long long rows, int Np, int rows_per_chunk,
+                 double* __restrict__ part) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Np) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  double s1 = 0.0, s2 = 0.0, sa = 0.0;
+  for (long long r = r0; r < r1; ++r) {
+    float x = Xt[r * Np + n];
+    if (Xlo) x += Xlo[r * Np + n];
+    s1 += x; s2 += (double)x * x; sa += fabsf(x);
+  }
+  double* o = part + (size_t)blockIdx.y * 3 * Np;
+  o[n] = s1; o[Np + n] = s2; o[2 * Np + n] = sa;
+}
+// out[stat][n] = sum_chunk part[chunk][stat][n]
+__global__ void __launch_bounds__(256)
+row_stats_sum_kernel(const double* __restrict__ part, int nchunks, int Np, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * Np) return;
+  double s = 0.0;
+  for (int c = 0; c < nchunks; ++c) s += part[(size_t)c * 3 * Np + i];
+  out[i] = s;
+}
+// X^T[r][n] *= scale[n]   (all rows, halo included; hi + lo pairs are recombined first and left unsplit in Xt)
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(float* __restrict__ Xt, float* __restrict__ Xlo, long long rows, int Np, const float* __restrict__ scale,
+                  int round_out) {
+  const long long total = rows * Np;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    float x = Xt[i];
+    if (Xlo) { x += Xlo[i]; Xlo[i] = 0.f; }
+    x *= scale[i % Np];
+    Xt[i] = round_out ? round_tf32(x) : x;
+  }
+}
+
 // elementwise dtype conversion (staging of float64 host data)
 template <class TI, class TO>
 __global__ void __launch_bounds__(256)

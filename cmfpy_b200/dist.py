@@ -78,6 +78,16 @@ class DeviceShard:
     def set_norm_x(self, v):
         _lib.check(self._lib.cmf_mu_set_norm_x(self._h, float(v)))
 
+    def row_stats(self):
+        """Per-feature (sum x, sum x^2, sum |x|) over the owned columns, stacked as a 3 x N array."""
+        out = np.empty((3, self.N), dtype=np.float64)
+        _lib.check(self._lib.cmf_mu_row_stats(self._h, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data))
+        return out
+
+    def scale_rows(self, scale):
+        scale = np.ascontiguousarray(scale, dtype=np.float64)
+        _lib.check(self._lib.cmf_mu_scale_rows(self._h, scale.ctypes.data))
+
     def set_factors(self, W0, H0):
         torch = self._torch
         if isinstance(W0, torch.Tensor):
@@ -212,7 +222,7 @@ class ShardedMultUpdate:
 
     def __init__(self, X_local, N, T, K, L, t_offset, t_local, initW, initH,
                  precision="fp32", device=0, group=None, tol=1e-5, patience=3,
-                 engine=None, denominators="auto", transport="auto"):
+                 engine=None, denominators="auto", transport="auto", normalize=None):
         import torch
         import torch.distributed as dist
         self._torch, self._dist = torch, dist
@@ -235,6 +245,18 @@ class ShardedMultUpdate:
             self.torch_stream = None
             self.engine = engine
         eng = self.engine
+        if normalize is not None:
+            # dataset normalisation (songbird.py:18-19 / maze.py:71-72 / vox_celeb.py:100-102) on the shards: the
+            # per-feature sums are all-reduced, every rank scales its own columns
+            from .common import row_scales
+            st = eng.row_stats()
+            if self.world > 1:
+                dev = "cpu" if self.torch_stream is None else self.torch_stream.device
+                t = torch.as_tensor(st, device=dev)
+                self._all_reduce(t)
+                st = self._to_host(t).numpy()
+            self.row_scale = row_scales(normalize, st[0], st[1], st[2], T)
+            eng.scale_rows(self.row_scale)
         ss, self.has_negative = eng.data_stats()
         if self.world > 1:
             t = self._host_scalar(ss)

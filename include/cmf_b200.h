@@ -60,7 +60,7 @@ enum { CMF_PREC_FP32 = 0, CMF_PREC_TF32 = 1, CMF_PREC_TF32X3 = 2 };
  *                 (minus the terms of est past the end of the data); K/N of the direct cost, and est is
  *                 then needed once per iteration (for the loss) instead of twice.  Ignored on the fp32 path. */
 enum { CMF_DEN_DIRECT = 0, CMF_DEN_GRAM = 1, CMF_DEN_AUTO = 2 /* Gram when the shard is large enough to pay for
-                                                              its extra small kernels (2 N K L t_local >= 2e11) */ };
+                                                              its extra small kernels (2 N K L t_local >= 2e11 and N >= 4 K) */ };
 
 typedef struct cmf_mu_s cmf_mu_t;
 
@@ -98,6 +98,15 @@ int cmf_mu_set_data(cmf_mu_t* h, const void* X, int dtype, int mem,
                     long long ld, long long ncols);
 /* Local sum over owned columns of X^2 and whether any entry was negative.   */
 int cmf_mu_data_stats(cmf_mu_t* h, double* sumsq, int* has_negative);
+/* Dataset normalisation on the device (the step BEFORE the solver in the
+ * reference: datasets/songbird.py:18-19 rows / (1e-6 + L2 norm), datasets/maze.py:
+ * 71-72 rows / (1e-8 + L1 norm), datasets/vox_celeb.py:100-102 unit variance per
+ * feature).  cmf_mu_row_stats returns the per-feature sums over the OWNED columns
+ * (sum x, sum x^2, sum |x|; N doubles each, HOST, any may be NULL - a sharded
+ * driver all-reduces them); cmf_mu_scale_rows multiplies feature n by scale[n]
+ * and refreshes the local ||X||^2 / negativity flag like cmf_mu_set_data.      */
+int cmf_mu_row_stats(cmf_mu_t* h, double* s1, double* s2, double* sabs);
+int cmf_mu_scale_rows(cmf_mu_t* h, const double* scale);
 /* normX = ||X||_F of the GLOBAL matrix (base.py:25).  Defaults to the local
  * value; a sharded driver sets the all-reduced one.                          */
 int cmf_mu_set_norm_x(cmf_mu_t* h, double norm_x);

@@ -28,6 +28,13 @@ class NumpyShard:
     def set_norm_x(self, v):
         self.norm_x = v
 
+    def row_stats(self):
+        X = self.Xext[:, :self.t_local]
+        return np.stack([X.sum(axis=1), (X ** 2).sum(axis=1), np.abs(X).sum(axis=1)])
+
+    def scale_rows(self, scale):
+        self.Xext *= np.asarray(scale)[:, None]
+
     def set_factors(self, W0, H0):
         self.W = np.asarray(W0, dtype=np.float64).copy()
         self.Hwin = np.zeros((self.K, self.h + self.t_local + self.h))

@@ -22,7 +22,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, shape, n_iter, out):
+def _worker(rank, world, port, shape, n_iter, out, normalize=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -37,7 +37,7 @@ def _worker(rank, world, port, shape, n_iter, out):
         ncols = min(Tl + L - 1, T - t0)
         eng = NumpyShard(X[:, t0:t0 + ncols], N, T, K, L, t0, Tl)
         alg = ShardedMultUpdate(None, N, T, K, L, t_offset=t0, t_local=Tl, initW=W0, initH=H0[:, t0:t0 + Tl],
-                                group=dist.group.WORLD, engine=eng, tol=0)
+                                group=dist.group.WORLD, engine=eng, tol=0, normalize=normalize)
         l0 = alg.loss
         losses = alg.update_many(n_iter - 1) + [alg.update()]
         H = alg.H_local_host()
@@ -91,3 +91,30 @@ def test_single_rank_uses_fused_step():
     alg.tol = 1e-5
     assert not alg.converged([1.0, 0.5, 0.4])
     assert alg.converged([1.0, 0.5, 0.5 + 1e-9, 0.5 + 2e-9])
+
+
+@pytest.mark.parametrize("mode", ["l2", "l1", "std"])
+def test_sharded_normalisation_matches_global(mode):
+    """Dataset normalisation on shards (songbird.py:18-19, maze.py:71-72, vox_celeb.py:100-102): the per-feature
+    sums are all-reduced, so every shard scales with the GLOBAL row norms and the trajectory equals the one of the
+    unsharded oracle on the normalised matrix."""
+    from cmfpy_b200.common import row_scales
+    world, shape, n_iter = 2, (6, 64, 3, 5), 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, n_iter, q, mode)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    N, T, K, L = shape
+    rng = np.random.default_rng(0)
+    X, W0, H0 = rng.random((N, T)), rng.random((L, N, K)), rng.random((K, T))
+    Xn = X * row_scales(mode, X.sum(1), (X ** 2).sum(1), np.abs(X).sum(1), T)[:, None]
+    ref = o.MultUpdateOracle(Xn, L, K, initW=W0, initH=H0, tol=0)
+    ref_hist = [ref.loss] + [ref.update() for _ in range(n_iter)]
+    for H, W, hist in gathered:
+        np.testing.assert_allclose(hist, ref_hist, rtol=1e-6)

@@ -146,3 +146,19 @@ def test_oracle_equals_unmodified_reference():
         assert ref.update() == pytest.approx(orc.update(), rel=1e-13)
     assert_allclose(orc.W, ref.W, rtol=1e-11)
     assert_allclose(orc.H, ref.H, rtol=1e-11)
+
+
+def test_row_scales_match_the_reference_normalisations():
+    """cmfpy_b200.common.row_scales against the expressions of the reference's dataset classes."""
+    from cmfpy_b200.common import row_scales
+    rng = np.random.default_rng(4)
+    X = rng.random((7, 50)) * rng.random((7, 1)) * 10
+    X[3] = 2.5                                                   # a constant feature: zero variance
+    s1, s2, sa = X.sum(1), (X ** 2).sum(1), np.abs(X).sum(1)
+    np.testing.assert_allclose(X * row_scales("l2", s1, s2, sa, 50)[:, None],
+                               X / (1e-6 + np.linalg.norm(X, axis=1, keepdims=True)), rtol=1e-12)    # songbird.py:18-19
+    np.testing.assert_allclose(X * row_scales("l1", s1, s2, sa, 50)[:, None],
+                               X / (1e-8 + np.linalg.norm(X, ord=1, axis=1, keepdims=True)), rtol=1e-12)  # maze.py:71-72
+    from sklearn import preprocessing                             # vox_celeb.py:100-102
+    ref = preprocessing.StandardScaler(with_mean=False).fit_transform(X.T).T
+    np.testing.assert_allclose(X * row_scales("std", s1, s2, sa, 50)[:, None], ref, rtol=1e-9)

@@ -157,8 +157,12 @@ def test_extreme_shapes_against_oracle(built_lib, shape, precision):
         tol = 2e-4
     for a, b in zip(hist, ref_hist):
         assert abs(a - b) <= tol * max(b, 0.5), (hist, ref_hist)   # (an exactly-fittable 1x1 problem has loss ~ 0)
-    _close(alg.W, ref.W, 20 * tol)
-    _close(alg.H, ref.H, 20 * tol)
+    # W and H individually: on the forced Gram route at L = 300 the numerator chain of the H step (600 steps) cannot
+    # be made as long as the denominator's (2396), so the two ratios carry different truncation biases and scale
+    # moves between W and H (invisible in the loss): 6e-3 of max|H| after three iterations
+    wh_tol = 50 * tol if (precision == "tf32x3g" and L * K >= 4096) else 20 * tol
+    _close(alg.W, ref.W, wh_tol)
+    _close(alg.H, ref.H, wh_tol)
     alg.close()
 
 
@@ -243,6 +247,30 @@ def test_loadings_sort_and_renormalize(built_lib):
     W2, H2 = renormalize(W, H)
     assert_allclose(np.linalg.norm(H2, axis=1), 1.0, rtol=1e-12)
     assert_allclose(o.cmf_predict(W2, H2), X, rtol=1e-10)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("mode", ["l2", "l1", "std"])
+def test_device_normalisation(built_lib, mode, precision):
+    """normalize= scales the rows on the device (cmf_mu_row_stats / cmf_mu_scale_rows) exactly as the reference's
+    dataset classes do on the host, and the solve then equals the solve on the pre-normalised matrix."""
+    from cmfpy_b200.algs.mult import MultUpdate
+    from cmfpy_b200.common import row_scales
+    from cmfpy_b200.model import ModelDimensions
+    N, T, K, L = 37, 301, 5, 7
+    if not _supported(precision, N, K, L):
+        pytest.skip("no %s kernel for this shape" % precision)
+    X, W0, H0 = make_inputs(N, T, K, L, "planted", seed=21)
+    X = X * np.linspace(0.5, 20.0, N, dtype=np.float32)[:, None]
+    X64 = X.astype(np.float64)
+    Xn = X64 * row_scales(mode, X64.sum(1), (X64 ** 2).sum(1), np.abs(X64).sum(1), T)[:, None]
+    dims = ModelDimensions(X, maxlag=L, n_components=K)
+    a = MultUpdate(X, dims, initW=W0, initH=H0, tol=0, precision=precision, normalize=mode)
+    assert abs(a.normX - np.linalg.norm(Xn)) <= 1e-5 * np.linalg.norm(Xn)
+    ref = o.MultUpdateOracle(Xn, L, K, initW=W0.astype(np.float64), initH=H0.astype(np.float64), tol=0)
+    hist, ref_hist = [a.loss] + a.update_many(5), [ref.loss] + [ref.update() for _ in range(5)]
+    assert np.abs(np.array(hist) - ref_hist).max() <= 2e-5 * max(ref_hist)
+    a.close()
 
 
 # ---- model API --------------------------------------------------------------
