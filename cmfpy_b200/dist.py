@@ -178,13 +178,22 @@ class DeviceShard:
         return [float(x) for x in losses]
 
     # -- read-back --------------------------------------------------------------
-    def get_W(self):
-        out = np.empty((self.L, self.N, self.K), dtype=np.float32)
+    def _host_out(self, out, shape):
+        """A caller-supplied float32 C-contiguous array (e.g. the NumPy view of a pinned torch tensor: the copy is
+        then a direct DMA instead of a staged copy into freshly faulted pages), or a new one."""
+        if out is None:
+            return np.empty(shape, dtype=np.float32)
+        if out.shape != shape or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 array of shape %s" % (shape,))
+        return out
+
+    def get_W(self, out=None):
+        out = self._host_out(out, (self.L, self.N, self.K))
         _lib.check(self._lib.cmf_mu_get_W(self._h, out.ctypes.data, _lib.CMF_F32, _lib.CMF_HOST))
         return out
 
-    def get_H(self):
-        out = np.empty((self.K, self.t_local), dtype=np.float32)
+    def get_H(self, out=None):
+        out = self._host_out(out, (self.K, self.t_local))
         _lib.check(self._lib.cmf_mu_get_H(self._h, out.ctypes.data, _lib.CMF_F32, _lib.CMF_HOST, self.t_local))
         return out
 
@@ -435,11 +444,11 @@ class ShardedMultUpdate:
         return bool(np.all(np.abs(d) < self.tol))
 
     # -- read-back ----------------------------------------------------------------
-    def W_host(self):
-        return self.engine.get_W()
+    def W_host(self, out=None):
+        return self.engine.get_W(out) if out is not None else self.engine.get_W()
 
-    def H_local_host(self):
-        return self.engine.get_H()
+    def H_local_host(self, out=None):
+        return self.engine.get_H(out) if out is not None else self.engine.get_H()
 
     def est_local_host(self):
         return self.engine.get_est()
