@@ -3,9 +3,11 @@ driving the GPU multiplicative-update solver.
 
 Kept from the reference: constructor arguments, `fit`, `predict`, `score`,
 `motifs` (W: L x N x K), `factors` (H: K x T), `n_features`, `n_timesteps`,
-`loss_hist`, `time_hist`, `argsort_units`, the error types.  Out of scope
-(SURVEY.md section 2): plotting, HDF5 loading and the helpers that are broken in
-the reference itself.
+`loss_hist`, `time_hist`, `argsort_units`, the error types; working versions of
+`sort_components`, `compute_loadings`, `renormalize`; `load_cmfjl_model` (needs
+h5py, as in the reference) and an .npz checkpoint with the same dataset names
+(`save_model` / `load_model`) for warm restarts through `initW` / `initH`.
+Out of scope: plotting.
 """
 import time
 
@@ -205,3 +207,50 @@ def renormalize(W, H):
     from .common import EPSILON
     row_norms = np.linalg.norm(H, axis=1) + EPSILON
     return W * row_norms[None, None, :], H / row_norms[:, None]
+
+
+# ---- model files --------------------------------------------------------------------------
+_MODEL_KEYS = ("data", "W", "H", "time_hist", "loss_hist")
+
+
+def load_cmfjl_model(path):
+    """Loads a model saved by cmf.jl (HDF5 / JLD) into a CMF object; returns (data, model) like reference
+    model.py:346-363: Julia stores column-major, so `data` and `H` are transposed and the axes of `W` swapped."""
+    try:
+        import h5py
+    except ImportError as e:                       # the reference imports h5py at module level (model.py:7)
+        raise ImportError("load_cmfjl_model needs h5py, which is not installed") from e
+    with h5py.File(path, "r") as f:
+        data = np.array(f["data"]).T
+        W = np.swapaxes(np.array(f["W"]), 0, 2)
+        L, _, K = W.shape
+        model = CMF(K, L)
+        model._W = W
+        model._H = np.array(f["H"]).T
+        model.time_hist = np.array(f["time_hist"])
+        model.loss_hist = np.array(f["loss_hist"])
+    return data, model
+
+
+def save_model(path, model, data=None):
+    """Checkpoint of a fitted model under the dataset names cmf.jl uses (`data`, `W`, `H`, `time_hist`,
+    `loss_hist`), in this package's own row-major layouts, as a compressed .npz.  `data` is optional."""
+    out = {"W": model.motifs, "H": model.factors,
+           "time_hist": np.asarray(getattr(model, "time_hist", [])),
+           "loss_hist": np.asarray(getattr(model, "loss_hist", []))}
+    if data is not None:
+        out["data"] = np.asarray(data)
+    np.savez_compressed(path, **out)
+
+
+def load_model(path, **cmf_kwargs):
+    """Inverse of `save_model`: returns (data or None, model).  Resume a fit with
+    `CMF(K, L, initW=model.motifs, initH=model.factors, ...).fit(data)`."""
+    with np.load(path) as f:
+        W, H = f["W"], f["H"]
+        L, _, K = W.shape
+        model = CMF(K, L, **cmf_kwargs)
+        model._W, model._H = W, H
+        model.time_hist, model.loss_hist = list(f["time_hist"]), list(f["loss_hist"])
+        data = f["data"] if "data" in f.files else None
+    return data, model

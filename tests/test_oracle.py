@@ -162,3 +162,23 @@ def test_row_scales_match_the_reference_normalisations():
     from sklearn import preprocessing                             # vox_celeb.py:100-102
     ref = preprocessing.StandardScaler(with_mean=False).fit_transform(X.T).T
     np.testing.assert_allclose(X * row_scales("std", s1, s2, sa, 50)[:, None], ref, rtol=1e-9)
+
+
+def test_model_checkpoint_round_trip(tmp_path):
+    """save_model / load_model (.npz with cmf.jl's dataset names) and the h5py-gated cmf.jl loader."""
+    from cmfpy_b200.model import CMF, load_cmfjl_model, load_model, save_model
+    rng = np.random.default_rng(1)
+    m = CMF(3, 4)
+    m._W, m._H = rng.random((4, 6, 3)), rng.random((3, 20))
+    m.loss_hist, m.time_hist = [0.9, 0.5, 0.4], [0.0, 0.1, 0.2]
+    X = rng.random((6, 20))
+    path = str(tmp_path / "ckpt.npz")
+    save_model(path, m, X)
+    data, m2 = load_model(path, verbose=False)
+    assert np.array_equal(data, X) and np.array_equal(m2.motifs, m.motifs) and np.array_equal(m2.factors, m.factors)
+    assert m2.loss_hist == m.loss_hist and m2.n_components == 3 and m2.maxlag == 4
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            load_cmfjl_model(path)
