@@ -63,6 +63,10 @@ _SIGNATURES = {
     "cmf_mu_peer_attach": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
     "cmf_mu_peer_detach": (C.c_int, [_H]),
     "cmf_mu_step_sharded": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double)]),
+    "cmf_hals_begin": (C.c_int, [_H]),
+    "cmf_hals_sweep_w": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "cmf_hals_sweep_h": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "cmf_hals_end": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "cmf_gd_cache": (C.c_int, [_H]),
     "cmf_gd_lipschitz_w": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "cmf_gd_step": (C.c_int, [_H, C.c_int, C.c_double, C.POINTER(C.c_double)]),

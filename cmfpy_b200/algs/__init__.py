@@ -1,11 +1,13 @@
-"""Solver registry: same plug-in point as reference cmfpy/algs/__init__.py:10-15.
-The multiplicative-update solver is the hot path; the two
-gradient solvers reuse its contraction kernels (section 8f).  HALS is not provided."""
+"""Solver registry: same plug-in point and the same four names as reference cmfpy/algs/__init__.py:10-15.
+The multiplicative-update solver is the hot path; the gradient solvers reuse its contraction
+kernels and HALS keeps its residual on the device (section 8f)."""
 from .gradient_descent import BlockDescent, GradDescent
+from .hals import HALSUpdate
 from .mult import MultUpdate
 
 ALGORITHMS = {
-    "mult": MultUpdate,
     "gd": GradDescent,
     "bcd": BlockDescent,
+    "mult": MultUpdate,
+    "hals": HALSUpdate,
 }

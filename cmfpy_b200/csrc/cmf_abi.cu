@@ -23,6 +23,7 @@
 #include "tc_path.cuh"
 #include "peer_kernels.cuh"
 #include "gd_kernels.cuh"
+#include "hals_kernels.cuh"
 
 namespace cmf {
 
@@ -93,6 +94,14 @@ struct cmf_mu_s {
     gd::PowerState* st = nullptr;
     int max_iter = 64;
   } gdst;
+
+  // ---- HALS (hals_kernels.cuh) ----
+  struct HalsState {
+    bool ready = false, open = false;    // open: between cmf_hals_begin and cmf_hals_end (the residual is current)
+    float *Rt = nullptr, *part = nullptr, *part_h = nullptr, *delta = nullptr, *Wk = nullptr, *prev = nullptr;
+    double *w2 = nullptr, *d_diff = nullptr;
+    int n_chunks = 1, rows_per_chunk = 1;
+  } halsst;
 
   // ---- peer-memory collectives of the sharded iteration (peer_kernels.cuh) ----
   struct PeerState {
@@ -446,6 +455,8 @@ void free_all(cmf_mu_s* h) {
   cudaFree(h->peer.shared);
   cudaFree(h->gdst.P); cudaFree(h->gdst.Ppart); cudaFree(h->gdst.Pt); cudaFree(h->gdst.v); cudaFree(h->gdst.y);
   cudaFree(h->gdst.d_inv); cudaFree(h->gdst.d_lam); cudaFree(h->gdst.st);
+  cudaFree(h->halsst.Rt); cudaFree(h->halsst.part); cudaFree(h->halsst.part_h); cudaFree(h->halsst.delta);
+  cudaFree(h->halsst.Wk); cudaFree(h->halsst.prev); cudaFree(h->halsst.w2); cudaFree(h->halsst.d_diff);
   tc::destroy(h->tcs);
   cudaFree(h->Xt); cudaFree(h->Et); cudaFree(h->Ht); cudaFree(h->W); cudaFree(h->Xlo); cudaFree(h->Elo);
   cudaFree(h->numden); cudaFree(h->wpart); cudaFree(h->hterms);
@@ -1443,6 +1454,134 @@ int cmf_gd_step(cmf_mu_t* h, int block_descent, double step_size_h, double* loss
   }
   if (loss_out) CMF_TRY(cmf_mu_loss(h, loss_out));
   else CMF_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ---- HALS (reference algs/hals.py + algs/accelerated.py) -------------------------------------------
+namespace {
+int hals_ensure(cmf_mu_s* h) {
+  auto& s = h->halsst;
+  if (s.ready) return 0;
+  CMF_CHECK(h->p.t_local == h->p.t_global, "HALS runs on one GPU (no time sharding)");
+  CMF_CHECK(h->Tloc > h->L, "HALS needs more time points than lags (T=%lld, L=%d)", h->Tloc, h->L);
+  const long long bx = ceil_div_ll(h->Np, 256);
+  long long nc = ceil_div_ll(4ll * h->num_sms, bx);
+  const long long max_nc = ceil_div_ll(h->Tloc, 64);
+  if (nc > max_nc) nc = max_nc;
+  if (nc < 1) nc = 1;
+  s.rows_per_chunk = (int)ceil_div_ll(h->Tloc, nc);
+  s.n_chunks = (int)ceil_div_ll(h->Tloc, s.rows_per_chunk);
+  const long long big = (h->wcount > h->RH * h->Kp) ? h->wcount : h->RH * h->Kp;
+  CMF_TRY(dmalloc(&s.Rt, h->RT * h->Np));
+  CMF_TRY(dmalloc(&s.part, (long long)s.n_chunks * h->Np));
+  CMF_TRY(dmalloc(&s.part_h, s.n_chunks));
+  CMF_TRY(dmalloc(&s.delta, h->Np));
+  CMF_TRY(dmalloc(&s.Wk, (long long)h->L * h->Np));
+  CMF_TRY(dmalloc(&s.prev, big));
+  CMF_TRY(dmalloc(&s.w2, h->L));
+  CMF_TRY(dmalloc(&s.d_diff, 1));
+  s.ready = true;
+  return 0;
+}
+}  // namespace
+
+// setup: the residual est - X of the current factors (cache_resids, base.py:57-62), on the device
+int cmf_hals_begin(cmf_mu_t* h) {
+  CMF_ENTER(h);
+  CMF_CHECK(h->have_data && h->have_factors, "HALS before data/factors were set");
+  CMF_TRY(hals_ensure(h));
+  CMF_TRY(ensure_est_stored(h));
+  const long long n4 = h->RT * h->Np / 4;
+  hals::resid_kernel<<<ew_grid(h, n4), 256, 0, h->stream>>>((float4*)h->halsst.Rt, (const float4*)h->Et, (const float4*)h->Xt,
+                                                            (const float4*)h->Elo, (const float4*)h->Xlo, n4);
+  CMF_TRY(launch_check(h, "hals_resid"));
+  h->halsst.open = true;
+  return 0;
+}
+
+// one sweep over all (k, l) blocks of W (update_W, hals.py:47-48, 78-105); diff_norm = ||W_new - W_old||_F
+// (the quantity the inner-iteration stop rule compares, accelerated.py:57-69; may be NULL)
+int cmf_hals_sweep_w(cmf_mu_t* h, double* diff_norm) {
+  CMF_ENTER(h);
+  auto& s = h->halsst;
+  CMF_CHECK(s.open, "cmf_hals_sweep_w outside cmf_hals_begin / cmf_hals_end");
+  if (diff_norm) CMF_CUDA(cudaMemcpyAsync(s.prev, h->W, (size_t)h->wcount * 4, cudaMemcpyDeviceToDevice, h->stream));
+  const dim3 grid((unsigned)ceil_div_ll(h->Np, 256), (unsigned)s.n_chunks);
+  const float* hprev = nullptr;
+  for (int k = 0; k < h->K; ++k)
+    for (int l = 0; l < h->L; ++l) {
+      const float* hcur = h->Ht + (long long)(h->h - l) * h->Kp + k;      // h(t) = H^T[h + t - l][k]
+      hals::w_pass_kernel<<<grid, 256, 0, h->stream>>>(s.Rt, h->Np, h->Tloc, s.rows_per_chunk, hprev, s.delta, hcur, h->Kp,
+                                                       s.part, s.part_h);
+      hals::w_solve_kernel<<<grid.x, 256, 0, h->stream>>>(h->W + (long long)l * h->Np * h->Kp + k, h->Np, h->Kp, s.part,
+                                                          s.part_h, s.n_chunks, s.delta);
+      h->launches += 2;
+      hprev = hcur;
+    }
+  hals::w_pass_kernel<<<grid, 256, 0, h->stream>>>(s.Rt, h->Np, h->Tloc, s.rows_per_chunk, hprev, s.delta, nullptr, h->Kp,
+                                                   s.part, s.part_h);
+  CMF_TRY(launch_check(h, "hals_w_sweep"));
+  h->est_valid = false;
+  h->wterms_valid = false;
+  if (diff_norm) {
+    hals::diff_sumsq_kernel<<<1, 1024, 0, h->stream>>>(h->W, s.prev, h->wcount, s.d_diff);
+    CMF_TRY(launch_check(h, "hals_diff"));
+    double ss = 0.0;
+    CMF_CUDA(cudaMemcpyAsync(&ss, s.d_diff, 8, cudaMemcpyDeviceToHost, h->stream));
+    CMF_CUDA(cudaStreamSynchronize(h->stream));
+    *diff_norm = std::sqrt(ss);
+  }
+  return 0;
+}
+
+// one sweep over H (update_H, hals.py:68-70, 113-181): per component and lag the batch t = l (mod L), t < T - L,
+// then the entry t = T - L + l with the motif cut by the end of the data
+int cmf_hals_sweep_h(cmf_mu_t* h, double* diff_norm) {
+  CMF_ENTER(h);
+  auto& s = h->halsst;
+  CMF_CHECK(s.open, "cmf_hals_sweep_h outside cmf_hals_begin / cmf_hals_end");
+  const long long hcount = h->RH * h->Kp;
+  if (diff_norm) CMF_CUDA(cudaMemcpyAsync(s.prev, h->Ht, (size_t)hcount * 4, cudaMemcpyDeviceToDevice, h->stream));
+  const long long T = h->Tloc;
+  const int L = h->L;
+  for (int k = 0; k < h->K; ++k) {
+    hals::gather_component_kernel<<<L, 256, 0, h->stream>>>(h->W, h->Np, h->Kp, k, s.Wk, s.w2);
+    h->launches++;
+    float* Hcol = h->Ht + (long long)h->h * h->Kp + k;
+    for (int l = 0; l < L; ++l) {
+      const long long span = T - L - l;                          // batch entries: range(l, T - L, L)
+      const long long n_batch = span > 0 ? ceil_div_ll(span, L) : 0;
+      if (n_batch > 0) {
+        hals::h_entries_kernel<<<(unsigned)n_batch, 256, 0, h->stream>>>(s.Rt, h->Np, s.Wk, s.w2, L, Hcol, h->Kp, l, L);
+        h->launches++;
+      }
+      hals::h_entries_kernel<<<1, 256, 0, h->stream>>>(s.Rt, h->Np, s.Wk, s.w2, L - l, Hcol, h->Kp, T - L + l, 0);
+      h->launches++;
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  CMF_CHECK(e == cudaSuccess, "HALS H sweep launch failed: %s", cudaGetErrorString(e));
+  h->est_valid = false;
+  if (diff_norm) {
+    hals::diff_sumsq_kernel<<<1, 1024, 0, h->stream>>>(h->Ht, s.prev, hcount, s.d_diff);
+    CMF_TRY(launch_check(h, "hals_diff"));
+    double ss = 0.0;
+    CMF_CUDA(cudaMemcpyAsync(&ss, s.d_diff, 8, cudaMemcpyDeviceToHost, h->stream));
+    CMF_CUDA(cudaStreamSynchronize(h->stream));
+    *diff_norm = std::sqrt(ss);
+  }
+  return 0;
+}
+
+// end of update(): cache_resids from scratch and the loss (accelerated.py:83-84)
+int cmf_hals_end(cmf_mu_t* h, double* loss_out) {
+  CMF_ENTER(h);
+  CMF_CHECK(h->halsst.open, "cmf_hals_end without cmf_hals_begin");
+  h->halsst.open = false;
+  CMF_TRY(sync_ops_W(h));
+  CMF_TRY(sync_ops_H(h, 0, h->RH));
+  CMF_TRY(do_recon(h));
+  if (loss_out) CMF_TRY(cmf_mu_loss(h, loss_out));
   return 0;
 }
 

@@ -209,6 +209,22 @@ int cmf_gd_cache(cmf_mu_t* h);
 int cmf_gd_lipschitz_w(cmf_mu_t* h, double* lambda_max);
 int cmf_gd_step(cmf_mu_t* h, int block_descent, double step_size_h, double* loss_out);
 
+/* ---- HALS: HALSUpdate, algs/hals.py on algs/accelerated.py ----------------- */
+/* Hierarchical alternating least squares with the residual est - X kept
+ * current on the device after every coordinate block.  Single GPU, T > L.
+ *   cmf_hals_begin   : the residual of the current factors (cache_resids).
+ *   cmf_hals_sweep_w : update_W (hals.py:47-48, 78-105): all (k, l) columns in
+ *                      the reference's order; *diff_norm = ||W_new - W_old||_F,
+ *                      what the inner-iteration stop rule compares
+ *                      (accelerated.py:50-69); NULL skips it.
+ *   cmf_hals_sweep_h : update_H (hals.py:68-70, 113-181): per (k, l) the batch of
+ *                      entries t = l (mod L), t < T - L, then the entry T - L + l.
+ *   cmf_hals_end     : cache_resids from scratch and the loss (accelerated.py:83-84). */
+int cmf_hals_begin(cmf_mu_t* h);
+int cmf_hals_sweep_w(cmf_mu_t* h, double* diff_norm);
+int cmf_hals_sweep_h(cmf_mu_t* h, double* diff_norm);
+int cmf_hals_end(cmf_mu_t* h, double* loss_out);
+
 /* ---- read-back: algorithm.W / algorithm.H (model.py:175-176) ------------ */
 int cmf_mu_get_W(cmf_mu_t* h, void* W_out, int dtype, int mem);
 int cmf_mu_get_H(cmf_mu_t* h, void* H_out, int dtype, int mem, long long ldh);

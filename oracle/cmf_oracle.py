@@ -313,6 +313,92 @@ class GradDescentOracle(MultUpdateOracle):
 
 
 # --------------------------------------------------------------------------
+# HALS (reference cmfpy/algs/hals.py on top of cmfpy/algs/accelerated.py)
+# --------------------------------------------------------------------------
+FACTOR_MIN = 0.0                                                 # common.py:10
+
+
+class HALSOracle(MultUpdateOracle):
+    """Duck-type of reference ``HALSUpdate``: hierarchical alternating least squares, one coordinate block at a
+    time with the residual ``est - X`` kept current after every block.
+
+    The reference removes a block's own contribution from the residual, solves for the block and adds the new
+    contribution back (hals.py:89-96, 129-157, 165-181).  With r the residual BEFORE the removal that is
+
+        W[l,:,k] <- max((W[l,:,k] ||h||^2 - r h) / (||h||^2 + eps), 0),  h = H[k] shifted right by l   (:89-105)
+        H[k,t]   <- max((H[k,t] ||Wk||^2 - <Wk, r[:, t:t+L]>) / (||Wk||^2 + eps), 0)                   (:129-157)
+
+    followed by r += (new - old) * block; both forms are the same arithmetic up to rounding.  Order of the sweeps:
+    components outermost, lags inside (:80-84, :115-123); within the H sweep the entries t = l (mod L), t < T - L are
+    independent (disjoint windows, "batches") and the entry t = T - L + l, whose motif is cut off by the end of the
+    data, follows on its own (:122-123, :165-181).
+    """
+
+    def __init__(self, data, maxlag, n_components, max_iter=1, weightW=1, weightH=1, stop_thresh=0, **kw):
+        super().__init__(data, maxlag, n_components, **kw)
+        self.W, self.H = self.W.copy(), self.H.copy()
+        self.max_iter, self.stop_thresh, self.weightW, self.weightH = max_iter, stop_thresh, weightW, weightH
+        if max_iter * min(1, weightH, weightW) < 1:              # accelerated.py:47-48
+            raise ValueError("Requires at least 1 iteration for both W and H.")
+
+    # -- one sweep over W (hals.py:40-48, 78-105) ---------------------------
+    def sweep_W(self):
+        L, N, K = self.W.shape
+        T = self.n_timepoints
+        r = self.resids
+        for k in range(K):
+            for l in range(L):
+                h = np.zeros(T)
+                h[l:] = self.H[k, :T - l]
+                hn2 = float(h @ h)
+                old = self.W[l, :, k].copy()
+                new = np.maximum((old * hn2 - r @ h) / (hn2 + EPSILON), FACTOR_MIN)
+                r += np.outer(new - old, h)
+                self.W[l, :, k] = new
+
+    # -- one sweep over H (hals.py:54-70, 113-181) ----------------------------
+    def sweep_H(self):
+        L, N, K = self.W.shape
+        T = self.n_timepoints
+        r = self.resids
+        w2 = (self.W ** 2).sum(axis=1).T                        # K x L: squared norms along the features (:58)
+        for k in range(K):
+            Wk = self.W[:, :, k].T                               # N x L
+            for l in range(L):
+                for t in range(l, T - L, L):                     # the batch: disjoint windows (:32-33, 126-157)
+                    win = r[:, t:t + L]
+                    old = self.H[k, t]
+                    new = max((old * w2[k].sum() - float((Wk * win).sum())) / (w2[k].sum() + EPSILON), FACTOR_MIN)
+                    win += (new - old) * Wk
+                    self.H[k, t] = new
+                t = T - L + l                                    # the entry whose motif is cut by the end (:123, 165-181)
+                m = T - t
+                win = r[:, t:t + L]
+                n2 = w2[k, :m].sum()
+                old = self.H[k, t]
+                new = max((old * n2 - float((Wk[:, :m] * win).sum())) / (n2 + EPSILON), FACTOR_MIN)
+                win += (new - old) * Wk[:, :m]
+                self.H[k, t] = new
+
+    def _accelerated(self, var_name, weight, sweep):             # accelerated.py:50-69
+        prev = getattr(self, var_name).copy()
+        sweep()
+        init_diff = diff = float(np.linalg.norm(getattr(self, var_name) - prev))
+        itr = 1
+        while itr < self.max_iter * weight and diff > self.stop_thresh * init_diff:
+            itr += 1
+            prev = getattr(self, var_name).copy()
+            sweep()
+            diff = float(np.linalg.norm(getattr(self, var_name) - prev))
+
+    def update(self):                                            # accelerated.py:71-84
+        self._accelerated("W", self.weightW, self.sweep_W)
+        self._accelerated("H", self.weightH, self.sweep_H)
+        self.cache_resids()
+        return self.loss
+
+
+# --------------------------------------------------------------------------
 # T-sharded restatement (what the multi-GPU path must reproduce)
 # --------------------------------------------------------------------------
 def sharded_update(X, W, H, n_shards):

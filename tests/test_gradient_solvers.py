@@ -1,4 +1,5 @@
-"""Gradient solvers (reference cmfpy/algs/gradient_descent.py: GradDescent, BlockDescent).
+"""Gradient solvers (reference cmfpy/algs/gradient_descent.py: GradDescent, BlockDescent) and HALS
+(cmfpy/algs/hals.py on cmfpy/algs/accelerated.py).
 
 CPU part (`-m "not gpu"`): the NumPy restatement in oracle/cmf_oracle.py against golden trajectories generated from
 the reference itself (oracle/make_golden_gd.py), and the identity the device path rests on: the gradients are the
@@ -74,6 +75,29 @@ def test_step_size_adaptation():
     assert alg.converged([1.0, 0.9, 0.85]) is True and alg.step_size == 1e-4 / 5.0
 
 
+HALS_VARIANTS = {"hals": {}, "hals_acc": dict(max_iter=3, weightW=1, weightH=2, stop_thresh=0.05)}
+
+
+@pytest.mark.parametrize("key", list(HALS_VARIANTS))
+@pytest.mark.parametrize("name", GD_CASES)
+def test_hals_oracle_against_reference_golden(name, key):
+    g, X, W0, H0 = _inputs(name)
+    N, T, K, L = (int(v) for v in g["shape"])
+    alg = o.HALSOracle(X.astype(np.float64), L, K, initW=W0.astype(np.float64), initH=H0.astype(np.float64), tol=0,
+                       **HALS_VARIANTS[key])
+    ref = g[key + "_loss_hist"]
+    hist = [alg.loss] + [alg.update() for _ in range(len(ref) - 1)]
+    assert np.abs(np.array(hist) - ref).max() <= 1e-12
+    if key + "_W" in g.files:
+        assert np.abs(alg.W - g[key + "_W"]).max() <= 1e-10 and np.abs(alg.H - g[key + "_H"]).max() <= 1e-10
+
+
+def test_hals_argument_check():
+    rng = np.random.default_rng(0)
+    with pytest.raises(ValueError):                              # accelerated.py:47-48
+        o.HALSOracle(rng.random((5, 40)), 3, 2, initW=rng.random((3, 5, 2)), initH=rng.random((2, 40)), max_iter=1, weightW=0.5)
+
+
 # ---------------------------------------------------------------- GPU: device solvers vs reference goldens
 def _device(cls_name, X, W0, H0, L, K, precision):
     from cmfpy_b200.algs import ALGORITHMS
@@ -128,3 +152,41 @@ def test_cmf_fit_with_gradient_solvers(built_lib):
         assert len(model.loss_hist) == len(ref)
         assert (np.abs(np.array(model.loss_hist) - ref) / ref).max() <= TRAJ_TOL
         assert (model.motifs >= 0).all() and (model.factors >= 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("key", list(HALS_VARIANTS))
+@pytest.mark.parametrize("name", GD_CASES)
+def test_device_hals_against_reference_golden(built_lib, name, key, precision):
+    """HALSUpdate on the device (residual kept current by csrc/hals_kernels.cuh) against the reference's own
+    trajectories; `precision` only selects the kernel of the closing reconstruction."""
+    g, X, W0, H0 = _inputs(name)
+    N, T, K, L = (int(v) for v in g["shape"])
+    if not _supported(precision, N, K, L):
+        pytest.skip("no %s kernel for this shape" % precision)
+    from cmfpy_b200.algs import ALGORITHMS
+    from cmfpy_b200.model import ModelDimensions
+    alg = ALGORITHMS["hals"](X, ModelDimensions(X, maxlag=L, n_components=K), initW=W0, initH=H0, tol=0,
+                             precision=precision, **HALS_VARIANTS[key])
+    ref = g[key + "_loss_hist"]
+    hist = np.array([alg.loss] + alg.update_many(len(ref) - 1))
+    rel = np.abs(hist - ref) / ref
+    print("%s/%s/%s: max rel loss err %.3e" % (name, key, precision, rel.max()))
+    assert rel.max() <= TRAJ_TOL
+    if key + "_W" in g.files:
+        assert np.abs(alg.W - g[key + "_W"]).max() <= 2e-3 * np.abs(g[key + "_W"]).max()
+        assert np.abs(alg.H - g[key + "_H"]).max() <= 2e-3 * np.abs(g[key + "_H"]).max()
+    alg.close()
+
+
+@pytest.mark.gpu
+def test_cmf_fit_with_hals(built_lib):
+    from cmfpy_b200 import CMF
+    g, X, W0, H0 = _inputs("A")
+    model = CMF(3, 20, n_iter_max=10, alg_name="hals", verbose=False, tol=0, initW=W0, initH=H0)
+    model.fit(X)
+    ref = g["hals_loss_hist"][:11]
+    assert (np.abs(np.array(model.loss_hist) - ref) / ref).max() <= TRAJ_TOL
+    with pytest.raises(ValueError):
+        CMF(3, 20, alg_name="hals", verbose=False, max_iter=1, weightH=0.5, initW=W0, initH=H0).fit(X)
