@@ -86,6 +86,11 @@ struct cmf_mu_s {
 
   tc::TcState tcs;
 
+  // staging for host <-> device conversions (grown on demand, kept: cudaMalloc / cudaFree in the read-back
+  // path cost up to 0.7 s per call on a busy driver)
+  void* stage_buf = nullptr;
+  size_t stage_bytes = 0;
+
   // ---- gradient solvers (gd_kernels.cuh) ----
   struct GdState {
     bool ready = false, cached = false;  // cached: numden / hterms hold the terms of the CURRENT W, H
@@ -155,6 +160,20 @@ inline int ew_grid(const cmf_mu_s* h, long long n_items) {
 
 template <class T> int dmalloc(T** p, long long count) {
   CMF_CUDA(cudaMalloc((void**)p, (size_t)(count > 0 ? count : 1) * sizeof(T)));
+  return 0;
+}
+
+// the handle's staging buffer, at least `bytes` large (the previous contents are not kept)
+int stage_get(cmf_mu_s* h, size_t bytes, void** out) {
+  if (h->stage_bytes < bytes) {
+    CMF_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(h->stage_buf);
+    h->stage_buf = nullptr;
+    h->stage_bytes = 0;
+    CMF_CUDA(cudaMalloc(&h->stage_buf, bytes));
+    h->stage_bytes = bytes;
+  }
+  *out = h->stage_buf;
   return 0;
 }
 
@@ -373,7 +392,7 @@ int load_transposed(cmf_mu_s* h, const TI* src, int mem, long long ld, long long
   if (ch < 32) ch = 32;
   if (ch > cols) ch = cols;
   TI* stg = nullptr;
-  CMF_TRY(dmalloc(&stg, rows * ch));
+  CMF_TRY(stage_get(h, (size_t)rows * ch * sizeof(TI), (void**)&stg));
   int rc = 0;
   for (long long c0 = 0; c0 < cols && rc == 0; c0 += ch) {
     const long long w = (cols - c0 < ch) ? cols - c0 : ch;
@@ -385,7 +404,6 @@ int load_transposed(cmf_mu_s* h, const TI* src, int mem, long long ld, long long
     // the staging buffer is reused by the next chunk
     if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) { set_error("sync failed in load_transposed"); rc = 1; }
   }
-  cudaFree(stg);
   return rc;
 }
 
@@ -420,7 +438,7 @@ int store_transposed(cmf_mu_s* h, const float* src, long long lds, long long row
   if (ch < 32) ch = 32;
   if (ch > cols_out) ch = cols_out;
   TO* stg = nullptr;
-  CMF_TRY(dmalloc(&stg, rows_out * ch));
+  CMF_TRY(stage_get(h, (size_t)rows_out * ch * sizeof(TO), (void**)&stg));
   int rc = 0;
   for (long long c0 = 0; c0 < cols_out && rc == 0; c0 += ch) {
     const long long w = (cols_out - c0 < ch) ? cols_out - c0 : ch;
@@ -436,7 +454,6 @@ int store_transposed(cmf_mu_s* h, const float* src, long long lds, long long row
       rc = 1;
     }
   }
-  cudaFree(stg);
   return rc;
 }
 
@@ -453,6 +470,7 @@ int peer_detach(cmf_mu_s* h) {
 void free_all(cmf_mu_s* h) {
   peer_detach(h);
   cudaFree(h->peer.shared);
+  cudaFree(h->stage_buf);
   cudaFree(h->gdst.P); cudaFree(h->gdst.Ppart); cudaFree(h->gdst.Pt); cudaFree(h->gdst.v); cudaFree(h->gdst.y);
   cudaFree(h->gdst.d_inv); cudaFree(h->gdst.d_lam); cudaFree(h->gdst.st);
   cudaFree(h->halsst.Rt); cudaFree(h->halsst.part); cudaFree(h->halsst.part_h); cudaFree(h->halsst.delta);
@@ -764,9 +782,9 @@ int cmf_mu_set_factors(cmf_mu_t* h, const void* W0, const void* H0, int dtype, i
   const void* wsrc = W0;
   void* wstage = nullptr;
   if (mem == CMF_HOST) {
-    CMF_CUDA(cudaMalloc(&wstage, (size_t)wn * es));
+    CMF_TRY(stage_get(h, (size_t)wn * es, &wstage));
     if (cudaMemcpyAsync(wstage, W0, (size_t)wn * es, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
-      cudaFree(wstage); set_error("H2D copy of W failed"); return 1;
+      set_error("H2D copy of W failed"); return 1;
     }
     wsrc = wstage;
   }
@@ -785,7 +803,6 @@ int cmf_mu_set_factors(cmf_mu_t* h, const void* W0, const void* H0, int dtype, i
   if (rc == 0) rc = sync_ops_W(h);
   if (rc == 0) rc = sync_ops_H(h, 0, h->RH);
   if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) { set_error("sync failed in set_factors"); rc = 1; }
-  if (wstage) cudaFree(wstage);
   if (rc) return rc;
   h->have_factors = true;
   h->est_valid = false;
@@ -1027,7 +1044,7 @@ int cmf_mu_get_W(cmf_mu_t* h, void* W_out, int dtype, int mem) {
   const size_t es = dtype == CMF_F32 ? 4 : 8;
   void* dst = W_out;
   void* stage = nullptr;
-  if (mem == CMF_HOST) { CMF_CUDA(cudaMalloc(&stage, (size_t)wn * es)); dst = stage; }
+  if (mem == CMF_HOST) { CMF_TRY(stage_get(h, (size_t)wn * es, &stage)); dst = stage; }
   const int grid = ew_grid(h, wn);
   if (dtype == CMF_F32) ew::w_pad_out_kernel<float><<<grid, 256, 0, h->stream>>>(h->W, (float*)dst, h->L, h->N, h->K, h->Np, h->Kp);
   else ew::w_pad_out_kernel<double><<<grid, 256, 0, h->stream>>>(h->W, (double*)dst, h->L, h->N, h->K, h->Np, h->Kp);
@@ -1035,7 +1052,6 @@ int cmf_mu_get_W(cmf_mu_t* h, void* W_out, int dtype, int mem) {
   if (rc == 0 && mem == CMF_HOST &&
       cudaMemcpyAsync(W_out, stage, (size_t)wn * es, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { set_error("D2H copy of W failed"); rc = 1; }
   if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) { set_error("sync failed: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
-  if (stage) cudaFree(stage);
   return rc;
 }
 
@@ -1089,7 +1105,7 @@ int cmf_mu_get_w_terms(cmf_mu_t* h, void* num_out, void* den_out, int dtype) {
   const long long wn = (long long)h->L * h->N * h->K;
   const size_t es = dtype == CMF_F32 ? 4 : 8;
   void* stage = nullptr;
-  CMF_CUDA(cudaMalloc(&stage, (size_t)wn * es));
+  CMF_TRY(stage_get(h, (size_t)wn * es, &stage));
   int rc = 0;
   for (int s = 0; s < 2 && rc == 0; ++s) {
     void* out = s ? den_out : num_out;
@@ -1102,7 +1118,6 @@ int cmf_mu_get_w_terms(cmf_mu_t* h, void* num_out, void* den_out, int dtype) {
     if (rc == 0 && (cudaMemcpyAsync(out, stage, (size_t)wn * es, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
                     cudaStreamSynchronize(h->stream) != cudaSuccess)) { set_error("D2H copy failed"); rc = 1; }
   }
-  cudaFree(stage);
   return rc;
 }
 
