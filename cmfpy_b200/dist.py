@@ -292,6 +292,8 @@ class ShardedMultUpdate:
         self.transport = "nccl"
         if self.world > 1 and transport != "nccl" and hasattr(eng, "peer_export") and self.world <= 8:
             self._attach_peers(required=(transport == "peer"))
+        elif self.world > 1 and transport == "peer":
+            raise RuntimeError("transport='peer' needs the device engine and at most 8 ranks")
 
     def _attach_peers(self, required):
         dist, eng = self._dist, self.engine

@@ -118,3 +118,43 @@ def test_sharded_normalisation_matches_global(mode):
     ref_hist = [ref.loss] + [ref.update() for _ in range(n_iter)]
     for H, W, hist in gathered:
         np.testing.assert_allclose(hist, ref_hist, rtol=1e-6)
+
+
+def _peer_required_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cmfpy_b200.dist import ShardedMultUpdate
+        from tests.numpy_shard import NumpyShard
+        N, T, K, L = 4, 40, 2, 3
+        rng = np.random.default_rng(0)
+        X, W0, H0 = rng.random((N, T)), rng.random((L, N, K)), rng.random((K, T))
+        Tl, t0 = T // world, rank * (T // world)
+        eng = NumpyShard(X[:, t0:min(T, t0 + Tl + L - 1)], N, T, K, L, t0, Tl)
+        try:
+            ShardedMultUpdate(None, N, T, K, L, t_offset=t0, t_local=Tl, initW=W0, initH=H0[:, t0:t0 + Tl],
+                              group=dist.group.WORLD, engine=eng, tol=0, transport="peer")
+            res = "no error"
+        except RuntimeError as e:
+            res = str(e)
+        if rank == 0:
+            out.put(res)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_transport_must_be_available_when_required():
+    """transport="peer" is a demand, not a hint: an engine without peer memory (here the NumPy stand-in) must not
+    fall back to another transport silently."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_required_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    msg = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert "peer" in msg and msg != "no error"
