@@ -127,3 +127,68 @@ class NumpyShard:
 
     def close(self):
         pass
+
+
+class NumpyPeerShard(NumpyShard):
+    """NumpyShard plus the engine-side transport interface (`peer_export / peer_attach / peer_detach /
+    step_sharded`) of cmfpy_b200.dist.DeviceShard.  The device engine moves the data with its own kernels over NVLink
+    peer memory; this stand-in moves the same data with gloo collectives INSIDE the engine, in the protocol's order -
+    reduce-scatter of slice r of the W terms in rank order, update of that slice, all-gather of W; halo columns to both
+    neighbours; one residual sum per rank and step, added in rank order - so the host side of transport="peer"
+    (blob exchange, attach handshake, the step_sharded loop, detach on close) runs on CPU."""
+
+    BLOB = 512                                               # cmfpy_b200._lib.CMF_PEER_BLOB_BYTES
+
+    def __init__(self, *a, group=None, fail_attach_on=None, **kw):
+        super().__init__(*a, **kw)
+        self.group, self.fail_attach_on = group, fail_attach_on
+        self.attached = False
+
+    def peer_export(self):
+        import torch.distributed as dist
+        return bytes([dist.get_rank(self.group) % 256]) * self.BLOB
+
+    def peer_attach(self, rank, world, blobs):
+        assert len(blobs) == world and all(len(b) == self.BLOB for b in blobs)
+        assert [b[0] for b in blobs] == [r % 256 for r in range(world)]
+        if self.fail_attach_on == rank:
+            raise RuntimeError("simulated cudaIpcOpenMemHandle failure")
+        self.rank, self.world, self.attached = rank, world, True
+
+    def peer_detach(self):
+        self.attached = False
+
+    def step_sharded(self, n):
+        import torch.distributed as dist
+        assert self.attached
+        losses = []
+        for _ in range(n):
+            self.w_terms()
+            # W exchange: every rank owns slice r of the elements; partial sums are added in rank order
+            parts = [torch.zeros_like(self.numden) for _ in range(self.world)]
+            dist.all_gather(parts, self.numden, group=self.group)
+            total = parts[0].clone()
+            for p in parts[1:]:
+                total += p
+            self.numden[:] = total
+            self.w_apply()
+            self.recon()
+            self.h_step()
+            # halo pushes
+            sl, sr, rl, rr = self.halo_buffers()
+            self.halo_export(sl, sr)
+            if self.h:
+                ops = []
+                if self.rank + 1 < self.world:
+                    ops += [dist.P2POp(dist.isend, sr, self.rank + 1, self.group), dist.P2POp(dist.irecv, rr, self.rank + 1, self.group)]
+                if self.rank > 0:
+                    ops += [dist.P2POp(dist.isend, sl, self.rank - 1, self.group), dist.P2POp(dist.irecv, rl, self.rank - 1, self.group)]
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+                self.halo_import(rl if self.rank > 0 else None, rr if self.rank + 1 < self.world else None)
+            self.recon()
+            # loss ring: one value per rank, added in rank order
+            ring = [torch.zeros_like(self.sumsq) for _ in range(self.world)]
+            dist.all_gather(ring, self.sumsq, group=self.group)
+            losses.append(float(np.sqrt(sum(float(v.item()) for v in ring)) / self.norm_x))
+        return losses

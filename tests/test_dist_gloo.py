@@ -158,3 +158,61 @@ def test_peer_transport_must_be_available_when_required():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert "peer" in msg and msg != "no error"
+
+
+def _peer_worker(rank, world, port, shape, n_iter, out, fail_attach_on):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cmfpy_b200.dist import ShardedMultUpdate
+        from tests.numpy_shard import NumpyPeerShard
+        N, T, K, L = shape
+        rng = np.random.default_rng(0)
+        X, W0, H0 = rng.random((N, T)), rng.random((L, N, K)), rng.random((K, T))
+        Tl = T // world
+        t0 = rank * Tl
+        eng = NumpyPeerShard(X[:, t0:min(T, t0 + Tl + L - 1)], N, T, K, L, t0, Tl, group=dist.group.WORLD,
+                             fail_attach_on=fail_attach_on)
+        alg = ShardedMultUpdate(None, N, T, K, L, t_offset=t0, t_local=Tl, initW=W0, initH=H0[:, t0:t0 + Tl],
+                                group=dist.group.WORLD, engine=eng, tol=0, transport="auto")
+        transport = alg.transport
+        l0 = alg.loss
+        losses = alg.update_many(n_iter - 1) + [alg.update()]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (alg.H_local_host(), alg.W_host(), [l0] + losses, transport, eng.attached))
+        alg.close()
+        if rank == 0:
+            out.put((gathered, eng.attached))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_attach_on", [None, 1])
+def test_peer_transport_host_logic(fail_attach_on):
+    """transport="auto" with an engine that offers peer memory: every rank exports a blob, all blobs are gathered,
+    every rank attaches, and the iterations run through step_sharded.  When ONE rank cannot map its peers
+    (fail_attach_on), ALL ranks must fall back to the collective transport together - a split decision would deadlock."""
+    world, shape, n_iter = 3, (5, 90, 2, 9), 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, shape, n_iter, q, fail_attach_on)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered, attached_after_close = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    N, T, K, L = shape
+    rng = np.random.default_rng(0)
+    X, W0, H0 = rng.random((N, T)), rng.random((L, N, K)), rng.random((K, T))
+    ref = o.MultUpdateOracle(X, L, K, initW=W0, initH=H0, tol=0)
+    ref_hist = [ref.loss] + [ref.update() for _ in range(n_iter)]
+    want = "peer" if fail_attach_on is None else "nccl"
+    for H, W, hist, transport, attached in gathered:
+        assert transport == want and attached == (want == "peer")
+        np.testing.assert_allclose(hist, ref_hist, rtol=1e-6)
+        np.testing.assert_allclose(W, ref.W, rtol=1e-5, atol=1e-7)
+    assert attached_after_close is False
+    np.testing.assert_allclose(np.concatenate([g[0] for g in gathered], axis=1), ref.H, rtol=1e-5, atol=1e-7)
