@@ -454,7 +454,7 @@ def run_b200(args):
             "peak_gbs": peaks["hbm_gbs"]},
     }
     cb = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU baseline is a 1-GPU-run item (rank 0, N = 1 only)
         cb = cpu_baseline(N, T, K, L)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
