@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libcmf_b200.so")
+LIB_PATH = os.environ.get("CMF_B200_LIB") or os.path.join(HERE, "lib", "libcmf_b200.so")   # (override: A/B builds)
 
 CMF_F32, CMF_F64 = 0, 1
 CMF_HOST, CMF_DEVICE = 0, 1

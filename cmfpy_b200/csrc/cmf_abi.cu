@@ -253,10 +253,10 @@ bool gram_h(const cmf_mu_s* h) { return h->use_tc && (h->tcs.mask & 4) && (h->tc
 
 int ensure_est_buffer(cmf_mu_s* h) {
   if (h->Et) return 0;
-  CMF_CUDA(cudaMalloc((void**)&h->Et, (size_t)h->RT * h->Np * 4));
+  CMF_CUDA(cudaMalloc((void**)&h->Et, ((size_t)h->RT * h->Np + 128) * 4));   // + slack: see make_map_k2src
   CMF_CUDA(cudaMemsetAsync(h->Et, 0, (size_t)h->RT * h->Np * 4, h->stream));
   if (h->x3) {
-    CMF_CUDA(cudaMalloc((void**)&h->Elo, (size_t)h->RT * h->Np * 4));
+    CMF_CUDA(cudaMalloc((void**)&h->Elo, ((size_t)h->RT * h->Np + 128) * 4));
     CMF_CUDA(cudaMemsetAsync(h->Elo, 0, (size_t)h->RT * h->Np * 4, h->stream));
   }
   if (h->use_tc) CMF_TRY(tc::attach_est(h->tcs, h->Et, h->Elo));
@@ -596,8 +596,8 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
 
   int rc = 0;
   auto A = [&](int r) { if (rc == 0) rc = r; };
-  A(dmalloc(&h->Xt, h->RT * h->Np));
-  if (h->x3) A(dmalloc(&h->Xlo, h->RT * h->Np));
+  A(dmalloc(&h->Xt, h->RT * h->Np + 128));        // + slack: the K2 box of a ragged feature count reads on
+  if (h->x3) A(dmalloc(&h->Xlo, h->RT * h->Np + 128));
   A(dmalloc(&h->Ht, h->RH * h->Kp));
   A(dmalloc(&h->W, h->wcount));
   A(dmalloc(&h->numden, 2 * h->wcount));

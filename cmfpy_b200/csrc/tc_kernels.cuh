@@ -56,6 +56,27 @@ struct Abort {
   }
 };
 
+// The same bounded wait for warps that have time (the epilogue warps of the two-level kernels wait for whole
+// sub-chunks): they back off between polls so that their spinning does not take issue slots from the MMA and TMA
+// threads that share their schedulers.
+__device__ __forceinline__ bool wait_relaxed(const Abort& ab, uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (true) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+      __nanosleep(128);
+      if (mbar_try_wait(bar, parity)) return true;
+    }
+    if (*ab.flag) return false;
+    if ((unsigned long long)(clock64() - t0) > kTimeoutCycles) {
+      *ab.flag = 1;
+      atomicExch(ab.global_err, kErrTimeout);
+      return false;
+    }
+  }
+}
+
 struct PipeState {
   int stage = 0;
   uint32_t phase = 0;
@@ -102,6 +123,7 @@ struct ReconParams {
                                    // with its own window of 256 + s (LB - 1) rows, into the same accumulator
   float* Elo;                      // x3: est^T = Et (hi) + Elo; null: the result is stored unsplit
   const float* Xlo;                // x3: X^T = Xt (hi) + Xlo
+  int sub_units;                   // tc_recon_x3_kernel: (lag, reduction block) units per tensor-memory sub-chunk
   int* err;
 };
 
@@ -123,9 +145,8 @@ __host__ __device__ inline size_t recon_smem_bytes(int wrows) {
   return 1024 + (size_t)kReconStages * kReconStageBytes + 2 * (size_t)wrows * kKp * 4 + 256;
 }
 
-// kX3 = 1: the 3xTF32 instantiation (operand-half selection in the producer, hi/lo epilogue); kX3 = 0 compiles
-// to exactly the plain TF32 kernel.
-template <int kX3>
+// Plain TF32 (one operand pass, one tensor-memory chain per tile); the 3xTF32 mode runs tc_recon_x3_kernel
+// (tc_strict_kernels.cuh) on the same tiles and operands.
 __global__ void __launch_bounds__(kReconThreads, 1)
 tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
                 const ReconParams p) {
@@ -182,30 +203,34 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         }
         return c;
       };
-      auto issue_window = [&](const Chunk& c, long long wc) -> bool {
+      // window of chunk number wc; block = false: only if its buffer is already free
+      auto issue_window = [&](const Chunk& c, long long wc, bool block, bool& done) -> bool {
         const int hb = (int)(wc & 1);
-        if (!ab.wait(&hempty[hb], (uint32_t)((wc >> 1) & 1) ^ 1)) return false;
+        const uint32_t par = (uint32_t)((wc >> 1) & 1) ^ 1;
+        if (!block && !mbar_try_wait(&hempty[hb], par)) return true;
+        if (!ab.wait(&hempty[hb], par)) return false;
         const long long tt = c.tile / p.n_tiles_n;
         mbar_arrive_expect_tx(&hfull[hb], hbytes);
         uint8_t* hdst = Hs + (size_t)hb * hbytes;
-        const X3Sel sel = x3_select(kX3, p.cbx, p.lo_off, p.lo_off_b, c.cb);
+        const X3Sel sel = x3_select(0, p.cbx, p.lo_off, p.lo_off_b, c.cb);
         const int l1 = min(L, (c.lb + 1) * LB);                 // window row 0 holds lag l1 - 1 of this block
         for (int rb = 0; rb < wrows / 64; ++rb)
           tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], sel.cbr * 32 + sel.b_off,
                       (int)(tt * 256 + p.h_shift + p.s * (L - l1) + rb * 64));
+        done = true;
         return true;
       };
       Chunk cur{(long long)blockIdx.x, 0, 0, (long long)blockIdx.x < p.n_tiles};
       long long wc = 0;
-      if (cur.valid) ok = issue_window(cur, 0);
+      bool dummy = false;
+      if (cur.valid) ok = issue_window(cur, 0, true, dummy);
       while (cur.valid && ok) {
         const Chunk nxt = next_chunk(cur);
         bool prefetched = !nxt.valid;
         const int nt = (int)(cur.tile % p.n_tiles_n);
-        const X3Sel sel = x3_select(kX3, p.cbx, p.lo_off, p.lo_off_b, cur.cb);
+        const X3Sel sel = x3_select(0, p.cbx, p.lo_off, p.lo_off_b, cur.cb);
         const int l0 = cur.lb * LB, l1 = min(L, l0 + LB);
-        int stage_in_chunk = 0;
-        for (int l = l0; l < l1; l += kReconLagsPerStage, ++stage_in_chunk) {
+        for (int l = l0; l < l1; l += kReconLagsPerStage) {
           if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
           const int nl = min(kReconLagsPerStage, l1 - l);
           mbar_arrive_expect_tx(&full[ps.stage], nl * kReconABytes);
@@ -213,12 +238,12 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             tma_load_2d(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes, &tmW, &full[ps.stage],
                         (sel.cbr % p.cb_cols) * 32 + sel.a_off, (l + u + sel.cbr / p.cb_cols) * p.Np + nt * 128);
           ps.advance(kReconStages);
-          if (!prefetched && stage_in_chunk >= 1) {
-            if (!issue_window(nxt, wc + 1)) { ok = false; break; }
-            prefetched = true;
-          }
+          // The next window goes out as soon as its buffer is free.  (Blocking on it here, as round 1 did after
+          // the second stage of a chunk, parks this thread until the MMAs of the PREVIOUS chunk retire while the
+          // W ring runs dry.)
+          if (!prefetched && !issue_window(nxt, wc + 1, false, prefetched)) { ok = false; break; }
         }
-        if (ok && !prefetched) ok = issue_window(nxt, wc + 1);
+        if (ok && !prefetched) ok = issue_window(nxt, wc + 1, true, prefetched);
         cur = nxt;
         ++wc;
       }
@@ -281,9 +306,7 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       const bool n_ok = n < p.n_rows;
       float tile_loss = 0.f;
       const float* __restrict__ Xt = p.Xt;
-      const float* __restrict__ Xlo = p.Xlo;
       float* __restrict__ Et = p.Et;
-      float* __restrict__ Elo = p.Elo;
       const size_t np = (size_t)p.ld_out;
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
@@ -296,10 +319,6 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (n_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = (tau0 + j < p.t_own) ? __ldcs(Xt + off0 + (size_t)j * np) : 0.f;
-          if (kX3 && Xlo) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] += (tau0 + j < p.t_own) ? __ldcs(Xlo + off0 + (size_t)j * np) : 0.f;
-          }
         }
         tmem_ld_wait();
         if (p.store_mode == 2) {
@@ -327,14 +346,8 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               tile_loss = fmaf(d, d, tile_loss);
             }
             if (!p.skip_store) {
-              if (kX3 && Elo) {
-                const float hi = round_tf32(v);
-                Et[off0 + (size_t)j * np] = hi;
-                Elo[off0 + (size_t)j * np] = round_tf32(v - hi);
-              } else {
-                if (p.round_out) v = round_tf32(v);
-                Et[off0 + (size_t)j * np] = v;
-              }
+              if (p.round_out) v = round_tf32(v);
+              Et[off0 + (size_t)j * np] = v;
             }
           }
         }
@@ -353,192 +366,6 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
-}
-
-// --------------------------------------------------------------------------
-// K1 on a CTA pair (cta_group::2).  The single-CTA kernel above sits at the shared-memory bandwidth
-// of a 128x256x8 TF32 MMA (4 KB of A + 8 KB of B per 128 cycles, plus the TMA fills).  Two CTAs of one
-// TPC compute D[256 n][256 tau] together: each holds its own 128 rows of A and supplies HALF of the B rows
-// (its half-window of H^T), so the operand reads per SM drop from 96 to 64 B/cycle.  The leader CTA issues
-// the MMAs; TMA loads of both CTAs complete on the leader's barriers; commits are multicast to both.
-// --------------------------------------------------------------------------
-constexpr int kRecon2Stages = 8;
-
-__host__ __device__ inline size_t recon2_smem_bytes(int wrows2) {
-  return 1024 + (size_t)kRecon2Stages * kReconABytes + 2 * (size_t)wrows2 * kKp * 4 + 256;
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kReconThreads, 1)
-tc_recon2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
-                 const ReconParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* As = smem;                                           // [stages][16 KB]: this CTA's 128 rows of A
-  uint8_t* Hs = As + kRecon2Stages * kReconABytes;              // [2][wrows * 128]: this CTA's half window
-  const uint32_t hbytes = (uint32_t)p.wrows * kKp * 4;
-  uint64_t* bars = (uint64_t*)(Hs + 2 * hbytes);
-  uint64_t* full = bars;                                        // used in the leader CTA
-  uint64_t* empty = bars + kRecon2Stages;                       // per CTA
-  uint64_t* hfull = bars + 2 * kRecon2Stages;                   // leader
-  uint64_t* hempty = hfull + 2;                                 // per CTA
-  uint64_t* tfull = hempty + 2;                                 // per CTA
-  uint64_t* tempty = tfull + 2;                                 // leader (count 8)
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
-  volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
-  __shared__ double red[4];
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  if (tid == 0) {
-    // full barriers live in the leader: ONE arrival (the leader's producer, which announces the bytes of
-    // both CTAs); the peer's TMA loads only complete_tx on them.  The peer cannot run a ring cycle ahead:
-    // its empty barrier flips only after the leader's MMAs consumed the stage.
-    for (int i = 0; i < kRecon2Stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1);
-      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8);
-    }
-    *abort_flag = 0;
-    fence_mbar_init();
-    prefetch_tmap(&tmW);
-    prefetch_tmap(&tmH);
-  }
-  if (warp == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const Abort ab{abort_flag, p.err};
-  const int L = p.L, wrows = p.wrows;
-  const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-
-  if (warp == 0) {
-    // ---------------- TMA producer (both CTAs) ----------------
-    if (lane == 0) {
-      PipeState ps;
-      long long wcount = 0;
-      bool ok = true;
-      for (long long tile = pair; tile < p.n_tiles && ok; tile += npairs) {
-        const int nt = (int)(tile % p.n_tiles_n);
-        const long long tt = tile / p.n_tiles_n;
-        for (int cb = 0; cb < p.CB && ok; ++cb, ++wcount) {
-          const int hb = (int)(wcount & 1);
-          if (!ab.wait(&hempty[hb], (uint32_t)((wcount >> 1) & 1) ^ 1)) { ok = false; break; }
-          const uint32_t hbar = mapa_u32(smem_u32(&hfull[hb]), 0);
-          if (leader) mbar_arrive_expect_tx(&hfull[hb], 2 * hbytes);
-          uint8_t* hdst = Hs + (size_t)hb * hbytes;
-          for (int rb = 0; rb < wrows / 64; ++rb)
-            tma_load_2d_2sm(hdst + (size_t)rb * 64 * 128, &tmH, hbar, cb * 32,
-                            (int)(tt * 256 + rank * 128 + p.h_shift + rb * 64));
-          for (int l = 0; l < L; ++l) {
-            if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
-            const uint32_t fbar = mapa_u32(smem_u32(&full[ps.stage]), 0);
-            if (leader) mbar_arrive_expect_tx(&full[ps.stage], 2 * kReconABytes);
-            tma_load_2d_2sm(As + (size_t)ps.stage * kReconABytes, &tmW, fbar, (cb % p.cb_cols) * 32,
-                            (l + cb / p.cb_cols) * p.Np + nt * 256 + (int)rank * 128);
-            ps.advance(kRecon2Stages);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer (leader CTA only) ----------------
-    if (lane == 0 && leader) {
-      const uint32_t idesc = make_idesc_tf32(256, 256, 0, 0);
-      PipeState ps;
-      long long wcount = 0;
-      int it = 0;
-      bool ok = true;
-      for (long long tile = pair; tile < p.n_tiles && ok; tile += npairs, ++it) {
-        const int b = it & 1;
-        if (!ab.wait(&tempty[b], (uint32_t)((it >> 1) & 1) ^ 1)) break;
-        tc_fence_after();
-        const uint32_t dtm = tmem + (uint32_t)b * 256;
-        for (int cb = 0; cb < p.CB && ok; ++cb, ++wcount) {
-          const int hb = (int)(wcount & 1);
-          if (!ab.wait(&hfull[hb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
-          tc_fence_after();
-          const uint32_t hbase = smem_u32(Hs + (size_t)hb * hbytes);
-          for (int l = 0; l < L; ++l) {
-            if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
-            tc_fence_after();
-            const uint32_t abase = smem_u32(As + (size_t)ps.stage * kReconABytes);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ad = make_smem_desc(abase + ks * 32, 16, 1024, kSwz128);
-              const uint64_t bd = make_smem_desc(hbase + (uint32_t)(p.s * (L - 1 - l)) * 128 + ks * 32, 16, 1024, kSwz128);
-              mma_tf32_ss_2sm(dtm, ad, bd, idesc, (cb | l | ks) != 0 ? 1u : 0u);
-            }
-            mma_commit_2sm(&empty[ps.stage], 3);
-            ps.advance(kRecon2Stages);
-          }
-          if (!ok) break;
-          mma_commit_2sm(&hempty[hb], 3);
-        }
-        if (!ok) break;
-        mma_commit_2sm(&tfull[b], 3);
-      }
-    }
-  } else {
-    // ---------------- epilogue (both CTAs): own 128 rows of the pair's tile ----------------
-    const int q = warp & 3;
-    double loss_acc = 0.0;
-    int it = 0;
-    for (long long tile = pair; tile < p.n_tiles; tile += npairs, ++it) {
-      const int nt = (int)(tile % p.n_tiles_n);
-      const long long tt = tile / p.n_tiles_n;
-      const int b = it & 1;
-      if (!ab.wait(&tfull[b], (it >> 1) & 1)) break;
-      tc_fence_after();
-      const int n = nt * 256 + (int)rank * 128 + q * 32 + lane;
-      const bool n_ok = n < p.n_rows;
-      float tile_loss = 0.f;
-      const float* __restrict__ Xt = p.Xt;
-      float* __restrict__ Et = p.Et;
-      const size_t np = (size_t)p.ld_out;
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t r[32];
-        float x[32];
-        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + c * 32), r);
-        const long long tau0 = tt * 256 + c * 32;
-        const size_t off0 = (size_t)tau0 * np + n;
-        if (n_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = (tau0 + j < p.t_own) ? __ldcs(Xt + off0 + (size_t)j * np) : 0.f;
-        }
-        tmem_ld_wait();
-        if (n_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long long tau = tau0 + j;
-            float v = __uint_as_float(r[j]);
-            if (tau >= p.t_valid) v = 0.f;
-            if (tau < p.t_own) {
-              const float d = v - x[j];
-              tile_loss = fmaf(d, d, tile_loss);
-            }
-            if (!p.skip_store) {
-              if (p.round_out) v = round_tf32(v);
-              Et[off0 + (size_t)j * np] = v;
-            }
-          }
-        }
-      }
-      loss_acc += (double)tile_loss;
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[b]), 0));
-    }
-    loss_acc = warp_sum(loss_acc);
-    if (lane == 0) red[q] = loss_acc;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (warp == 2 && lane == 0) p.loss_partials[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 2) tmem_dealloc_2sm(tmem, 512);
 }
 
 // ==========================================================================
@@ -561,8 +388,9 @@ struct WTermsParams {
   long long stages_total;         // ceil(t_own / 32)
   float* part;                    // [chunk][src][L][Np][Kp]
   long long per_src;              // L * Np * Kp
-  int x3, lo_off;                 // 3xTF32: three passes over the item's time range - (S lo, H hi), (S hi, H lo),
-                                  // (S hi, H hi) - into one accumulator; H lo sits lo_off columns to the right
+  int x3, lo_off;                 // tc_wterms_x3_kernel: three passes over the item's time range - (S lo, H hi),
+                                  // (S hi, H lo), (S hi, H hi); H lo sits lo_off columns to the right
+  int sub_units;                  // tc_wterms_x3_kernel: 32-row time stages per tensor-memory sub-chunk
   int* err;
 };
 
@@ -576,8 +404,7 @@ __host__ __device__ inline size_t wterms_smem_bytes(int s) { return 1024 + (size
 
 __global__ void __launch_bounds__(kWtThreads, 1)
 tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmE,
-                 const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmXlo,
-                 const __grid_constant__ CUtensorMap tmElo, const WTermsParams p) {
+                 const __grid_constant__ CUtensorMap tmH, const WTermsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* St = smem;                                            // [stages][A 16 KB | B brows x 128 B]
@@ -597,7 +424,7 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     mbar_init(tempty, 4);
     *abort_flag = 0;
     fence_mbar_init();
-    prefetch_tmap(&tmX); prefetch_tmap(&tmE); prefetch_tmap(&tmH); prefetch_tmap(&tmXlo); prefetch_tmap(&tmElo);
+    prefetch_tmap(&tmX); prefetch_tmap(&tmE); prefetch_tmap(&tmH);
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
@@ -630,17 +457,15 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         decode(item, lg, cb, src, nt, ch);
         long long s0, s1;
         chunk_range(ch, s0, s1);
-        for (int combo = p.x3 ? 0 : 2; combo < 3 && ok; ++combo) {
-          const CUtensorMap* tmS = combo == 0 ? (src ? &tmElo : &tmXlo) : (src ? &tmE : &tmX);
-          const int hcol = cb * 32 + (combo == 1 ? p.lo_off : 0);
+        {
+          const CUtensorMap* tmS = src ? &tmE : &tmX;
+          const int hcol = cb * 32;
           for (long long s = s0; s < s1; ++s) {
             if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
             uint8_t* dst = St + (size_t)ps.stage * kWtStageBytes;
             mbar_arrive_expect_tx(&full[ps.stage], kWtStageBytes);
             const int tau0 = (int)(s * 32);
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-              tma_load_2d(dst + r * 4096, tmS, &full[ps.stage], nt * 128 + r * 32, tau0);
+            tma_load_3d(dst, tmS, &full[ps.stage], 0, tau0, nt * 4);      // four 32-feature regions in one box
             // Hv rows tau0 - s*(l0+15) .. tau0 + 32; row index in Hv is tau + h
             tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], hcol, tau0 - p.s * (lg * 16 + 15) + p.h);
             ps.advance(kWtStages);
@@ -661,7 +486,6 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         chunk_range(ch, s0, s1);
         if (!ab.wait(tempty, (it & 1) ^ 1)) break;
         tc_fence_after();
-        if (p.x3) s1 = s0 + 3 * (s1 - s0);          // three operand passes, one accumulation
         for (long long s = s0; s < s1; ++s) {
           if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
           tc_fence_after();
@@ -743,485 +567,6 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
-}
-
-// ==========================================================================
-// K3  H terms
-//   out[src][tau][k] = sum_l sum_n W[l][n][k] * S^T[tau+l][n],  S = X | est
-//   (reference tensor_transconv, cmfpy/common.py:61-86, via mult.py:42-48)
-// The output has only K rows, so four lag groups share the 128 MMA rows:
-//   row (g,k) of D accumulates lags l = j + J*g (J = Lp/4, j = 0..J-1):
-//   D[(g,k)][c] += W[j+J*g][n][k] * S^T[base + c + j][n]      (M=128, N=256)
-//   => D[(g,k)][c] is the group-g part of out[k][base + c - J*g].
-//   A = W rows of 4 lags, MN-major SWIZZLE_128B_BASE32B (4 regions: one per g)
-//   B = S^T window, K-major SWIZZLE_128B rows of 32 features, row shift j = +128 B
-// Two accumulators: X (numerator) and est (denominator) share every A stage.
-// The epilogue stores the four group partials as they are (plain 16-byte
-// stores, time-contiguous): scratch[src][g][k][base + c]; combine_groups_kernel
-// then forms out[src][t][k] = sum_g scratch[src][g][k][t + J*g].  No atomics,
-// deterministic.
-// ==========================================================================
-struct HTermsParams {
-  int Np, J, n_chunks_n, wrows;    // n chunks of 32 features; window rows >= 256 + s*(J-1)
-  int s, CB;                       // lag stride in rows; column blocks (regions = (4/CB lag groups) x CB)
-  int n_src;                       // 2: X and est (numerator, denominator); 1: X only (denominator via Gram)
-  int n_slots;                     // scratch slots per split (2: numerator and denominator; 1 in pair mode)
-  int pair_mode;                   // n_src == 2 with BOTH sources = X: source 1 is the next time tile (base + 256),
-                                   // so every W stage still feeds 8 MMAs when only the numerator is computed
-  long long n_time_tiles;          // time tiles (pairs in pair_mode) ; n_tiles = n_time_tiles * n_split
-  int n_split, nc_per_split;       // the feature chunks of a tile are shared by n_split work items (shorter
-                                   // accumulation chains in tensor memory; partials summed by combine_groups)
-  long long n_tiles;               // TO / 256 + 1
-  long long ts;                    // scratch row length (TO + 256)
-  float* scratch;                  // [n_split][n_slots][4][32][ts]
-  int x3, lo_off;                  // 3xTF32: the feature chunks of an item are walked three times - (W lo, S hi),
-                                   // (W hi, S lo), (W hi, S hi) - into the same accumulators
-  int dbg;                         // timing experiments only (CMF_HT_DBG; results are then WRONG): 1 = drain without
-                                   // stores, 2 = no drain at all, 4 = every window from time tile 0 (L2-resident)
-  int* err;
-};
-
-constexpr int kHtLagsPerStage = 1;                 // virtual lags per pipeline stage (2 with 2 stages measured slower: 8.2 vs 8.0 ms)
-constexpr int kHtStages = 4;
-constexpr int kHtThreads = 192;
-constexpr int kHtABytes = 4 * 32 * 128;            // 4 lag groups x 32 n x 32 k
-constexpr int kHtStageBytes = kHtLagsPerStage * kHtABytes;
-
-__host__ __device__ inline size_t hterms_smem_bytes(int wrows) {
-  return 1024 + (size_t)kHtStages * kHtStageBytes + 2 * 2 * (size_t)wrows * 128 + 256;
-}
-
-__global__ void __launch_bounds__(kHtThreads, 1)
-tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
-                 const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmXlo,
-                 const __grid_constant__ CUtensorMap tmElo, const HTermsParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* As = smem;                                             // [stages][16 KB]
-  const uint32_t wbytes = (uint32_t)p.wrows * 128;                // one source, one 32-feature chunk
-  uint8_t* Ws = As + kHtStages * kHtStageBytes;                   // [2 buffers][2 sources][wbytes]
-  uint64_t* bars = (uint64_t*)(Ws + 4 * (size_t)wbytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kHtStages;
-  uint64_t* wfull = bars + 2 * kHtStages;                         // [2]
-  uint64_t* wempty = wfull + 2;                                   // [2]
-  uint64_t* tfull = wempty + 2;                                   // [1]
-  uint64_t* tempty = tfull + 1;                                   // [1]
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
-  volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    for (int i = 0; i < kHtStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, 4);
-    *abort_flag = 0;
-    fence_mbar_init();
-    prefetch_tmap(&tmW); prefetch_tmap(&tmX); prefetch_tmap(&tmE); prefetch_tmap(&tmXlo); prefetch_tmap(&tmElo);
-  }
-  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const Abort ab{abort_flag, p.err};
-  const int J = p.J, wrows = p.wrows;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      PipeState ps;
-      bool ok = true;
-      // chunks = (work item, 32-feature chunk) in execution order; chunk c uses window buffer c & 1.
-      // The window of chunk c+1 is requested while the W stages of chunk c stream, i.e. a whole chunk
-      // (J stages) before the MMAs need it - not merely the depth of the W ring ahead.
-      struct Chunk { long long item; int nc, nc0, nc1, combo; bool valid; };
-      auto make_chunk = [&](long long item) {
-        Chunk c{item, 0, 0, 0, p.x3 ? 0 : 2, item < p.n_tiles};
-        if (c.valid) {
-          c.nc0 = c.nc = (int)(item % p.n_split) * p.nc_per_split;
-          c.nc1 = min(c.nc + p.nc_per_split, p.n_chunks_n);
-        }
-        return c;
-      };
-      auto next_chunk = [&](Chunk c) {
-        if (++c.nc >= c.nc1) {
-          if (c.combo < 2) { ++c.combo; c.nc = c.nc0; }
-          else c = make_chunk(c.item + gridDim.x);
-        }
-        return c;
-      };
-      auto issue_window = [&](const Chunk& c, long long wc) -> bool {
-        const int wb = (int)(wc & 1);
-        if (!ab.wait(&wempty[wb], (uint32_t)((wc >> 1) & 1) ^ 1)) return false;
-        const long long tile = c.item / p.n_split;
-        mbar_arrive_expect_tx(&wfull[wb], p.n_src * wbytes);
-        for (int src = 0; src < p.n_src; ++src) {
-          uint8_t* wdst = Ws + ((size_t)wb * 2 + src) * wbytes;
-          const CUtensorMap* tmS = (src && !p.pair_mode) ? (c.combo == 1 ? &tmElo : &tmE)
-                                                         : (c.combo == 1 ? &tmXlo : &tmX);
-          const int base = (p.dbg & 4) ? 0 : (int)((p.pair_mode ? 2 * tile + src : tile) * 256);
-          for (int rb = 0; rb < wrows / 32; ++rb)
-            tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], c.nc * 32, base + rb * 32);
-        }
-        return true;
-      };
-      Chunk cur = make_chunk(blockIdx.x);
-      long long wc = 0;
-      if (cur.valid) ok = issue_window(cur, 0);
-      while (cur.valid && ok) {
-        const Chunk nxt = next_chunk(cur);
-        bool prefetched = !nxt.valid;
-        int stage_in_chunk = 0;
-        for (int j = 0; j < J; j += kHtLagsPerStage, ++stage_in_chunk) {
-          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
-          const int nl = min(kHtLagsPerStage, J - j);
-          mbar_arrive_expect_tx(&full[ps.stage], nl * kHtABytes);
-          for (int u = 0; u < nl; ++u) {
-            uint8_t* dst = As + (size_t)ps.stage * kHtStageBytes + u * kHtABytes;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)      // region g = (lag group g / CB, column block g % CB)
-              tma_load_2d(dst + g * 4096, &tmW, &full[ps.stage], (g % p.CB) * 32 + (cur.combo == 0 ? p.lo_off : 0),
-                          (j + u + J * (g / p.CB)) * p.Np + cur.nc * 32);
-          }
-          ps.advance(kHtStages);
-          if (!prefetched && stage_in_chunk >= 1) {       // by now the MMAs are inside `cur`: the other buffer is free
-            if (!issue_window(nxt, wc + 1)) { ok = false; break; }
-            prefetched = true;
-          }
-        }
-        if (ok && !prefetched) ok = issue_window(nxt, wc + 1);
-        cur = nxt;
-        ++wc;
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(128, 256, 1, 0);
-      PipeState ps;
-      long long wcount = 0;
-      int it = 0;
-      bool ok = true;
-      for (long long item = blockIdx.x; item < p.n_tiles && ok; item += gridDim.x, ++it) {
-        const int nc0 = (int)(item % p.n_split) * p.nc_per_split;
-        const int nc1 = min(nc0 + p.nc_per_split, p.n_chunks_n);
-        if (!ab.wait(tempty, (it & 1) ^ 1)) break;
-        tc_fence_after();
-        const int nchunks = (p.x3 ? 3 : 1) * (nc1 - nc0);        // x3: three operand passes, one accumulation
-        for (int nc = nc0; nc < nc0 + nchunks && ok; ++nc, ++wcount) {
-          const int wb = (int)(wcount & 1);
-          if (!ab.wait(&wfull[wb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
-          tc_fence_after();
-          const uint32_t wbase = smem_u32(Ws + (size_t)wb * 2 * wbytes);
-          for (int j = 0; j < J; j += kHtLagsPerStage) {
-            if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
-            tc_fence_after();
-            const int nl = min(kHtLagsPerStage, J - j);
-            for (int u = 0; u < nl; ++u) {
-              const uint32_t abase = smem_u32(As + (size_t)ps.stage * kHtStageBytes + u * kHtABytes);
-#pragma unroll
-              for (int src = 0; src < 2; ++src) {
-                if (src >= p.n_src) break;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
-                  const uint64_t bd = make_smem_desc(wbase + src * wbytes + (uint32_t)(p.s * (j + u)) * 128 + ks * 32, 16, 1024, kSwz128);
-                  mma_tf32_ss(tmem + src * 256, ad, bd, idesc, ((nc - nc0) | (j + u) | ks) != 0 ? 1u : 0u);
-                }
-              }
-            }
-            mma_commit(&empty[ps.stage]);
-            ps.advance(kHtStages);
-          }
-          if (!ok) break;
-          mma_commit(&wempty[wb]);
-        }
-        if (!ok) break;
-        mma_commit(tfull);
-      }
-    }
-  } else {
-    const int q = warp & 3;                 // lag group g of this warp's 32 TMEM lanes; lane = k
-    int it = 0;
-    for (long long item = blockIdx.x; item < p.n_tiles; item += gridDim.x, ++it) {
-      const long long tile = item / p.n_split;
-      const int split = (int)(item % p.n_split);
-      if (!ab.wait(tfull, it & 1)) break;
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 8 * p.n_src; ++c) {
-        if (p.dbg & 2) break;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
-        const int src = c >> 3;
-        const int slot = p.pair_mode ? 0 : src;                       // pair mode: both halves are numerators
-        const long long ttile = p.pair_mode ? 2 * tile + src : tile;
-        if ((ttile + 1) * 256 > p.ts) continue;                       // odd tile count: the pair's second half does not exist
-        if ((p.dbg & 1) && r[0] != 0x7fc00001u) continue;
-        float4* o = reinterpret_cast<float4*>(p.scratch + ((size_t)((split * p.n_slots + slot) * 4 + q) * kKp + lane) * p.ts +
-                                              ttile * 256 + (c & 7) * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
-}
-
-// --------------------------------------------------------------------------
-// K3, ping-pong form.  One source per work item and the two 256-column accumulators ALTERNATE between
-// consecutive items, so the drain of item i (tensor memory -> scratch) overlaps the MMAs of item i+1; a stage
-// holds two lags (8 MMAs per barrier round trip, as in K1).  Needs half the window memory of the paired form
-// (wider lag ranges fit) but streams every W stage for one source only: measured 4 % (tf32 + Gram) to 30 %
-// (tf32x3, two sources) SLOWER than the paired form at config C, so it is used only where the paired form does
-// not fit shared memory (CMF_HTERMS_PP=1 forces it).
-//   item -> (time tile, source, split):  source 0 = X, 1 = est;  scratch slot = source.
-// --------------------------------------------------------------------------
-constexpr int kHpLagsPerStage = 2;
-constexpr int kHpStages = 3;
-constexpr int kHpStageBytes = kHpLagsPerStage * kHtABytes;
-
-__host__ __device__ inline size_t hterms_pp_smem_bytes(int wrows) {
-  return 1024 + (size_t)kHpStages * kHpStageBytes + 2 * (size_t)wrows * 128 + 256;
-}
-
-__global__ void __launch_bounds__(kHtThreads, 1)
-tc_hterms_pp_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
-                    const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmXlo,
-                    const __grid_constant__ CUtensorMap tmElo, const HTermsParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* As = smem;                                             // [stages][2 lags x 16 KB]
-  const uint32_t wbytes = (uint32_t)p.wrows * 128;                // one 32-feature chunk of the window
-  uint8_t* Ws = As + kHpStages * kHpStageBytes;                   // [2 buffers][wbytes]
-  uint64_t* bars = (uint64_t*)(Ws + 2 * (size_t)wbytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kHpStages;
-  uint64_t* wfull = bars + 2 * kHpStages;                         // [2]
-  uint64_t* wempty = wfull + 2;                                   // [2]
-  uint64_t* tfull = wempty + 2;                                   // [2]
-  uint64_t* tempty = tfull + 2;                                   // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
-  volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    for (int i = 0; i < kHpStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1);
-      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4);
-    }
-    *abort_flag = 0;
-    fence_mbar_init();
-    prefetch_tmap(&tmW); prefetch_tmap(&tmX); prefetch_tmap(&tmE); prefetch_tmap(&tmXlo); prefetch_tmap(&tmElo);
-  }
-  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const Abort ab{abort_flag, p.err};
-  const int J = p.J, wrows = p.wrows;
-  const int n_pass = p.x3 ? 3 : 1;
-
-  // item -> (tile, src, split)
-  auto decode = [&](long long item, long long& tile, int& src, int& split) {
-    split = (int)(item % p.n_split); item /= p.n_split;
-    src = (int)(item % p.n_src);
-    tile = item / p.n_src;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      PipeState ps;
-      bool ok = true;
-      // chunks = (item, operand pass, 32-feature chunk) in execution order; chunk c uses window buffer c & 1 and
-      // its window is requested while the W stages of chunk c-1 stream
-      struct Chunk { long long item, tile; int src, nc, nc0, nc1, combo; bool valid; };
-      auto make_chunk = [&](long long item) {
-        Chunk c{item, 0, 0, 0, 0, 0, p.x3 ? 0 : 2, item < p.n_tiles};
-        if (c.valid) {
-          int split;
-          decode(item, c.tile, c.src, split);
-          c.nc0 = c.nc = split * p.nc_per_split;
-          c.nc1 = min(c.nc + p.nc_per_split, p.n_chunks_n);
-        }
-        return c;
-      };
-      auto next_chunk = [&](Chunk c) {
-        if (++c.nc >= c.nc1) {
-          if (c.combo < 2) { ++c.combo; c.nc = c.nc0; }
-          else c = make_chunk(c.item + gridDim.x);
-        }
-        return c;
-      };
-      auto issue_window = [&](const Chunk& c, long long wc) -> bool {
-        const int wb = (int)(wc & 1);
-        if (!ab.wait(&wempty[wb], (uint32_t)((wc >> 1) & 1) ^ 1)) return false;
-        mbar_arrive_expect_tx(&wfull[wb], wbytes);
-        uint8_t* wdst = Ws + (size_t)wb * wbytes;
-        const CUtensorMap* tmS = c.src ? (c.combo == 1 ? &tmElo : &tmE) : (c.combo == 1 ? &tmXlo : &tmX);
-        const int base = (int)(c.tile * 256);
-        for (int rb = 0; rb < wrows / 32; ++rb)
-          tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], c.nc * 32, base + rb * 32);
-        return true;
-      };
-      Chunk cur = make_chunk(blockIdx.x);
-      long long wc = 0;
-      if (cur.valid) ok = issue_window(cur, 0);
-      while (cur.valid && ok) {
-        const Chunk nxt = next_chunk(cur);
-        bool prefetched = !nxt.valid;
-        int stage_in_chunk = 0;
-        for (int j = 0; j < J; j += kHpLagsPerStage, ++stage_in_chunk) {
-          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
-          const int nl = min(kHpLagsPerStage, J - j);
-          mbar_arrive_expect_tx(&full[ps.stage], nl * kHtABytes);
-          for (int u = 0; u < nl; ++u) {
-            uint8_t* dst = As + (size_t)ps.stage * kHpStageBytes + u * kHtABytes;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)      // region g = (lag group g / CB, column block g % CB)
-              tma_load_2d(dst + g * 4096, &tmW, &full[ps.stage], (g % p.CB) * 32 + (cur.combo == 0 ? p.lo_off : 0),
-                          (j + u + J * (g / p.CB)) * p.Np + cur.nc * 32);
-          }
-          ps.advance(kHpStages);
-          if (!prefetched && stage_in_chunk >= 1) {      // the MMAs are about to enter `cur`: the other window buffer
-            if (!issue_window(nxt, wc + 1)) { ok = false; break; }   // frees without stalling this ring
-            prefetched = true;
-          }
-        }
-        if (ok && !prefetched) ok = issue_window(nxt, wc + 1);
-        cur = nxt;
-        ++wc;
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(128, 256, 1, 0);
-      PipeState ps;
-      long long wcount = 0;
-      int it = 0;
-      bool ok = true;
-      for (long long item = blockIdx.x; item < p.n_tiles && ok; item += gridDim.x, ++it) {
-        const int split = (int)(item % p.n_split);
-        const int nc0 = split * p.nc_per_split;
-        const int nc1 = min(nc0 + p.nc_per_split, p.n_chunks_n);
-        const int b = it & 1;
-        if (!ab.wait(&tempty[b], (uint32_t)((it >> 1) & 1) ^ 1)) break;
-        tc_fence_after();
-        const uint32_t dtm = tmem + (uint32_t)b * 256;
-        const int nchunks = n_pass * (nc1 - nc0);
-        for (int c = 0; c < nchunks && ok; ++c, ++wcount) {
-          const int wb = (int)(wcount & 1);
-          if (!ab.wait(&wfull[wb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
-          tc_fence_after();
-          const uint32_t wbase = smem_u32(Ws + (size_t)wb * wbytes);
-          for (int j = 0; j < J; j += kHpLagsPerStage) {
-            if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
-            tc_fence_after();
-            const int nl = min(kHpLagsPerStage, J - j);
-            for (int u = 0; u < nl; ++u) {
-              const uint32_t abase = smem_u32(As + (size_t)ps.stage * kHpStageBytes + u * kHtABytes);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
-                const uint64_t bd = make_smem_desc(wbase + (uint32_t)(p.s * (j + u)) * 128 + ks * 32, 16, 1024, kSwz128);
-                mma_tf32_ss(dtm, ad, bd, idesc, (c | (j + u) | ks) != 0 ? 1u : 0u);
-              }
-            }
-            mma_commit(&empty[ps.stage]);
-            ps.advance(kHpStages);
-          }
-          if (!ok) break;
-          mma_commit(&wempty[wb]);
-        }
-        if (!ok) break;
-        mma_commit(&tfull[b]);
-      }
-    }
-  } else {
-    const int q = warp & 3;                 // lag group g of this warp's 32 TMEM lanes; lane = k
-    int it = 0;
-    for (long long item = blockIdx.x; item < p.n_tiles; item += gridDim.x, ++it) {
-      long long tile; int src, split;
-      decode(item, tile, src, split);
-      const int b = it & 1;
-      if (!ab.wait(&tfull[b], (it >> 1) & 1)) break;
-      tc_fence_after();
-      float* orow = p.scratch + ((size_t)((split * p.n_slots + src) * 4 + q) * kKp + lane) * p.ts + tile * 256;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 8; c0 += 2) {
-        uint32_t r[2][32];
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-          tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + (c0 + u) * 32), r[u]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          float4* o = reinterpret_cast<float4*>(orow + (c0 + u) * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o[j] = make_float4(__uint_as_float(r[u][4 * j]), __uint_as_float(r[u][4 * j + 1]),
-                               __uint_as_float(r[u][4 * j + 2]), __uint_as_float(r[u][4 * j + 3]));
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[b]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
-}
-
-// out[src][t][k] = sum over splits sp, lag groups g and folded lags dl of
-//     scratch[sp][src][g*CB + cb][kk][t + dl + s*J*g]
-// with (cb, kk) = (k/32, k%32), dl = 0 when s == 1, and (0, dl*Kp + k), dl < s when s > 1.
-// 128-wide time tiles through smem: the time-contiguous reads (512 B per warp row segment) and
-// the k-contiguous writes both coalesce.
-__global__ void __launch_bounds__(256)
-combine_groups_kernel(const float* __restrict__ scratch, float* __restrict__ out, long long ts, long long t_rows,
-                      int J, int s, int CB, int Kp, int n_src, int n_split, int n_slots) {
-  extern __shared__ float tile[];             // [Kp][129]
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const long long t0 = (long long)blockIdx.x * 128;
-  const int n_glag = 4 / CB;
-  for (int src = 0; src < n_src; ++src) {
-    for (int k = ty; k < Kp; k += 8) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int sp = 0; sp < n_split; ++sp)
-        for (int g = 0; g < n_glag; ++g)
-          for (int dl = 0; dl < s; ++dl) {
-            const int region = g * CB + (s == 1 ? k / 32 : 0);
-            const int kk = (s == 1) ? (k % 32) : (dl * Kp + k);
-            const long long sh = dl + (long long)s * J * g;
-            const float* row = scratch + ((size_t)((sp * n_slots + src) * 4 + region) * kKp + kk) * ts + t0 + 4 * tx + sh;
-            if ((sh & 3) == 0) {
-              const float4 v = __ldcs(reinterpret_cast<const float4*>(row));
-              a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
-            } else {
-              a0 += __ldcs(row); a1 += __ldcs(row + 1); a2 += __ldcs(row + 2); a3 += __ldcs(row + 3);
-            }
-          }
-      float* tk = tile + k * 129 + 4 * tx;
-      tk[0] = a0; tk[1] = a1; tk[2] = a2; tk[3] = a3;
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 128 * Kp; idx += 256) {
-      const int t = idx / Kp, k = idx % Kp;
-      if (t0 + t < t_rows) out[((size_t)src * t_rows + t0 + t) * Kp + k] = tile[k * 129 + t];
-    }
-    __syncthreads();
-  }
 }
 
 // Hv[r][(dl,k)] = round_tf32(H^T[r - dl][k])     (s > 1; rows before 0 read as zero)

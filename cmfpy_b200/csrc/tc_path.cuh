@@ -8,7 +8,7 @@
 #include "common.cuh"
 #include "ew_kernels.cuh"
 #include "simt_gemm.cuh"
-#include "tc_kernels.cuh"
+#include "tc_strict_kernels.cuh"
 
 namespace cmf {
 namespace tc {
@@ -35,6 +35,8 @@ struct Fold {
   int J = 1, n_glag = 4;                          // H terms: virtual lags per lag group, lag groups (4 / CB)
   int recon_wrows = 320, hterms_wrows = 288;
   int recon_LB = 0;                               // K1: lags per window (0: all of them in one window)
+  int h_hd = 0;                                   // H terms: columns before a time tile that its lag groups reach
+  int h_stages = 0;                               // H terms: W ring depth that fits shared memory (0: none does)
 };
 
 constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
@@ -56,6 +58,11 @@ inline Fold make_fold(int Kp, int L) {
     f.recon_wrows = round_up(256 + f.s * (f.recon_LB - 1), 64);
   }
   f.hterms_wrows = round_up(256 + f.s * (f.J - 1), 32);
+  f.h_hd = (f.n_glag - 1) * f.s * f.J + f.s - 1;
+  const bool direct = f.n_glag == 1 && f.s == 1;
+  f.h_stages = 0;
+  for (int st = 3; st >= 2 && !f.h_stages; --st)
+    if (hterms_smem_bytes(st, f.hterms_wrows, Kp, f.h_hd, direct) <= kMaxSmem) f.h_stages = st;
   return f;
 }
 
@@ -63,8 +70,7 @@ inline bool shape_supported(int N, int K, int L) {
   const int Kp = padded_k(K);
   if (N < 1 || K < 1 || L < 1 || Kp == 0) return false;
   const Fold f = make_fold(Kp, L);
-  return recon_smem_bytes(f.recon_wrows) <= kMaxSmem && hterms_pp_smem_bytes(f.hterms_wrows) <= kMaxSmem &&
-         wterms_smem_bytes(f.s) <= kMaxSmem;
+  return recon_smem_bytes(f.recon_wrows) <= kMaxSmem && f.h_stages > 0 && wterms_smem_bytes(f.s) <= kMaxSmem;
 }
 
 struct TcState {
@@ -81,18 +87,15 @@ struct TcState {
   CUtensorMap tmXlo_k2, tmElo_k2, tmXlo_k3, tmElo_k3;
   double *loss_partials = nullptr, *d_sumsq = nullptr;
   float* wpart = nullptr;
-  float* hscratch = nullptr;       // [2][4][32][TO + 256] lag-group partials of the H terms
+  float* hcarry = nullptr;         // [2][time tiles][h_hd][Kp]: the part of each K3 tile that belongs to the tile before it
   int* d_err = nullptr;
-  int n_chunks = 1, n_lag_groups = 1;
-  int h_split = 1, h_nc_per_split = 1;   // H terms: feature-chunk splits per time tile
-  int h_pp = 0;                          // 1: ping-pong form of K3 (one source per item), 0: paired form
+  int n_chunks = 1, n_lag_groups = 1;    // K2: time chunks; lag groups of 16 (tf32) or 8 (3xTF32) virtual lags
+  int h_sub = 0;                         // K3: units per tensor-memory sub-chunk (0: one chain per item)
   int recon_grid = 1, wterms_grid = 1, hterms_grid = 1;
   long long wcount = 0, wv_count = 0, hv_count = 0;
   CUtensorMap tmW_k1, tmH_k1, tmX_k2, tmE_k2, tmH_k2, tmW_k3, tmX_k3, tmE_k3;
 
   // ---- Gram route for the denominators (gram & 1: H step, gram & 2: W step) ----
-  int recon2 = 0;                   // 1: reconstruction on CTA pairs (cta_group::2)
-  int recon2_wrows = 192;
   int gram = 0;
   int gram_request = 0;             // from cmf_mu_params.denominators (CMF_GRAM in the environment overrides)
   int LK = 0, Lr = 0, Lrv = 0, dh_wrows = 0;
@@ -142,12 +145,45 @@ inline int make_map(CUtensorMap* m, const float* base, long long rows, long long
   return 0;
 }
 
+// fp32 map of rank <= 5: dims (innermost first; dim 0 contiguous), byte strides of dims 1.., box
+inline int make_map_nd(CUtensorMap* m, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                       const cuuint32_t* box, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  CMF_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CMF_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for a rank-%d map", (int)r, rank);
+  return 0;
+}
+
+// K2 data operand: a 32-row stage of S^T (rows x cols, row pitch `pitch` floats) as ONE box of four 32-feature
+// regions: dims (feature in block, time row, 32-feature block) -> shared memory [block][row][32 features].
+// (The last block of a ragged feature count reads on into the next row: those accumulator rows are never stored.)
+inline int make_map_k2src(CUtensorMap* m, const float* base, long long rows, long long cols, long long pitch) {
+  cuuint64_t dims[3] = {(cuuint64_t)(cols < 32 ? cols : 32), (cuuint64_t)rows, (cuuint64_t)ceil_div_ll(cols, 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, 128};
+  cuuint32_t box[3] = {32, 32, 4};
+  return make_map_nd(m, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
+// K3 motif operand: both lags of a stage and all four (lag group, column block) regions as ONE box:
+// dims (k in block, feature, 32-column block, lag group, lag in group) -> shared memory [lag][region][32 n][32 k].
+// Wv must be allocated for n_glag * J lags (zeros past Lv).
+inline int make_map_k3w(CUtensorMap* m, const float* Wv, const Fold& f, long long Np, long long KWs) {
+  cuuint64_t dims[5] = {32, (cuuint64_t)Np, (cuuint64_t)(KWs / 32), (cuuint64_t)f.n_glag, (cuuint64_t)f.J};
+  cuuint64_t strides[4] = {(cuuint64_t)KWs * 4, 128, (cuuint64_t)f.J * Np * KWs * 4, (cuuint64_t)Np * KWs * 4};
+  cuuint32_t box[5] = {32, 32, (cuuint32_t)f.CB, (cuuint32_t)f.n_glag, (cuuint32_t)kHtLagsPerStage};
+  return make_map_nd(m, Wv, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
 inline void destroy(TcState& s) {
-  cudaFree(s.wpart); cudaFree(s.hscratch); cudaFree(s.d_err); cudaFree(s.Wv); cudaFree(s.Hv);
+  cudaFree(s.wpart); cudaFree(s.hcarry); cudaFree(s.d_err); cudaFree(s.Wv); cudaFree(s.Hv);
   cudaFree(s.Wt); cudaFree(s.G); cudaFree(s.Rw); cudaFree(s.Rwv); cudaFree(s.Etail);
   cudaFree(s.P); cudaFree(s.Ppart); cudaFree(s.Mt);
   s.Wt = s.G = s.Rw = s.Rwv = s.Etail = s.P = s.Ppart = s.Mt = nullptr;
-  s.wpart = s.hscratch = s.Wv = s.Hv = nullptr;
+  s.wpart = s.hcarry = s.Wv = s.Hv = nullptr;
   s.d_err = nullptr;
   s.ready = false;
 }
@@ -218,20 +254,34 @@ inline int refresh_h(TcState& s, cudaStream_t stream, long long row0, long long 
   return launch_ok("fold_h");
 }
 
+// units per tensor-memory sub-chunk of the 3xTF32 kernels (CMF_X3_SUB overrides; 0: one chain per work item)
+inline int strict_sub_units() {
+  static const int v = [] { const char* e = getenv("CMF_X3_SUB"); return e ? atoi(e) : kStrictSubUnits; }();
+  return v;
+}
+
 // 3xTF32 bookkeeping of a launch on the recon kernel: p.CB holds the reduction blocks of ONE operand pass on entry
 inline void set_x3(const TcState& s, ReconParams& p, int lo_a, int lo_b) {
   if (!s.x3) return;
   p.x3 = 1; p.cbx = p.CB; p.CB = 3 * p.cbx; p.lo_off = lo_a; p.lo_off_b = lo_b;
+  p.sub_units = strict_sub_units();
 }
+// 3xTF32 runs the two-level-accumulation kernel (tc_strict_kernels.cuh), plain TF32 the single-chain one
 inline void launch_recon(const TcState& s, int grid, size_t smem, cudaStream_t stream, const CUtensorMap& a,
                          const CUtensorMap& b, const ReconParams& p) {
-  if (s.x3) tc_recon_kernel<1><<<grid, kReconThreads, smem, stream>>>(a, b, p);
-  else tc_recon_kernel<0><<<grid, kReconThreads, smem, stream>>>(a, b, p);
+  static const bool force = [] { const char* e = getenv("CMF_FORCE_STRICT_K1"); return e && atoi(e); }();   // A/B timing only
+  if (s.x3 || force) tc_recon_x3_kernel<<<grid, kSThreads, smem, stream>>>(a, b, p);
+  else tc_recon_kernel<<<grid, kReconThreads, smem, stream>>>(a, b, p);
 }
 inline int set_recon_smem(size_t bytes) {
-  CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CMF_CUDA(cudaFuncSetAttribute(tc_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CMF_CUDA(cudaFuncSetAttribute(tc_recon_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 0;
+}
+inline void launch_wterms(const TcState& s, int grid, cudaStream_t stream, const CUtensorMap& x, const CUtensorMap& e,
+                          const CUtensorMap& xlo, const CUtensorMap& elo, const WTermsParams& p) {
+  if (s.x3) tc_wterms_x3_kernel<<<grid, kSThreads, wterms8_smem_bytes(s.f.s), stream>>>(x, e, s.tmH_k2, xlo, elo, p);
+  else tc_wterms_kernel<<<grid, kWtThreads, wterms_smem_bytes(s.f.s), stream>>>(x, e, s.tmH_k2, p);
 }
 
 // ---- lag autocorrelation of H:  P[d][a][b] = sum_t H[a][t] H[b][t-d]  (the W-terms kernel run on H^T itself) ----
@@ -254,11 +304,10 @@ inline int ensure_autocorr(TcState& s) {
   CMF_CUDA(cudaMalloc((void**)&s.P, (size_t)pcount * 4));
   CMF_CUDA(cudaMalloc((void**)&s.Ppart, (size_t)pcount * s.p_chunks * 4));
   // H^T itself as the "data" operand: the first Kp columns of Hv are the unfolded, rounded H^T
-  CMF_TRY(make_map(&s.tmHx_k2, s.Hv + (long long)d.h * s.KWs, d.Tloc, d.Kp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, s.KWs));
+  CMF_TRY(make_map_k2src(&s.tmHx_k2, s.Hv + (long long)d.h * s.KWs, d.Tloc, d.Kp, s.KWs));
   s.tmHxlo_k2 = s.tmHx_k2;
   if (s.x3)
-    CMF_TRY(make_map(&s.tmHxlo_k2, s.Hv + (long long)d.h * s.KWs + f.KW, d.Tloc, d.Kp, 32, 32,
-                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, s.KWs));
+    CMF_TRY(make_map_k2src(&s.tmHxlo_k2, s.Hv + (long long)d.h * s.KWs + f.KW, d.Tloc, d.Kp, s.KWs));
   s.autocorr_ready = true;
   return 0;
 }
@@ -270,14 +319,13 @@ inline int autocorr(TcState& s, cudaStream_t stream) {
   const long long pcount = (long long)d.L * d.Kp * d.Kp;
   WTermsParams p{};
   p.Np = d.Kp; p.L = d.L; p.n_tiles_n = 1; p.n_lag_groups = s.n_lag_groups; p.n_chunks = s.p_chunks; p.h = d.h;
-  p.Lv = f.Lv; p.Kp = d.Kp; p.s = f.s; p.CB = f.CB; p.brows = wterms_brows(f.s); p.n_src = 1;
+  p.Lv = f.Lv; p.Kp = d.Kp; p.s = f.s; p.CB = f.CB; p.brows = s.x3 ? wterms8_brows(f.s) : wterms_brows(f.s); p.n_src = 1;
   p.n_items = (long long)p.n_lag_groups * f.CB * p.n_chunks;
   p.stages_total = ceil_div_ll(d.Tloc, 32);
   p.part = (s.p_chunks == 1) ? s.P : s.Ppart;
   p.per_src = pcount; p.err = s.d_err;
-  p.x3 = s.x3; p.lo_off = f.KW;
-  tc_wterms_kernel<<<s.p_grid, kWtThreads, wterms_smem_bytes(f.s), stream>>>(s.tmHx_k2, s.tmHx_k2, s.tmH_k2, s.tmHxlo_k2,
-                                                                           s.tmHxlo_k2, p);
+  p.x3 = s.x3; p.lo_off = f.KW; p.sub_units = s.x3 ? strict_sub_units() : 0;
+  launch_wterms(s, s.p_grid, stream, s.tmHx_k2, s.tmHx_k2, s.tmHxlo_k2, s.tmHxlo_k2, p);
   CMF_TRY(launch_ok("autocorr_H"));
   if (s.p_chunks > 1) {
     ew::sum_splits_kernel<<<ew_blocks(s, pcount / 4), 256, 0, stream>>>((float4*)s.P, (const float4*)s.Ppart, pcount / 4,
@@ -309,9 +357,12 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
 
   CMF_CUDA(cudaMalloc((void**)&s.d_err, 4));
   CMF_CUDA(cudaMemsetAsync(s.d_err, 0, 4, stream));
-  CMF_CUDA(cudaMalloc((void**)&s.Wv, (size_t)s.wv_count * halves * 4));
+  // (K3 addresses Wv as n_glag x J lags: the lags past Lv exist and stay zero)
+  const long long lv_alloc = (long long)f.n_glag * f.J > f.Lv ? (long long)f.n_glag * f.J : f.Lv;
+  const size_t wv_bytes = (size_t)lv_alloc * d.Np * f.KW * halves * 4;
+  CMF_CUDA(cudaMalloc((void**)&s.Wv, wv_bytes));
   CMF_CUDA(cudaMalloc((void**)&s.Hv, (size_t)s.hv_count * halves * 4));
-  CMF_CUDA(cudaMemsetAsync(s.Wv, 0, (size_t)s.wv_count * halves * 4, stream));
+  CMF_CUDA(cudaMemsetAsync(s.Wv, 0, wv_bytes, stream));
   CMF_CUDA(cudaMemsetAsync(s.Hv, 0, (size_t)s.hv_count * halves * 4, stream));
 
   // ---- K1 -------------------------------------------------------------
@@ -323,16 +374,8 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   CMF_TRY(make_map(&s.tmH_k1, s.Hv, d.RH, s.KWs, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
   CMF_TRY(set_recon_smem(recon_smem_bytes(f.recon_wrows)));
 
-  s.recon2 = 0;
-  if (const char* e = getenv("CMF_RECON2")) s.recon2 = atoi(e);
-  s.recon2_wrows = round_up(128 + f.s * (f.Lv - 1), 64);
-  if (recon2_smem_bytes(s.recon2_wrows) > kMaxSmem || f.recon_LB) s.recon2 = 0;
-  if (s.recon2)
-    CMF_CUDA(cudaFuncSetAttribute(tc_recon2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)recon2_smem_bytes(s.recon2_wrows)));
-
   // ---- K2 -------------------------------------------------------------
-  s.n_lag_groups = (int)ceil_div_ll(f.Lv, 16);
+  s.n_lag_groups = (int)ceil_div_ll(f.Lv, s.x3 ? 8 : 16);
   {
     const long long units = ceil_div_ll(d.Np, 128) * s.n_lag_groups * f.CB * 2;
     const long long stages_total = ceil_div_ll(d.Tloc, 32);
@@ -345,13 +388,13 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     // the chunk count that fills the machine in whole waves (37 at config C on one GPU); short shards (T split
     // over 8 GPUs) take fewer, larger chunks because the partial traffic no longer amortises.  Among counts
     // within 1 % of the best the largest wins: shorter accumulation chains in tensor memory.
-    const double t_stage = 0.6 * (s.x3 ? 3.0 : 1.0), t_drain = 4.0;
+    const double t_stage = s.x3 ? 0.3 * 3.0 : 0.6, t_drain = s.x3 ? 1.0 : 4.0;   // 3xTF32: 4 MMAs per stage, overlapped folds
     const double t_partial = 2.0 * 2.0 * (double)s.wcount * 4.0 / 5.0e6;     // both sources; 5 TB/s
     double best = 1e300;
     std::vector<double> cost((size_t)cmax + 1, 1e300);
     // On the Gram route the autocorrelation pass of H (den_w_gram) uses the same chunks - equal accumulation
     // chains - but has only n_lag_groups * CB units: too few chunks would leave most SMs idle there.
-    const long long p_units = (s.gram_request & 2) && !s.x3 ? (long long)s.n_lag_groups * f.CB : 0;
+    const long long p_units = (s.gram_request & 2) ? (long long)s.n_lag_groups * f.CB : 0;
     for (long long c = 1; c <= cmax; ++c) {
       const double item = (double)ceil_div_ll(stages_total, c) * t_stage + t_drain;
       cost[c] = (double)ceil_div_ll(units * c, d.num_sms) * item + (c > 1 ? c * t_partial : 0.0);
@@ -366,31 +409,27 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     const long long items = units * s.n_chunks;
     s.wterms_grid = (int)(items < d.num_sms ? items : d.num_sms);
   }
-  CMF_TRY(make_map(&s.tmX_k2, Xt, d.Tloc, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  CMF_TRY(make_map_k2src(&s.tmX_k2, Xt, d.Tloc, d.Np, d.Np));
   s.tmXlo_k2 = s.tmX_k2;
-  if (s.x3) CMF_TRY(make_map(&s.tmXlo_k2, Xlo, d.Tloc, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  CMF_TRY(make_map(&s.tmH_k2, s.Hv, d.RH, s.KWs, 32, wterms_brows(f.s), CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  if (s.x3) CMF_TRY(make_map_k2src(&s.tmXlo_k2, Xlo, d.Tloc, d.Np, d.Np));
+  CMF_TRY(make_map(&s.tmH_k2, s.Hv, d.RH, s.KWs, 32, s.x3 ? wterms8_brows(f.s) : wterms_brows(f.s),
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   CMF_CUDA(cudaFuncSetAttribute(tc_wterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)wterms_smem_bytes(f.s)));
+  CMF_CUDA(cudaFuncSetAttribute(tc_wterms_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)wterms8_smem_bytes(f.s)));
 
   // ---- K3 -------------------------------------------------------------
   {
     const long long tiles = d.TO / 256 + 1;
     s.hterms_grid = (int)(tiles < d.num_sms ? tiles : d.num_sms);
   }
-  CMF_TRY(make_map(&s.tmW_k3, s.Wv, (long long)f.Lv * d.Np, s.KWs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  CMF_TRY(make_map_k3w(&s.tmW_k3, s.Wv, f, d.Np, s.KWs));
   CMF_TRY(make_map(&s.tmX_k3, Xt, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
   s.tmXlo_k3 = s.tmX_k3;
   if (s.x3) CMF_TRY(make_map(&s.tmXlo_k3, Xlo, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
-  if (const char* e = getenv("CMF_HTERMS_PP")) s.h_pp = atoi(e) ? 1 : 0;
-  if (hterms_smem_bytes(f.hterms_wrows) > kMaxSmem) s.h_pp = 1;
-  if (!s.h_pp)
-    CMF_CUDA(cudaFuncSetAttribute(tc_hterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)hterms_smem_bytes(f.hterms_wrows)));
-  CMF_CUDA(cudaFuncSetAttribute(tc_hterms_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)hterms_pp_smem_bytes(f.hterms_wrows)));
-  if (d.Kp * 129 * 4 > 48 * 1024)
-    CMF_CUDA(cudaFuncSetAttribute(combine_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.Kp * 129 * 4));
+  CMF_CUDA(cudaFuncSetAttribute(tc_hterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)hterms_smem_bytes(f.h_stages, f.hterms_wrows, d.Kp, f.h_hd, f.n_glag == 1 && f.s == 1)));
 
   // ---- Gram route ---------------------------------------------------------
   s.gram = s.gram_request;
@@ -426,26 +465,16 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
                                                                                         : recon_smem_bytes(f.recon_wrows);
     CMF_TRY(set_recon_smem(need));
   }
-  // H terms: split the feature chunks of a tile so that the tensor-memory accumulation chain of the
-  // numerator is about as long as the one of the Gram denominator (equal truncation bias => no drift of
-  // the W/H scale split); the direct route needs no split (numerator and denominator share the chain).
+  // H terms.  3xTF32: short tensor-memory sub-chunks folded in fp32 registers (no truncation bias to speak of).
+  // Plain TF32 with the Gram denominator: sub-chunks as long as the chain of R (*) H, so that numerator and
+  // denominator carry the same truncation bias and the W / H scale split does not drift; direct route: numerator
+  // and denominator share one chain per item anyway.
   {
-    const int n_chunks_n = (int)ceil_div_ll(d.Np, 32);
-    int Q = 1;
-    if (s.gram & 1) {
-      const double chain_num = (double)n_chunks_n * f.J * 4, chain_den = (double)s.Lrv * f.CB * 4;
-      Q = (int)(chain_num / chain_den + 0.5);
-      if (Q < 1) Q = 1;
-      if (Q > n_chunks_n) Q = n_chunks_n;
-      while (Q > 1 && (size_t)Q * 4 * kKp * (d.TO + 256) * 4 > ((size_t)6 << 30)) --Q;
-    }
-    if (const char* e = getenv("CMF_HSPLIT")) { Q = atoi(e); if (Q < 1) Q = 1; if (Q > n_chunks_n) Q = n_chunks_n; }
-    s.h_nc_per_split = (n_chunks_n + Q - 1) / Q;
-    s.h_split = (n_chunks_n + s.h_nc_per_split - 1) / s.h_nc_per_split;
-    const size_t bytes = (size_t)s.h_split * ((s.gram & 1) ? 1 : 2) * 4 * kKp * (d.TO + 256) * 4;
-    CMF_CUDA(cudaMalloc((void**)&s.hscratch, bytes));    // fully rewritten by every launch: no memset
+    s.h_sub = s.x3 ? strict_sub_units() : ((s.gram & 1) ? s.Lrv * f.CB : 0);
+    if (const char* e = getenv("CMF_HSUB")) s.h_sub = atoi(e);
     const long long tt = d.TO / 256 + 1;
-    const long long items = s.h_pp ? tt * ((s.gram & 1) ? 1 : 2) * s.h_split : ((s.gram & 1) ? (tt + 1) / 2 : tt) * s.h_split;
+    if (f.h_hd > 0) CMF_CUDA(cudaMalloc((void**)&s.hcarry, (size_t)2 * tt * f.h_hd * d.Kp * 4));
+    const long long items = tt * ((s.gram & 1) ? 1 : 2);
     s.hterms_grid = (int)(items < d.num_sms ? items : d.num_sms);
   }
   if ((long long)s.g_rows * f.Lv * f.KW * halves * 4 > (1ll << 30)) s.gram &= ~2;
@@ -473,11 +502,11 @@ inline int attach_est(TcState& s, float* Et, float* Elo = nullptr) {
   s.tmElo_k2 = s.tmX_k2;
   s.tmElo_k3 = s.tmX_k3;
   if (!Et) return 0;
-  CMF_TRY(make_map(&s.tmE_k2, Et, d.Tloc, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  CMF_TRY(make_map_k2src(&s.tmE_k2, Et, d.Tloc, d.Np, d.Np));
   CMF_TRY(make_map(&s.tmE_k3, Et, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
   if (s.x3) {
     CMF_CHECK(Elo != nullptr, "3xTF32 needs the lo half of est");
-    CMF_TRY(make_map(&s.tmElo_k2, Elo, d.Tloc, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    CMF_TRY(make_map_k2src(&s.tmElo_k2, Elo, d.Tloc, d.Np, d.Np));
     CMF_TRY(make_map(&s.tmElo_k3, Elo, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   return 0;
@@ -552,22 +581,11 @@ inline int recon(TcState& s, cudaStream_t stream, bool store_est = true) {
   p.Et = s.Et; p.Xt = s.Xt; p.loss_partials = s.loss_partials; p.round_out = 1; p.err = s.d_err;
   p.LB = f.recon_LB;
   if (s.x3) {
-    p.x3 = 1; p.cbx = f.CB; p.CB = 3 * f.CB; p.lo_off = f.KW;
+    set_x3(s, p, f.KW, 0);
     p.Elo = s.Elo; p.Xlo = s.Xlo;
   }
-  int grid = s.recon_grid;
-  if (s.recon2 && !s.x3) {
-    p.n_tiles_n = (int)ceil_div_ll(d.Np, 256);
-    p.n_tiles = (long long)p.n_tiles_n * (d.RT / 256);
-    p.wrows = s.recon2_wrows;
-    long long g2 = 2 * p.n_tiles;
-    if (g2 > (d.num_sms & ~1)) g2 = d.num_sms & ~1;
-    grid = (int)g2;
-    tc_recon2_kernel<<<grid, kReconThreads, recon2_smem_bytes(s.recon2_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
-  } else {
-    if (s.x3) tc_recon_kernel<1><<<grid, kReconThreads, recon_smem_bytes(f.recon_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
-    else tc_recon_kernel<0><<<grid, kReconThreads, recon_smem_bytes(f.recon_wrows), stream>>>(s.tmW_k1, s.tmH_k1, p);
-  }
+  const int grid = s.recon_grid;
+  launch_recon(s, grid, recon_smem_bytes(f.recon_wrows), stream, s.tmW_k1, s.tmH_k1, p);
   CMF_TRY(launch_ok("tc_recon"));
   ew::sum_doubles_kernel<<<1, 1024, 0, stream>>>(s.loss_partials, grid, s.d_sumsq);
   return launch_ok("loss_sum");
@@ -579,15 +597,14 @@ inline int w_terms(TcState& s, cudaStream_t stream) {
   WTermsParams p;
   p.Np = d.Np; p.L = d.L; p.n_tiles_n = (int)ceil_div_ll(d.Np, 128); p.n_lag_groups = s.n_lag_groups;
   p.n_chunks = s.n_chunks; p.h = d.h;
-  p.Lv = f.Lv; p.Kp = d.Kp; p.s = f.s; p.CB = f.CB; p.brows = wterms_brows(f.s);
+  p.Lv = f.Lv; p.Kp = d.Kp; p.s = f.s; p.CB = f.CB; p.brows = s.x3 ? wterms8_brows(f.s) : wterms_brows(f.s);
   p.n_src = (s.gram & 2) ? 1 : 2;
   p.n_items = (long long)p.n_tiles_n * p.n_lag_groups * f.CB * p.n_src * p.n_chunks;
   p.stages_total = ceil_div_ll(d.Tloc, 32);
   p.part = (s.n_chunks == 1) ? s.numden : s.wpart;
   p.per_src = s.wcount; p.err = s.d_err;
-  p.x3 = s.x3; p.lo_off = f.KW;
-  tc_wterms_kernel<<<s.wterms_grid, kWtThreads, wterms_smem_bytes(f.s), stream>>>(s.tmX_k2, s.tmE_k2, s.tmH_k2, s.tmXlo_k2,
-                                                                                  s.tmElo_k2, p);
+  p.x3 = s.x3; p.lo_off = f.KW; p.sub_units = s.x3 ? strict_sub_units() : 0;
+  launch_wterms(s, s.wterms_grid, stream, s.tmX_k2, s.tmE_k2, s.tmXlo_k2, s.tmElo_k2, p);
   CMF_TRY(launch_ok("tc_wterms"));
   if (s.n_chunks > 1) {
     const long long n4 = p.n_src * s.wcount / 4;
@@ -691,42 +708,27 @@ inline int den_h_gram(TcState& s, cudaStream_t stream) {
 inline int h_terms(TcState& s, cudaStream_t stream) {
   const Dims& d = s.d;
   const Fold& f = s.f;
-  HTermsParams p;
+  HTermsParams p{};
   p.Np = d.Np; p.J = f.J; p.n_chunks_n = (int)ceil_div_ll(d.Np, 32); p.wrows = f.hterms_wrows;
-  p.s = f.s; p.CB = f.CB;
-  p.pair_mode = (s.gram & 1) ? 1 : 0;
-  p.n_slots = p.pair_mode ? 1 : 2;
-  p.n_src = 2;
-  p.n_split = s.h_split; p.nc_per_split = s.h_nc_per_split;
-  const long long time_tiles = d.TO / 256 + 1;
-  p.n_time_tiles = p.pair_mode ? (time_tiles + 1) / 2 : time_tiles;
-  p.n_tiles = p.n_time_tiles * s.h_split; p.ts = d.TO + 256; p.scratch = s.hscratch; p.err = s.d_err;
-  p.x3 = s.x3; p.lo_off = f.KW;
-  p.dbg = 0;
-  if (const char* e = getenv("CMF_HT_DBG")) p.dbg = atoi(e);
-  if (s.h_pp) {
-    // one source per item: the numerator only on the Gram route, numerator and denominator otherwise
-    const int n_slots = p.n_slots;
-    p.pair_mode = 0;
-    p.n_src = n_slots;
-    p.n_time_tiles = time_tiles;
-    p.n_tiles = time_tiles * p.n_src * s.h_split;
-    tc_hterms_pp_kernel<<<s.hterms_grid, kHtThreads, hterms_pp_smem_bytes(f.hterms_wrows), stream>>>(
-        s.tmW_k3, s.tmX_k3, s.tmE_k3, s.tmXlo_k3, s.tmElo_k3, p);
-    CMF_TRY(launch_ok("tc_hterms_pp"));
-    combine_groups_kernel<<<(unsigned)(d.TO / 128), 256, d.Kp * 129 * 4, stream>>>(s.hscratch, s.hterms, p.ts, d.TO, f.J,
-                                                                                f.s, f.CB, d.Kp, n_slots, s.h_split, n_slots);
-    CMF_TRY(launch_ok("combine_groups"));
-    if (s.gram & 1) CMF_TRY(den_h_gram(s, stream));
-    return 0;
-  }
-  tc_hterms_kernel<<<s.hterms_grid, kHtThreads, hterms_smem_bytes(f.hterms_wrows), stream>>>(s.tmW_k3, s.tmX_k3, s.tmE_k3,
-                                                                                             s.tmXlo_k3, s.tmElo_k3, p);
+  p.s = f.s; p.CB = f.CB; p.Kp = d.Kp;
+  p.n_src = (s.gram & 1) ? 1 : 2;                 // the Gram route contracts X only
+  p.n_time_tiles = d.TO / 256 + 1;
+  p.n_items = p.n_time_tiles * p.n_src;
+  p.TO = d.TO; p.out = s.hterms; p.carry = s.hcarry; p.hd = f.h_hd;
+  p.sub_units = s.h_sub; p.n_stages = f.h_stages;
+  p.x3 = s.x3; p.lo_off = f.KW; p.err = s.d_err;
+  const bool direct = f.n_glag == 1 && f.s == 1;
+  tc_hterms_kernel<<<s.hterms_grid, kSThreads, hterms_smem_bytes(f.h_stages, f.hterms_wrows, d.Kp, f.h_hd, direct), stream>>>(
+      s.tmW_k3, s.tmX_k3, s.tmE_k3, s.tmXlo_k3, s.tmElo_k3, p);
   CMF_TRY(launch_ok("tc_hterms"));
-  combine_groups_kernel<<<(unsigned)(d.TO / 128), 256, d.Kp * 129 * 4, stream>>>(s.hscratch, s.hterms, p.ts, d.TO, f.J,
-                                                                              f.s, f.CB, d.Kp, p.pair_mode ? 1 : 2, s.h_split,
-                                                                              p.n_slots);
-  CMF_TRY(launch_ok("combine_groups"));
+  if (f.h_hd > 0) {
+    const long long wmax = f.h_hd < 256 ? f.h_hd : 256;
+    const long long total = (p.n_time_tiles - 1) * wmax * (d.Kp / 4) * p.n_src;
+    if (total > 0) {
+      hterms_carry_kernel<<<ew_blocks(s, total), 256, 0, stream>>>(s.hterms, s.hcarry, d.TO, p.n_time_tiles, f.h_hd, d.Kp, p.n_src);
+      CMF_TRY(launch_ok("hterms_carry"));
+    }
+  }
   if (s.gram & 1) CMF_TRY(den_h_gram(s, stream));
   return 0;
 }

@@ -1,0 +1,836 @@
+// tcgen05 shift-GEMM kernels with TWO-LEVEL accumulation (the fp32-grade 3xTF32 mode, and K3 in every mode).
+//
+// Tensor memory adds with round-toward-zero: a chain of n MMA steps of non-negative terms carries a relative bias
+// of about -5.7e-8 n (tools/acc_bias_probe.py), which no operand splitting removes.  These kernels therefore never
+// let a chain grow: the MMA warp accumulates SUB-CHUNKS of `sub_units` units (a unit = 4 MMA k-steps = one lag or one
+// 32-row time stage) into one of two 128 x 256 tensor-memory buffers S0 / S1, alternating; eight epilogue warps
+// (TMEM lane quarter x column half) fold every finished sub-chunk into a MASTER accumulator of 128 fp32 registers
+// per thread with round-to-nearest adds while the MMAs of the next sub-chunk run into the other buffer.  The bias
+// of a result is then that of ONE sub-chunk (8 units = 32 steps: ~7e-7, independent of L, K, N and T), the fold is
+// hidden behind the MMAs, and nothing but the final result leaves the SM.
+//
+//   tc_recon_x3_kernel   K1  reconstruction + loss           (reference common.py:50-58, base.py:57-62, 90-97)
+//   tc_wterms_x3_kernel  K2  W terms, 8 lags per work item   (reference mult.py:35-38)
+//   tc_hterms_kernel     K3  H terms, every precision mode   (reference common.py:61-86)
+//
+// Layouts, folding (s, CB) and the shifted-window descriptors are those of tc_kernels.cuh.
+#pragma once
+#include "tc_kernels.cuh"
+
+namespace cmf {
+namespace tc {
+
+constexpr int kSThreads = 384;        // warpgroup 0: TMA producer (warp 0), MMA issuer (warp 1), TMEM allocator (warp 2);
+                                      // warpgroups 1-2: epilogue.  setmaxnreg moves registers from the first to the others
+constexpr int kSEpiThreads = 256;
+#ifndef CMF_CTL_REGS
+#define CMF_CTL_REGS 40
+#define CMF_EPI_REGS 232
+#endif
+constexpr int kSCtlRegs = CMF_CTL_REGS, kSEpiRegs = CMF_EPI_REGS;   // 128 * 40 + 256 * 232 = 64512 <= 65536
+constexpr int kStrictSubUnits = 8;    // units per sub-chunk in the 3xTF32 mode (32 MMA k-steps)
+
+// Orders the 32 adds of one block before the next tensor-memory load: without it the compiler issues all four
+// loads first and needs 128 staging registers next to the 128 of the master.
+__device__ __forceinline__ void pin32(float* v) {
+  asm volatile(""
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                 "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
+                 "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]),
+                 "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+               :
+               : "memory");
+}
+
+// master (+)= S[32 lanes of this warp][128 columns at taddr]
+template <bool kFirst>
+__device__ __forceinline__ void fold_sub(float (&m)[128], uint32_t taddr) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + (uint32_t)(i * 32), r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      m[i * 32 + j] = kFirst ? __uint_as_float(r[j]) : m[i * 32 + j] + __uint_as_float(r[j]);
+    pin32(&m[i * 32]);
+  }
+}
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// The MMA side of the sub-chunk protocol: a sub-chunk goes to buffer (sc & 1); its first unit waits until the
+// epilogue has folded the buffer's previous contents, its last one commits it.  The first n_cross units of a work
+// item - the two cross-term passes of 3xTF32, a_lo b_hi and a_hi b_lo, 2^-11 of the result - form ONE sub-chunk
+// (their truncation is relative to their own small partial sum); the a_hi b_hi units after them are cut every
+// sub_units units.
+struct SubPlan {
+  long long n_units, n_cross;
+  int sub_units;
+  __device__ __forceinline__ SubPlan(long long units, long long cross, int sub) {
+    n_units = units;
+    sub_units = sub > 0 ? sub : (int)(units < 0x7fffffff ? units : 0x7fffffff);
+    n_cross = sub > 0 ? cross : 0;
+  }
+  __device__ __forceinline__ long long n_sub() const {
+    return (n_cross > 0 ? 1 : 0) + (n_units - n_cross + sub_units - 1) / sub_units;
+  }
+};
+struct SubIssue {
+  long long sc = 0;       // sub-chunks issued so far by this CTA
+  int us = 0;             // units already in the current sub-chunk
+  __device__ __forceinline__ bool begin_unit(const Abort& ab, uint64_t* sempty, uint32_t tmem, uint32_t& dtm) {
+    const int b = (int)(sc & 1);
+    if (us == 0) {
+      if (!ab.wait(&sempty[b], (uint32_t)((sc >> 1) & 1) ^ 1)) return false;
+      tc_fence_after();
+    }
+    dtm = tmem + (uint32_t)b * 256;
+    return true;
+  }
+  // `done` = units of the item issued so far, this one included
+  __device__ __forceinline__ void end_unit(uint64_t* sfull, const SubPlan& pl, long long done) {
+    ++us;
+    if (done == pl.n_units || done == pl.n_cross || (done > pl.n_cross && us == pl.sub_units)) {
+      mma_commit(&sfull[sc & 1]);
+      ++sc;
+      us = 0;
+    }
+  }
+};
+
+// ==========================================================================
+// K1, two-level accumulation.  Same tiles, operands and stores as tc_recon_kernel; a unit is one lag of one
+// reduction block (4 MMAs of 128 x 256 x 8).
+// ==========================================================================
+__global__ void __launch_bounds__(kSThreads, 1)
+tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
+                   const ReconParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* As = smem;                                           // [stages][2 lags x 16 KB]
+  uint8_t* Hs = As + kReconStages * kReconStageBytes;           // [2][wrows * 128]
+  const uint32_t hbytes = (uint32_t)p.wrows * kKp * 4;
+  uint64_t* bars = (uint64_t*)(Hs + 2 * hbytes);
+  uint64_t* full = bars;                                        // [stages]
+  uint64_t* empty = bars + kReconStages;                        // [stages]
+  uint64_t* hfull = bars + 2 * kReconStages;                    // [2]
+  uint64_t* hempty = hfull + 2;                                 // [2]
+  uint64_t* sfull = hempty + 2;                                 // [2]
+  uint64_t* sempty = sfull + 2;                                 // [2]
+  uint32_t* tmem_slot = (uint32_t*)(sempty + 2);
+  volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
+  __shared__ double red[8];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kReconStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1);
+      mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 8);
+    }
+    *abort_flag = 0;
+    fence_mbar_init();
+    prefetch_tmap(&tmW);
+    prefetch_tmap(&tmH);
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const Abort ab{abort_flag, p.err};
+  const int L = p.L, wrows = p.wrows;
+  const int LB = (p.LB > 0 && p.LB < L) ? p.LB : L;             // lags per window
+  const int n_lb = (L + LB - 1) / LB;
+  const SubPlan plan((long long)p.CB * L, p.x3 ? 2ll * p.cbx * L : 0, p.sub_units);     // units per tile
+
+  if (warp == 0) {
+    reg_dec<kSCtlRegs>();
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      PipeState ps;
+      bool ok = true;
+      struct Chunk { long long tile; int cb, lb; bool valid; };
+      auto next_chunk = [&](Chunk c) {
+        if (++c.lb >= n_lb) {
+          c.lb = 0;
+          if (++c.cb >= p.CB) { c.cb = 0; c.tile += gridDim.x; c.valid = c.tile < p.n_tiles; }
+        }
+        return c;
+      };
+      // window of chunk number wc; `block` = false: only if its buffer is already free
+      auto issue_window = [&](const Chunk& c, long long wc, bool block, bool& done) -> bool {
+        const int hb = (int)(wc & 1);
+        const uint32_t par = (uint32_t)((wc >> 1) & 1) ^ 1;
+        if (!block && !mbar_try_wait(&hempty[hb], par)) return true;
+        if (!ab.wait(&hempty[hb], par)) return false;
+        const long long tt = c.tile / p.n_tiles_n;
+        mbar_arrive_expect_tx(&hfull[hb], hbytes);
+        uint8_t* hdst = Hs + (size_t)hb * hbytes;
+        const X3Sel sel = x3_select(p.x3, p.cbx, p.lo_off, p.lo_off_b, c.cb);
+        const int l1 = min(L, (c.lb + 1) * LB);                 // window row 0 holds lag l1 - 1 of this block
+        for (int rb = 0; rb < wrows / 64; ++rb)
+          tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], sel.cbr * 32 + sel.b_off,
+                      (int)(tt * 256 + p.h_shift + p.s * (L - l1) + rb * 64));
+        done = true;
+        return true;
+      };
+      Chunk cur{(long long)blockIdx.x, 0, 0, (long long)blockIdx.x < p.n_tiles};
+      long long wc = 0;
+      bool dummy = false;
+      if (cur.valid) ok = issue_window(cur, 0, true, dummy);
+      while (cur.valid && ok) {
+        const Chunk nxt = next_chunk(cur);
+        bool prefetched = !nxt.valid;
+        const int nt = (int)(cur.tile % p.n_tiles_n);
+        const X3Sel sel = x3_select(p.x3, p.cbx, p.lo_off, p.lo_off_b, cur.cb);
+        const int l0 = cur.lb * LB, l1 = min(L, l0 + LB);
+        for (int l = l0; l < l1; l += kReconLagsPerStage) {
+          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+          const int nl = min(kReconLagsPerStage, l1 - l);
+          mbar_arrive_expect_tx(&full[ps.stage], nl * kReconABytes);
+          for (int u = 0; u < nl; ++u)
+            tma_load_2d(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes, &tmW, &full[ps.stage],
+                        (sel.cbr % p.cb_cols) * 32 + sel.a_off, (l + u + sel.cbr / p.cb_cols) * p.Np + nt * 128);
+          ps.advance(kReconStages);
+          // the next window goes out as soon as its buffer is free; waiting for it here would starve the W ring
+          if (!prefetched && !issue_window(nxt, wc + 1, false, prefetched)) { ok = false; break; }
+        }
+        if (ok && !prefetched) ok = issue_window(nxt, wc + 1, true, prefetched);
+        cur = nxt;
+        ++wc;
+      }
+    }
+  } else if (warp == 1) {
+    reg_dec<kSCtlRegs>();
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, 256, 0, 0);
+      PipeState ps;
+      SubIssue si;
+      long long wcount = 0;
+      bool ok = true;
+      for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+        int unit = 0;
+        for (int chunk = 0; chunk < p.CB * n_lb && ok; ++chunk, ++wcount) {
+          const int cb = chunk / n_lb, lb = chunk - cb * n_lb;
+          const int l0 = lb * LB, l1 = min(L, l0 + LB);
+          const int hb = (int)(wcount & 1);
+          if (!ab.wait(&hfull[hb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t hbase = smem_u32(Hs + (size_t)hb * hbytes);
+          for (int l = l0; l < l1 && ok; l += kReconLagsPerStage) {
+            if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+            tc_fence_after();
+            const int nl = min(kReconLagsPerStage, l1 - l);
+            for (int u = 0; u < nl; ++u) {
+              uint32_t dtm;
+              if (!si.begin_unit(ab, sempty, tmem, dtm)) { ok = false; break; }
+              const uint32_t abase = smem_u32(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ad = make_smem_desc(abase + ks * 32, 16, 1024, kSwz128);
+                const uint64_t bd = make_smem_desc(hbase + (uint32_t)(p.s * (l1 - 1 - l - u)) * 128 + ks * 32, 16, 1024, kSwz128);
+                mma_tf32_ss(dtm, ad, bd, idesc, (si.us | ks) != 0 ? 1u : 0u);
+              }
+              si.end_unit(sfull, plan, ++unit);
+            }
+            mma_commit(&empty[ps.stage]);
+            ps.advance(kReconStages);
+          }
+          if (!ok) break;
+          mma_commit(&hempty[hb]);
+        }
+      }
+    }
+  } else if (warp < 4) {
+    reg_dec<kSCtlRegs>();
+  } else {
+    reg_inc<kSEpiRegs>();
+    // ---------------- epilogue: fold sub-chunks, then master -> est^T, fused loss ----------------
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;             // column half of the 256-column buffers
+    const int n_sub = (int)plan.n_sub();
+    float m[128];
+    double loss_acc = 0.0;
+    long long sc = 0;
+    bool ok = true;
+    for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+      const int nt = (int)(tile % p.n_tiles_n);
+      const long long tt = tile / p.n_tiles_n;
+      for (int sub = 0; sub < n_sub; ++sub, ++sc) {
+        const int b = (int)(sc & 1);
+        if (!wait_relaxed(ab, &sfull[b], (uint32_t)((sc >> 1) & 1))) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + half * 128);
+        if (sub == 0) fold_sub<true>(m, taddr); else fold_sub<false>(m, taddr);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sempty[b]);
+      }
+      if (!ok) break;
+      const int n = nt * 128 + q * 32 + lane;
+      const bool n_ok = n < p.n_rows;
+      float tile_loss = 0.f;
+      const float* __restrict__ Xt = p.Xt;
+      const float* __restrict__ Xlo = p.Xlo;
+      float* __restrict__ Et = p.Et;
+      float* __restrict__ Elo = p.Elo;
+      const size_t np = (size_t)p.ld_out;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const long long tau0 = tt * 256 + half * 128 + c * 32;
+        const size_t off0 = (size_t)tau0 * np + n;
+        if (p.store_mode == 2) {
+          // tau = l*Kp + k: 32 consecutive tau are whole groups of 4 components of one lag
+          if (n_ok) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const long long tau = tau0 + 4 * j4;
+              const long long l = tau / p.w_kp;
+              const int k = (int)(tau % p.w_kp);
+              if (tau < p.t_valid)
+                *reinterpret_cast<float4*>(Et + ((size_t)l * p.w_np + n) * p.w_kp + k) =
+                    make_float4(m[c * 32 + 4 * j4], m[c * 32 + 4 * j4 + 1], m[c * 32 + 4 * j4 + 2], m[c * 32 + 4 * j4 + 3]);
+            }
+          }
+        } else if (n_ok) {
+          float x[32];
+          // (t_own is 0 whenever there is no X: the plain GEMMs of the Gram route)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = (tau0 + j < p.t_own) ? __ldcs(Xt + off0 + (size_t)j * np) : 0.f;
+          if (Xlo) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] += (tau0 + j < p.t_own) ? __ldcs(Xlo + off0 + (size_t)j * np) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long tau = tau0 + j;
+            float v = m[c * 32 + j];
+            if (tau >= p.t_valid) v = 0.f;
+            if (tau < p.t_own) {
+              const float d = v - x[j];
+              tile_loss = fmaf(d, d, tile_loss);
+            }
+            if (!p.skip_store) {
+              if (Elo) {
+                const float hi = round_tf32(v);
+                Et[off0 + (size_t)j * np] = hi;
+                Elo[off0 + (size_t)j * np] = round_tf32(v - hi);
+              } else {
+                if (p.round_out) v = round_tf32(v);
+                Et[off0 + (size_t)j * np] = v;
+              }
+            }
+          }
+        }
+      }
+      loss_acc += (double)tile_loss;
+    }
+    // block partial of the loss (epilogue warps only)
+    loss_acc = warp_sum(loss_acc);
+    if (lane == 0) red[warp - 4] = loss_acc;
+    epi_bar();
+    if (warp == 4 && lane == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += red[i];
+      p.loss_partials[blockIdx.x] = s;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ==========================================================================
+// K2, two-level accumulation.  Work item = (128 features, 8 virtual lags, X or est, a chunk of time): one
+// 128 x 256 buffer per sub-chunk, so consecutive sub-chunks alternate between S0 and S1.  A unit is one 32-row
+// time stage (4 MMAs).  Output as tc_wterms_kernel: part[chunk][src][L][Np][Kp].
+// ==========================================================================
+__host__ __device__ inline int wterms8_brows(int s) { return ((32 + 7 * s + 7) / 8) * 8; }
+__host__ __device__ inline size_t wterms8_stage_bytes(int s) { return (size_t)kWtABytes + (size_t)wterms8_brows(s) * 128; }
+__host__ __device__ inline size_t wterms8_smem_bytes(int s) { return 1024 + (size_t)kWtStages * wterms8_stage_bytes(s) + 256; }
+
+__global__ void __launch_bounds__(kSThreads, 1)
+tc_wterms_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmE,
+                    const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmXlo,
+                    const __grid_constant__ CUtensorMap tmElo, const WTermsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* St = smem;                                            // [stages][A 16 KB | B brows x 128 B]
+  const uint32_t stage_bytes = (uint32_t)wterms8_stage_bytes(p.s);
+  uint64_t* bars = (uint64_t*)(St + (size_t)kWtStages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWtStages;
+  uint64_t* sfull = bars + 2 * kWtStages;                        // [2]
+  uint64_t* sempty = sfull + 2;                                  // [2]
+  uint32_t* tmem_slot = (uint32_t*)(sempty + 2);
+  volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kWtStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 8); }
+    *abort_flag = 0;
+    fence_mbar_init();
+    prefetch_tmap(&tmX); prefetch_tmap(&tmE); prefetch_tmap(&tmH); prefetch_tmap(&tmXlo); prefetch_tmap(&tmElo);
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const Abort ab{abort_flag, p.err};
+  const int n_pass = p.x3 ? 3 : 1;
+
+  // item -> (chunk, n tile, src, column block, lag group); lag group fastest so that the CTAs that stream the
+  // same S^T rows run at the same time (L2 reuse)
+  auto decode = [&](long long item, int& lg, int& cb, int& src, int& nt, int& ch) {
+    lg = (int)(item % p.n_lag_groups); item /= p.n_lag_groups;
+    cb = (int)(item % p.CB); item /= p.CB;
+    src = (int)(item % p.n_src); item /= p.n_src;
+    nt = (int)(item % p.n_tiles_n); item /= p.n_tiles_n;
+    ch = (int)item;
+  };
+  auto chunk_range = [&](int ch, long long& s0, long long& s1) {
+    const long long base = p.stages_total / p.n_chunks, rem = p.stages_total % p.n_chunks;
+    s0 = ch * base + (ch < rem ? ch : rem);
+    s1 = s0 + base + (ch < rem ? 1 : 0);
+  };
+
+  if (warp == 0) {
+    reg_dec<kSCtlRegs>();
+    if (lane == 0) {
+      PipeState ps;
+      bool ok = true;
+      for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+        int lg, cb, src, nt, ch;
+        decode(item, lg, cb, src, nt, ch);
+        long long s0, s1;
+        chunk_range(ch, s0, s1);
+        // 3xTF32: (S lo, H hi), (S hi, H lo), (S hi, H hi)
+        for (int combo = p.x3 ? 0 : 2; combo < 3 && ok; ++combo) {
+          const CUtensorMap* tmS = combo == 0 ? (src ? &tmElo : &tmXlo) : (src ? &tmE : &tmX);
+          const int hcol = cb * 32 + (combo == 1 ? p.lo_off : 0);
+          for (long long s = s0; s < s1; ++s) {
+            if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+            uint8_t* dst = St + (size_t)ps.stage * stage_bytes;
+            mbar_arrive_expect_tx(&full[ps.stage], stage_bytes);
+            const int tau0 = (int)(s * 32);
+            tma_load_3d(dst, tmS, &full[ps.stage], 0, tau0, nt * 4);      // four 32-feature regions in one box
+            // Hv rows tau0 - s*(8 lg + 7) .. tau0 + 32; row index in Hv is tau + h
+            tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], hcol, tau0 - p.s * (lg * 8 + 7) + p.h);
+            ps.advance(kWtStages);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    reg_dec<kSCtlRegs>();
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, 256, 1, 1);
+      PipeState ps;
+      SubIssue si;
+      bool ok = true;
+      for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+        int lg, cb, src, nt, ch;
+        decode(item, lg, cb, src, nt, ch);
+        long long s0, s1;
+        chunk_range(ch, s0, s1);
+        const long long n_units = n_pass * (s1 - s0);
+        const SubPlan plan(n_units, p.x3 ? 2 * (s1 - s0) : 0, p.sub_units);
+        for (long long u = 0; u < n_units; ++u) {
+          if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+          tc_fence_after();
+          uint32_t dtm;
+          if (!si.begin_unit(ab, sempty, tmem, dtm)) { ok = false; break; }
+          const uint32_t abase = smem_u32(St + (size_t)ps.stage * stage_bytes);
+          const uint32_t bbase = abase + kWtABytes;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
+            // N-atom a starts a * s rows further down: lag 8 lg + 7 - a
+            const uint64_t bd = make_smem_desc(bbase + (uint32_t)(ks * 8) * 128, (uint32_t)p.s * 128, 512, 1);
+            mma_tf32_ss(dtm, ad, bd, idesc, (si.us | ks) != 0 ? 1u : 0u);
+          }
+          si.end_unit(sfull, plan, u + 1);
+          mma_commit(&empty[ps.stage]);
+          ps.advance(kWtStages);
+        }
+      }
+    }
+  } else if (warp < 4) {
+    reg_dec<kSCtlRegs>();
+  } else {
+    reg_inc<kSEpiRegs>();
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    float m[128];
+    long long sc = 0;
+    bool ok = true;
+    for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+      int lg, cb, src, nt, ch;
+      decode(item, lg, cb, src, nt, ch);
+      long long s0, s1;
+      chunk_range(ch, s0, s1);
+      const SubPlan plan(n_pass * (s1 - s0), p.x3 ? 2 * (s1 - s0) : 0, p.sub_units);
+      const long long n_sub = plan.n_sub();
+      for (long long sub = 0; sub < n_sub; ++sub, ++sc) {
+        const int b = (int)(sc & 1);
+        if (!wait_relaxed(ab, &sfull[b], (uint32_t)((sc >> 1) & 1))) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + half * 128);
+        if (sub == 0) fold_sub<true>(m, taddr); else fold_sub<false>(m, taddr);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sempty[b]);
+      }
+      if (!ok) break;
+      const int n = nt * 128 + q * 32 + lane;
+      float* obase = p.part + ((long long)ch * p.n_src + src) * p.per_src;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {              // 4 column blocks of 32 = one virtual lag each
+        const int a = half * 4 + c;
+        const int lv = lg * 8 + 7 - a;
+        if (n < p.Np && lv < p.Lv) {
+          if (p.s == 1) {                         // 32 components of column block cb, real lag lv
+            float4* o = reinterpret_cast<float4*>(obase + ((long long)lv * p.Np + n) * p.Kp + cb * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(m[c * 32 + 4 * j], m[c * 32 + 4 * j + 1], m[c * 32 + 4 * j + 2], m[c * 32 + 4 * j + 3]);
+          } else if (p.s == 2) {                  // Kp = 16: two real lags of 16 components
+#pragma unroll
+            for (int dl = 0; dl < 2; ++dl) {
+              const int l = 2 * lv + dl;
+              if (l < p.L) {
+                float4* o = reinterpret_cast<float4*>(obase + ((long long)l * p.Np + n) * 16);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  o[j] = make_float4(m[c * 32 + 16 * dl + 4 * j], m[c * 32 + 16 * dl + 4 * j + 1],
+                                     m[c * 32 + 16 * dl + 4 * j + 2], m[c * 32 + 16 * dl + 4 * j + 3]);
+              }
+            }
+          } else {                                // s == 4, Kp = 8: four real lags of 8 components
+#pragma unroll
+            for (int dl = 0; dl < 4; ++dl) {
+              const int l = 4 * lv + dl;
+              if (l < p.L) {
+                float4* o = reinterpret_cast<float4*>(obase + ((long long)l * p.Np + n) * 8);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  o[j] = make_float4(m[c * 32 + 8 * dl + 4 * j], m[c * 32 + 8 * dl + 4 * j + 1],
+                                     m[c * 32 + 8 * dl + 4 * j + 2], m[c * 32 + 8 * dl + 4 * j + 3]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ==========================================================================
+// K3  H terms (every tensor-core precision mode)
+//   out[src][tau][k] = sum_l sum_n W[l][n][k] * S^T[tau+l][n],  S = X | est
+//   (reference tensor_transconv, cmfpy/common.py:61-86, via mult.py:42-48)
+// The output has only K rows, so the lag groups share the 128 MMA rows:
+//   row (g,k) of D accumulates lags l = j + J*g (j = 0..J-1):
+//   D[(g,k)][c] += W[j+J*g][n][k] * S^T[base + c + j][n]      (M=128, N=256)
+//   => D[(g,k)][c] is the group-g part of out[k][base + c - s*J*g].
+//   A = W rows of the lag groups, MN-major SWIZZLE_128B_BASE32B (4 regions = (lag group, column block))
+//   B = S^T window, K-major SWIZZLE_128B rows of 32 features, row shift j = +128 B
+// Work item = (time tile of 256 columns, source); a unit is one lag of one 32-feature chunk.  The eight epilogue
+// warps hold the item's accumulator in registers and reduce the lag groups INSIDE the CTA: a shared-memory tile
+// R[u][k], u = tau - base + hd, is zeroed and the warps add their rows at their group's shift one after the other
+// (fixed order: deterministic, no atomics).  R covers hd = (groups-1) s J + s - 1 columns before the tile: the
+// complete part goes straight to out, the head (which the previous tile's groups also feed) to a small carry
+// buffer that hterms_carry_kernel adds afterwards - 6 % of the output at config C instead of the 16-fold
+// partial round trip of a separate combine pass.
+// ==========================================================================
+struct HTermsParams {
+  int Np, J, n_chunks_n, wrows;    // n chunks of 32 features; window rows >= 256 + s*(J-1)
+  int s, CB, Kp;                   // lag stride in rows; column blocks (regions = (4/CB lag groups) x CB); padded K
+  int n_src;                       // 2: X and est (numerator, denominator); 1: X only (denominator via Gram)
+  long long n_time_tiles;          // TO / 256 + 1 (the last tile only feeds the carry of the final columns)
+  long long n_items;               // n_time_tiles * n_src
+  long long TO;                    // output rows per source
+  float* out;                      // [n_src][TO][Kp]
+  float* carry;                    // [n_src][n_time_tiles][hd][Kp]
+  int hd;                          // columns before the tile that its lag groups reach: (4/CB - 1) s J + s - 1
+  int sub_units;                   // units per sub-chunk (0: the whole item in one tensor-memory chain)
+  int n_stages;                    // W ring depth (2 lags per stage)
+  int x3, lo_off;                  // 3xTF32: the feature chunks of an item are walked three times - (W lo, S hi),
+                                   // (W hi, S lo), (W hi, S hi)
+  int* err;
+};
+
+constexpr int kHtLagsPerStage = 2;
+constexpr int kHtABytes = 4 * 32 * 128;            // 4 regions x 32 n x 32 k
+constexpr int kHtStageBytes = kHtLagsPerStage * kHtABytes;
+constexpr int kHtMaxStages = 4;
+
+__host__ __device__ inline size_t hterms_r_bytes(int Kp, int hd, bool direct) {
+  return direct ? 0 : (size_t)(256 + hd) * Kp * 4;
+}
+__host__ __device__ inline size_t hterms_smem_bytes(int n_stages, int wrows, int Kp, int hd, bool direct) {
+  return 1024 + (size_t)n_stages * kHtStageBytes + 2 * (size_t)wrows * 128 + hterms_r_bytes(Kp, hd, direct) + 256;
+}
+
+__global__ void __launch_bounds__(kSThreads, 1)
+tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                 const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmXlo,
+                 const __grid_constant__ CUtensorMap tmElo, const HTermsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int n_glag = 4 / p.CB;
+  const bool direct = (n_glag == 1 && p.s == 1);                  // nothing to reduce: rows are whole outputs
+  const int n_stages = p.n_stages;
+  uint8_t* As = smem;                                             // [stages][2 lags x 16 KB]
+  const uint32_t wbytes = (uint32_t)p.wrows * 128;                // one 32-feature chunk of the window
+  uint8_t* Ws = As + (size_t)n_stages * kHtStageBytes;            // [2][wbytes]
+  float* R = (float*)(Ws + 2 * (size_t)wbytes);                   // [256 + hd][Kp]
+  uint64_t* bars = (uint64_t*)((uint8_t*)R + hterms_r_bytes(p.Kp, p.hd, direct));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kHtMaxStages;
+  uint64_t* wfull = bars + 2 * kHtMaxStages;                      // [2]
+  uint64_t* wempty = wfull + 2;                                   // [2]
+  uint64_t* sfull = wempty + 2;                                   // [2]
+  uint64_t* sempty = sfull + 2;                                   // [2]
+  uint32_t* tmem_slot = (uint32_t*)(sempty + 2);
+  volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1);
+      mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 8);
+    }
+    *abort_flag = 0;
+    fence_mbar_init();
+    prefetch_tmap(&tmW); prefetch_tmap(&tmX); prefetch_tmap(&tmE); prefetch_tmap(&tmXlo); prefetch_tmap(&tmElo);
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const Abort ab{abort_flag, p.err};
+  const int J = p.J, wrows = p.wrows;
+  const int n_pass = p.x3 ? 3 : 1;
+  const SubPlan plan((long long)n_pass * p.n_chunks_n * J, p.x3 ? 2ll * p.n_chunks_n * J : 0, p.sub_units);   // units per item
+
+  if (warp == 0) {
+    reg_dec<kSCtlRegs>();
+    if (lane == 0) {
+      PipeState ps;
+      bool ok = true;
+      // chunks = (item, operand pass, 32-feature chunk) in execution order; chunk c uses window buffer c & 1
+      struct Chunk { long long item; int nc, combo; bool valid; };
+      auto make_chunk = [&](long long item) { return Chunk{item, 0, p.x3 ? 0 : 2, item < p.n_items}; };
+      auto next_chunk = [&](Chunk c) {
+        if (++c.nc >= p.n_chunks_n) {
+          if (c.combo < 2) { ++c.combo; c.nc = 0; }
+          else c = make_chunk(c.item + gridDim.x);
+        }
+        return c;
+      };
+      auto issue_window = [&](const Chunk& c, long long wc, bool block, bool& done) -> bool {
+        const int wb = (int)(wc & 1);
+        const uint32_t par = (uint32_t)((wc >> 1) & 1) ^ 1;
+        if (!block && !mbar_try_wait(&wempty[wb], par)) return true;
+        if (!ab.wait(&wempty[wb], par)) return false;
+        const long long tile = c.item / p.n_src;
+        const int src = (int)(c.item % p.n_src);
+        mbar_arrive_expect_tx(&wfull[wb], wbytes);
+        uint8_t* wdst = Ws + (size_t)wb * wbytes;
+        const CUtensorMap* tmS = src ? (c.combo == 1 ? &tmElo : &tmE) : (c.combo == 1 ? &tmXlo : &tmX);
+        for (int rb = 0; rb < wrows / 32; ++rb)
+          tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], c.nc * 32, (int)(tile * 256 + rb * 32));
+        done = true;
+        return true;
+      };
+      Chunk cur = make_chunk(blockIdx.x);
+      long long wc = 0;
+      bool dummy = false;
+      if (cur.valid) ok = issue_window(cur, 0, true, dummy);
+      while (cur.valid && ok) {
+        const Chunk nxt = next_chunk(cur);
+        bool prefetched = !nxt.valid;
+        for (int j = 0; j < J; j += kHtLagsPerStage) {
+          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+          // one box: lags j, j+1 x regions (lag group, column block) x 32 features x 32 components (lags >= J
+          // and features >= Np arrive as zeros)
+          mbar_arrive_expect_tx(&full[ps.stage], kHtStageBytes);
+          tma_load_5d(As + (size_t)ps.stage * kHtStageBytes, &tmW, &full[ps.stage], 0, cur.nc * 32,
+                      cur.combo == 0 ? p.lo_off / 32 : 0, 0, j);
+          ps.advance(n_stages);
+          // the next window goes out as soon as its buffer is free; waiting for it here would starve the W ring
+          if (!prefetched && !issue_window(nxt, wc + 1, false, prefetched)) { ok = false; break; }
+        }
+        if (ok && !prefetched) ok = issue_window(nxt, wc + 1, true, prefetched);
+        cur = nxt;
+        ++wc;
+      }
+    }
+  } else if (warp == 1) {
+    reg_dec<kSCtlRegs>();
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, 256, 1, 0);
+      PipeState ps;
+      SubIssue si;
+      long long wcount = 0;
+      bool ok = true;
+      for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+        int unit = 0;
+        for (int chunk = 0; chunk < n_pass * p.n_chunks_n && ok; ++chunk, ++wcount) {
+          const int wb = (int)(wcount & 1);
+          if (!ab.wait(&wfull[wb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t wbase = smem_u32(Ws + (size_t)wb * wbytes);
+          for (int j = 0; j < J && ok; j += kHtLagsPerStage) {
+            if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+            tc_fence_after();
+            const int nl = min(kHtLagsPerStage, J - j);
+            for (int u = 0; u < nl; ++u) {
+              uint32_t dtm;
+              if (!si.begin_unit(ab, sempty, tmem, dtm)) { ok = false; break; }
+              const uint32_t abase = smem_u32(As + (size_t)ps.stage * kHtStageBytes + u * kHtABytes);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
+                const uint64_t bd = make_smem_desc(wbase + (uint32_t)(p.s * (j + u)) * 128 + ks * 32, 16, 1024, kSwz128);
+                mma_tf32_ss(dtm, ad, bd, idesc, (si.us | ks) != 0 ? 1u : 0u);
+              }
+              si.end_unit(sfull, plan, ++unit);
+            }
+            mma_commit(&empty[ps.stage]);
+            ps.advance(n_stages);
+          }
+          if (!ok) break;
+          mma_commit(&wempty[wb]);
+        }
+      }
+    }
+  } else if (warp < 4) {
+    reg_dec<kSCtlRegs>();
+  } else {
+    reg_inc<kSEpiRegs>();
+    const int e = warp - 4;                   // epilogue warp 0..7
+    const int q = warp & 3;                   // region (lag group, column block) of this warp's 32 TMEM lanes
+    const int half = e >> 2;
+    const int etid = tid - 128;               // 0..255
+    const int n_sub = (int)plan.n_sub();
+    const int gl = q / p.CB;                  // lag group
+    const int dl = p.s > 1 ? lane / p.Kp : 0; // real lag inside a folded virtual lag
+    const int kcol = p.s > 1 ? lane % p.Kp : (q % p.CB) * 32 + lane;
+    const int u0 = half * 128 + (n_glag - 1 - gl) * p.s * J + (p.s - 1 - dl);     // R row of this thread's column 0
+    const int U = 256 + p.hd;
+    float m[128];
+    long long sc = 0;
+    bool ok = true;
+    for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+      const long long tile = item / p.n_src;
+      const int src = (int)(item % p.n_src);
+      for (int sub = 0; sub < n_sub; ++sub, ++sc) {
+        const int b = (int)(sc & 1);
+        if (!wait_relaxed(ab, &sfull[b], (uint32_t)((sc >> 1) & 1))) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + half * 128);
+        if (sub == 0) fold_sub<true>(m, taddr); else fold_sub<false>(m, taddr);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sempty[b]);
+      }
+      if (!ok) break;
+      float* outs = p.out + (size_t)src * p.TO * p.Kp;
+      const long long base = tile * 256;
+      if (direct) {
+        // Kp = 128: row (cb, k) at column c is out[base + c][cb*32 + k] itself
+        float* o = outs + (size_t)(base + half * 128) * p.Kp + kcol;
+        const long long left = p.TO - (base + half * 128);
+        const int rows = left > 128 ? 128 : (int)left;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          if (i < rows) *o = m[i];
+          o += p.Kp;
+        }
+        continue;
+      }
+      // ---- reduce the lag groups through R ----
+      {
+        float4* R4 = reinterpret_cast<float4*>(R);
+        const int n4 = U * p.Kp / 4;
+        for (int i = etid; i < n4; i += kSEpiThreads) R4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      epi_bar();
+      for (int w = 0; w < 8; ++w) {
+        if (w == e) {
+          for (int d = 0; d < p.s; ++d) {          // folded lags of one warp overlap in R: one at a time
+            if (d == dl) {
+              float* r = R + (size_t)u0 * p.Kp + kcol;
+#pragma unroll
+              for (int i = 0; i < 128; ++i) r[(size_t)i * p.Kp] += m[i];
+            }
+            __syncwarp();
+          }
+        }
+        epi_bar();
+      }
+      // ---- R -> carry (the hd columns before the tile) and out (the tile's own 256 columns) ----
+      {
+        const float4* R4 = reinterpret_cast<const float4*>(R);
+        const int kp4 = p.Kp / 4;
+        const int head4 = p.hd * kp4;
+        float4* c4 = reinterpret_cast<float4*>(p.carry + ((size_t)src * p.n_time_tiles + tile) * p.hd * p.Kp);
+        float4* o4 = reinterpret_cast<float4*>(outs + (size_t)base * p.Kp);
+        long long rows_left = p.TO - base;
+        if (rows_left > 256) rows_left = 256;
+        const int main4 = rows_left > 0 ? (int)rows_left * kp4 : 0;
+        for (int i = etid; i < head4; i += kSEpiThreads) c4[i] = R4[i];
+        for (int i = etid; i < main4; i += kSEpiThreads) o4[i] = R4[head4 + i];
+      }
+      epi_bar();                                   // R is zeroed again by the next item
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// out[src][t][:] += sum over the tiles i > t / 256 whose head reaches t of carry[src][i][t - (256 i - hd)][:]
+// (ascending i: deterministic).  One thread per float4 of the min(hd, 256) columns before each tile boundary.
+__global__ void __launch_bounds__(256)
+hterms_carry_kernel(float* __restrict__ out, const float* __restrict__ carry, long long TO, long long n_time_tiles,
+                    int hd, int Kp, int n_src) {
+  const int kp4 = Kp / 4;
+  const int wmax = hd < 256 ? hd : 256;
+  const long long per_src = (n_time_tiles - 1) * wmax * kp4;
+  const long long total = per_src * n_src;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int src = (int)(idx / per_src);
+    long long r = idx % per_src;
+    const int k4 = (int)(r % kp4); r /= kp4;
+    const int w = (int)(r % wmax) + 1;                 // distance to the next tile boundary
+    const long long i0 = r / wmax + 1;                 // that tile
+    const long long t = i0 * 256 - w;
+    if (t >= TO) continue;
+    float4* o = reinterpret_cast<float4*>(out + ((size_t)src * TO + t) * Kp) + k4;
+    float4 acc = *o;
+    for (long long i = i0; i < n_time_tiles && i * 256 - t <= hd; ++i) {
+      const long long u = t - (i * 256 - hd);
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(carry + (((size_t)src * n_time_tiles + i) * hd + u) * Kp) + k4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *o = acc;
+  }
+}
+
+}  // namespace tc
+}  // namespace cmf
