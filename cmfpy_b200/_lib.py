@@ -58,6 +58,8 @@ _SIGNATURES = {
     "cmf_mu_resid_sumsq": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "cmf_mu_resid_sumsq_buffer": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "cmf_mu_loss": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "cmf_mu_peer_attach_local": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(_H)]),
+    "cmf_mu_halo_exchange_peer": (C.c_int, [_H]),
     "cmf_mu_step": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "cmf_mu_peer_export": (C.c_int, [_H, C.c_void_p]),
     "cmf_mu_peer_attach": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
@@ -79,6 +81,7 @@ _SIGNATURES = {
     "cmf_mu_path_name": (C.c_char_p, [_H]),
     "cmf_mu_kernel_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "cmf_mu_set_profiling": (C.c_int, [_H, C.c_int]),
+    "cmf_mu_launch_table": (C.c_int, [_H, C.c_char_p, C.c_longlong]),
     "cmf_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
                               C.c_int, C.c_int, C.c_int, C.c_int]),
     "cmf_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
@@ -123,6 +126,17 @@ def check(rc):
     if rc == 2:
         raise ValueError(msg)
     raise RuntimeError("cmfpy_b200: " + msg)
+
+
+def launch_table(lib, handle):
+    """{kernel label: (launches, total ms)} recorded since cmf_mu_set_profiling(handle, 2)."""
+    buf = C.create_string_buffer(1 << 16)
+    check(lib.cmf_mu_launch_table(handle, buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.rsplit(" ", 2)
+        out[name] = (int(n), float(ms))
+    return out
 
 
 def np_dtype_code(a):

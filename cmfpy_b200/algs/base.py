@@ -23,17 +23,26 @@ def _as_host_matrix(a, name):
     return a
 
 
+def resolve_precision(lib, precision, N, K, L):
+    """'auto' = the fastest mode that meets the reference's fp32 parity bar (loss trajectory within 1e-4 of the
+    float64 reference): the error-compensated tensor-core mode 'tf32x3' where its kernels cover the shape, the
+    exact-fp32 FFMA kernels otherwise.  Plain 'tf32' is faster and less accurate; it is never chosen implicitly."""
+    if precision != "auto":
+        return precision
+    return "tf32x3" if lib.cmf_precision_supported(_lib.CMF_PREC_TF32X3, N, K, L) else "fp32"
+
+
 class DeviceOptimizer:
     """Common plumbing for solvers that live behind libcmf_b200."""
 
     def __init__(self, data, model_dimensions, initW=None, initH=None,
-                 tol=1e-5, patience=3, precision="fp32", device=0, seed=None,
+                 tol=1e-5, patience=3, precision="auto", device=0, seed=None,
                  denominators="auto", normalize=None):
         # reference base.py:20-21
         if patience < 1 or not isinstance(patience, Integral):
             raise ValueError("Patience must be a positive integer.")
-        if precision not in _lib.PRECISIONS:
-            raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
+        if precision != "auto" and precision not in _lib.PRECISIONS:
+            raise ValueError("precision must be 'auto' or one of %s" % sorted(_lib.PRECISIONS))
         if denominators not in _lib.DENOMINATORS:
             raise ValueError("denominators must be one of %s" % sorted(_lib.DENOMINATORS))
         self.denominators = denominators
@@ -41,13 +50,13 @@ class DeviceOptimizer:
         self._h = C.c_void_p()
         self.patience = patience
         self.tol = tol
-        self.precision = precision
         self.device = device
 
         # reference base.py:33-34: copy the model dimensions onto the solver
         for k, v in model_dimensions:
             setattr(self, k, v)
         N, T, K, L = self.n_features, self.n_timepoints, self.n_components, self.maxlag
+        self.precision = precision = resolve_precision(self._lib, precision, N, K, L)
 
         X = _as_host_matrix(data, "data")
         if X.shape != (N, T):

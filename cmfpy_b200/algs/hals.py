@@ -21,6 +21,8 @@ class HALSUpdate(DeviceOptimizer):
 
     def __init__(self, data, dims, patience=3, tol=1e-5, max_iter=1,
                  weightW=1, weightH=1, stop_thresh=0, **kwargs):
+        if kwargs.get("precision", "auto") == "auto":
+            kwargs["precision"] = "fp32"        # the sweeps are fp32 passes over the residual; nothing for tensor cores
         super().__init__(data, dims, patience=patience, tol=tol, **kwargs)
         self.max_iter = max_iter
         self.stop_thresh = stop_thresh

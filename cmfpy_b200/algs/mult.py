@@ -12,14 +12,27 @@ class MultUpdate(DeviceOptimizer):
     """Multiplicative update rule (reference cmfpy/algs/mult.py:7-48).
 
     Extra keyword options (all optional, passed through `CMF(**alg_opts)`):
-      precision : "fp32" (exact FFMA contractions) or "tf32" (tcgen05 tensor cores)
+      precision : "auto" (default: "tf32x3" where the tensor-core kernels cover the shape, else "fp32"),
+                  "tf32x3" (tcgen05 tensor cores, every product as three TF32 MMAs on hi/lo operand pairs,
+                  two-level accumulation: meets the fp32 parity bar), "fp32" (exact FFMA contractions) or
+                  "tf32" (plain TF32 tensor cores: ~3x faster, loss trajectories within ~1e-3)
       denominators : "direct" (contract est, as the reference does), "gram" (exact identity
-                  through the lag Gram operators of W and H; tf32 only) or "auto"
+                  through the lag Gram operators of W and H; tensor-core modes only) or "auto"
       device    : CUDA device ordinal
+      devices   : list of CUDA ordinals: time-sharded solve over several GPUs (algs/multi_gpu.py)
       seed      : seed of the random initialisation when initW/initH are absent
     """
 
-    def __init__(self, data, dims, patience=3, tol=1e-5, **kwargs):
+    def __new__(cls, data=None, dims=None, *args, devices=None, **kwargs):
+        # devices=[g0, g1, ...]: the time-sharded solve, one GPU per shard, driven from this process
+        if cls is MultUpdate and devices is not None and len(devices) > 1:
+            from .multi_gpu import MultiGpuMultUpdate
+            return MultiGpuMultUpdate(data, dims, *args, devices=devices, **kwargs)
+        return super().__new__(cls)
+
+    def __init__(self, data, dims, patience=3, tol=1e-5, devices=None, **kwargs):
+        if devices is not None:
+            kwargs.setdefault("device", int(list(devices)[0]))
         super().__init__(data, dims, patience=patience, tol=tol, **kwargs)
 
     def update(self):
@@ -63,3 +76,7 @@ class MultUpdate(DeviceOptimizer):
 
     def set_profiling(self, on=True):
         _lib.check(self._lib.cmf_mu_set_profiling(self._h, int(on)))
+
+    def launch_table(self):
+        """{kernel label: (launches, total ms)} since set_profiling(2)."""
+        return _lib.launch_table(self._lib, self._h)

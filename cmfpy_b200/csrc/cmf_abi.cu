@@ -15,6 +15,8 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cmath>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -83,6 +85,8 @@ struct cmf_mu_s {
   int* d_counter = nullptr;
   float kernel_ms[4] = {0, 0, 0, 0};
   std::vector<cudaEvent_t> ev_pool;
+  tc::LaunchLog llog;                              // profiling == 2: an event after every launch
+  std::vector<std::pair<std::string, std::pair<long long, double>>> launch_table;   // label -> (launches, ms)
 
   tc::TcState tcs;
 
@@ -179,6 +183,7 @@ int stage_get(cmf_mu_s* h, size_t bytes, void** out) {
 
 int launch_check(cmf_mu_s* h, const char* what) {
   h->launches++;
+  tc::log_launch(what);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
@@ -357,6 +362,29 @@ int sync_ops_H(cmf_mu_s* h, long long row0, long long nrows) {
   return rc;
 }
 
+// profiling == 2: install / harvest the per-launch log around a batch of iterations (the caller has synchronised)
+void launch_log_begin(cmf_mu_s* h) {
+  if (h->profiling < 2) return;
+  h->llog.stream = h->stream;
+  h->llog.labels.clear();
+  tc::launch_log() = &h->llog;
+  tc::log_launch("<start>");
+}
+void launch_log_end(cmf_mu_s* h) {
+  if (tc::launch_log() != &h->llog) return;
+  tc::launch_log() = nullptr;
+  auto& L = h->llog;
+  for (size_t i = 1; i < L.labels.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, L.pool[i - 1], L.pool[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+    bool found = false;
+    for (auto& row : h->launch_table)
+      if (row.first == L.labels[i]) { row.second.first++; row.second.second += ms; found = true; break; }
+    if (!found) h->launch_table.push_back({L.labels[i], {1, (double)ms}});
+  }
+  L.labels.clear();
+}
+
 cudaEvent_t get_event(cmf_mu_s* h, size_t i) {
   while (h->ev_pool.size() <= i) {
     cudaEvent_t e;
@@ -483,6 +511,7 @@ void free_all(cmf_mu_s* h) {
   cudaFree(h->d_counter);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
+  for (auto e : h->llog.pool) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
 }
 
@@ -960,10 +989,14 @@ static void capture_iteration(cmf_mu_s* h) {
     return;
   }
   const long long l0 = h->launches;
+  // issue_iteration walks the host-side state flags although nothing executes during capture: put them back, so
+  // that a capture that fails half-way leaves the plain-launch fallback a consistent state
+  const bool est_valid = h->est_valid, est_stored = h->est_stored, wterms_valid = h->wterms_valid;
   size_t ne = 0;
   const int rc = issue_iteration(h, false, ne, -1);
   cudaGraph_t graph = nullptr;
   const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  h->est_valid = est_valid; h->est_stored = est_stored; h->wterms_valid = wterms_valid;
   h->graph_launches = h->launches - l0;
   h->launches = l0;                       // nothing ran yet; replays add graph_launches each
   if (rc != 0 || e != cudaSuccess || graph == nullptr ||
@@ -997,6 +1030,7 @@ int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
     const int chunk = (n_steps - done < h->ring_cap) ? n_steps - done : h->ring_cap;
     size_t ne = 0;
     if (use_graph) CMF_CUDA(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
+    launch_log_begin(h);
     for (int i = 0; i < chunk; ++i) {
       if (ms_out) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
       if (use_graph) {
@@ -1011,6 +1045,7 @@ int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
     if (loss_out)
       CMF_CUDA(cudaMemcpyAsync(loss_out + done, h->d_ring, (size_t)chunk * 8, cudaMemcpyDeviceToHost, h->stream));
     CMF_CUDA(cudaStreamSynchronize(h->stream));
+    launch_log_end(h);
     if (h->use_tc) CMF_TRY(tc::check(h->tcs, h->stream));
     // unpack event timings
     const int per = (ms_out ? 1 : 0) + (prof ? 7 : 0);
@@ -1144,7 +1179,22 @@ int cmf_mu_kernel_ms(cmf_mu_t* h, float out[4]) {
 
 int cmf_mu_set_profiling(cmf_mu_t* h, int on) {
   CMF_CHECK(h != nullptr, "null solver handle");
-  h->profiling = on ? 1 : 0;
+  h->profiling = on < 0 ? 0 : (on > 2 ? 2 : on);
+  if (on >= 2) h->launch_table.clear();
+  return 0;
+}
+
+// profiling level 2: one line "label launches total_ms" per kernel label seen since profiling was switched on
+int cmf_mu_launch_table(cmf_mu_t* h, char* buf, long long cap) {
+  CMF_CHECK(h != nullptr && buf != nullptr && cap > 0, "null argument");
+  std::string out;
+  char line[256];
+  for (auto& row : h->launch_table) {
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", row.first.c_str(), row.second.first, row.second.second);
+    out += line;
+  }
+  CMF_CHECK((long long)out.size() + 1 <= cap, "buffer too small for the launch table (%zu bytes needed)", out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
   return 0;
 }
 
@@ -1240,6 +1290,76 @@ int cmf_mu_peer_detach(cmf_mu_t* h) {
   return peer_detach(h);
 }
 
+namespace {
+int peer_ensure_shared(cmf_mu_s* h) {
+  auto& ps = h->peer;
+  if (ps.shared) return 0;
+  DeviceGuard guard(h->dev);
+  CMF_CHECK(guard.ok, "cannot select CUDA device %d", h->dev);
+  ps.shared_bytes = 256 + peer_halo_bytes(h) + (size_t)ps.ring_cap * peer::kMaxPeers * 8;
+  CMF_CUDA(cudaMalloc(&ps.shared, ps.shared_bytes));
+  CMF_CUDA(cudaMemset(ps.shared, 0, ps.shared_bytes));
+  return 0;
+}
+}  // namespace
+
+int cmf_mu_peer_attach_local(cmf_mu_t* h, int rank, int world, cmf_mu_t* const* handles) {
+  CMF_ENTER(h);
+  CMF_CHECK(handles != nullptr, "null argument");
+  CMF_CHECK(world >= 1 && world <= peer::kMaxPeers && rank >= 0 && rank < world, "rank %d / world %d out of range (at most %d peers)",
+            rank, world, peer::kMaxPeers);
+  CMF_CHECK(handles[rank] == h, "handles[rank] must be this solver");
+  auto& ps = h->peer;
+  CMF_CHECK(!ps.attached, "peers already attached");
+  CMF_CHECK(h->wcount % 4 == 0, "W element count must be a multiple of 4");
+  peer::Peers P{};
+  P.rank = rank; P.world = world;
+  for (int p = 0; p < world; ++p) {
+    cmf_mu_s* o = handles[p];
+    CMF_CHECK(o != nullptr, "null peer handle %d", p);
+    CMF_CHECK(o->h == h->h && o->Kp == h->Kp && o->wcount == h->wcount && o->peer.ring_cap == ps.ring_cap,
+              "peer %d was created with different dimensions", p);
+    CMF_TRY(peer_ensure_shared(o));
+    if (p != rank) {
+      CMF_CHECK(o->dev != h->dev, "peer %d shares device %d with rank %d: one GPU per shard", p, o->dev, rank);
+      int can = 0;
+      CMF_CUDA(cudaDeviceCanAccessPeer(&can, h->dev, o->dev));
+      CMF_CHECK(can, "device %d cannot access device %d over NVLink / PCIe peer-to-peer", h->dev, o->dev);
+      cudaError_t e = cudaDeviceEnablePeerAccess(o->dev, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+      CMF_CHECK(e == cudaSuccess, "cudaDeviceEnablePeerAccess(%d) failed: %s", o->dev, cudaGetErrorString(e));
+    }
+    char* sh = (char*)o->peer.shared;
+    P.numden[p] = o->numden;
+    P.W[p] = o->W;
+    P.ctl[p] = (peer::Control*)sh;
+    P.halo_in[p] = (float*)(sh + 256);
+    P.ring[p] = (double*)(sh + 256 + peer_halo_bytes(o));
+  }
+  ps.P = P;
+  ps.attached = true;
+  return 0;
+}
+
+int cmf_mu_halo_exchange_peer(cmf_mu_t* h) {
+  CMF_ENTER(h);
+  auto& ps = h->peer;
+  CMF_CHECK(ps.attached, "cmf_mu_halo_exchange_peer needs attached peers");
+  CMF_CHECK(h->have_factors, "W or H not initalized.");
+  if (h->h > 0) {
+    peer::halo_exchange_kernel<<<2, 256, 0, h->stream>>>(ps.P, h->Ht, h->h, h->Kp, h->Tloc, ++ps.halo_epoch);
+    CMF_TRY(launch_check(h, "halo_exchange"));
+    CMF_TRY(sync_ops_H(h, 0, h->h));
+    CMF_TRY(sync_ops_H(h, h->h + h->Tloc, h->h));
+  }
+  h->est_valid = false;
+  int perr = 0;
+  CMF_CUDA(cudaMemcpyAsync(&perr, &ps.P.ctl[ps.P.rank]->err, 4, cudaMemcpyDeviceToHost, h->stream));
+  CMF_CUDA(cudaStreamSynchronize(h->stream));
+  if (perr != 0) { set_error("peer halo exchange timed out (error %d): a rank did not reach the exchange", perr); return 1; }
+  return 0;
+}
+
 // n_steps x MultUpdate.update() on a time shard, collectives over peer memory; every rank calls it
 // with the same n_steps.  loss_out[i] = GLOBAL loss after step i (identical on all ranks).
 int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out) {
@@ -1263,6 +1383,7 @@ int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out) {
   while (done < n_steps) {
     const int chunk = (n_steps - done < ps.ring_cap) ? n_steps - done : ps.ring_cap;
     size_t ne = 0;
+    launch_log_begin(h);
     for (int i = 0; i < chunk; ++i) {
       if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
       CMF_TRY(do_w_terms(h));
@@ -1299,8 +1420,12 @@ int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out) {
     int perr = 0;
     CMF_CUDA(cudaMemcpyAsync(&perr, &ps.P.ctl[ps.P.rank]->err, 4, cudaMemcpyDeviceToHost, h->stream));
     CMF_CUDA(cudaStreamSynchronize(h->stream));
+    launch_log_end(h);
     if (h->use_tc) CMF_TRY(tc::check(h->tcs, h->stream));
-    CMF_CHECK(perr == 0, "peer exchange timed out (error %d): a rank did not reach the collective", perr);
+    if (perr != 0) {      // a runtime failure, not an argument error
+      set_error("peer exchange timed out (error %d): a rank did not reach the collective", perr);
+      return 1;
+    }
     for (int i = 0; i < chunk; ++i) {
       double ssum = 0.0;
       for (int p = 0; p < G; ++p) ssum += ring[(size_t)i * peer::kMaxPeers + p];

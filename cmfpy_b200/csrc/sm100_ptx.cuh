@@ -50,6 +50,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking test of a phase (try_wait may suspend the thread for a system-dependent time before it answers)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a pipeline bug must never hang the GPU.  Returns false on
 // timeout (the caller records the failure and bails out).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t max_spins = (1u << 26)) {
@@ -112,7 +124,12 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, issued by ONE thread
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, issued by ONE thread.
+// The MMA warp runs its issue loop with all 32 lanes in uniform control flow and wraps the issue in
+// `if (elect_one()) { ... }`: ptxas then keeps descriptors and addresses in uniform registers and emits bare UTCHMMA
+// instructions.  Inside an `if (lane == 0)` region (or with the instruction predicated on a lane test) it wraps every
+// MMA in an elect / R2UR.BROADCAST loop of ~17 instructions, and at 128 tensor-pipe cycles per MMA the issuing
+// thread's own instruction stream is then what the tensor pipe waits for.
 __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"

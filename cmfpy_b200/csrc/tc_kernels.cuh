@@ -77,6 +77,15 @@ __device__ __forceinline__ bool wait_relaxed(const Abort& ab, uint64_t* bar, uin
   }
 }
 
+// The MMA-issuing warp waits with this form: the outcome does not steer its control flow (after a timeout the
+// error word is set, every later wait returns at once and the kernel runs to its end on garbage, which the host
+// reports), so its loop counters, descriptors and tensor-memory addresses stay provably warp-uniform and the
+// compiler keeps them in uniform registers - tcgen05.mma takes its operands from there.
+__device__ __forceinline__ void wait_uniform(const Abort& ab, uint64_t* bar, uint32_t parity) {
+  (void)ab.wait(bar, parity);
+  __syncwarp();            // the lanes may leave the spin loop apart: converge before the uniform code goes on
+}
+
 struct PipeState {
   int stage = 0;
   uint32_t phase = 0;
@@ -166,7 +175,8 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
   __shared__ double red[4];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler, too
   if (tid == 0) {
     for (int i = 0; i < kReconStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
@@ -190,11 +200,10 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
-    if (lane == 0) {
+    {
+      // all 32 lanes run the loop in uniform control flow; one elected lane issues the TMA instructions
+      // (see mma_tf32_ss in sm100_ptx.cuh for why)
       PipeState ps;
-      bool ok = true;
-      // chunks = (tile, reduction block) in execution order; chunk c uses window buffer c & 1 and its
-      // window is requested while the previous chunk's W stages stream (a whole chunk of lead time)
       struct Chunk { long long tile; int cb, lb; bool valid; };
       auto next_chunk = [&](Chunk c) {
         if (++c.lb >= n_lb) {
@@ -203,92 +212,104 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         }
         return c;
       };
-      // window of chunk number wc; block = false: only if its buffer is already free
-      auto issue_window = [&](const Chunk& c, long long wc, bool block, bool& done) -> bool {
+      // window of chunk number wc (its buffer is known to be free)
+      auto issue_window = [&](const Chunk& c, long long wc) {
         const int hb = (int)(wc & 1);
-        const uint32_t par = (uint32_t)((wc >> 1) & 1) ^ 1;
-        if (!block && !mbar_try_wait(&hempty[hb], par)) return true;
-        if (!ab.wait(&hempty[hb], par)) return false;
         const long long tt = c.tile / p.n_tiles_n;
-        mbar_arrive_expect_tx(&hfull[hb], hbytes);
         uint8_t* hdst = Hs + (size_t)hb * hbytes;
         const X3Sel sel = x3_select(0, p.cbx, p.lo_off, p.lo_off_b, c.cb);
         const int l1 = min(L, (c.lb + 1) * LB);                 // window row 0 holds lag l1 - 1 of this block
-        for (int rb = 0; rb < wrows / 64; ++rb)
-          tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], sel.cbr * 32 + sel.b_off,
-                      (int)(tt * 256 + p.h_shift + p.s * (L - l1) + rb * 64));
-        done = true;
-        return true;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&hfull[hb], hbytes);
+          for (int rb = 0; rb < wrows / 64; ++rb)
+            tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], sel.cbr * 32 + sel.b_off,
+                        (int)(tt * 256 + p.h_shift + p.s * (L - l1) + rb * 64));
+        }
       };
       Chunk cur{(long long)blockIdx.x, 0, 0, (long long)blockIdx.x < p.n_tiles};
       long long wc = 0;
-      bool dummy = false;
-      if (cur.valid) ok = issue_window(cur, 0, true, dummy);
-      while (cur.valid && ok) {
+      if (cur.valid) issue_window(cur, 0);
+      while (cur.valid) {
         const Chunk nxt = next_chunk(cur);
         bool prefetched = !nxt.valid;
+        const int nhb = (int)((wc + 1) & 1);
+        const uint32_t npar = (uint32_t)(((wc + 1) >> 1) & 1) ^ 1;
         const int nt = (int)(cur.tile % p.n_tiles_n);
         const X3Sel sel = x3_select(0, p.cbx, p.lo_off, p.lo_off_b, cur.cb);
         const int l0 = cur.lb * LB, l1 = min(L, l0 + LB);
         for (int l = l0; l < l1; l += kReconLagsPerStage) {
-          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+          wait_uniform(ab, &empty[ps.stage], ps.phase ^ 1);
           const int nl = min(kReconLagsPerStage, l1 - l);
-          mbar_arrive_expect_tx(&full[ps.stage], nl * kReconABytes);
-          for (int u = 0; u < nl; ++u)
-            tma_load_2d(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes, &tmW, &full[ps.stage],
-                        (sel.cbr % p.cb_cols) * 32 + sel.a_off, (l + u + sel.cbr / p.cb_cols) * p.Np + nt * 128);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[ps.stage], nl * kReconABytes);
+            for (int u = 0; u < nl; ++u)
+              tma_load_2d(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes, &tmW, &full[ps.stage],
+                          (sel.cbr % p.cb_cols) * 32 + sel.a_off, (l + u + sel.cbr / p.cb_cols) * p.Np + nt * 128);
+          }
           ps.advance(kReconStages);
-          // The next window goes out as soon as its buffer is free.  (Blocking on it here, as round 1 did after
-          // the second stage of a chunk, parks this thread until the MMAs of the PREVIOUS chunk retire while the
-          // W ring runs dry.)
-          if (!prefetched && !issue_window(nxt, wc + 1, false, prefetched)) { ok = false; break; }
+          // The next window goes out as soon as its buffer is free.  (Blocking on it here, as round 1 did after the
+          // second stage of a chunk, parks the producer until the MMAs of the PREVIOUS chunk retire while the W ring
+          // runs dry.)
+          if (!prefetched && __shfl_sync(0xffffffffu, (int)mbar_test_wait(&hempty[nhb], npar), 0)) {
+            issue_window(nxt, wc + 1);
+            prefetched = true;
+          }
         }
-        if (ok && !prefetched) ok = issue_window(nxt, wc + 1, true, prefetched);
+        if (!prefetched) {
+          wait_uniform(ab, &hempty[nhb], npar);
+          issue_window(nxt, wc + 1);
+        }
         cur = nxt;
         ++wc;
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_tf32(128, 256, 0, 0);
+      // ONE thread issues every MMA of the CTA: its instruction stream is kept to a few adds per MMA (descriptors
+      // differ only in their 14-bit start-address field, bytes >> 4), or the tensor pipe ends up waiting for it
+      const uint64_t adesc0 = make_smem_desc(smem_u32(As), 16, 1024, kSwz128);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(Hs), 16, 1024, kSwz128);
       PipeState ps;
-      long long wcount = 0;
+      uint32_t hb = 0, hph = 0;
       int it = 0;
-      bool ok = true;
-      for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x, ++it) {
+      for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
-        if (!ab.wait(&tempty[b], (uint32_t)((it >> 1) & 1) ^ 1)) break;
+        wait_uniform(ab, &tempty[b], (uint32_t)((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t dtm = tmem + (uint32_t)b * 256;
-        for (int chunk = 0; chunk < p.CB * n_lb && ok; ++chunk, ++wcount) {
-          const int cb = chunk / n_lb, lb = chunk - cb * n_lb;
+        uint32_t acc = 0;
+        for (int chunk = 0; chunk < p.CB * n_lb; ++chunk) {
+          const int lb = chunk % n_lb;
           const int l0 = lb * LB, l1 = min(L, l0 + LB);
-          const int hb = (int)(wcount & 1);
-          if (!ab.wait(&hfull[hb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
+          wait_uniform(ab, &hfull[hb], hph);
           tc_fence_after();
-          const uint32_t hbase = smem_u32(Hs + (size_t)hb * hbytes);
+          uint64_t bd = bdesc0 + (uint64_t)((hb * hbytes) >> 4) + (uint64_t)((uint32_t)(p.s * (l1 - 1 - l0)) * 8);
           for (int l = l0; l < l1; l += kReconLagsPerStage) {
-            if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+            wait_uniform(ab, &full[ps.stage], ps.phase);
             tc_fence_after();
             const int nl = min(kReconLagsPerStage, l1 - l);
+            uint64_t ad = adesc0 + (uint64_t)(ps.stage * (kReconStageBytes >> 4));
             for (int u = 0; u < nl; ++u) {
-              const uint32_t abase = smem_u32(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ad = make_smem_desc(abase + ks * 32, 16, 1024, kSwz128);
-                const uint64_t bd = make_smem_desc(hbase + (uint32_t)(p.s * (l1 - 1 - l - u)) * 128 + ks * 32, 16, 1024, kSwz128);
-                mma_tf32_ss(dtm, ad, bd, idesc, (cb | (l + u) | ks) != 0 ? 1u : 0u);
+              if (elect_one()) {
+                mma_tf32_ss(dtm, ad, bd, idesc, acc);
+                mma_tf32_ss(dtm, ad + 2, bd + 2, idesc, 1u);
+                mma_tf32_ss(dtm, ad + 4, bd + 4, idesc, 1u);
+                mma_tf32_ss(dtm, ad + 6, bd + 6, idesc, 1u);
               }
+              acc = 1u;
+              ad += kReconABytes >> 4;
+              bd -= (uint64_t)((uint32_t)p.s * 8);
             }
-            mma_commit(&empty[ps.stage]);
+            if (elect_one()) mma_commit(&empty[ps.stage]);
             ps.advance(kReconStages);
           }
-          if (!ok) break;
-          mma_commit(&hempty[hb]);
+          if (elect_one()) mma_commit(&hempty[hb]);
+          hb ^= 1;
+          hph ^= (hb == 0);
         }
-        if (!ok) break;
-        mma_commit(&tfull[b]);
+        if (elect_one()) mma_commit(&tfull[b]);
       }
     }
   } else {
@@ -417,7 +438,8 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
   volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler, too
   if (tid == 0) {
     for (int i = 0; i < kWtStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(tfull, 1);
@@ -449,63 +471,62 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       PipeState ps;
-      bool ok = true;
-      for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int lg, cb, src, nt, ch;
         decode(item, lg, cb, src, nt, ch);
         long long s0, s1;
         chunk_range(ch, s0, s1);
-        {
-          const CUtensorMap* tmS = src ? &tmE : &tmX;
-          const int hcol = cb * 32;
-          for (long long s = s0; s < s1; ++s) {
-            if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
-            uint8_t* dst = St + (size_t)ps.stage * kWtStageBytes;
+        const CUtensorMap* tmS = src ? &tmE : &tmX;
+        const int hcol = cb * 32;
+        for (long long s = s0; s < s1; ++s) {
+          wait_uniform(ab, &empty[ps.stage], ps.phase ^ 1);
+          uint8_t* dst = St + (size_t)ps.stage * kWtStageBytes;
+          const int tau0 = (int)(s * 32);
+          if (elect_one()) {
             mbar_arrive_expect_tx(&full[ps.stage], kWtStageBytes);
-            const int tau0 = (int)(s * 32);
             tma_load_3d(dst, tmS, &full[ps.stage], 0, tau0, nt * 4);      // four 32-feature regions in one box
             // Hv rows tau0 - s*(l0+15) .. tau0 + 32; row index in Hv is tau + h
             tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], hcol, tau0 - p.s * (lg * 16 + 15) + p.h);
-            ps.advance(kWtStages);
           }
+          ps.advance(kWtStages);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_tf32(128, 256, 1, 1);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(St), 4096, 512, 1 /*SW128_BASE32B*/);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(St) + kWtABytes, (uint32_t)p.s * 128, 512, 1);
+      const uint32_t stage16 = kWtStageBytes >> 4;
       PipeState ps;
       int it = 0;
-      bool ok = true;
-      for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x, ++it) {
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
         int lg, cb, src, nt, ch;
         decode(item, lg, cb, src, nt, ch);
         long long s0, s1;
         chunk_range(ch, s0, s1);
-        if (!ab.wait(tempty, (it & 1) ^ 1)) break;
+        wait_uniform(ab, tempty, (it & 1) ^ 1);
         tc_fence_after();
         for (long long s = s0; s < s1; ++s) {
-          if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+          wait_uniform(ab, &full[ps.stage], ps.phase);
           tc_fence_after();
-          const uint32_t abase = smem_u32(St + (size_t)ps.stage * kWtStageBytes);
-          const uint32_t bbase = abase + kWtABytes;
+          const uint64_t ad = adesc0 + (uint64_t)(ps.stage * stage16);
+          const uint64_t bd1 = bdesc0 + (uint64_t)(ps.stage * stage16);      // lags 8..15 of the group: rows 0..
+          const uint64_t bd0 = bd1 + (uint64_t)((uint32_t)p.s * 64);         // lags 0..7: 8 s rows further down
+          const uint32_t acc = s > s0 ? 1u : 0u;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const uint64_t bd = make_smem_desc(bbase + (uint32_t)(p.s * (8 - 8 * g) + ks * 8) * 128,
-                                                 (uint32_t)p.s * 128, 512, 1);
-              mma_tf32_ss(tmem + g * 256, ad, bd, idesc, (s > s0 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks) {                                   // k-step: A +1 KB, B +8 rows
+            if (elect_one()) {
+              mma_tf32_ss(tmem, ad + 64 * ks, bd0 + 64 * ks, idesc, ks ? 1u : acc);
+              mma_tf32_ss(tmem + 256, ad + 64 * ks, bd1 + 64 * ks, idesc, ks ? 1u : acc);
             }
           }
-          mma_commit(&empty[ps.stage]);
+          if (elect_one()) mma_commit(&empty[ps.stage]);
           ps.advance(kWtStages);
         }
-        if (!ok) break;
-        mma_commit(tfull);
+        if (elect_one()) mma_commit(tfull);
       }
     }
   } else {

@@ -195,8 +195,33 @@ inline long long& launch_counter() {
   return n;
 }
 
+// Per-launch device times (cmf_mu_set_profiling(h, 2)): while a log is installed, every launch that goes through
+// launch_ok() or the ABI's launch_check() is followed by an event on the solver's stream; consecutive events
+// bracket one kernel (all launches of a solver are on one stream).
+struct LaunchLog {
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> pool;
+  std::vector<const char*> labels;         // labels[i]: the launch that ends at event i (labels[0]: the start mark)
+};
+inline LaunchLog*& launch_log() {
+  static thread_local LaunchLog* p = nullptr;
+  return p;
+}
+inline void log_launch(const char* what) {
+  LaunchLog* l = launch_log();
+  if (!l) return;
+  if (l->labels.size() == l->pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    l->pool.push_back(e);
+  }
+  cudaEventRecord(l->pool[l->labels.size()], l->stream);
+  l->labels.push_back(what);
+}
+
 inline int launch_ok(const char* what) {
   ++launch_counter();
+  log_launch(what);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
@@ -739,7 +764,10 @@ inline int check(TcState& s, cudaStream_t stream) {
   int e = 0;
   CMF_CUDA(cudaMemcpyAsync(&e, s.d_err, 4, cudaMemcpyDeviceToHost, stream));
   CMF_CUDA(cudaStreamSynchronize(stream));
-  CMF_CHECK(e == 0, "tensor-core kernel pipeline error %d (a barrier wait timed out)", e);
+  if (e != 0) {         // a runtime failure, not an argument error
+    set_error("tensor-core kernel pipeline error %d (a barrier wait timed out)", e);
+    return 1;
+  }
   return 0;
 }
 

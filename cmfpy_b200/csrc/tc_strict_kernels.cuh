@@ -57,6 +57,15 @@ __device__ __forceinline__ void fold_sub(float (&m)[128], uint32_t taddr) {
   }
 }
 
+// m[0..95] <- m[32..127]: lets a loop that is NOT unrolled walk the master accumulator 32 columns at a time with
+// static register indices.  (Unrolling the epilogues four-fold made these kernels ~250 KB of code; the eight
+// epilogue warps then evicted the MMA and TMA loops from the instruction caches and the tensor pipe starved:
+// ncu showed 2.6 no-instruction stalls per issue against 0.12 for the single-chain kernel.)
+__device__ __forceinline__ void rotate32(float (&m)[128]) {
+#pragma unroll
+  for (int j = 0; j < 96; ++j) m[j] = m[j + 32];
+}
+
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // The MMA side of the sub-chunk protocol: a sub-chunk goes to buffer (sc & 1); its first unit waits until the
@@ -65,38 +74,43 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: 
 // (their truncation is relative to their own small partial sum); the a_hi b_hi units after them are cut every
 // sub_units units.
 struct SubPlan {
-  long long n_units, n_cross;
-  int sub_units;
+  int n_units, n_cross, sub_units;
   __device__ __forceinline__ SubPlan(long long units, long long cross, int sub) {
-    n_units = units;
-    sub_units = sub > 0 ? sub : (int)(units < 0x7fffffff ? units : 0x7fffffff);
-    n_cross = sub > 0 ? cross : 0;
+    n_units = (int)units;
+    sub_units = sub > 0 ? sub : (int)units;
+    n_cross = sub > 0 ? (int)cross : 0;
   }
-  __device__ __forceinline__ long long n_sub() const {
+  __device__ __forceinline__ int n_sub() const {
     return (n_cross > 0 ? 1 : 0) + (n_units - n_cross + sub_units - 1) / sub_units;
   }
 };
+// (kept to a handful of 32-bit instructions per unit: ONE thread issues every MMA of the CTA, and at four MMAs -
+// 512 tensor-pipe cycles - per unit its own instruction stream is what the tensor pipe ends up waiting for)
 struct SubIssue {
-  long long sc = 0;       // sub-chunks issued so far by this CTA
-  int us = 0;             // units already in the current sub-chunk
-  __device__ __forceinline__ bool begin_unit(const Abort& ab, uint64_t* sempty, uint32_t tmem, uint32_t& dtm) {
-    const int b = (int)(sc & 1);
+  uint32_t b = 0, ph = 0;   // buffer of the current sub-chunk; parity of that buffer's use count
+  int us = 0;               // units already in the current sub-chunk
+  __device__ __forceinline__ uint32_t begin_unit(const Abort& ab, uint64_t* sempty, uint32_t tmem) {
     if (us == 0) {
-      if (!ab.wait(&sempty[b], (uint32_t)((sc >> 1) & 1) ^ 1)) return false;
+      wait_uniform(ab, &sempty[b], ph ^ 1);
       tc_fence_after();
     }
-    dtm = tmem + (uint32_t)b * 256;
-    return true;
+    return tmem + b * 256;
   }
   // `done` = units of the item issued so far, this one included
-  __device__ __forceinline__ void end_unit(uint64_t* sfull, const SubPlan& pl, long long done) {
+  __device__ __forceinline__ void end_unit(uint64_t* sfull, const SubPlan& pl, int done) {
     ++us;
     if (done == pl.n_units || done == pl.n_cross || (done > pl.n_cross && us == pl.sub_units)) {
-      mma_commit(&sfull[sc & 1]);
-      ++sc;
+      if (elect_one()) mma_commit(&sfull[b]);
       us = 0;
+      b ^= 1;
+      ph ^= (b == 0);
     }
   }
+};
+// the epilogue side of the same sequence
+struct SubDrain {
+  uint32_t b = 0, ph = 0;
+  __device__ __forceinline__ void next() { b ^= 1; ph ^= (b == 0); }
 };
 
 // ==========================================================================
@@ -122,7 +136,8 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
   __shared__ double red[8];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler, too
   if (tid == 0) {
     for (int i = 0; i < kReconStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
@@ -148,9 +163,10 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   if (warp == 0) {
     reg_dec<kSCtlRegs>();
     // ---------------- TMA producer ----------------
-    if (lane == 0) {
+    {
+      // all 32 lanes run the loop in uniform control flow; one elected lane issues the TMA instructions
+      // (see mma_tf32_ss in sm100_ptx.cuh for why)
       PipeState ps;
-      bool ok = true;
       struct Chunk { long long tile; int cb, lb; bool valid; };
       auto next_chunk = [&](Chunk c) {
         if (++c.lb >= n_lb) {
@@ -159,45 +175,53 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         }
         return c;
       };
-      // window of chunk number wc; `block` = false: only if its buffer is already free
-      auto issue_window = [&](const Chunk& c, long long wc, bool block, bool& done) -> bool {
+      // window of chunk number wc (its buffer is known to be free)
+      auto issue_window = [&](const Chunk& c, long long wc) {
         const int hb = (int)(wc & 1);
-        const uint32_t par = (uint32_t)((wc >> 1) & 1) ^ 1;
-        if (!block && !mbar_try_wait(&hempty[hb], par)) return true;
-        if (!ab.wait(&hempty[hb], par)) return false;
         const long long tt = c.tile / p.n_tiles_n;
-        mbar_arrive_expect_tx(&hfull[hb], hbytes);
         uint8_t* hdst = Hs + (size_t)hb * hbytes;
         const X3Sel sel = x3_select(p.x3, p.cbx, p.lo_off, p.lo_off_b, c.cb);
         const int l1 = min(L, (c.lb + 1) * LB);                 // window row 0 holds lag l1 - 1 of this block
-        for (int rb = 0; rb < wrows / 64; ++rb)
-          tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], sel.cbr * 32 + sel.b_off,
-                      (int)(tt * 256 + p.h_shift + p.s * (L - l1) + rb * 64));
-        done = true;
-        return true;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&hfull[hb], hbytes);
+          for (int rb = 0; rb < wrows / 64; ++rb)
+            tma_load_2d(hdst + (size_t)rb * 64 * 128, &tmH, &hfull[hb], sel.cbr * 32 + sel.b_off,
+                        (int)(tt * 256 + p.h_shift + p.s * (L - l1) + rb * 64));
+        }
       };
       Chunk cur{(long long)blockIdx.x, 0, 0, (long long)blockIdx.x < p.n_tiles};
       long long wc = 0;
-      bool dummy = false;
-      if (cur.valid) ok = issue_window(cur, 0, true, dummy);
-      while (cur.valid && ok) {
+      if (cur.valid) issue_window(cur, 0);
+      while (cur.valid) {
         const Chunk nxt = next_chunk(cur);
         bool prefetched = !nxt.valid;
+        const int nhb = (int)((wc + 1) & 1);
+        const uint32_t npar = (uint32_t)(((wc + 1) >> 1) & 1) ^ 1;
         const int nt = (int)(cur.tile % p.n_tiles_n);
         const X3Sel sel = x3_select(p.x3, p.cbx, p.lo_off, p.lo_off_b, cur.cb);
         const int l0 = cur.lb * LB, l1 = min(L, l0 + LB);
         for (int l = l0; l < l1; l += kReconLagsPerStage) {
-          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+          wait_uniform(ab, &empty[ps.stage], ps.phase ^ 1);
           const int nl = min(kReconLagsPerStage, l1 - l);
-          mbar_arrive_expect_tx(&full[ps.stage], nl * kReconABytes);
-          for (int u = 0; u < nl; ++u)
-            tma_load_2d(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes, &tmW, &full[ps.stage],
-                        (sel.cbr % p.cb_cols) * 32 + sel.a_off, (l + u + sel.cbr / p.cb_cols) * p.Np + nt * 128);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[ps.stage], nl * kReconABytes);
+            for (int u = 0; u < nl; ++u)
+              tma_load_2d(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes, &tmW, &full[ps.stage],
+                          (sel.cbr % p.cb_cols) * 32 + sel.a_off, (l + u + sel.cbr / p.cb_cols) * p.Np + nt * 128);
+          }
           ps.advance(kReconStages);
-          // the next window goes out as soon as its buffer is free; waiting for it here would starve the W ring
-          if (!prefetched && !issue_window(nxt, wc + 1, false, prefetched)) { ok = false; break; }
+          // The next window goes out as soon as its buffer is free.  (Blocking on it here, as round 1 did after the
+          // second stage of a chunk, parks the producer until the MMAs of the PREVIOUS chunk retire while the W ring
+          // runs dry.)
+          if (!prefetched && __shfl_sync(0xffffffffu, (int)mbar_test_wait(&hempty[nhb], npar), 0)) {
+            issue_window(nxt, wc + 1);
+            prefetched = true;
+          }
         }
-        if (ok && !prefetched) ok = issue_window(nxt, wc + 1, true, prefetched);
+        if (!prefetched) {
+          wait_uniform(ab, &hempty[nhb], npar);
+          issue_window(nxt, wc + 1);
+        }
         cur = nxt;
         ++wc;
       }
@@ -205,42 +229,47 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   } else if (warp == 1) {
     reg_dec<kSCtlRegs>();
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_tf32(128, 256, 0, 0);
+      // descriptors differ only in their 14-bit start-address field (bytes >> 4): one add each per MMA
+      const uint64_t adesc0 = make_smem_desc(smem_u32(As), 16, 1024, kSwz128);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(Hs), 16, 1024, kSwz128);
       PipeState ps;
       SubIssue si;
-      long long wcount = 0;
-      bool ok = true;
-      for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+      uint32_t hb = 0, hph = 0;
+      for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         int unit = 0;
-        for (int chunk = 0; chunk < p.CB * n_lb && ok; ++chunk, ++wcount) {
-          const int cb = chunk / n_lb, lb = chunk - cb * n_lb;
+        for (int chunk = 0; chunk < p.CB * n_lb; ++chunk) {
+          const int lb = chunk % n_lb;
           const int l0 = lb * LB, l1 = min(L, l0 + LB);
-          const int hb = (int)(wcount & 1);
-          if (!ab.wait(&hfull[hb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
+          wait_uniform(ab, &hfull[hb], hph);
           tc_fence_after();
-          const uint32_t hbase = smem_u32(Hs + (size_t)hb * hbytes);
-          for (int l = l0; l < l1 && ok; l += kReconLagsPerStage) {
-            if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+          const uint64_t bwin = bdesc0 + (uint64_t)((hb * hbytes) >> 4);
+          uint32_t brow8 = (uint32_t)(p.s * (l1 - 1 - l0)) * 8;              // (row shift * 128 B) >> 4
+          for (int l = l0; l < l1; l += kReconLagsPerStage) {
+            wait_uniform(ab, &full[ps.stage], ps.phase);
             tc_fence_after();
             const int nl = min(kReconLagsPerStage, l1 - l);
+            uint64_t ad = adesc0 + (uint64_t)(ps.stage * (kReconStageBytes >> 4));
             for (int u = 0; u < nl; ++u) {
-              uint32_t dtm;
-              if (!si.begin_unit(ab, sempty, tmem, dtm)) { ok = false; break; }
-              const uint32_t abase = smem_u32(As + (size_t)ps.stage * kReconStageBytes + u * kReconABytes);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ad = make_smem_desc(abase + ks * 32, 16, 1024, kSwz128);
-                const uint64_t bd = make_smem_desc(hbase + (uint32_t)(p.s * (l1 - 1 - l - u)) * 128 + ks * 32, 16, 1024, kSwz128);
-                mma_tf32_ss(dtm, ad, bd, idesc, (si.us | ks) != 0 ? 1u : 0u);
+              const uint32_t dtm = si.begin_unit(ab, sempty, tmem);
+              const uint64_t bd = bwin + brow8;
+              if (elect_one()) {
+                mma_tf32_ss(dtm, ad, bd, idesc, si.us != 0 ? 1u : 0u);
+                mma_tf32_ss(dtm, ad + 2, bd + 2, idesc, 1u);
+                mma_tf32_ss(dtm, ad + 4, bd + 4, idesc, 1u);
+                mma_tf32_ss(dtm, ad + 6, bd + 6, idesc, 1u);
               }
               si.end_unit(sfull, plan, ++unit);
+              ad += kReconABytes >> 4;
+              brow8 -= (uint32_t)p.s * 8;
             }
-            mma_commit(&empty[ps.stage]);
+            if (elect_one()) mma_commit(&empty[ps.stage]);
             ps.advance(kReconStages);
           }
-          if (!ok) break;
-          mma_commit(&hempty[hb]);
+          if (elect_one()) mma_commit(&hempty[hb]);
+          hb ^= 1;
+          hph ^= (hb == 0);
         }
       }
     }
@@ -251,23 +280,22 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     // ---------------- epilogue: fold sub-chunks, then master -> est^T, fused loss ----------------
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int half = (warp - 4) >> 2;             // column half of the 256-column buffers
-    const int n_sub = (int)plan.n_sub();
+    const int n_sub = plan.n_sub();
     float m[128];
     double loss_acc = 0.0;
-    long long sc = 0;
+    SubDrain sd;
     bool ok = true;
     for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
       const int nt = (int)(tile % p.n_tiles_n);
       const long long tt = tile / p.n_tiles_n;
-      for (int sub = 0; sub < n_sub; ++sub, ++sc) {
-        const int b = (int)(sc & 1);
-        if (!wait_relaxed(ab, &sfull[b], (uint32_t)((sc >> 1) & 1))) { ok = false; break; }
+      for (int sub = 0; sub < n_sub; ++sub, sd.next()) {
+        if (!wait_relaxed(ab, &sfull[sd.b], sd.ph)) { ok = false; break; }
         tc_fence_after();
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + half * 128);
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(sd.b * 256 + half * 128);
         if (sub == 0) fold_sub<true>(m, taddr); else fold_sub<false>(m, taddr);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sempty[b]);
+        if (lane == 0) mbar_arrive(&sempty[sd.b]);
       }
       if (!ok) break;
       const int n = nt * 128 + q * 32 + lane;
@@ -278,7 +306,7 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       float* __restrict__ Et = p.Et;
       float* __restrict__ Elo = p.Elo;
       const size_t np = (size_t)p.ld_out;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const long long tau0 = tt * 256 + half * 128 + c * 32;
         const size_t off0 = (size_t)tau0 * np + n;
@@ -292,7 +320,7 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
               const int k = (int)(tau % p.w_kp);
               if (tau < p.t_valid)
                 *reinterpret_cast<float4*>(Et + ((size_t)l * p.w_np + n) * p.w_kp + k) =
-                    make_float4(m[c * 32 + 4 * j4], m[c * 32 + 4 * j4 + 1], m[c * 32 + 4 * j4 + 2], m[c * 32 + 4 * j4 + 3]);
+                    make_float4(m[4 * j4], m[4 * j4 + 1], m[4 * j4 + 2], m[4 * j4 + 3]);
             }
           }
         } else if (n_ok) {
@@ -307,7 +335,7 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const long long tau = tau0 + j;
-            float v = m[c * 32 + j];
+            float v = m[j];
             if (tau >= p.t_valid) v = 0.f;
             if (tau < p.t_own) {
               const float d = v - x[j];
@@ -325,6 +353,7 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             }
           }
         }
+        rotate32(m);
       }
       loss_acc += (double)tile_loss;
     }
@@ -369,7 +398,8 @@ tc_wterms_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint32_t* tmem_slot = (uint32_t*)(sempty + 2);
   volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler, too
   if (tid == 0) {
     for (int i = 0; i < kWtStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 8); }
@@ -402,26 +432,27 @@ tc_wterms_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
   if (warp == 0) {
     reg_dec<kSCtlRegs>();
-    if (lane == 0) {
+    {
       PipeState ps;
-      bool ok = true;
-      for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int lg, cb, src, nt, ch;
         decode(item, lg, cb, src, nt, ch);
         long long s0, s1;
         chunk_range(ch, s0, s1);
         // 3xTF32: (S lo, H hi), (S hi, H lo), (S hi, H hi)
-        for (int combo = p.x3 ? 0 : 2; combo < 3 && ok; ++combo) {
+        for (int combo = p.x3 ? 0 : 2; combo < 3; ++combo) {
           const CUtensorMap* tmS = combo == 0 ? (src ? &tmElo : &tmXlo) : (src ? &tmE : &tmX);
           const int hcol = cb * 32 + (combo == 1 ? p.lo_off : 0);
           for (long long s = s0; s < s1; ++s) {
-            if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+            wait_uniform(ab, &empty[ps.stage], ps.phase ^ 1);
             uint8_t* dst = St + (size_t)ps.stage * stage_bytes;
-            mbar_arrive_expect_tx(&full[ps.stage], stage_bytes);
             const int tau0 = (int)(s * 32);
-            tma_load_3d(dst, tmS, &full[ps.stage], 0, tau0, nt * 4);      // four 32-feature regions in one box
-            // Hv rows tau0 - s*(8 lg + 7) .. tau0 + 32; row index in Hv is tau + h
-            tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], hcol, tau0 - p.s * (lg * 8 + 7) + p.h);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full[ps.stage], stage_bytes);
+              tma_load_3d(dst, tmS, &full[ps.stage], 0, tau0, nt * 4);      // four 32-feature regions in one box
+              // Hv rows tau0 - s*(8 lg + 7) .. tau0 + 32; row index in Hv is tau + h
+              tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], hcol, tau0 - p.s * (lg * 8 + 7) + p.h);
+            }
             ps.advance(kWtStages);
           }
         }
@@ -429,34 +460,35 @@ tc_wterms_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
   } else if (warp == 1) {
     reg_dec<kSCtlRegs>();
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_tf32(128, 256, 1, 1);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(St), 4096, 512, 1 /*SW128_BASE32B*/);
+      // N-atom a starts a * s rows further down: lag 8 lg + 7 - a
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(St) + kWtABytes, (uint32_t)p.s * 128, 512, 1);
+      const uint32_t stage16 = stage_bytes >> 4;
       PipeState ps;
       SubIssue si;
-      bool ok = true;
-      for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int lg, cb, src, nt, ch;
         decode(item, lg, cb, src, nt, ch);
         long long s0, s1;
         chunk_range(ch, s0, s1);
-        const long long n_units = n_pass * (s1 - s0);
+        const int n_units = (int)(n_pass * (s1 - s0));
         const SubPlan plan(n_units, p.x3 ? 2 * (s1 - s0) : 0, p.sub_units);
-        for (long long u = 0; u < n_units; ++u) {
-          if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+        for (int u = 0; u < n_units; ++u) {
+          wait_uniform(ab, &full[ps.stage], ps.phase);
           tc_fence_after();
-          uint32_t dtm;
-          if (!si.begin_unit(ab, sempty, tmem, dtm)) { ok = false; break; }
-          const uint32_t abase = smem_u32(St + (size_t)ps.stage * stage_bytes);
-          const uint32_t bbase = abase + kWtABytes;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
-            // N-atom a starts a * s rows further down: lag 8 lg + 7 - a
-            const uint64_t bd = make_smem_desc(bbase + (uint32_t)(ks * 8) * 128, (uint32_t)p.s * 128, 512, 1);
-            mma_tf32_ss(dtm, ad, bd, idesc, (si.us | ks) != 0 ? 1u : 0u);
+          const uint32_t dtm = si.begin_unit(ab, sempty, tmem);
+          const uint64_t ad = adesc0 + (uint64_t)(ps.stage * stage16);
+          const uint64_t bd = bdesc0 + (uint64_t)(ps.stage * stage16);
+          if (elect_one()) {
+            mma_tf32_ss(dtm, ad, bd, idesc, si.us != 0 ? 1u : 0u);      // k-step ks: A +1 KB, B +8 rows
+            mma_tf32_ss(dtm, ad + 64, bd + 64, idesc, 1u);
+            mma_tf32_ss(dtm, ad + 128, bd + 128, idesc, 1u);
+            mma_tf32_ss(dtm, ad + 192, bd + 192, idesc, 1u);
           }
           si.end_unit(sfull, plan, u + 1);
-          mma_commit(&empty[ps.stage]);
+          if (elect_one()) mma_commit(&empty[ps.stage]);
           ps.advance(kWtStages);
         }
       }
@@ -468,7 +500,7 @@ tc_wterms_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     float m[128];
-    long long sc = 0;
+    SubDrain sd;
     bool ok = true;
     for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
       int lg, cb, src, nt, ch;
@@ -476,21 +508,20 @@ tc_wterms_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       long long s0, s1;
       chunk_range(ch, s0, s1);
       const SubPlan plan(n_pass * (s1 - s0), p.x3 ? 2 * (s1 - s0) : 0, p.sub_units);
-      const long long n_sub = plan.n_sub();
-      for (long long sub = 0; sub < n_sub; ++sub, ++sc) {
-        const int b = (int)(sc & 1);
-        if (!wait_relaxed(ab, &sfull[b], (uint32_t)((sc >> 1) & 1))) { ok = false; break; }
+      const int n_sub = plan.n_sub();
+      for (int sub = 0; sub < n_sub; ++sub, sd.next()) {
+        if (!wait_relaxed(ab, &sfull[sd.b], sd.ph)) { ok = false; break; }
         tc_fence_after();
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + half * 128);
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(sd.b * 256 + half * 128);
         if (sub == 0) fold_sub<true>(m, taddr); else fold_sub<false>(m, taddr);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sempty[b]);
+        if (lane == 0) mbar_arrive(&sempty[sd.b]);
       }
       if (!ok) break;
       const int n = nt * 128 + q * 32 + lane;
       float* obase = p.part + ((long long)ch * p.n_src + src) * p.per_src;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {              // 4 column blocks of 32 = one virtual lag each
         const int a = half * 4 + c;
         const int lv = lg * 8 + 7 - a;
@@ -499,33 +530,19 @@ tc_wterms_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             float4* o = reinterpret_cast<float4*>(obase + ((long long)lv * p.Np + n) * p.Kp + cb * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              o[j] = make_float4(m[c * 32 + 4 * j], m[c * 32 + 4 * j + 1], m[c * 32 + 4 * j + 2], m[c * 32 + 4 * j + 3]);
-          } else if (p.s == 2) {                  // Kp = 16: two real lags of 16 components
+              o[j] = make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
+          } else {                                // Kp = 16 / 8: s real lags of Kp components each
+            const int kq = p.Kp / 4;              // float4 per real lag
 #pragma unroll
-            for (int dl = 0; dl < 2; ++dl) {
-              const int l = 2 * lv + dl;
-              if (l < p.L) {
-                float4* o = reinterpret_cast<float4*>(obase + ((long long)l * p.Np + n) * 16);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  o[j] = make_float4(m[c * 32 + 16 * dl + 4 * j], m[c * 32 + 16 * dl + 4 * j + 1],
-                                     m[c * 32 + 16 * dl + 4 * j + 2], m[c * 32 + 16 * dl + 4 * j + 3]);
-              }
-            }
-          } else {                                // s == 4, Kp = 8: four real lags of 8 components
-#pragma unroll
-            for (int dl = 0; dl < 4; ++dl) {
-              const int l = 4 * lv + dl;
-              if (l < p.L) {
-                float4* o = reinterpret_cast<float4*>(obase + ((long long)l * p.Np + n) * 8);
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                  o[j] = make_float4(m[c * 32 + 8 * dl + 4 * j], m[c * 32 + 8 * dl + 4 * j + 1],
-                                     m[c * 32 + 8 * dl + 4 * j + 2], m[c * 32 + 8 * dl + 4 * j + 3]);
-              }
+            for (int j = 0; j < 8; ++j) {
+              const int dl = j / kq, l = p.s * lv + dl;
+              if (l < p.L)
+                reinterpret_cast<float4*>(obase + ((long long)l * p.Np + n) * p.Kp)[j - dl * kq] =
+                    make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
             }
           }
         }
+        rotate32(m);
       }
     }
   }
@@ -604,7 +621,8 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   uint32_t* tmem_slot = (uint32_t*)(sempty + 2);
   volatile int* abort_flag = (volatile int*)(tmem_slot + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler, too
   if (tid == 0) {
     for (int i = 0; i < n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
@@ -627,9 +645,8 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 
   if (warp == 0) {
     reg_dec<kSCtlRegs>();
-    if (lane == 0) {
+    {
       PipeState ps;
-      bool ok = true;
       // chunks = (item, operand pass, 32-feature chunk) in execution order; chunk c uses window buffer c & 1
       struct Chunk { long long item; int nc, combo; bool valid; };
       auto make_chunk = [&](long long item) { return Chunk{item, 0, p.x3 ? 0 : 2, item < p.n_items}; };
@@ -640,80 +657,89 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         }
         return c;
       };
-      auto issue_window = [&](const Chunk& c, long long wc, bool block, bool& done) -> bool {
+      // window of chunk number wc (its buffer is known to be free)
+      auto issue_window = [&](const Chunk& c, long long wc) {
         const int wb = (int)(wc & 1);
-        const uint32_t par = (uint32_t)((wc >> 1) & 1) ^ 1;
-        if (!block && !mbar_try_wait(&wempty[wb], par)) return true;
-        if (!ab.wait(&wempty[wb], par)) return false;
         const long long tile = c.item / p.n_src;
         const int src = (int)(c.item % p.n_src);
-        mbar_arrive_expect_tx(&wfull[wb], wbytes);
         uint8_t* wdst = Ws + (size_t)wb * wbytes;
         const CUtensorMap* tmS = src ? (c.combo == 1 ? &tmElo : &tmE) : (c.combo == 1 ? &tmXlo : &tmX);
-        for (int rb = 0; rb < wrows / 32; ++rb)
-          tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], c.nc * 32, (int)(tile * 256 + rb * 32));
-        done = true;
-        return true;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&wfull[wb], wbytes);
+          for (int rb = 0; rb < wrows / 32; ++rb)
+            tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], c.nc * 32, (int)(tile * 256 + rb * 32));
+        }
       };
       Chunk cur = make_chunk(blockIdx.x);
       long long wc = 0;
-      bool dummy = false;
-      if (cur.valid) ok = issue_window(cur, 0, true, dummy);
-      while (cur.valid && ok) {
+      if (cur.valid) issue_window(cur, 0);
+      while (cur.valid) {
         const Chunk nxt = next_chunk(cur);
         bool prefetched = !nxt.valid;
+        const int nwb = (int)((wc + 1) & 1);
+        const uint32_t npar = (uint32_t)(((wc + 1) >> 1) & 1) ^ 1;
         for (int j = 0; j < J; j += kHtLagsPerStage) {
-          if (!ab.wait(&empty[ps.stage], ps.phase ^ 1)) { ok = false; break; }
+          wait_uniform(ab, &empty[ps.stage], ps.phase ^ 1);
           // one box: lags j, j+1 x regions (lag group, column block) x 32 features x 32 components (lags >= J
           // and features >= Np arrive as zeros)
-          mbar_arrive_expect_tx(&full[ps.stage], kHtStageBytes);
-          tma_load_5d(As + (size_t)ps.stage * kHtStageBytes, &tmW, &full[ps.stage], 0, cur.nc * 32,
-                      cur.combo == 0 ? p.lo_off / 32 : 0, 0, j);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[ps.stage], kHtStageBytes);
+            tma_load_5d(As + (size_t)ps.stage * kHtStageBytes, &tmW, &full[ps.stage], 0, cur.nc * 32,
+                        cur.combo == 0 ? p.lo_off / 32 : 0, 0, j);
+          }
           ps.advance(n_stages);
           // the next window goes out as soon as its buffer is free; waiting for it here would starve the W ring
-          if (!prefetched && !issue_window(nxt, wc + 1, false, prefetched)) { ok = false; break; }
+          if (!prefetched && __shfl_sync(0xffffffffu, (int)mbar_test_wait(&wempty[nwb], npar), 0)) {
+            issue_window(nxt, wc + 1);
+            prefetched = true;
+          }
         }
-        if (ok && !prefetched) ok = issue_window(nxt, wc + 1, true, prefetched);
+        if (!prefetched) {
+          wait_uniform(ab, &wempty[nwb], npar);
+          issue_window(nxt, wc + 1);
+        }
         cur = nxt;
         ++wc;
       }
     }
   } else if (warp == 1) {
     reg_dec<kSCtlRegs>();
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_tf32(128, 256, 1, 0);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(As), 4096, 512, 1 /*SW128_BASE32B*/);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(Ws), 16, 1024, kSwz128);
       PipeState ps;
       SubIssue si;
-      long long wcount = 0;
-      bool ok = true;
-      for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
+      uint32_t wb = 0, wph = 0;
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int unit = 0;
-        for (int chunk = 0; chunk < n_pass * p.n_chunks_n && ok; ++chunk, ++wcount) {
-          const int wb = (int)(wcount & 1);
-          if (!ab.wait(&wfull[wb], (uint32_t)((wcount >> 1) & 1))) { ok = false; break; }
+        for (int chunk = 0; chunk < n_pass * p.n_chunks_n; ++chunk) {
+          wait_uniform(ab, &wfull[wb], wph);
           tc_fence_after();
-          const uint32_t wbase = smem_u32(Ws + (size_t)wb * wbytes);
-          for (int j = 0; j < J && ok; j += kHtLagsPerStage) {
-            if (!ab.wait(&full[ps.stage], ps.phase)) { ok = false; break; }
+          uint64_t bd = bdesc0 + (uint64_t)((wb * wbytes) >> 4);             // lag j: row shift s * j
+          for (int j = 0; j < J; j += kHtLagsPerStage) {
+            wait_uniform(ab, &full[ps.stage], ps.phase);
             tc_fence_after();
             const int nl = min(kHtLagsPerStage, J - j);
+            uint64_t ad = adesc0 + (uint64_t)(ps.stage * (kHtStageBytes >> 4));
             for (int u = 0; u < nl; ++u) {
-              uint32_t dtm;
-              if (!si.begin_unit(ab, sempty, tmem, dtm)) { ok = false; break; }
-              const uint32_t abase = smem_u32(As + (size_t)ps.stage * kHtStageBytes + u * kHtABytes);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ad = make_smem_desc(abase + ks * 1024, 4096, 512, 1 /*SW128_BASE32B*/);
-                const uint64_t bd = make_smem_desc(wbase + (uint32_t)(p.s * (j + u)) * 128 + ks * 32, 16, 1024, kSwz128);
-                mma_tf32_ss(dtm, ad, bd, idesc, (si.us | ks) != 0 ? 1u : 0u);
+              const uint32_t dtm = si.begin_unit(ab, sempty, tmem);
+              if (elect_one()) {
+                mma_tf32_ss(dtm, ad, bd, idesc, si.us != 0 ? 1u : 0u);  // k-step ks: A +1 KB, B +32 B
+                mma_tf32_ss(dtm, ad + 64, bd + 2, idesc, 1u);
+                mma_tf32_ss(dtm, ad + 128, bd + 4, idesc, 1u);
+                mma_tf32_ss(dtm, ad + 192, bd + 6, idesc, 1u);
               }
               si.end_unit(sfull, plan, ++unit);
+              ad += kHtABytes >> 4;
+              bd += (uint64_t)(p.s * 8);
             }
-            mma_commit(&empty[ps.stage]);
+            if (elect_one()) mma_commit(&empty[ps.stage]);
             ps.advance(n_stages);
           }
-          if (!ok) break;
-          mma_commit(&wempty[wb]);
+          if (elect_one()) mma_commit(&wempty[wb]);
+          wb ^= 1;
+          wph ^= (wb == 0);
         }
       }
     }
@@ -725,27 +751,26 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     const int q = warp & 3;                   // region (lag group, column block) of this warp's 32 TMEM lanes
     const int half = e >> 2;
     const int etid = tid - 128;               // 0..255
-    const int n_sub = (int)plan.n_sub();
+    const int n_sub = plan.n_sub();
     const int gl = q / p.CB;                  // lag group
     const int dl = p.s > 1 ? lane / p.Kp : 0; // real lag inside a folded virtual lag
     const int kcol = p.s > 1 ? lane % p.Kp : (q % p.CB) * 32 + lane;
     const int u0 = half * 128 + (n_glag - 1 - gl) * p.s * J + (p.s - 1 - dl);     // R row of this thread's column 0
     const int U = 256 + p.hd;
     float m[128];
-    long long sc = 0;
+    SubDrain sd;
     bool ok = true;
     for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
       const long long tile = item / p.n_src;
       const int src = (int)(item % p.n_src);
-      for (int sub = 0; sub < n_sub; ++sub, ++sc) {
-        const int b = (int)(sc & 1);
-        if (!wait_relaxed(ab, &sfull[b], (uint32_t)((sc >> 1) & 1))) { ok = false; break; }
+      for (int sub = 0; sub < n_sub; ++sub, sd.next()) {
+        if (!wait_relaxed(ab, &sfull[sd.b], sd.ph)) { ok = false; break; }
         tc_fence_after();
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + half * 128);
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(sd.b * 256 + half * 128);
         if (sub == 0) fold_sub<true>(m, taddr); else fold_sub<false>(m, taddr);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sempty[b]);
+        if (lane == 0) mbar_arrive(&sempty[sd.b]);
       }
       if (!ok) break;
       float* outs = p.out + (size_t)src * p.TO * p.Kp;
@@ -755,10 +780,14 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         float* o = outs + (size_t)(base + half * 128) * p.Kp + kcol;
         const long long left = p.TO - (base + half * 128);
         const int rows = left > 128 ? 128 : (int)left;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          if (i < rows) *o = m[i];
-          o += p.Kp;
+          for (int i = 0; i < 32; ++i) {
+            if (c * 32 + i < rows) *o = m[i];
+            o += p.Kp;
+          }
+          rotate32(m);
         }
         continue;
       }
@@ -771,13 +800,17 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       epi_bar();
       for (int w = 0; w < 8; ++w) {
         if (w == e) {
-          for (int d = 0; d < p.s; ++d) {          // folded lags of one warp overlap in R: one at a time
-            if (d == dl) {
-              float* r = R + (size_t)u0 * p.Kp + kcol;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float* r = R + (size_t)(u0 + c * 32) * p.Kp + kcol;
+            for (int d = 0; d < p.s; ++d) {        // folded lags of one warp overlap in R: one at a time
+              if (d == dl) {
 #pragma unroll
-              for (int i = 0; i < 128; ++i) r[(size_t)i * p.Kp] += m[i];
+                for (int i = 0; i < 32; ++i) r[i * p.Kp] += m[i];
+              }
+              __syncwarp();
             }
-            __syncwarp();
+            rotate32(m);
           }
         }
         epi_bar();

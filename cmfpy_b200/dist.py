@@ -219,6 +219,10 @@ class DeviceShard:
         _lib.check(self._lib.cmf_mu_kernel_ms(self._h, out))
         return dict(recon=out[0], w_terms=out[1], h_terms=out[2], elementwise=out[3])
 
+    def launch_table(self):
+        """{kernel label: (launches, total ms)} since set_profiling(2)."""
+        return _lib.launch_table(self._lib, self._h)
+
     def close(self):
         if self._h is not None and self._h.value:
             self._lib.cmf_mu_destroy(self._h)
@@ -467,6 +471,9 @@ class ShardedMultUpdate:
     def set_profiling(self, on):
         self._profiling = bool(on)
         self.engine.set_profiling(on)
+
+    def launch_table(self):
+        return self.engine.launch_table() if hasattr(self.engine, "launch_table") else {}
 
     def kernel_ms(self):
         """Device time per phase during the last update_many (CUDA events)."""

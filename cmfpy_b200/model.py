@@ -87,7 +87,10 @@ class CMF(object):
         self.loss_hist = [algorithm.loss]
         self.time_hist = [0.0]
 
-        if algorithm.tol == 0 and not self.verbose and self.n_iter_max > 0 and getattr(algorithm, "batchable", True):
+        # (patience == 1 makes np.diff(loss_hist[-1:]) empty and np.all([]) True: the reference then stops after the
+        # first iteration whatever tol is, so only patience >= 2 may skip the test)
+        if (algorithm.tol == 0 and algorithm.patience >= 2 and not self.verbose and self.n_iter_max > 0 and
+                getattr(algorithm, "batchable", True)):
             losses, secs = algorithm.update_many(self.n_iter_max, return_times=True)
             for loss, dur in zip(losses, secs):
                 self.time_hist.append(self.time_hist[-1] + dur)
@@ -232,6 +235,30 @@ def load_cmfjl_model(path):
     return data, model
 
 
+def save_cmfjl_model(path, model, data=None):
+    """Writes a fitted model in the HDF5 layout of cmf.jl, the inverse of `load_cmfjl_model` (reference
+    model.py:346-363): datasets `data`, `W`, `H`, `time_hist`, `loss_hist`, stored the way Julia's column-major
+    arrays appear to a row-major reader (`data`, `H` transposed, the lag and component axes of `W` swapped).
+    Needs h5py, like the reference's loader."""
+    try:
+        import h5py
+    except ImportError as e:
+        raise ImportError("save_cmfjl_model needs h5py, which is not installed") from e
+    with h5py.File(path, "w") as f:
+        if data is not None:
+            f["data"] = np.ascontiguousarray(np.asarray(data, dtype=np.float64).T)
+        f["W"] = np.ascontiguousarray(np.swapaxes(np.asarray(model.motifs, dtype=np.float64), 0, 2))
+        f["H"] = np.ascontiguousarray(np.asarray(model.factors, dtype=np.float64).T)
+        f["time_hist"] = np.asarray(getattr(model, "time_hist", []), dtype=np.float64)
+        f["loss_hist"] = np.asarray(getattr(model, "loss_hist", []), dtype=np.float64)
+
+
+def _npz_path(path):
+    """np.savez appends '.npz' to a name that lacks it; save and load must agree on the file name."""
+    path = str(path)
+    return path if path.endswith(".npz") else path + ".npz"
+
+
 def save_model(path, model, data=None):
     """Checkpoint of a fitted model under the dataset names cmf.jl uses (`data`, `W`, `H`, `time_hist`,
     `loss_hist`), in this package's own row-major layouts, as a compressed .npz.  `data` is optional."""
@@ -240,13 +267,13 @@ def save_model(path, model, data=None):
            "loss_hist": np.asarray(getattr(model, "loss_hist", []))}
     if data is not None:
         out["data"] = np.asarray(data)
-    np.savez_compressed(path, **out)
+    np.savez_compressed(_npz_path(path), **out)
 
 
 def load_model(path, **cmf_kwargs):
     """Inverse of `save_model`: returns (data or None, model).  Resume a fit with
     `CMF(K, L, initW=model.motifs, initH=model.factors, ...).fit(data)`."""
-    with np.load(path) as f:
+    with np.load(_npz_path(path)) as f:
         W, H = f["W"], f["H"]
         L, _, K = W.shape
         model = CMF(K, L, **cmf_kwargs)

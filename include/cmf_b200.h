@@ -192,6 +192,13 @@ int cmf_mu_peer_export(cmf_mu_t* h, void* blob);
 int cmf_mu_peer_attach(cmf_mu_t* h, int rank, int world, const void* blobs);
 int cmf_mu_peer_detach(cmf_mu_t* h);
 int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out);
+/* The same wiring when all shards live in ONE process (CMF(..., devices=[0, 1, ...]), reference plug-in point
+ * cmfpy/model.py:80-82, :146): `handles` are the `world` solvers in rank order, each on its own GPU; peers are
+ * reached through cudaDeviceEnablePeerAccess instead of CUDA IPC.  One host thread per device then calls
+ * cmf_mu_step_sharded.  cmf_mu_halo_exchange_peer runs one exchange of the L-1 boundary columns of H through
+ * peer memory (every rank calls it, concurrently): the halos of the initial factors. */
+int cmf_mu_peer_attach_local(cmf_mu_t* h, int rank, int world, cmf_mu_t* const* handles);
+int cmf_mu_halo_exchange_peer(cmf_mu_t* h);
 
 /* ---- gradient solvers: GradDescent / BlockDescent, algs/gradient_descent.py -- */
 /* Their gradients are the MU terms: gW[l] = s_T_dot(resids, H, l) = den_W - num_W
@@ -246,6 +253,10 @@ const char* cmf_mu_path_name(cmf_mu_t* h);
 int cmf_mu_kernel_ms(cmf_mu_t* h, float out[4]);
 /* Toggle per-kernel event timing inside cmf_mu_step (off by default).       */
 int cmf_mu_set_profiling(cmf_mu_t* h, int on);
+/* on = 2: additionally one CUDA event after EVERY kernel launch of the following steps; cmf_mu_launch_table then
+ * returns one text line "label launches total_ms" per kernel label (a measurement aid of bench.py: the per-kernel
+ * roofline table; the reference only has wall-clock time_hist, cmfpy/model.py:160-167). */
+int cmf_mu_launch_table(cmf_mu_t* h, char* buf, long long cap);
 
 /* ---- stateless primitives (cmfpy/common.py) ----------------------------- */
 /* cmf_predict(W, H) -> est, N x T (common.py:50-58).  Host pointers.        */
