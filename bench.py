@@ -3,7 +3,7 @@
 (N=1024, T=2^20, K=32, L=64), T-sharded over --gpus GPUs of one box.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--precision tf32|fp32] [--config C|B|D|E|A] [--t-scale S]
+                    [--precision auto|tf32x3|tf32|fp32] [--config C|B|D|E|A] [--t-scale S]
 
 One "step" = one MultUpdate.update() (W terms, W update, reconstruction,
 H terms, H update, reconstruction + loss).  Prints ONE JSON line (rank 0).
@@ -42,11 +42,12 @@ def parse_args():
     ap.add_argument("--t-scale", type=float, default=1.0,
                     help="shrink T (debug only; the line is then labelled reduced)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-profile", action="store_true",
-                    help="no per-kernel events in the timed region (lets the iteration replay as a CUDA graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fp32-grade", action="store_true",
-                    help="skip the short secondary measurement of the error-compensated tf32x3 mode")
+    ap.add_argument("--no-tf32", action="store_true", help="skip the separately reported plain-TF32 variant")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the quick lines of BASELINE configs B and D")
+    ap.add_argument("--no-peak", action="store_true", help="skip the cuBLAS TF32 peak measurement (4 s)")
+    ap.add_argument("--no-fp32-grade", action="store_true", help=argparse.SUPPRESS)      # (round-1 flag, ignored)
+    ap.add_argument("--no-profile", action="store_true", help=argparse.SUPPRESS)         # (round-1 flag, ignored)
     return ap.parse_args()
 
 
@@ -159,29 +160,55 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def cublas_tf32_tflops(torch, dev, n=8192, iters=10):
-    """cuBLAS TF32 GEMM rate measured here and now (context for the roofline:
-    MEASURED_PEAKS.json holds bf16 only).  Best of `iters`, CUDA events."""
+def measure_tf32_peak(torch, dev, n=8192, burst_iters=10, sustain_s=4.0):
+    """cuBLAS TF32 GEMM rate on THIS GPU, measured the way MEASURED_PEAKS.json measures bf16 (BASELINE.md section 4,
+    SURVEY 8d): torch.matmul fp32 with allow_tf32, n^3, best of `burst_iters` (burst) and back to back for
+    `sustain_s` seconds under the power cap (sustained)."""
     try:
         old = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = True
         a = torch.randn((n, n), device=dev, dtype=torch.float32)
         b = torch.randn((n, n), device=dev, dtype=torch.float32)
         torch.matmul(a, b)
+        torch.cuda.synchronize()
+        flop = 2.0 * n ** 3
         best = 1e30
-        for _ in range(iters):
+        for _ in range(burst_iters):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
+        # sustained: batches of 20 GEMMs until sustain_s seconds have passed; the rate of the LAST batches counts
+        rates, t0 = [], time.perf_counter()
+        while time.perf_counter() - t0 < sustain_s:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                torch.matmul(a, b)
+            e1.record(); torch.cuda.synchronize()
+            rates.append(20 * flop / (e0.elapsed_time(e1) * 1e-3) / 1e12)
         torch.backends.cuda.matmul.allow_tf32 = old
-        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
-    except Exception:
-        return None
+        tail = rates[len(rates) // 2:] or rates
+        return {"burst": flop / (best * 1e-3) / 1e12, "sustained": float(np.median(tail)),
+                "how": "torch.matmul fp32 allow_tf32 %d^3: best of %d (burst); back to back for %.0f s, median of the "
+                       "second half (sustained)" % (n, burst_iters, sustain_s)}
+    except Exception as e:          # noqa: BLE001
+        return {"burst": None, "sustained": None, "how": "failed: %s" % e}
 
 
 def algorithmic_flops(N, T, K, L):
     """six shift-contractions of 2 N K L T flops per iteration."""
     return 12.0 * N * K * L * T
+
+
+def set_blas_threads():
+    """All host cores for the CPU arm, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n, user_api="blas")
+    except Exception:
+        pass
+    return blas_threads()
 
 
 def reference_iteration_seconds(N, T, K, L, n_iter, seed=0):
@@ -208,17 +235,25 @@ def blas_threads():
         return os.cpu_count()
 
 
+# The port (oracle/cmf_oracle.py) against the UNMODIFIED reference, both float64 on the 8 cores of the build container
+# at N=1024 T=16384 K=32 L=64 (the reference cannot travel to the GPU box): see DESIGN.md section 4.
+PORT_VS_REFERENCE = ("the port is FASTER than the unmodified reference: 10.0 vs 39.1 s per iteration at this shape with "
+                     "T=16384 on the 8 cores of the build container (oracle/ref_shim.py import, measured once), so the "
+                     "reference itself would sit about 3.9x lower")
+
+
 def cpu_baseline(N, T, K, L, budget_iters=2):
     """Bounded sample: the reference update at T_s = min(T, 16384) columns with
     identical N, K, L, extrapolated linearly in T (the reference's cost is
     linear in N*T*L)."""
+    cores = set_blas_threads()
     Ts = int(min(T, 16384))
     sec = reference_iteration_seconds(N, Ts, K, L, budget_iters)
     sec_full = sec * (T / Ts)
-    return {"value": 1.0 / sec_full, "unit": UNIT, "cores": int(blas_threads()), "kind": "port",
-            "sample": "oracle port of reference MultUpdate.update (float64 NumPy/BLAS), %d iterations at "
-                      "N=%d T=%d K=%d L=%d (%.3f s/it), extrapolated linearly in T to T=%d"
-                      % (budget_iters, N, Ts, K, L, sec, T)}
+    return {"value": 1.0 / sec_full, "unit": UNIT, "cores": int(cores), "kind": "port",
+            "sample": "oracle port of reference MultUpdate.update (float64 NumPy/BLAS, %d BLAS threads), %d iterations "
+                      "at N=%d T=%d K=%d L=%d (%.3f s/it), extrapolated linearly in T to T=%d; %s"
+                      % (cores, budget_iters, N, Ts, K, L, sec, T, PORT_VS_REFERENCE)}
 
 
 # --------------------------------------------------------------------------
@@ -228,6 +263,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = int(set_blas_threads())
     N, T, K, L = FULL[args.config]
     T = int(T * args.t_scale)
     total = max(1, args.steps)
@@ -256,14 +292,13 @@ def run_reference(args):
     sec = (time.perf_counter() - t0) / total
     sec_full = sec * (T / Ts)
     value = 1.0 / sec_full
-    cores = int(blas_threads())
-    sample = ("oracle port of reference MultUpdate.update (float64 NumPy/BLAS, %d BLAS threads; same per-lag "
-              "GEMMs and three reconstructions as the reference but without its zero-pad copies, so it is "
-              "faster than the unmodified reference), %d timed iterations at N=%d T=%d K=%d L=%d (%.3f s/it), "
-              "extrapolated linearly in T to T=%d" % (cores, total, N, Ts, K, L, sec, T))
+    sample = ("oracle port of reference MultUpdate.update (float64 NumPy/BLAS, %d BLAS threads set through threadpoolctl "
+              "whatever OMP_NUM_THREADS says; same per-lag GEMMs and three reconstructions as the reference), %d timed "
+              "iterations at N=%d T=%d K=%d L=%d (%.3f s/it), extrapolated linearly in T to T=%d; %s"
+              % (cores, total, N, Ts, K, L, sec, T, PORT_VS_REFERENCE))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_full * 1e3,
-            "higher_is_better": True, "scaling": "weak" if False else "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config %s: N=%d T=%d K=%d L=%d MU" % (args.config, N, T, K, L)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -275,38 +310,21 @@ def run_reference(args):
 # --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import __graft_entry__ as g
-    g.build()
-    from cmfpy_b200 import _lib
-    lib = _lib.load()
+DTYPE_NAMES = {"tf32": "tf32", "tf32x3": "tf32x3 (3 TF32 MMAs per product on hi/lo operand pairs, fp32 two-level "
+                                         "accumulation: fp32-grade)", "fp32": "f32"}
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    affinity = bind_to_gpu_numa_node(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
 
-    N, T, K, L = FULL[args.config]
-    T = int(T * args.t_scale)
-    assert T % world == 0
+def resolve_precision(lib, _lib, precision, N, K, L):
+    """'auto' = what CMF(...).fit uses: the fastest mode that meets the 1e-4 parity bar."""
+    if precision != "auto":
+        return precision
+    return "tf32x3" if lib.cmf_precision_supported(_lib.CMF_PREC_TF32X3, N, K, L) else "fp32"
+
+
+def device_inputs(torch, dev, N, T, K, L, rank, world):
+    """Synthetic inputs generated on the device, identical for any world size: global column t of X / H0 depends
+    only on (seed, t).  Returns (X with its static right halo, W0, H0, t_begin, ncols_x)."""
     Tloc = T // world
-    precision = args.precision
-    if precision == "auto":
-        precision = "tf32" if lib.cmf_precision_supported(_lib.CMF_PREC_TF32, N, K, L) else "fp32"
-
-    from cmfpy_b200.dist import ShardedMultUpdate
-    # synthetic inputs generated on the device, identical for any world size:
-    # global column t of X / H0 depends only on (seed, t)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234)
     W0 = torch.rand((L, N, K), generator=gen, device=dev, dtype=torch.float32)
@@ -330,133 +348,260 @@ def run_b200(args):
     s = float(np.sqrt(0.5 / (L * K / 4.0)))
     W0 *= s
     H0 *= s
+    return X, W0, H0, t_begin, ncols_x
 
-    alg = ShardedMultUpdate(X[:, :ncols_x], N, T, K, L, t_offset=t_begin, t_local=Tloc,
-                            initW=W0, initH=H0, precision=precision, device=local_rank,
-                            group=dist.group.WORLD if dist else None, denominators=args.denominators)
-    torch.cuda.synchronize()
 
+def timed_steps(torch, dist, dev, alg, steps, warmup, sampler=None):
+    """W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the solver's stream, max
+    over ranks.  No per-kernel events inside: the iteration replays as the CUDA graph the product ships."""
     def barrier():
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
-
-    alg.update_many(args.warmup)
+    alg.set_profiling(0)
+    alg.update_many(warmup)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = alg.launch_count
-    alg.set_profiling(not args.no_profile)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stream = alg.torch_stream
     barrier()
-    sampler.mark_begin()
+    if sampler:
+        sampler.mark_begin()
     ev0.record(stream)
-    losses = alg.update_many(args.steps)
+    losses = alg.update_many(steps)
     ev1.record(stream)
     barrier()
-    sampler.mark_end()
+    if sampler:
+        sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    kms = alg.kernel_ms()
-    alg.set_profiling(False)
-    launches = alg.launch_count - launches0
     if dist:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = args.steps / (ms * 1e-3)
+    return ms, losses, alg.launch_count - launches0
 
-    # ---- end-to-end through the public host API (pinned host buffers) -------
+
+def kernel_breakdown(alg, steps):
+    """Second pass, outside the timed region: one CUDA event after every launch (cmf_mu_set_profiling level 2).
+    Returns ({label: (launches per step, ms per launch)}, phase ms per step)."""
+    alg.set_profiling(2)
+    alg.update_many(steps)
+    table = alg.launch_table()
+    phases = {k: v / steps for k, v in alg.kernel_ms().items()}
+    alg.set_profiling(0)
+    return {k: (n / steps, ms / max(n, 1)) for k, (n, ms) in table.items()}, phases
+
+
+def ncu_traffic(kernel_name, path_name):
+    """DRAM bytes per launch of `kernel_name` from the committed `ncu --set full` summary of this round (the largest
+    launch of that kernel), or (None, None) when no capture is on file."""
+    import glob
+    import re
+    tag = path_name.replace("tcgen05-", "").replace("+", "_")
+    best = (None, None)
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_ncu_kernels_%s*.txt" % tag))):
+        for line in open(f):
+            if not line.startswith("kernel=") or ("::" + kernel_name + "(") not in line.replace("kernel=", "kernel=::", 1):
+                continue
+            tot = 0.0
+            for key in ("dram_rd", "dram_wr"):
+                m = re.search(key + r"=([0-9.]+)([GMK]?)byte", line)
+                if m:
+                    tot += float(m.group(1)) * {"G": 1e9, "M": 1e6, "K": 1e3, "": 1.0}[m.group(2)]
+            if best[0] is None or tot > best[0]:
+                best = (tot, os.path.relpath(f, ROOT))
+    return best
+
+
+def roofline_report(N, Tloc, K, L, path_name, precision, table, phases, clocks, tf32_peak, peaks, peaks_src, world):
+    """Per-kernel roofline table of one iteration and the headline entry for the dominant kernel."""
+    gram = path_name.endswith("+gram")
+    x3 = precision == "tf32x3"
+    main = 2.0 * N * K * L * Tloc                                   # one shift-contraction over the local shard
+    LK = L * K
+    flops = {"tc_recon": main, "tc_wterms": main * (1 if gram else 2), "tc_hterms": main * (1 if gram else 2),
+             "autocorr_H": 2.0 * K * K * L * Tloc, "gram_den_w": 2.0 * N * LK * LK, "gram_G": 2.0 * LK * LK * N,
+             "gram_den_h": 2.0 * K * K * (2 * L - 1) * Tloc,
+             "recon": main, "w_terms": 2 * main, "h_terms": 2 * main}           # (labels of the FFMA path)
+    hbm = {"w_update": 16.0 * L * N * K, "h_update": 16.0 * K * Tloc}            # SURVEY 8d: 3 reads + 1 write
+    sm_mhz = clocks.get("sm_mhz") if clocks else None
+    pipe = 148 * 4096.0 * sm_mhz * 1e6 / 1e12 if sm_mhz else None                # one 128x256x8 MMA per 128 cycles
+    peak = tf32_peak.get("sustained") or peaks["bf16_tflops_sustained"] / 2.0
+    rows, dominant = [], None
+    for label, (per_step, ms) in sorted(table.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
+        row = {"kernel": label, "launches_per_step": round(per_step, 3), "ms_per_launch": ms,
+               "ms_per_step": per_step * ms}
+        if label in flops and ms > 0:
+            a = flops[label] / (ms * 1e-3) / 1e12
+            row.update(bound="tensor", algorithmic_tflops=a, frac_of_measured_tf32=a / peak,
+                       executed_tflops=a * (3 if x3 else 1),
+                       executed_frac_of_tensor_pipe=(a * (3 if x3 else 1) / pipe) if pipe else None)
+            if dominant is None:
+                dominant = row
+        elif label in hbm and ms > 0:
+            g = hbm[label] / (ms * 1e-3) / 1e9
+            row.update(bound="hbm", algorithmic_gbs=g, frac_of_measured_hbm=g / peaks["hbm_gbs"])
+        rows.append(row)
+    out = {"bound": "tensor", "kernel": None, "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None,
+           "traffic": None}
+    if dominant:
+        kname = {"tc_recon": "tc_recon_x3_kernel" if x3 else "tc_recon_kernel",
+                 "tc_wterms": "tc_wterms_x3_kernel" if x3 else "tc_wterms_kernel",
+                 "tc_hterms": "tc_hterms_kernel"}.get(dominant["kernel"], dominant["kernel"])
+        traffic, traffic_file = ncu_traffic(kname, path_name) if world == 1 else (None, None)
+        out.update(kernel="%s (%s, %s)" % (dominant["kernel"], kname, path_name),
+                   achieved=dominant["algorithmic_tflops"], frac=dominant["frac_of_measured_tf32"],
+                   traffic=traffic, traffic_source=traffic_file,
+                   algorithmic_bytes=(4.0 if dominant["kernel"] == "tc_recon" and gram else 8.0) * N * Tloc *
+                                     (2 if x3 else 1),
+                   executed_tflops=dominant["executed_tflops"],
+                   executed_frac_of_tensor_pipe=dominant["executed_frac_of_tensor_pipe"])
+    out.update(
+        what="algorithmic flops of the dominant kernel (2 N K L T per contraction; the three operand passes of tf32x3 "
+             "count once) / its mean launch time measured with CUDA events in a second pass of the same solver; "
+             "`executed_*` counts the MMAs actually issued",
+        peak_source="cuBLAS TF32 %s (this run, this GPU); %s bf16_tflops_sustained / 2 = %.1f for reference"
+                    % ("sustained" if tf32_peak.get("sustained") else "unavailable", peaks_src,
+                       peaks["bf16_tflops_sustained"] / 2.0),
+        tf32_peak_measured=tf32_peak, tensor_pipe_tflops_at_observed_clock=pipe,
+        kernels=rows, phase_ms_per_step=phases)
+    return out
+
+
+def run_mode(torch, dist, dev, lib, _lib, args, cfg, precision, X, ncols_x, W0, H0, t_begin, Tloc, local_rank,
+             sampler=None, profile_steps=3):
+    """Builds the solver of one precision mode, times it, and takes the per-kernel table in a second pass."""
+    from cmfpy_b200.dist import ShardedMultUpdate
+    N, T, K, L = cfg
+    alg = ShardedMultUpdate(X[:, :ncols_x], N, T, K, L, t_offset=t_begin, t_local=Tloc,
+                            initW=W0, initH=H0, precision=precision, device=local_rank,
+                            group=dist.group.WORLD if dist else None, denominators=args.denominators)
+    torch.cuda.synchronize()
+    ms, losses, launches = timed_steps(torch, dist, dev, alg, args.steps, args.warmup, sampler)
+    clocks = None
+    if sampler is not None:
+        clocks = sampler.stop()
+    table, phases = kernel_breakdown(alg, min(profile_steps, args.steps))
+    info = {"precision": precision, "path": alg.path_name, "ms": ms, "losses": losses, "launches": launches,
+            "table": table, "phases": phases, "clocks": clocks,
+            "transport": alg.transport if dist else None}
+    alg.close()
+    return info
+
+
+def quick_config(torch, dev, lib, _lib, args, letter, peaks, tf32_peak, steps, warmup):
+    """One of the other BASELINE configs on one GPU (device-timed, graph replay), with the roofline that bounds it."""
+    from cmfpy_b200.dist import ShardedMultUpdate
+    N, T, K, L = FULL[letter]
+    out = {}
+    X, W0, H0, t_begin, ncols_x = device_inputs(torch, dev, N, T, K, L, 0, 1)
+    for name, prec in (("parity_grade", resolve_precision(lib, _lib, "auto", N, K, L)), ("tf32", "tf32")):
+        if not lib.cmf_precision_supported(_lib.PRECISIONS[prec], N, K, L):
+            continue
+        alg = ShardedMultUpdate(X[:, :ncols_x], N, T, K, L, t_offset=0, t_local=T, initW=W0, initH=H0,
+                                precision=prec, device=dev.index, group=None, denominators="auto")
+        torch.cuda.synchronize()
+        ms, losses, launches = timed_steps(torch, None, dev, alg, steps, warmup)
+        per = ms / steps
+        flops = algorithmic_flops(N, T, K, L)
+        bytes_iter = 28.0 * N * T + 36.0 * K * T                    # SURVEY 8d: whole-iteration lower bound
+        peak_tf = tf32_peak.get("sustained") or peaks["bf16_tflops_sustained"] / 2.0
+        t_tensor, t_hbm = flops / (peak_tf * 1e12), bytes_iter / (peaks["hbm_gbs"] * 1e9)
+        bound = "tensor" if t_tensor >= t_hbm else "hbm"
+        ach = flops / (per * 1e-3) / 1e12 if bound == "tensor" else bytes_iter / (per * 1e-3) / 1e9
+        pk = peak_tf if bound == "tensor" else peaks["hbm_gbs"]
+        out[name] = {"precision": prec, "path": alg.path_name, "value": steps / (ms * 1e-3), "unit": UNIT,
+                     "ms_per_step": per, "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
+                     "final_loss": losses[-1],
+                     "roofline": {"bound": bound, "achieved": ach, "peak": pk,
+                                  "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": ach / pk,
+                                  "what": "whole iteration: 12 N K L T reference-equivalent flops (tensor) or "
+                                          "28 N T + 36 K T bytes (hbm), whichever bound is the longer, over the "
+                                          "measured time"}}
+        alg.close()
+    del X, W0, H0
+    torch.cuda.empty_cache()
+    return {"workload": "config %s: N=%d T=%d K=%d L=%d MU" % (letter, N, T, K, L), **out}
+
+
+def run_b200(args):
+    import torch
+    import __graft_entry__ as g
+    g.build()
+    from cmfpy_b200 import _lib
+    lib = _lib.load()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, T, K, L = cfg = FULL[args.config]
+    T = int(T * args.t_scale)
+    cfg = (N, T, K, L)
+    assert T % world == 0
+    Tloc = T // world
+    precision = resolve_precision(lib, _lib, args.precision, N, K, L)
+
+    X, W0, H0, t_begin, ncols_x = device_inputs(torch, dev, N, T, K, L, rank, world)
+
+    # ---- the headline: the mode CMF(...).fit uses (parity-grade) ------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    main = run_mode(torch, dist, dev, lib, _lib, args, cfg, precision, X, ncols_x, W0, H0, t_begin, Tloc, local_rank,
+                    sampler if rank == 0 else None)
+    ms_per_step = main["ms"] / args.steps
+    value = args.steps / (main["ms"] * 1e-3)
+
+    # ---- the TF32 variant, reported separately (north_star), same steps and warm-up ------------------------
+    tf32 = None
+    if (precision != "tf32" and not args.no_tf32 and lib.cmf_precision_supported(_lib.CMF_PREC_TF32, N, K, L)):
+        s2 = ClockSampler(local_rank)
+        if rank == 0:
+            s2.start()
+        tf32 = run_mode(torch, dist, dev, lib, _lib, args, cfg, "tf32", X, ncols_x, W0, H0, t_begin, Tloc, local_rank,
+                        s2 if rank == 0 else None)
+
+    # ---- end-to-end through the public host API (pinned host buffers) ---------------------------------------
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, torch, N, T, K, L, Tloc, rank, world, local_rank, precision, dist)
-
-    # fp32-grade companion number (north_star: the 1e-4 parity bar is an fp32 bar, "TF32 variant reported
-    # separately"): the same workload on the error-compensated tensor-core mode, a few steps, outside the timed region
-    fp32_grade = None
-    if (precision == "tf32" and not args.no_fp32_grade and
-            lib.cmf_precision_supported(_lib.CMF_PREC_TF32X3, N, K, L)):
-        alg3 = ShardedMultUpdate(X[:, :ncols_x], N, T, K, L, t_offset=t_begin, t_local=Tloc,
-                                 initW=W0, initH=H0, precision="tf32x3", device=local_rank,
-                                 group=dist.group.WORLD if dist else None)
-        alg3.update_many(2)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0.record(alg3.torch_stream)
-        l3 = alg3.update_many(5)
-        e1.record(alg3.torch_stream)
-        torch.cuda.synchronize()
-        ms3 = e0.elapsed_time(e1)
-        if dist:
-            t3 = torch.tensor([ms3], device=dev)
-            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-            ms3 = float(t3.item())
-        fp32_grade = {"precision": "tf32x3", "path": alg3.path_name, "value": 5 / (ms3 * 1e-3), "unit": UNIT,
-                      "steps": 5, "warmup": 2, "loss_after_7_steps": l3[-1],
-                      "what": "same workload, every product as three TF32 MMAs on hi/lo operand pairs; loss "
-                              "trajectories within 1e-4 of the float64 reference on all golden cases but config B "
-                              "(profiles/r01_trajectory_errors_tf32x3.log)"}
-        alg3.close()
-        del alg3
-    del X, H0
+    del X, H0, W0
+    torch.cuda.empty_cache()
     if rank != 0:
-        alg.close()
         if dist:
             dist.destroy_process_group()
         return
 
     peaks, peaks_src = measured_peaks()
-    tf32_live = cublas_tf32_tflops(torch, dev)
-    flops_iter = algorithmic_flops(N, T, K, L)
-    # reconstructions per step: two with the direct denominators, one with the Gram route (est is then
-    # needed for the loss only)
-    recon_launches = (1 if alg.path_name.endswith("+gram") else 2) * args.steps
-    recon_ms = max(kms["recon"] / recon_launches, 1e-9)
-    recon_flops = 2.0 * N * K * L * Tloc            # per launch, per GPU
-    achieved = recon_flops / (recon_ms * 1e-3) / 1e12 if kms["recon"] > 0 else None
-    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
-    roofline = {
-        "bound": "tensor", "kernel": "recon (shift-GEMM, %s)" % alg.path_name,
-        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-        "frac": (achieved / tf32_peak) if achieved else None,
-        # DRAM bytes per K1 launch from `ncu --set full` (profiles/r01_ncu_tc_kernels_gram.txt /
-        # _direct.txt); captured for config C on one GPU only
-        "traffic": ((4.44e9 if alg.path_name.endswith("+gram") else 8.70e9)
-                    if (args.config == "C" and world == 1 and args.t_scale == 1.0 and precision == "tf32") else None),
-        "traffic_unit": "bytes per launch (algorithmic: %.2e)" % ((4.0 if alg.path_name.endswith("+gram") else 8.0) * N * Tloc),
-        "peak_source": "%s bf16_tflops_sustained / 2 (TF32 dense = half of bf16; not separately measured)" % peaks_src,
-        "cublas_tf32_tflops_live": tf32_live,
-        # the tensor pipe itself: one 128x256x8 TF32 MMA (524288 flop) per 128 cycles per SM at the SM clock
-        # observed DURING the timed region (the run is power-capped well below the 1965 MHz maximum)
-        "hw_tf32_tflops_at_observed_clock": (148 * 4096.0 * clocks["sm_mhz"] * 1e6 / 1e12
-                                             if clocks and clocks.get("sm_mhz") else None),
-        "frac_of_hw_at_observed_clock": (achieved / (148 * 4096.0 * clocks["sm_mhz"] * 1e6 / 1e12)
-                                         if achieved and clocks and clocks.get("sm_mhz") else None),
-        # 12 N K L T per iteration (what the direct algorithm needs) over the measured time; with
-        # the Gram-route denominators about half of those flops are not executed at all, so this figure is a
-        # reference-equivalent rate, not a hardware utilisation
-        "reference_equivalent_tflops": flops_iter / world / (ms_per_step * 1e-3) / 1e12,
-        "executed_tflops_approx": (flops_iter * (0.5 + (2.0 * K + 4.0 * K * (2 * L - 1) / L) / (6.0 * N))
-                                   if alg.path_name.endswith("+gram") else
-                                   (3.0 * flops_iter if precision == "tf32x3" else flops_iter))
-                                  / world / (ms_per_step * 1e-3) / 1e12,
-        "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
-        "hbm_update_kernels": {
-            # W and H multiplicative updates: 16 B/element algorithmic (+4 B for the TF32 operand copy)
-            "bytes_per_step": (20 if precision == "tf32" else 16) * (L * N * K + K * Tloc),
-            "achieved_gbs": (20 if precision == "tf32" else 16) * (L * N * K + K * Tloc) /
-                            max(kms["elementwise"] / args.steps * 1e-3, 1e-12) / 1e9,
-            "peak_gbs": peaks["hbm_gbs"]},
-    }
-    if world > 1:
-        # the "elementwise" interval of a sharded step also holds the exchange kernels and their waits for the
-        # slowest rank: the update kernels are not isolated there, so no bandwidth is claimed for them
-        roofline["hbm_update_kernels"] = None
+    tf32_peak = measure_tf32_peak(torch, dev) if not args.no_peak else {"burst": None, "sustained": None, "how": "skipped"}
+    roofline = roofline_report(N, Tloc, K, L, main["path"], precision, main["table"], main["phases"], main["clocks"],
+                               tf32_peak, peaks, peaks_src, world)
+    tf32_line = None
+    if tf32:
+        r2 = roofline_report(N, Tloc, K, L, tf32["path"], "tf32", tf32["table"], tf32["phases"], tf32["clocks"],
+                             tf32_peak, peaks, peaks_src, world)
+        tf32_line = {"precision": "tf32", "path": tf32["path"], "value": args.steps / (tf32["ms"] * 1e-3), "unit": UNIT,
+                     "steps": args.steps, "warmup": args.warmup, "ms_per_step": tf32["ms"] / args.steps,
+                     "gpu_launches": int(tf32["launches"]), "final_loss": tf32["losses"][-1], "clocks": tf32["clocks"],
+                     "roofline": r2,
+                     "parity": "plain TF32 operands (10-bit mantissa): loss trajectories within 4e-8 .. 2.1e-3 of the "
+                               "float64 reference on the golden cases (profiles/r02_trajectory_errors.log), not held to "
+                               "the 1e-4 bar; reported separately as north_star asks"}
+    other = None
+    if world == 1 and not args.no_other_configs and args.config == "C" and args.t_scale == 1.0:
+        other = {c: quick_config(torch, dev, lib, _lib, args, c, peaks, tf32_peak, steps=max(10, args.steps), warmup=3)
+                 for c in ("B", "D")}
     cb = None
     if not args.no_cpu_baseline and world == 1:          # the CPU baseline is a 1-GPU-run item (rank 0, N = 1 only)
         cb = cpu_baseline(N, T, K, L)
@@ -464,22 +609,27 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
-        "dtype": {"tf32": "tf32", "tf32x3": "tf32x3 (3 TF32 MMAs per product, fp32-grade)"}.get(precision, "f32"), "data": "synthetic",
+        "dtype": DTYPE_NAMES.get(precision, precision), "data": "synthetic",
         "config": {"workload": "config %s: N=%d T=%d K=%d L=%d MU%s" %
                    (args.config, N, T, K, L, "" if args.t_scale == 1.0 else " (T reduced: debug)"),
                    "sharding": "time axis, %d x %d columns, halo %d" % (world, Tloc, L - 1),
-                   "l2": "inputs_exceed_l2 (X and est are %.1f GiB each per GPU)" % (N * Tloc * 4 / 2**30),
-                   "precision": precision, "denominators": args.denominators, "path": alg.path_name,
+                   "l2": "inputs_exceed_l2 (X is %.1f GiB per GPU)" % (N * Tloc * 4 * (2 if precision == "tf32x3" else 1) / 2**30),
+                   "precision": precision, "precision_requested": args.precision,
+                   "parity": "loss trajectory within 1e-4 of the float64 reference on every golden case "
+                             "(tests/test_parity_gpu.py, profiles/r02_trajectory_errors.log)"
+                             if precision != "tf32" else "TF32 variant: reported, not held to the 1e-4 bar",
+                   "denominators": args.denominators, "path": main["path"],
+                   "timed_region": "CUDA-graph replay of the iteration, no per-kernel events (the shipped path)",
                    "collectives": ("none (1 GPU)" if world == 1 else
                                    {"peer": "own kernels over NVLink peer memory (all-reduce fused with the W update, "
                                             "halo pushes, loss ring)",
-                                    "nccl": "NCCL all-reduce + send/recv between the phases"}[alg.transport])},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "cpu_affinity": affinity,
-        "roofline": roofline, "cpu_baseline": cb, "fp32_grade": fp32_grade,
-        "final_loss": losses[-1],
+                                    "nccl": "NCCL all-reduce + send/recv between the phases"}[main["transport"]])},
+        "clocks": main["clocks"], "e2e": e2e, "gpu_launches": int(main["launches"]), "cpu_affinity": affinity,
+        "roofline": roofline, "cpu_baseline": cb, "tf32": tf32_line, "other_configs": other,
+        "reference_equivalent_tflops": algorithmic_flops(N, T, K, L) / world / (ms_per_step * 1e-3) / 1e12,
+        "final_loss": main["losses"][-1],
     }
     print(json.dumps(line), flush=True)
-    alg.close()
     if dist:
         dist.destroy_process_group()
 
@@ -535,7 +685,7 @@ def run_e2e(args, torch, N, T, K, L, Tloc, rank, world, local_rank, precision, d
     h2d = (Xh.numel() + W0h.numel() + H0h.numel()) * 4
     d2h = (W.size + H.size) * 4 + 8 * args.steps
     alg.close()
-    return {"value": args.steps / sec, "unit": UNIT,
+    return {"value": args.steps / sec, "unit": UNIT, "precision": precision,
             "h2d_bytes_per_step": int(h2d * world / args.steps),
             "d2h_bytes_per_step": int(d2h * world / args.steps),
             "seconds_total": sec, "seconds_rank0": parts, "final_loss": last,

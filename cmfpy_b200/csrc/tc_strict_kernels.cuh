@@ -805,8 +805,13 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             float* r = R + (size_t)(u0 + c * 32) * p.Kp + kcol;
             for (int d = 0; d < p.s; ++d) {        // folded lags of one warp overlap in R: one at a time
               if (d == dl) {
+                // the 32 rows are distinct addresses, which the compiler cannot know (Kp is a run-time stride): load
+                // them all, then store them all, or every += waits for the store before it (~45 cycles each)
+                float t[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) r[i * p.Kp] += m[i];
+                for (int i = 0; i < 32; ++i) t[i] = r[i * p.Kp];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i * p.Kp] = t[i] + m[i];
               }
               __syncwarp();
             }

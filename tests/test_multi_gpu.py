@@ -95,3 +95,58 @@ def test_sharded_equals_single_gpu(built_lib, precision, shape, transport):
         assert np.array_equal(o[1], out[0][1]), "W must be bit-identical across ranks"
     assert np.abs(H - ref.H).max() <= 50 * tol * np.abs(ref.H).max()
     ref.close()
+
+
+# ---- the same sharded solve from ONE process: CMF(..., devices=[...]) --------------------------------
+@pytest.mark.parametrize("precision,shape", [("fp32", (96, 2048, 5, 12)), ("tf32x3", (200, 4096, 32, 64)),
+                                             ("tf32x3", (130, 3001, 8, 20)), ("tf32", (128, 2048, 30, 9))])
+def test_cmf_fit_on_several_devices(built_lib, precision, shape):
+    """`devices` travels through alg_opts like every solver option (reference model.py:80-82, :146); the fit over
+    all GPUs must reproduce the single-GPU fit, and the float64 oracle where the mode is parity-grade."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from cmfpy_b200 import CMF
+    from oracle import cmf_oracle as o
+    from tests.cases import make_inputs
+    N, T, K, L = shape
+    X, W0, H0 = make_inputs(N, T, K, L, "planted", seed=5)
+    devices = list(range(min(n, 4)))
+    if T // len(devices) < L:
+        devices = devices[:2]
+    many = CMF(K, L, n_iter_max=8, verbose=False, tol=0, initW=W0, initH=H0, precision=precision, devices=devices)
+    many.fit(X)
+    one = CMF(K, L, n_iter_max=8, verbose=False, tol=0, initW=W0, initH=H0, precision=precision, devices=[0])
+    one.fit(X)
+    tol = 5e-3 if precision == "tf32" else 2e-5
+    a, b = np.array(many.loss_hist), np.array(one.loss_hist)
+    assert len(a) == 9 and np.abs(a - b).max() <= tol * b.max()
+    assert np.abs(many.motifs - one.motifs).max() <= 50 * tol * np.abs(one.motifs).max()
+    assert np.abs(many.factors - one.factors).max() <= 50 * tol * np.abs(one.factors).max()
+    if precision != "tf32":
+        ref = o.MultUpdateOracle(X.astype(np.float64), L, K, initW=W0.astype(np.float64), initH=H0.astype(np.float64), tol=0)
+        ref_hist = np.array([ref.loss] + [ref.update() for _ in range(8)])
+        assert (np.abs(a - ref_hist) / ref_hist).max() <= 1e-4
+
+
+def test_multi_device_random_init_and_early_stop(built_lib):
+    """rand_init (reference base.py:78-88) summed over the shards: <X, est0> = ||est0||^2; converged() fires."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from cmfpy_b200.algs.mult import MultUpdate
+    from cmfpy_b200.model import ModelDimensions
+    from tests.cases import make_inputs
+    X, _, _ = make_inputs(40, 1200, 3, 9, "planted", seed=9)
+    alg = MultUpdate(X, ModelDimensions(X, maxlag=9, n_components=3), seed=1, devices=[0, 1], tol=1e-3)
+    assert type(alg).__name__ == "MultiGpuMultUpdate"
+    est = alg.est
+    assert abs((X * est).sum() / (est ** 2).sum() - 1.0) < 1e-4
+    hist = [alg.loss]
+    for _ in range(2000):
+        hist.append(alg.update())
+        if alg.converged(hist):
+            break
+    assert 3 < len(hist) < 2000
+    assert np.all(np.diff(hist) < 1e-6)
+    alg.close()
