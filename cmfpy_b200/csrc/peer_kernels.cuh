@@ -96,15 +96,10 @@ wstep_exchange_kernel(const Peers P, long long n4, uint32_t epoch) {
     __threadfence_system();
     st_release_sys(&P.ctl[threadIdx.x]->ready[P.rank], epoch);
   }
-  // (2) wait until every peer's partials are complete
-  __shared__ int ok_s;
-  if (threadIdx.x == 0) ok_s = 1;
-  __syncthreads();
-  if (threadIdx.x < G) {
-    if (!wait_epoch(&me->ready[threadIdx.x], epoch, &me->err)) ok_s = 0;
-  }
-  __syncthreads();
-  if (ok_s) {
+  // (2) wait until every peer's partials are complete (block-wide AND of the per-peer waits)
+  int ok = 1;
+  if (threadIdx.x < G) ok = wait_epoch(&me->ready[threadIdx.x], epoch, &me->err) ? 1 : 0;
+  if (__syncthreads_and(ok)) {
     // (3) my slice: sum over ranks in rank order, update, store into every rank's W
     const long long s0 = n4 * P.rank / G, s1 = n4 * (P.rank + 1) / G;
     const long long stride = (long long)gridDim.x * blockDim.x;

@@ -743,21 +743,22 @@ transpose_round_w_kernel(const float* __restrict__ W, float* __restrict__ Wt, in
   }
 }
 
-// Rw[j][k][k'] = R[L-1-j][k][k'] = sum_{l'} G[(l'+d)*Kp + k][l'*Kp + k'],  d = L-1-j, j in [0, 2L-1)
-// (the order the recon kernel wants its "lags": out[tau + L-1] = sum_j Rw[j] H^T[tau + L-1 - j])
+// Rt[l][k'][k] = R[l-(L-1)][k][k'] = sum_{l'} G[(l'+d)*Kp + k][l'*Kp + k'],  d = l - (L-1), l in [0, 2L-1):
+// R as a W-like operand (lag, "feature" k', component k) for the H-terms kernel, which then computes
+// den_H^T[t][k] = sum_l sum_k' Rt[l][k'][k] H^T[t + d][k']
 __global__ void __launch_bounds__(256)
-diag_sum_kernel(const float* __restrict__ G, long long ldg, float* __restrict__ Rw, int L, int Kp) {
+diag_sum_kernel(const float* __restrict__ G, long long ldg, float* __restrict__ Rt, int L, int Kp) {
   const long long total = (long long)(2 * L - 1) * Kp * Kp;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int kq = (int)(i % Kp);
-    const int k = (int)((i / Kp) % Kp);
-    const int j = (int)(i / ((long long)Kp * Kp));
-    const int d = L - 1 - j;
+    const int k = (int)(i % Kp);
+    const int kq = (int)((i / Kp) % Kp);
+    const int l = (int)(i / ((long long)Kp * Kp));
+    const int d = l - (L - 1);
     const int lo = d < 0 ? -d : 0, hi = d > 0 ? L - d : L;     // l' range with 0 <= l'+d < L
     float acc = 0.f;
     for (int lp = lo; lp < hi; ++lp) acc += G[((size_t)(lp + d) * Kp + k) * ldg + (size_t)lp * Kp + kq];
-    Rw[i] = acc;
+    Rt[i] = acc;
   }
 }
 

@@ -98,13 +98,17 @@ struct TcState {
   // ---- Gram route for the denominators (gram & 1: H step, gram & 2: W step) ----
   int gram = 0;
   int gram_request = 0;             // from cmf_mu_params.denominators (CMF_GRAM in the environment overrides)
-  int LK = 0, Lr = 0, Lrv = 0, dh_wrows = 0;
-  int dh_LB = 0;                    // lags per window of R (*) H (0: one window; > 0: the 2L-1 lags are walked in blocks)
+  int LK = 0, Lr = 0, Lrv = 0;
+  // den_H = R (*) H runs on the H-terms kernel with R in the role of W, H^T in the role of the data and the
+  // K components in the role of the features (Fold of that problem: J, head columns, window rows, ring depth)
+  Fold fr{};
+  float* hcarry_r = nullptr;
+  CUtensorMap tmRw_k3, tmHs_k3, tmHslo_k3;
   int NpA = 0;                      // row half-width of Wt (Np rounded up to 32: the lo half starts on a TMA box boundary)
   long long g_rows = 0;             // rows allocated for G (LK rounded up to 256)
   float *Wt = nullptr, *G = nullptr, *Rw = nullptr, *Rwv = nullptr, *Etail = nullptr;
   long long ntail = 0;              // rows of est past the end of the data that fall inside this shard's window
-  CUtensorMap tmWt_a, tmWt_b, tmRw_a;
+  CUtensorMap tmWt_a, tmWt_b;
   // W step
   float *P = nullptr, *Ppart = nullptr, *Mt = nullptr;
   int p_chunks = 1, p_grid = 1;
@@ -171,7 +175,7 @@ inline int make_map_k2src(CUtensorMap* m, const float* base, long long rows, lon
 // K3 motif operand: both lags of a stage and all four (lag group, column block) regions as ONE box:
 // dims (k in block, feature, 32-column block, lag group, lag in group) -> shared memory [lag][region][32 n][32 k].
 // Wv must be allocated for n_glag * J lags (zeros past Lv).
-inline int make_map_k3w(CUtensorMap* m, const float* Wv, const Fold& f, long long Np, long long KWs) {
+inline int make_map_k3w(CUtensorMap* m, const float* Wv, const Fold& f, long long Np, long long KWs) {   // f.J, f.n_glag, f.CB
   cuuint64_t dims[5] = {32, (cuuint64_t)Np, (cuuint64_t)(KWs / 32), (cuuint64_t)f.n_glag, (cuuint64_t)f.J};
   cuuint64_t strides[4] = {(cuuint64_t)KWs * 4, 128, (cuuint64_t)f.J * Np * KWs * 4, (cuuint64_t)Np * KWs * 4};
   cuuint32_t box[5] = {32, 32, (cuuint32_t)f.CB, (cuuint32_t)f.n_glag, (cuuint32_t)kHtLagsPerStage};
@@ -180,9 +184,9 @@ inline int make_map_k3w(CUtensorMap* m, const float* Wv, const Fold& f, long lon
 
 inline void destroy(TcState& s) {
   cudaFree(s.wpart); cudaFree(s.hcarry); cudaFree(s.d_err); cudaFree(s.Wv); cudaFree(s.Hv);
-  cudaFree(s.Wt); cudaFree(s.G); cudaFree(s.Rw); cudaFree(s.Rwv); cudaFree(s.Etail);
+  cudaFree(s.Wt); cudaFree(s.G); cudaFree(s.Rw); cudaFree(s.Rwv); cudaFree(s.Etail); cudaFree(s.hcarry_r);
   cudaFree(s.P); cudaFree(s.Ppart); cudaFree(s.Mt);
-  s.Wt = s.G = s.Rw = s.Rwv = s.Etail = s.P = s.Ppart = s.Mt = nullptr;
+  s.Wt = s.G = s.Rw = s.Rwv = s.Etail = s.P = s.Ppart = s.Mt = s.hcarry_r = nullptr;
   s.wpart = s.hcarry = s.Wv = s.Hv = nullptr;
   s.d_err = nullptr;
   s.ready = false;
@@ -462,15 +466,18 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   s.LK = d.L * d.Kp;
   s.Lr = 2 * d.L - 1;
   s.Lrv = (s.Lr + f.s - 1) / f.s;
-  s.dh_wrows = round_up(256 + f.s * (s.Lrv - 1), 64);
   s.g_rows = round_up_ll(s.LK, 256);
   s.ntail = d.Tloc + d.h - d.t_valid;
-  if (recon_smem_bytes(s.dh_wrows) > kMaxSmem) {
-    // the 2L-1 lags of R do not fit one window: blocks of LB lags, each with a window of 256 + s (LB - 1) rows
-    const int max_rows = (int)((kMaxSmem - recon_smem_bytes(0)) / (2 * kKp * 4) / 64) * 64;
-    s.dh_LB = ((max_rows - 256) / f.s + 1) & ~1;
-    if (s.dh_LB < 2) s.gram &= ~1;
-    else s.dh_wrows = round_up(256 + f.s * (s.dh_LB - 1), 64);
+  {   // the fold of den_H = R (*) H on the H-terms kernel: 2L-1 lags, Kp "features"
+    s.fr = f;
+    s.fr.Lv = s.Lrv;
+    s.fr.J = (s.Lrv + f.n_glag - 1) / f.n_glag;
+    s.fr.hterms_wrows = round_up(256 + f.s * (s.fr.J - 1), 32);
+    s.fr.h_hd = (f.n_glag - 1) * f.s * s.fr.J + f.s - 1;
+    s.fr.h_stages = 0;
+    for (int st = 3; st >= 2 && !s.fr.h_stages; --st)
+      if (hterms_smem_bytes(st, s.fr.hterms_wrows, d.Kp, s.fr.h_hd, f.n_glag == 1 && f.s == 1) <= kMaxSmem) s.fr.h_stages = st;
+    if (!s.fr.h_stages) s.gram &= ~1;
   }
   if ((long long)s.g_rows * s.LK * 4 > (1ll << 30)) s.gram &= ~1;
   if (s.gram & 1) {
@@ -481,21 +488,31 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     CMF_CUDA(cudaMemsetAsync(s.Wt, 0, (size_t)s.LK * wt_ld * 4, stream));
     CMF_CUDA(cudaMalloc((void**)&s.G, (size_t)s.g_rows * s.LK * 4));
     CMF_CUDA(cudaMalloc((void**)&s.Rw, (size_t)s.Lr * d.Kp * d.Kp * 4));
-    CMF_CUDA(cudaMalloc((void**)&s.Rwv, (size_t)s.Lrv * d.Kp * s.KWs * 4));
-    CMF_CUDA(cudaMemsetAsync(s.Rwv, 0, (size_t)s.Lrv * d.Kp * s.KWs * 4, stream));
+    // Rwv: R as a W-like operand [lag][k' (feature)][k], folded like Wv; allocated for n_glag * J lags (zeros past Lrv)
+    const long long lr_alloc = (long long)f.n_glag * s.fr.J > s.Lrv ? (long long)f.n_glag * s.fr.J : s.Lrv;
+    CMF_CUDA(cudaMalloc((void**)&s.Rwv, (size_t)lr_alloc * d.Kp * s.KWs * 4));
+    CMF_CUDA(cudaMemsetAsync(s.Rwv, 0, (size_t)lr_alloc * d.Kp * s.KWs * 4, stream));
     CMF_TRY(make_map(&s.tmWt_a, s.Wt, s.LK, wt_ld, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
     CMF_TRY(make_map(&s.tmWt_b, s.Wt, s.LK, wt_ld, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
-    CMF_TRY(make_map(&s.tmRw_a, s.Rwv, (long long)s.Lrv * d.Kp, s.KWs, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
-    const size_t need = recon_smem_bytes(s.dh_wrows) > recon_smem_bytes(f.recon_wrows) ? recon_smem_bytes(s.dh_wrows)
-                                                                                        : recon_smem_bytes(f.recon_wrows);
-    CMF_TRY(set_recon_smem(need));
+    CMF_TRY(make_map_k3w(&s.tmRw_k3, s.Rwv, s.fr, d.Kp, s.KWs));
+    // H^T itself as the data operand: the first Kp columns of Hv (row 0 of Hv is time -(L-1): lag l of R is d = l - (L-1))
+    CMF_TRY(make_map(&s.tmHs_k3, s.Hv, d.RH, d.Kp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B, s.KWs));
+    s.tmHslo_k3 = s.tmHs_k3;
+    if (s.x3) CMF_TRY(make_map(&s.tmHslo_k3, s.Hv + f.KW, d.RH, d.Kp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B, s.KWs));
+    if (s.fr.h_hd > 0) CMF_CUDA(cudaMalloc((void**)&s.hcarry_r, (size_t)(d.TO / 256 + 1) * s.fr.h_hd * d.Kp * 4));
+    // one attribute for both uses of the H-terms kernel
+    const bool direct = f.n_glag == 1 && f.s == 1;
+    const size_t a = hterms_smem_bytes(f.h_stages, f.hterms_wrows, d.Kp, f.h_hd, direct);
+    const size_t b = hterms_smem_bytes(s.fr.h_stages, s.fr.hterms_wrows, d.Kp, s.fr.h_hd, direct);
+    CMF_CUDA(cudaFuncSetAttribute(tc_hterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(a > b ? a : b)));
   }
   // H terms.  3xTF32: short tensor-memory sub-chunks folded in fp32 registers (no truncation bias to speak of).
   // Plain TF32 with the Gram denominator: sub-chunks as long as the chain of R (*) H, so that numerator and
   // denominator carry the same truncation bias and the W / H scale split does not drift; direct route: numerator
   // and denominator share one chain per item anyway.
   {
-    s.h_sub = s.x3 ? strict_sub_units() : ((s.gram & 1) ? s.Lrv * f.CB : 0);
+    // (the Gram denominator is one chain of ceil(Kp / 32) * J_r units per time tile on the same kernel)
+    s.h_sub = s.x3 ? strict_sub_units() : ((s.gram & 1) ? (int)ceil_div_ll(d.Kp, 32) * s.fr.J : 0);
     if (const char* e = getenv("CMF_HSUB")) s.h_sub = atoi(e);
     const long long tt = d.TO / 256 + 1;
     if (f.h_hd > 0) CMF_CUDA(cudaMalloc((void**)&s.hcarry, (size_t)2 * tt * f.h_hd * d.Kp * 4));
@@ -509,8 +526,6 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     CMF_TRY(ensure_autocorr(s));
     CMF_CUDA(cudaMalloc((void**)&s.Mt, (size_t)s.g_rows * f.Lv * f.KW * halves * 4));
     CMF_TRY(make_map(&s.tmMt_b, s.Mt, s.g_rows, (long long)f.Lv * f.KW * halves, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
-    CMF_TRY(set_recon_smem(recon_smem_bytes(s.dh_wrows) <= kMaxSmem && recon_smem_bytes(s.dh_wrows) > recon_smem_bytes(f.recon_wrows)
-                               ? recon_smem_bytes(s.dh_wrows) : recon_smem_bytes(f.recon_wrows)));
   }
   s.ready = true;
   return 0;
@@ -665,7 +680,7 @@ inline int den_h_gram(TcState& s, cudaStream_t stream) {
     launch_recon(s, grid, recon_smem_bytes(256), stream, s.tmWt_a, s.tmWt_b, p);
     CMF_TRY(launch_ok("gram_G"));
   }
-  // (c) R = lag-diagonal sums of G, as a W-like operand (rounded / folded like W)
+  // (c) R = lag-diagonal sums of G as a W-like operand Rt[l][k'][k] = R[l - (L-1)][k][k'] (rounded / folded like W)
   diag_sum_kernel<<<ew_blocks(s, (long long)s.Lr * d.Kp * d.Kp), 256, 0, stream>>>(s.G, s.LK, s.Rw, d.L, d.Kp);
   CMF_TRY(launch_ok("diag_sum"));
   if (s.x3) {
@@ -677,20 +692,34 @@ inline int den_h_gram(TcState& s, cudaStream_t stream) {
     fold_w_kernel<<<ew_blocks(s, (long long)s.Lrv * d.Kp * 32), 256, 0, stream>>>(s.Rwv, s.Rw, s.Lr, s.Lrv, d.Kp, d.Kp, f.s);
   }
   CMF_TRY(launch_ok("fold_R"));
-  // (d) den_H^T[tau][k] = sum_j Rw[j][k][:] . H^T[tau + L-1 - j][:]  on the recon kernel (features := components)
+  // (d) den_H^T[t][k] = sum_l sum_k' Rt[l][k'][k] H^T[t + l - (L-1)][k']: tensor_transconv of R with H on the
+  //     H-terms kernel (features := components; the four lag groups fill the 128 MMA rows, where the reconstruction
+  //     kernel used for this until round 2 left 96 of them idle)
   float* den = s.hterms + d.TO * d.Kp;
   {
-    ReconParams p{};
-    p.Np = d.Kp; p.L = s.Lrv; p.n_tiles_n = 1; p.wrows = s.dh_wrows; p.LB = s.dh_LB;
-    p.s = f.s; p.CB = f.CB; p.cb_cols = f.CB; p.h_shift = d.h + (d.L - 1) - f.s * (s.Lrv - 1);
-    p.n_rows = d.Kp; p.ld_out = d.Kp; p.store_mode = 0; p.w_kp = d.Kp; p.w_np = d.Np;
-    p.n_tiles = d.TO / 256;
-    p.t_own = 0; p.t_valid = d.TO;
-    p.Et = den; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
-    const int grid = (int)(p.n_tiles < d.num_sms ? p.n_tiles : d.num_sms);
-    set_x3(s, p, f.KW, f.KW);
-    launch_recon(s, grid, recon_smem_bytes(s.dh_wrows), stream, s.tmRw_a, s.tmH_k1, p);
+    const Fold& r = s.fr;
+    HTermsParams p{};
+    p.Np = d.Kp; p.J = r.J; p.n_chunks_n = (int)ceil_div_ll(d.Kp, 32); p.wrows = r.hterms_wrows;
+    p.s = f.s; p.CB = f.CB; p.Kp = d.Kp;
+    p.n_src = 1;
+    p.n_time_tiles = d.TO / 256 + 1;
+    p.n_items = p.n_time_tiles;
+    p.TO = d.TO; p.out = den; p.carry = s.hcarry_r; p.hd = r.h_hd;
+    p.sub_units = s.x3 ? strict_sub_units() : 0; p.n_stages = r.h_stages;
+    p.x3 = s.x3; p.lo_off = f.KW; p.err = s.d_err;
+    const bool direct = f.n_glag == 1 && f.s == 1;
+    const int grid = (int)(p.n_items < d.num_sms ? p.n_items : d.num_sms);
+    tc_hterms_kernel<<<grid, kSThreads, hterms_smem_bytes(r.h_stages, r.hterms_wrows, d.Kp, r.h_hd, direct), stream>>>(
+        s.tmRw_k3, s.tmHs_k3, s.tmHs_k3, s.tmHslo_k3, s.tmHslo_k3, p);
     CMF_TRY(launch_ok("gram_den_h"));
+    if (r.h_hd > 0) {
+      const long long wmax = r.h_hd < 256 ? r.h_hd : 256;
+      const long long total = (p.n_time_tiles - 1) * wmax * (d.Kp / 4);
+      if (total > 0) {
+        hterms_carry_kernel<<<ew_blocks(s, total), 256, 0, stream>>>(den, s.hcarry_r, d.TO, p.n_time_tiles, r.h_hd, d.Kp, 1);
+        CMF_TRY(launch_ok("gram_den_h_carry"));
+      }
+    }
   }
   // (e) remove the terms of est that lie past the end of the data (only the shard that sees the end)
   if (s.ntail > 0) {
