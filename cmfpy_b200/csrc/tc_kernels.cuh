@@ -412,6 +412,12 @@ struct WTermsParams {
   int x3, lo_off;                 // tc_wterms_x3_kernel: three passes over the item's time range - (S lo, H hi),
                                   // (S hi, H lo), (S hi, H hi); H lo sits lo_off columns to the right
   int sub_units;                  // tc_wterms_x3_kernel: 32-row time stages per tensor-memory sub-chunk
+  // quad mode (data with at most 32 features: the lag autocorrelation of H^T): the four 32-row quarters of the
+  // accumulator hold the SAME features at four time shifts - quarter r reads S^T rows tau + r * LPR * s, which
+  // makes its columns lags r * LPR .. - so one item covers 4 x LPR virtual lags and no MMA row is idle.
+  // The time range starts stage0 (<= 0) stages early so that every quarter sees all of its rows.
+  int quad;
+  long long stage0;
   int* err;
 };
 
@@ -465,10 +471,12 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     ch = (int)item;
   };
   auto chunk_range = [&](int ch, long long& s0, long long& s1) {
-    const long long base = p.stages_total / p.n_chunks, rem = p.stages_total % p.n_chunks;
-    s0 = ch * base + (ch < rem ? ch : rem);
+    const long long total = p.stages_total - p.stage0;
+    const long long base = total / p.n_chunks, rem = total % p.n_chunks;
+    s0 = p.stage0 + ch * base + (ch < rem ? ch : rem);
     s1 = s0 + base + (ch < rem ? 1 : 0);
   };
+  const int lpi = p.quad ? 64 : 16;               // virtual lags per item
 
   if (warp == 0) {
     {
@@ -486,9 +494,15 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int tau0 = (int)(s * 32);
           if (elect_one()) {
             mbar_arrive_expect_tx(&full[ps.stage], kWtStageBytes);
-            tma_load_3d(dst, tmS, &full[ps.stage], 0, tau0, nt * 4);      // four 32-feature regions in one box
+            if (!p.quad) {
+              tma_load_3d(dst, tmS, &full[ps.stage], 0, tau0, nt * 4);    // four 32-feature regions in one box
+            } else {
+#pragma unroll
+              for (int r = 0; r < 4; ++r)                                 // the same features, 16 r lags later
+                tma_load_2d(dst + r * 4096, tmS, &full[ps.stage], 0, tau0 + r * 16 * p.s);
+            }
             // Hv rows tau0 - s*(l0+15) .. tau0 + 32; row index in Hv is tau + h
-            tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], hcol, tau0 - p.s * (lg * 16 + 15) + p.h);
+            tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], hcol, tau0 - p.s * (lg * lpi + 15) + p.h);
           }
           ps.advance(kWtStages);
         }
@@ -537,7 +551,7 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       decode(item, lg, cb, src, nt, ch);
       if (!ab.wait(tfull, it & 1)) break;
       tc_fence_after();
-      const int n = nt * 128 + q * 32 + lane;
+      const int n = p.quad ? lane : nt * 128 + q * 32 + lane;
       float* obase = p.part + ((long long)ch * p.n_src + src) * p.per_src;
 #pragma unroll 1
       for (int c = 0; c < 16; ++c) {            // 16 column blocks of 32 = (g, a): one virtual lag each
@@ -545,7 +559,7 @@ tc_wterms_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
         tmem_ld_wait();
         const int g = c >> 3, a = c & 7;
-        const int lv = lg * 16 + 8 * g + 7 - a;
+        const int lv = lg * lpi + (p.quad ? 16 * q : 0) + 8 * g + 7 - a;
         if (n < p.Np && lv < p.Lv) {
           if (p.s == 1) {                       // 32 components of column block cb, real lag lv
             float4* o = reinterpret_cast<float4*>(obase + ((long long)lv * p.Np + n) * p.Kp + cb * 32);

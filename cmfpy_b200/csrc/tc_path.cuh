@@ -113,6 +113,8 @@ struct TcState {
   float *P = nullptr, *Ppart = nullptr, *Mt = nullptr;
   int p_chunks = 1, p_grid = 1;
   CUtensorMap tmHx_k2, tmHxlo_k2, tmMt_b;
+  int p_quad = 0, p_lag_groups = 1;     // autocorrelation pass: quad mode (Kp <= 32), its lag groups
+  long long p_stage0 = 0;
   bool autocorr_ready = false;
 };
 
@@ -320,10 +322,20 @@ inline int ensure_autocorr(TcState& s) {
   const Dims& d = s.d;
   const Fold& f = s.f;
   const long long pcount = (long long)d.L * d.Kp * d.Kp;
+  const int lpr = s.x3 ? 8 : 16;                    // virtual lags per accumulator quarter / per plain item
+  // quad mode (WTermsParams::quad): H^T has at most 32 "features", so the four row quarters of the accumulator
+  // take four consecutive lag blocks instead of 96 idle rows
+  // (3xTF32 only: plain TF32 keeps the time chunks of the numerator pass - equal chains, equal truncation bias -
+  // and with the chunk count fixed a wider item buys nothing)
+  s.p_quad = (d.Kp <= 32 && s.x3) ? 1 : 0;
+  if (const char* e = getenv("CMF_P_QUAD")) s.p_quad = atoi(e) && d.Kp <= 32;
+  s.p_lag_groups = (int)ceil_div_ll(f.Lv, s.p_quad ? 4 * lpr : lpr);
+  s.p_stage0 = s.p_quad ? -ceil_div_ll(3ll * lpr * f.s, 32) : 0;
   {   // same time chunks as the numerator pass: equal accumulation chains, equal truncation bias
-    const long long units = (long long)s.n_lag_groups * f.CB;
-    const long long stages_total = ceil_div_ll(d.Tloc, 32);
+    const long long units = (long long)s.p_lag_groups * f.CB;
+    const long long stages_total = ceil_div_ll(d.Tloc, 32) - s.p_stage0;
     long long c = s.n_chunks;
+    if (s.p_quad && c * units < d.num_sms) c = ceil_div_ll(d.num_sms, units);     // fewer items: keep the SMs busy
     if (c > stages_total) c = stages_total;
     if (c < 1) c = 1;
     s.p_chunks = (int)c;
@@ -333,10 +345,16 @@ inline int ensure_autocorr(TcState& s) {
   CMF_CUDA(cudaMalloc((void**)&s.P, (size_t)pcount * 4));
   CMF_CUDA(cudaMalloc((void**)&s.Ppart, (size_t)pcount * s.p_chunks * 4));
   // H^T itself as the "data" operand: the first Kp columns of Hv are the unfolded, rounded H^T
-  CMF_TRY(make_map_k2src(&s.tmHx_k2, s.Hv + (long long)d.h * s.KWs, d.Tloc, d.Kp, s.KWs));
-  s.tmHxlo_k2 = s.tmHx_k2;
-  if (s.x3)
-    CMF_TRY(make_map_k2src(&s.tmHxlo_k2, s.Hv + (long long)d.h * s.KWs + f.KW, d.Tloc, d.Kp, s.KWs));
+  const float* base = s.Hv + (long long)d.h * s.KWs;
+  if (s.p_quad) {
+    CMF_TRY(make_map(&s.tmHx_k2, base, d.Tloc, d.Kp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, s.KWs));
+    s.tmHxlo_k2 = s.tmHx_k2;
+    if (s.x3) CMF_TRY(make_map(&s.tmHxlo_k2, base + f.KW, d.Tloc, d.Kp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, s.KWs));
+  } else {
+    CMF_TRY(make_map_k2src(&s.tmHx_k2, base, d.Tloc, d.Kp, s.KWs));
+    s.tmHxlo_k2 = s.tmHx_k2;
+    if (s.x3) CMF_TRY(make_map_k2src(&s.tmHxlo_k2, base + f.KW, d.Tloc, d.Kp, s.KWs));
+  }
   s.autocorr_ready = true;
   return 0;
 }
@@ -347,10 +365,11 @@ inline int autocorr(TcState& s, cudaStream_t stream) {
   const Fold& f = s.f;
   const long long pcount = (long long)d.L * d.Kp * d.Kp;
   WTermsParams p{};
-  p.Np = d.Kp; p.L = d.L; p.n_tiles_n = 1; p.n_lag_groups = s.n_lag_groups; p.n_chunks = s.p_chunks; p.h = d.h;
+  p.Np = d.Kp; p.L = d.L; p.n_tiles_n = 1; p.n_lag_groups = s.p_lag_groups; p.n_chunks = s.p_chunks; p.h = d.h;
   p.Lv = f.Lv; p.Kp = d.Kp; p.s = f.s; p.CB = f.CB; p.brows = s.x3 ? wterms8_brows(f.s) : wterms_brows(f.s); p.n_src = 1;
   p.n_items = (long long)p.n_lag_groups * f.CB * p.n_chunks;
   p.stages_total = ceil_div_ll(d.Tloc, 32);
+  p.quad = s.p_quad; p.stage0 = s.p_stage0;
   p.part = (s.p_chunks == 1) ? s.P : s.Ppart;
   p.per_src = pcount; p.err = s.d_err;
   p.x3 = s.x3; p.lo_off = f.KW; p.sub_units = s.x3 ? strict_sub_units() : 0;
@@ -634,7 +653,7 @@ inline int recon(TcState& s, cudaStream_t stream, bool store_est = true) {
 inline int w_terms(TcState& s, cudaStream_t stream) {
   const Dims& d = s.d;
   const Fold& f = s.f;
-  WTermsParams p;
+  WTermsParams p{};
   p.Np = d.Np; p.L = d.L; p.n_tiles_n = (int)ceil_div_ll(d.Np, 128); p.n_lag_groups = s.n_lag_groups;
   p.n_chunks = s.n_chunks; p.h = d.h;
   p.Lv = f.Lv; p.Kp = d.Kp; p.s = f.s; p.CB = f.CB; p.brows = s.x3 ? wterms8_brows(f.s) : wterms_brows(f.s);

@@ -425,10 +425,12 @@ tc_wterms_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     ch = (int)item;
   };
   auto chunk_range = [&](int ch, long long& s0, long long& s1) {
-    const long long base = p.stages_total / p.n_chunks, rem = p.stages_total % p.n_chunks;
-    s0 = ch * base + (ch < rem ? ch : rem);
+    const long long total = p.stages_total - p.stage0;
+    const long long base = total / p.n_chunks, rem = total % p.n_chunks;
+    s0 = p.stage0 + ch * base + (ch < rem ? ch : rem);
     s1 = s0 + base + (ch < rem ? 1 : 0);
   };
+  const int lpi = p.quad ? 32 : 8;                // virtual lags per item (quad mode: see WTermsParams)
 
   if (warp == 0) {
     reg_dec<kSCtlRegs>();
@@ -449,9 +451,15 @@ tc_wterms_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const int tau0 = (int)(s * 32);
             if (elect_one()) {
               mbar_arrive_expect_tx(&full[ps.stage], stage_bytes);
-              tma_load_3d(dst, tmS, &full[ps.stage], 0, tau0, nt * 4);      // four 32-feature regions in one box
-              // Hv rows tau0 - s*(8 lg + 7) .. tau0 + 32; row index in Hv is tau + h
-              tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], hcol, tau0 - p.s * (lg * 8 + 7) + p.h);
+              if (!p.quad) {
+                tma_load_3d(dst, tmS, &full[ps.stage], 0, tau0, nt * 4);    // four 32-feature regions in one box
+              } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)                                 // the same features, 8 r lags later
+                  tma_load_2d(dst + r * 4096, tmS, &full[ps.stage], 0, tau0 + r * 8 * p.s);
+              }
+              // Hv rows tau0 - s*(l0 + 7) .. tau0 + 32; row index in Hv is tau + h
+              tma_load_2d(dst + kWtABytes, &tmH, &full[ps.stage], hcol, tau0 - p.s * (lg * lpi + 7) + p.h);
             }
             ps.advance(kWtStages);
           }
@@ -519,12 +527,12 @@ tc_wterms_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (lane == 0) mbar_arrive(&sempty[sd.b]);
       }
       if (!ok) break;
-      const int n = nt * 128 + q * 32 + lane;
+      const int n = p.quad ? lane : nt * 128 + q * 32 + lane;
       float* obase = p.part + ((long long)ch * p.n_src + src) * p.per_src;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {              // 4 column blocks of 32 = one virtual lag each
         const int a = half * 4 + c;
-        const int lv = lg * 8 + 7 - a;
+        const int lv = lg * lpi + (p.quad ? 8 * q : 0) + 7 - a;
         if (n < p.Np && lv < p.Lv) {
           if (p.s == 1) {                         // 32 components of column block cb, real lag lv
             float4* o = reinterpret_cast<float4*>(obase + ((long long)lv * p.Np + n) * p.Kp + cb * 32);
