@@ -81,6 +81,7 @@ _SIGNATURES = {
     "cmf_mu_path_name": (C.c_char_p, [_H]),
     "cmf_mu_kernel_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "cmf_mu_set_profiling": (C.c_int, [_H, C.c_int]),
+    "cmf_mu_set_loss_mode": (C.c_int, [_H, C.c_int]),
     "cmf_mu_launch_table": (C.c_int, [_H, C.c_char_p, C.c_longlong]),
     "cmf_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
                               C.c_int, C.c_int, C.c_int, C.c_int]),

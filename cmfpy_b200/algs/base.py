@@ -37,7 +37,7 @@ class DeviceOptimizer:
 
     def __init__(self, data, model_dimensions, initW=None, initH=None,
                  tol=1e-5, patience=3, precision="auto", device=0, seed=None,
-                 denominators="auto", normalize=None):
+                 denominators="auto", normalize=None, loss_precision="auto"):
         # reference base.py:20-21
         if patience < 1 or not isinstance(patience, Integral):
             raise ValueError("Patience must be a positive integer.")
@@ -67,6 +67,9 @@ class DeviceOptimizer:
                         t_offset=0, device=device, precision=_lib.PRECISIONS[precision],
                         stream=None, denominators=_lib.DENOMINATORS[denominators])
         _lib.check(self._lib.cmf_mu_create(C.byref(self._h), C.byref(p)))
+        if loss_precision not in ("auto", "full"):
+            raise ValueError("loss_precision must be 'auto' or 'full'")
+        _lib.check(self._lib.cmf_mu_set_loss_mode(self._h, 0 if loss_precision == "auto" else 1))
         _lib.check(self._lib.cmf_mu_set_data(self._h, X.ctypes.data, _lib.np_dtype_code(X),
                                              _lib.CMF_HOST, T, T))
         if normalize is not None:

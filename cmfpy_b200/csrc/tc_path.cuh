@@ -83,6 +83,7 @@ struct TcState {
   // 3xTF32 (CMF_PREC_TF32X3): every operand is a TF32 pair.  Wv / Hv rows are [hi (KW) | lo (KW)] (KWs = 2 KW
   // columns); Xt / Et hold the hi halves and Xlo / Elo the lo halves.
   int x3 = 0, KWs = 32;
+  int loss_fast = 0;               // 3xTF32, loss-only reconstruction: the hi x hi operand pass alone (see recon())
   float *Xlo = nullptr, *Elo = nullptr;
   CUtensorMap tmXlo_k2, tmElo_k2, tmXlo_k3, tmElo_k3;
   double *loss_partials = nullptr, *d_sumsq = nullptr;
@@ -639,13 +640,22 @@ inline int recon(TcState& s, cudaStream_t stream, bool store_est = true) {
   p.t_own = d.Tloc; p.t_valid = d.t_valid;
   p.Et = s.Et; p.Xt = s.Xt; p.loss_partials = s.loss_partials; p.round_out = 1; p.err = s.d_err;
   p.LB = f.recon_LB;
-  if (s.x3) {
+  const bool loss_only_fast = s.x3 && !store_est && s.loss_fast;
+  if (loss_only_fast) {
+    // The reconstruction that only feeds the loss (both denominators on the Gram route) runs the hi x hi operand
+    // pass alone, with the same two-level accumulation.  What it drops, W_lo (*) H_hi + W_hi (*) H_lo, are the
+    // rounding residuals of the factors (relative size 2^-12, random signs); the ABI switches this on only for
+    // problems where their effect on ||est - X||^2 is below 1e-6 relative (decide_loss_mode in cmf_abi.cu:
+    // a million or more factor entries, K L loss^2 >= 0.2); the factors W and H never see it.
+    p.sub_units = 4 * strict_sub_units();   // (a uniform scale bias of est moves the loss far less than it would move W or H)
+    p.Xlo = s.Xlo;
+  } else if (s.x3) {
     set_x3(s, p, f.KW, 0);
     p.Elo = s.Elo; p.Xlo = s.Xlo;
   }
   const int grid = s.recon_grid;
   launch_recon(s, grid, recon_smem_bytes(f.recon_wrows), stream, s.tmW_k1, s.tmH_k1, p);
-  CMF_TRY(launch_ok("tc_recon"));
+  CMF_TRY(launch_ok(loss_only_fast ? "tc_recon_loss_1pass" : "tc_recon"));
   ew::sum_doubles_kernel<<<1, 1024, 0, stream>>>(s.loss_partials, grid, s.d_sumsq);
   return launch_ok("loss_sum");
 }

@@ -253,6 +253,12 @@ const char* cmf_mu_path_name(cmf_mu_t* h);
 int cmf_mu_kernel_ms(cmf_mu_t* h, float out[4]);
 /* Toggle per-kernel event timing inside cmf_mu_step (off by default).       */
 int cmf_mu_set_profiling(cmf_mu_t* h, int on);
+/* How the 3xTF32 mode computes the loss of an iteration (reference base.py:90-97) when nothing else reads the
+ * reconstruction (both denominators on the Gram route).  0 (default, "auto"): on large problems (L N K and K T of a
+ * million entries or more, K L loss^2 >= 0.2) the reconstruction runs its hi x hi operand pass alone - the two
+ * cross passes it omits, the rounding residuals of W and H, then change the loss by less than 1e-6 relative;
+ * otherwise, and with mode 1 ("full"), all three passes.  W and H are never affected. */
+int cmf_mu_set_loss_mode(cmf_mu_t* h, int mode);
 /* on = 2: additionally one CUDA event after EVERY kernel launch of the following steps; cmf_mu_launch_table then
  * returns one text line "label launches total_ms" per kernel label (a measurement aid of bench.py: the per-kernel
  * roofline table; the reference only has wall-clock time_hist, cmfpy/model.py:160-167). */

@@ -349,3 +349,25 @@ def test_fp32_and_tf32_agree_large(built_lib, precision):
     # the scale split between W and H must not drift apart either
     assert abs(a.W.sum() / b.W.sum() - 1) < 1e-3 and abs(a.H.sum() / b.H.sum() - 1) < 1e-3
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "planted"])
+def test_one_pass_loss(built_lib, kind):
+    """tf32x3 on a large problem computes the loss from a one-pass reconstruction (loss_precision="auto",
+    cmf_mu_set_loss_mode); it must agree with the three-pass loss to 1e-6 relative, and W, H must be identical."""
+    from cmfpy_b200.algs.mult import MultUpdate
+    from cmfpy_b200.model import ModelDimensions
+    N, T, K, L = 1024, 1 << 16, 32, 64             # L N K = 2^21, K T = 2^21 factor entries
+    X, W0, H0 = make_inputs(N, T, K, L, kind, seed=17)
+    dims = ModelDimensions(X, maxlag=L, n_components=K)
+    out = {}
+    for mode in ("auto", "full"):
+        alg = MultUpdate(X, dims, initW=W0, initH=H0, tol=0, precision="tf32x3", denominators="gram", loss_precision=mode)
+        l0 = alg.loss                                 # the host has seen a loss: the next batch may go one-pass
+        hist = alg.update_many(3) + alg.update_many(3)
+        out[mode] = (np.array([l0] + hist), alg.W, alg.H, alg.launch_table() if False else None)
+        alg.close()
+    a, f = out["auto"][0], out["full"][0]
+    print("one-pass loss vs full (%s): max rel diff %.2e" % (kind, (np.abs(a - f) / f).max()))
+    assert (np.abs(a - f) / f).max() <= 1e-6
+    assert np.array_equal(out["auto"][1], out["full"][1]) and np.array_equal(out["auto"][2], out["full"][2])
