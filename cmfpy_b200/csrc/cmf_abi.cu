@@ -84,6 +84,9 @@ struct cmf_mu_s {
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_dirty = true, graph_ok = true;
   long long graph_launches = 0;
+  cudaGraphExec_t sgraph_exec = nullptr;           // the same for one iteration of cmf_mu_step_sharded
+  bool sgraph_dirty = true, sgraph_ok = true;
+  long long sgraph_launches = 0;
   int* d_counter = nullptr;
   float kernel_ms[4] = {0, 0, 0, 0};
   std::vector<cudaEvent_t> ev_pool;
@@ -121,7 +124,7 @@ struct cmf_mu_s {
     size_t shared_bytes = 0;
     void* opened[peer::kMaxPeers][3] = {};   // IPC mappings of the peers' allocations (bases, for close)
     peer::Peers P{};
-    uint32_t ex_epoch = 0, halo_epoch = 0, bar_epoch = 0;
+    uint32_t bar_epoch = 0;                 // (exchange / halo epochs live on the device: peer::Control)
     int ring_cap = 1024;
   } peer;
 };
@@ -267,7 +270,7 @@ int ensure_est_buffer(cmf_mu_s* h) {
     CMF_CUDA(cudaMemsetAsync(h->Elo, 0, (size_t)h->RT * h->Np * 4, h->stream));
   }
   if (h->use_tc) CMF_TRY(tc::attach_est(h->tcs, h->Et, h->Elo));
-  h->graph_dirty = true;             // kernel arguments baked into a captured iteration changed
+  h->graph_dirty = h->sgraph_dirty = true;             // kernel arguments baked into a captured iteration changed
   return 0;
 }
 
@@ -512,6 +515,7 @@ void free_all(cmf_mu_s* h) {
   cudaFree(h->d_neg);
   cudaFree(h->d_counter);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->sgraph_exec) cudaGraphExecDestroy(h->sgraph_exec);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   for (auto e : h->llog.pool) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -707,7 +711,7 @@ static int finish_data(cmf_mu_s* h) {
   CMF_CUDA(cudaMemcpyAsync(&h->has_neg, h->d_neg, 4, cudaMemcpyDeviceToHost, h->stream));
   CMF_CUDA(cudaStreamSynchronize(h->stream));
   h->norm_x = std::sqrt(h->sumsq_x);
-  h->graph_dirty = true;
+  h->graph_dirty = h->sgraph_dirty = true;
   h->last_loss = -1.0;
   h->have_data = true;
   h->est_valid = false;
@@ -799,7 +803,7 @@ int cmf_mu_set_norm_x(cmf_mu_t* h, double norm_x) {
   CMF_ENTER(h);
   CMF_CHECK(norm_x >= 0.0, "norm_x must be non-negative");
   h->norm_x = norm_x;
-  h->graph_dirty = true;
+  h->graph_dirty = h->sgraph_dirty = true;
   return 0;
 }
 
@@ -986,7 +990,7 @@ static void decide_loss_mode(cmf_mu_s* h) {
                     n_w >= 1048576.0 && n_h >= 1048576.0 && kl * h->last_loss * h->last_loss >= 0.2;
   if (fast != (h->tcs.loss_fast != 0)) {
     h->tcs.loss_fast = fast ? 1 : 0;
-    h->graph_dirty = true;
+    h->graph_dirty = h->sgraph_dirty = true;
   }
 }
 
@@ -1380,7 +1384,9 @@ int cmf_mu_halo_exchange_peer(cmf_mu_t* h) {
   CMF_CHECK(ps.attached, "cmf_mu_halo_exchange_peer needs attached peers");
   CMF_CHECK(h->have_factors, "W or H not initalized.");
   if (h->h > 0) {
-    peer::halo_exchange_kernel<<<2, 256, 0, h->stream>>>(ps.P, h->Ht, h->h, h->Kp, h->Tloc, ++ps.halo_epoch);
+    peer::tick_kernel<<<1, 1, 0, h->stream>>>(ps.P.ctl[ps.P.rank], peer::kTickHalo);
+    CMF_TRY(launch_check(h, "peer_tick"));
+    peer::halo_exchange_kernel<<<2, 256, 0, h->stream>>>(ps.P, h->Ht, h->h, h->Kp, h->Tloc);
     CMF_TRY(launch_check(h, "halo_exchange"));
     CMF_TRY(sync_ops_H(h, 0, h->h));
     CMF_TRY(sync_ops_H(h, h->h + h->Tloc, h->h));
@@ -1391,6 +1397,72 @@ int cmf_mu_halo_exchange_peer(cmf_mu_t* h) {
   CMF_CUDA(cudaStreamSynchronize(h->stream));
   if (perr != 0) { set_error("peer halo exchange timed out (error %d): a rank did not reach the exchange", perr); return 1; }
   return 0;
+}
+
+// one sharded MU iteration issued on the solver's stream (constant kernel arguments: epochs and the loss slot are
+// device counters, see peer::Control)
+static int issue_sharded_iteration(cmf_mu_s* h, bool prof, size_t& ne, int ex_grid) {
+  auto& ps = h->peer;
+  const long long n4 = h->wcount / 4;
+  peer::Control* me = ps.P.ctl[ps.P.rank];
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  CMF_TRY(do_w_terms(h));
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  // reduce-scatter of the partial W terms + W update + all-gather of W: one kernel
+  CMF_CHECK(h->wterms_valid, "w exchange before w_terms");
+  peer::tick_kernel<<<1, 1, 0, h->stream>>>(me, peer::kTickExchange | (h->h > 0 ? peer::kTickHalo : 0));
+  CMF_TRY(launch_check(h, "peer_tick"));
+  peer::wstep_exchange_kernel<<<ex_grid, 256, 0, h->stream>>>(ps.P, n4);
+  CMF_TRY(launch_check(h, "wstep_exchange"));
+  h->wterms_valid = false;
+  h->est_valid = false;
+  CMF_TRY(sync_ops_W(h));
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  if (!gram_h(h)) CMF_TRY(do_recon(h));
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  CMF_TRY(do_h_terms(h));
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  CMF_TRY(do_h_apply(h));
+  if (h->h > 0) {
+    peer::halo_exchange_kernel<<<2, 256, 0, h->stream>>>(ps.P, h->Ht, h->h, h->Kp, h->Tloc);
+    CMF_TRY(launch_check(h, "halo_exchange"));
+    CMF_TRY(sync_ops_H(h, 0, h->h));
+    CMF_TRY(sync_ops_H(h, h->h + h->Tloc, h->h));
+  }
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  CMF_TRY(do_recon(h, !(gram_w(h) && gram_h(h))));
+  if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
+  peer::sumsq_push_kernel<<<1, 32, 0, h->stream>>>(ps.P, h->d_sumsq);
+  return launch_check(h, "sumsq_push");
+}
+
+// capture one sharded iteration into h->sgraph_exec; on any failure fall back to plain launches for good
+static void capture_sharded_iteration(cmf_mu_s* h, int ex_grid) {
+  if (h->sgraph_exec) { cudaGraphExecDestroy(h->sgraph_exec); h->sgraph_exec = nullptr; }
+  h->sgraph_dirty = true;
+  if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    h->sgraph_ok = false;
+    return;
+  }
+  const long long l0 = h->launches;
+  const bool est_valid = h->est_valid, est_stored = h->est_stored, wterms_valid = h->wterms_valid;
+  size_t ne = 0;
+  const int rc = issue_sharded_iteration(h, false, ne, ex_grid);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  h->est_valid = est_valid; h->est_stored = est_stored; h->wterms_valid = wterms_valid;
+  h->sgraph_launches = h->launches - l0;
+  h->launches = l0;
+  if (rc != 0 || e != cudaSuccess || graph == nullptr ||
+      cudaGraphInstantiate(&h->sgraph_exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    h->sgraph_exec = nullptr;
+    h->sgraph_ok = false;
+  } else {
+    h->sgraph_dirty = false;
+  }
+  if (graph) cudaGraphDestroy(graph);
 }
 
 // n_steps x MultUpdate.update() on a time shard, collectives over peer memory; every rank calls it
@@ -1412,41 +1484,30 @@ int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out) {
   int ex_grid = (int)ceil_div_ll(slice, 256);
   if (ex_grid > h->num_sms) ex_grid = h->num_sms;       // every block spins: all must be resident
   if (ex_grid < 1) ex_grid = 1;
+  static const bool graphs_enabled = [] { const char* e = getenv("CMF_GRAPH"); return !e || atoi(e) != 0; }();
+  bool use_graph = graphs_enabled && !prof && h->sgraph_ok;
+  if (use_graph && (h->sgraph_dirty || !h->sgraph_exec)) {
+    capture_sharded_iteration(h, ex_grid);
+    use_graph = h->sgraph_ok && h->sgraph_exec != nullptr;
+    last_error().clear();
+  }
   std::vector<double> ring((size_t)ps.ring_cap * peer::kMaxPeers);
   int done = 0;
   while (done < n_steps) {
     const int chunk = (n_steps - done < ps.ring_cap) ? n_steps - done : ps.ring_cap;
     size_t ne = 0;
     launch_log_begin(h);
+    peer::tick_kernel<<<1, 1, 0, h->stream>>>(ps.P.ctl[ps.P.rank], peer::kTickSlotReset);
+    CMF_TRY(launch_check(h, "peer_tick"));
     for (int i = 0; i < chunk; ++i) {
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      CMF_TRY(do_w_terms(h));
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      // reduce-scatter of the partial W terms + W update + all-gather of W: one kernel
-      CMF_CHECK(h->wterms_valid, "w exchange before w_terms");
-      peer::wstep_exchange_kernel<<<ex_grid, 256, 0, h->stream>>>(ps.P, n4, ++ps.ex_epoch);
-      CMF_TRY(launch_check(h, "wstep_exchange"));
-      h->wterms_valid = false;
-      h->est_valid = false;
-      CMF_TRY(sync_ops_W(h));
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      if (!gram_h(h)) CMF_TRY(do_recon(h));
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      CMF_TRY(do_h_terms(h));
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      CMF_TRY(do_h_apply(h));
-      if (h->h > 0) {
-        peer::halo_exchange_kernel<<<2, 256, 0, h->stream>>>(ps.P, h->Ht, h->h, h->Kp, h->Tloc, ++ps.halo_epoch);
-        CMF_TRY(launch_check(h, "halo_exchange"));
-        CMF_TRY(sync_ops_H(h, 0, h->h));
-        CMF_TRY(sync_ops_H(h, h->h + h->Tloc, h->h));
+      if (use_graph) {
+        CMF_CUDA(cudaGraphLaunch(h->sgraph_exec, h->stream));
+        h->launches += h->sgraph_launches;
+      } else {
+        CMF_TRY(issue_sharded_iteration(h, prof, ne, ex_grid));
       }
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      CMF_TRY(do_recon(h, !(gram_w(h) && gram_h(h))));
-      if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-      peer::sumsq_push_kernel<<<1, 32, 0, h->stream>>>(ps.P, h->d_sumsq, i);
-      CMF_TRY(launch_check(h, "sumsq_push"));
     }
+    if (use_graph) { h->est_valid = true; h->est_stored = !(gram_w(h) && gram_h(h)); h->wterms_valid = false; }
     peer::barrier_kernel<<<1, 32, 0, h->stream>>>(ps.P, ++ps.bar_epoch);
     CMF_TRY(launch_check(h, "peer_barrier"));
     CMF_CUDA(cudaMemcpyAsync(ring.data(), ps.P.ring[ps.P.rank], (size_t)chunk * peer::kMaxPeers * 8, cudaMemcpyDeviceToHost,

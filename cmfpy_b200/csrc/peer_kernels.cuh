@@ -38,7 +38,9 @@ struct Control {
   uint32_t bar[kMaxPeers];       // end-of-call barrier
   uint32_t blocks_done;          // block counter of the running exchange kernel
   int err;
-  uint32_t pad[4];
+  // Epochs and the loss-ring slot live on the device and are advanced by tick_kernel, so that every kernel of a
+  // sharded iteration has constant arguments and the iteration can be captured once and replayed as a CUDA graph.
+  uint32_t ex_epoch, halo_epoch, slot, pad;
 };
 static_assert(sizeof(Control) % 16 == 0, "control block must keep the payload 16-byte aligned");
 
@@ -81,6 +83,14 @@ __device__ __forceinline__ bool wait_epoch(const uint32_t* flag, uint32_t epoch,
   return true;
 }
 
+// advances the device-side counters of this rank (one thread): what the next exchange kernels will use
+enum { kTickExchange = 1, kTickHalo = 2, kTickSlotReset = 4 };
+__global__ void tick_kernel(Control* me, int what) {
+  if (what & kTickExchange) me->ex_epoch += 1;
+  if (what & kTickHalo) me->halo_epoch += 1;
+  if (what & kTickSlotReset) me->slot = 0;
+}
+
 // --------------------------------------------------------------------------
 // W step: reduce-scatter of the partials + multiplicative update + all-gather of W.
 //   n4       : wcount / 4 (float4 elements of W); the den half of numden starts at float4 index n4
@@ -88,9 +98,10 @@ __device__ __forceinline__ bool wait_epoch(const uint32_t* flag, uint32_t epoch,
 // Launch: grid <= number of SMs (all blocks co-resident: they spin), 256 threads.
 // --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-wstep_exchange_kernel(const Peers P, long long n4, uint32_t epoch) {
+wstep_exchange_kernel(const Peers P, long long n4) {
   Control* me = P.ctl[P.rank];
   const int G = P.world;
+  const uint32_t epoch = me->ex_epoch;              // set by the tick kernel before this launch
   // (1) my partials are complete (previous kernels on this stream): tell every peer
   if (blockIdx.x == 0 && threadIdx.x < G) {
     __threadfence_system();
@@ -154,8 +165,9 @@ wstep_exchange_kernel(const Peers P, long long n4, uint32_t epoch) {
 // (zeros at the global boundaries).  One block per direction.
 // --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-halo_exchange_kernel(const Peers P, float* __restrict__ Ht, int h, int Kp, long long Tloc, uint32_t epoch) {
+halo_exchange_kernel(const Peers P, float* __restrict__ Ht, int h, int Kp, long long Tloc) {
   Control* me = P.ctl[P.rank];
+  const uint32_t epoch = me->halo_epoch;            // set by the tick kernel before this launch
   const int dir = blockIdx.x;                       // 0: talk to the left neighbour, 1: to the right
   const int nb = dir == 0 ? P.rank - 1 : P.rank + 1;
   const long long n4 = (long long)h * Kp / 4;
@@ -180,12 +192,16 @@ halo_exchange_kernel(const Peers P, float* __restrict__ Ht, int h, int Kp, long 
   for (long long i = threadIdx.x; i < n4; i += blockDim.x) halo_rows[i] = ld_peer(in + i);
 }
 
-// every rank's ring[slot][me] = my local residual sum of squares
-__global__ void sumsq_push_kernel(const Peers P, const double* __restrict__ sumsq, int slot) {
+// every rank's ring[slot][me] = my local residual sum of squares; the slot is this rank's device counter
+__global__ void sumsq_push_kernel(const Peers P, const double* __restrict__ sumsq) {
+  Control* me = P.ctl[P.rank];
+  const uint32_t slot = me->slot;
   if (threadIdx.x < P.world) {
     P.ring[threadIdx.x][(size_t)slot * kMaxPeers + P.rank] = *sumsq;
     __threadfence_system();
   }
+  __syncwarp();
+  if (threadIdx.x == 0) me->slot = slot + 1;
 }
 
 // end-of-call barrier: everything every peer stored before it (ring slots) is visible afterwards
