@@ -20,6 +20,18 @@ CMF_PEER_BLOB_BYTES = 512
 DENOMINATORS = {"direct": CMF_DEN_DIRECT, "gram": CMF_DEN_GRAM, "auto": CMF_DEN_AUTO}
 
 
+class SynthParams(C.Structure):
+    _fields_ = [
+        ("n_components", C.c_int), ("n_features", C.c_int), ("n_lags", C.c_int),
+        ("n_timebins", C.c_longlong), ("t_offset", C.c_longlong), ("t_local", C.c_longlong),
+        ("H_sparsity", C.c_double), ("noise_scale", C.c_double), ("seed", C.c_ulonglong),
+        ("device", C.c_int), ("precision", C.c_int),
+    ]
+
+
+SYNTH_W, SYNTH_H, SYNTH_NOISE, SYNTH_DATA, SYNTH_GENERATE = range(5)
+
+
 class Params(C.Structure):
     _fields_ = [
         ("n_features", C.c_int), ("n_components", C.c_int), ("maxlag", C.c_int),
@@ -89,6 +101,16 @@ _SIGNATURES = {
                             C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "cmf_tensor_transconv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cmf_dmat_info": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                                C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
+    "cmf_dmat_get": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_longlong]),
+    "cmf_dmat_destroy": (C.c_int, [_H]),
+    "cmf_synth_create": (C.c_int, [C.POINTER(_H), C.POINTER(SynthParams)]),
+    "cmf_synth_get": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int, C.c_longlong]),
+    "cmf_synth_matrix": (C.c_int, [_H, C.c_int, C.POINTER(_H)]),
+    "cmf_synth_destroy": (C.c_int, [_H]),
+    "cmf_spectrogram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_double, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_int, C.c_int, C.POINTER(_H)]),
 }
 
 _lib = None

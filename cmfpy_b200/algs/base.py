@@ -58,10 +58,21 @@ class DeviceOptimizer:
         N, T, K, L = self.n_features, self.n_timepoints, self.n_components, self.maxlag
         self.precision = precision = resolve_precision(self._lib, precision, N, K, L)
 
-        X = _as_host_matrix(data, "data")
-        if X.shape != (N, T):
-            raise ValueError("data has shape %s, dimensions say %s" % (X.shape, (N, T)))
-        self._X = X
+        # a NumPy array (the reference's contract) or a row-major float32 matrix already on the device
+        # (datasets.DeviceMatrix, a torch / cupy array: anything with __cuda_array_interface__)
+        from ..datasets import describe_device_matrix, is_device_matrix
+        on_device = is_device_matrix(data)
+        if on_device:
+            x_ptr, x_ld, x_shape = describe_device_matrix(data)
+            x_dt, x_mem = _lib.CMF_F32, _lib.CMF_DEVICE
+            self._X, self._X_device = None, data                 # read back only if `.X` / `.resids` are asked for
+        else:
+            X = _as_host_matrix(data, "data")
+            x_ptr, x_ld, x_shape = X.ctypes.data, T, X.shape
+            x_dt, x_mem = _lib.np_dtype_code(X), _lib.CMF_HOST
+            self._X = X
+        if tuple(x_shape) != (N, T):
+            raise ValueError("data has shape %s, dimensions say %s" % (tuple(x_shape), (N, T)))
 
         p = _lib.Params(n_features=N, n_components=K, maxlag=L, t_local=T, t_global=T,
                         t_offset=0, device=device, precision=_lib.PRECISIONS[precision],
@@ -70,8 +81,7 @@ class DeviceOptimizer:
         if loss_precision not in ("auto", "full"):
             raise ValueError("loss_precision must be 'auto' or 'full'")
         _lib.check(self._lib.cmf_mu_set_loss_mode(self._h, 0 if loss_precision == "auto" else 1))
-        _lib.check(self._lib.cmf_mu_set_data(self._h, X.ctypes.data, _lib.np_dtype_code(X),
-                                             _lib.CMF_HOST, T, T))
+        _lib.check(self._lib.cmf_mu_set_data(self._h, x_ptr, x_dt, x_mem, x_ld, T))
         if normalize is not None:
             # the reference normalises in its dataset classes, on the host, before the solver sees the data
             # (songbird.py:18-19, maze.py:71-72, vox_celeb.py:100-102); here the rows are scaled where they live
@@ -80,7 +90,8 @@ class DeviceOptimizer:
             _lib.check(self._lib.cmf_mu_row_stats(self._h, s1.ctypes.data, s2.ctypes.data, sa.ctypes.data))
             self.row_scale = row_scales(normalize, s1, s2, sa, T)
             _lib.check(self._lib.cmf_mu_scale_rows(self._h, self.row_scale.ctypes.data))
-            self._X = X * self.row_scale[:, None]
+            if not on_device:
+                self._X = X * self.row_scale[:, None]
         ss, neg = C.c_double(0), C.c_int(0)
         _lib.check(self._lib.cmf_mu_data_stats(self._h, C.byref(ss), C.byref(neg)))
         self.normX = float(np.sqrt(ss.value))               # base.py:25
@@ -130,7 +141,8 @@ class DeviceOptimizer:
                                                 _lib.CMF_F32, _lib.CMF_HOST, T))
         xe, ee = C.c_double(0), C.c_double(0)
         _lib.check(self._lib.cmf_mu_init_stats(self._h, C.byref(xe), C.byref(ee)))
-        s = np.float32(np.sqrt(xe.value / ee.value))
+        with np.errstate(invalid="ignore"):          # (negative data: CMF.fit raises right after construction)
+            s = np.float32(np.sqrt(xe.value / ee.value))
         return s * W, s * H
 
     def cache_resids(self):
@@ -151,6 +163,11 @@ class DeviceOptimizer:
 
     @property
     def X(self):
+        if self._X is None:                                  # device data: one read-back, on demand
+            d = self._X_device
+            X = d.to_host() if hasattr(d, "to_host") else np.asarray(d.cpu(), dtype=np.float64)
+            scale = getattr(self, "row_scale", None)
+            self._X = X if scale is None else X * scale[:, None]
         return self._X
 
     @property
@@ -176,7 +193,7 @@ class DeviceOptimizer:
 
     @property
     def resids(self):
-        return self.est - self._X
+        return self.est - self.X
 
     # -- extras --------------------------------------------------------------
     @property

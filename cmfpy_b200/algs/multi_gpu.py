@@ -56,6 +56,9 @@ class MultiGpuMultUpdate:
             setattr(self, k, v)
         N, T, K, L = self.n_features, self.n_timepoints, self.n_components, self.maxlag
         self.precision = resolve_precision(lib, precision, N, K, L)
+        from ..datasets import is_device_matrix
+        if is_device_matrix(data):          # the shards are loaded from one host copy (each GPU takes its columns)
+            data = data.to_host(np.float32) if hasattr(data, "to_host") else np.asarray(data.cpu())
         X = _as_host_matrix(data, "data")
         if X.shape != (N, T):
             raise ValueError("data has shape %s, dimensions say %s" % (X.shape, (N, T)))

@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cmath>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -26,6 +27,7 @@
 #include "peer_kernels.cuh"
 #include "gd_kernels.cuh"
 #include "hals_kernels.cuh"
+#include "dataset_kernels.cuh"
 
 namespace cmf {
 
@@ -1872,6 +1874,312 @@ int cmf_score(const void* W, const void* H, const void* X, int dtype, int n_feat
   if (rc == 0) *r2_out = 1.0 - ss / h->sumsq_x;
   cmf_mu_destroy(h);
   return rc;
+}
+
+
+// ==========================================================================
+// The step before the solver: device matrices, the synthetic data set, the spectrogram
+// ==========================================================================
+}  // extern "C"
+
+struct DevBuf {
+  float* p = nullptr;
+  int dev = 0;
+  ~DevBuf() {
+    if (p) { DeviceGuard g(dev); cudaFree(p); }
+  }
+};
+struct cmf_dmat_s {
+  std::shared_ptr<DevBuf> buf;
+  float* ptr = nullptr;
+  long long rows = 0, cols = 0, ld = 0;
+  int dev = 0;
+};
+struct cmf_synth_s {
+  cmf_synth_params p;
+  long long lead = 0, Tp = 0;          // H and the reconstruction start `lead` = min(L-1, t_offset) columns early
+  int num_sms = 148;
+  float *W = nullptr, *H = nullptr;    // L x N x K; K x Tp
+  cmf_dmat_s data;                     // N x t_local view (ld = Tp) of the N x Tp reconstruction buffer
+};
+
+namespace {
+
+int ds_grid(int num_sms, long long n_items) {
+  long long blocks = ceil_div_ll(n_items, 256);
+  const long long cap = (long long)num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+int new_dmat(cmf_dmat_s* m, long long rows, long long cols, int dev) {
+  auto buf = std::make_shared<DevBuf>();
+  buf->dev = dev;
+  CMF_CUDA(cudaMalloc((void**)&buf->p, (size_t)(rows * cols > 0 ? rows * cols : 1) * 4));
+  m->buf = buf; m->ptr = buf->p; m->rows = rows; m->cols = cols; m->ld = cols; m->dev = dev;
+  return 0;
+}
+
+// rows x cols fp32 on the device (ld lds) -> host array of `dtype` (ld ldd)
+int dmat_to_host(const float* src, long long lds, long long rows, long long cols, void* out, int dtype, long long ldd,
+                 int num_sms) {
+  CMF_CHECK(out != nullptr, "null argument");
+  CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
+  CMF_CHECK(ldd >= cols, "leading dimension %lld < %lld columns", ldd, cols);
+  if (rows == 0 || cols == 0) return 0;
+  if (dtype == CMF_F32) {
+    CMF_CUDA(cudaMemcpy2D(out, (size_t)ldd * 4, src, (size_t)lds * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  long long rch = (32ll << 20) / cols;                     // 256 MB of doubles at a time
+  if (rch < 1) rch = 1;
+  if (rch > rows) rch = rows;
+  double* tmp = nullptr;
+  CMF_CUDA(cudaMalloc((void**)&tmp, (size_t)rch * cols * 8));
+  int rc = 0;
+  for (long long r0 = 0; r0 < rows && rc == 0; r0 += rch) {
+    const long long nr = rows - r0 < rch ? rows - r0 : rch;
+    ds::copy_convert_kernel<double><<<ds_grid(num_sms, nr * cols), 256>>>(tmp, cols, src + r0 * lds, lds, nr, cols);
+    if (cudaMemcpy2D((double*)out + r0 * ldd, (size_t)ldd * 8, tmp, (size_t)cols * 8, (size_t)cols * 8, (size_t)nr,
+                     cudaMemcpyDeviceToHost) != cudaSuccess) {
+      set_error("device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = 1;
+    }
+  }
+  cudaFree(tmp);
+  return rc;
+}
+
+int synth_noise(const cmf_synth_s* s, float* dst, const float* base, long long ld, float times) {
+  const cmf_synth_params& p = s->p;
+  ds::synth_noise_kernel<<<ds_grid(s->num_sms, (long long)p.n_features * p.t_local), 256>>>(
+      dst, base, p.n_features, ld, p.t_local, p.t_offset, p.n_timebins, ds::stream_key(p.seed, ds::kStreamNoise),
+      (float)p.noise_scale, times);
+  CMF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cmf_dmat_info(cmf_dmat_t* m, const float** dev_ptr, long long* rows, long long* cols, long long* ld, int* device) {
+  CMF_CHECK(m != nullptr, "null matrix handle");
+  if (dev_ptr) *dev_ptr = m->ptr;
+  if (rows) *rows = m->rows;
+  if (cols) *cols = m->cols;
+  if (ld) *ld = m->ld;
+  if (device) *device = m->dev;
+  return 0;
+}
+
+int cmf_dmat_get(cmf_dmat_t* m, void* out, int dtype, long long ld) {
+  CMF_CHECK(m != nullptr, "null matrix handle");
+  DeviceGuard guard(m->dev);
+  CMF_CHECK(guard.ok, "cannot select CUDA device %d", m->dev);
+  cudaDeviceProp prop;
+  CMF_CUDA(cudaGetDeviceProperties(&prop, m->dev));
+  return dmat_to_host(m->ptr, m->ld, m->rows, m->cols, out, dtype, ld, prop.multiProcessorCount);
+}
+
+int cmf_dmat_destroy(cmf_dmat_t* m) {
+  delete m;
+  return 0;
+}
+
+int cmf_synth_destroy(cmf_synth_t* s) {
+  if (!s) return 0;
+  {
+    DeviceGuard guard(s->p.device);
+    cudaFree(s->W);
+    cudaFree(s->H);
+  }
+  delete s;
+  return 0;
+}
+
+int cmf_synth_create(cmf_synth_t** out, const cmf_synth_params* p) {
+  CMF_CHECK(out != nullptr && p != nullptr, "null argument");
+  *out = nullptr;
+  CMF_CHECK(p->n_components >= 1 && p->n_features >= 1 && p->n_lags >= 1 && p->n_timebins >= 1,
+            "dimensions must be positive");
+  CMF_CHECK(p->t_local >= 1 && p->t_offset >= 0 && p->t_offset + p->t_local <= p->n_timebins,
+            "inconsistent time range: t_local=%lld t_offset=%lld n_timebins=%lld", p->t_local, p->t_offset, p->n_timebins);
+  CMF_CHECK(p->H_sparsity >= 0.0 && p->H_sparsity <= 1.0, "H_sparsity must lie in [0, 1]");
+  CMF_CHECK(cmf_precision_supported(p->precision, p->n_features, p->n_components, p->n_lags),
+            "precision %d has no kernel for N=%d K=%d L=%d; use fp32", p->precision, p->n_features, p->n_components, p->n_lags);
+  int ndev = 0;
+  CMF_CUDA(cudaGetDeviceCount(&ndev));
+  CMF_CHECK(p->device >= 0 && p->device < ndev, "device %d out of range (%d visible)", p->device, ndev);
+  DeviceGuard guard(p->device);
+  CMF_CHECK(guard.ok, "cannot select CUDA device %d", p->device);
+  cudaDeviceProp prop;
+  CMF_CUDA(cudaGetDeviceProperties(&prop, p->device));
+
+  cmf_synth_s* s = new cmf_synth_s();
+  s->p = *p;
+  s->num_sms = prop.multiProcessorCount;
+  const int N = p->n_features, K = p->n_components, L = p->n_lags;
+  s->lead = p->t_offset < L - 1 ? p->t_offset : L - 1;
+  s->Tp = p->t_local + s->lead;
+  cmf_mu_t* h = nullptr;
+  auto body = [&]() -> int {
+    CMF_CUDA(cudaMalloc((void**)&s->W, (size_t)L * N * K * 4));
+    CMF_CUDA(cudaMalloc((void**)&s->H, (size_t)K * s->Tp * 4));
+    cmf_dmat_s buf;
+    CMF_TRY(new_dmat(&buf, N, s->Tp, p->device));
+    ds::synth_h_kernel<<<ds_grid(s->num_sms, (long long)K * s->Tp), 256>>>(
+        s->H, K, s->Tp, s->Tp, p->t_offset - s->lead, p->n_timebins, ds::stream_key(p->seed, ds::kStreamH),
+        (float)(1.0 - p->H_sparsity));
+    CMF_CUDA(cudaGetLastError());
+    ds::synth_w_kernel<<<(unsigned)ceil_div_ll(N, 128), 128>>>(s->W, L, N, K, ds::stream_key(p->seed, ds::kStreamMotif));
+    CMF_CUDA(cudaGetLastError());
+    CMF_CUDA(cudaDeviceSynchronize());
+    // data = cmf_predict(W, H) (+ noise below): the K1 kernel of a throw-away solver over the Tp columns
+    CMF_TRY(make_tmp(&h, N, s->Tp, K, L, p->device, p->precision));
+    h->have_data = true;            // X stays zero; only the reconstruction is wanted
+    CMF_TRY(cmf_mu_set_factors(h, s->W, s->H, CMF_F32, CMF_DEVICE, s->Tp));
+    CMF_TRY(cmf_mu_get_est(h, buf.ptr, CMF_F32, CMF_DEVICE, s->Tp));
+    s->data = buf;
+    s->data.ptr = buf.ptr + s->lead;
+    s->data.cols = p->t_local;
+    CMF_TRY(synth_noise(s, s->data.ptr, s->data.ptr, s->Tp, 1.f));
+    CMF_CUDA(cudaDeviceSynchronize());
+    return 0;
+  };
+  const int rc = body();
+  if (h) cmf_mu_destroy(h);
+  if (rc != 0) { cmf_synth_destroy(s); return rc; }
+  *out = s;
+  return 0;
+}
+
+int cmf_synth_get(cmf_synth_t* s, int what, void* out, int dtype, long long ld) {
+  CMF_CHECK(s != nullptr, "null generator handle");
+  DeviceGuard guard(s->p.device);
+  CMF_CHECK(guard.ok, "cannot select CUDA device %d", s->p.device);
+  const cmf_synth_params& p = s->p;
+  switch (what) {
+    case CMF_SYNTH_W: {
+      const long long cols = (long long)p.n_features * p.n_components;
+      return dmat_to_host(s->W, cols, p.n_lags, cols, out, dtype, cols, s->num_sms);
+    }
+    case CMF_SYNTH_H:
+      return dmat_to_host(s->H + s->lead, s->Tp, p.n_components, p.t_local, out, dtype, ld, s->num_sms);
+    case CMF_SYNTH_DATA:
+      return dmat_to_host(s->data.ptr, s->data.ld, p.n_features, p.t_local, out, dtype, ld, s->num_sms);
+    case CMF_SYNTH_NOISE:
+    case CMF_SYNTH_GENERATE: {
+      cmf_dmat_s tmp;
+      CMF_TRY(new_dmat(&tmp, p.n_features, p.t_local, p.device));
+      if (what == CMF_SYNTH_NOISE) {
+        CMF_TRY(synth_noise(s, tmp.ptr, nullptr, tmp.ld, 1.f));
+      } else {
+        CMF_CUDA(cudaMemcpy2D(tmp.ptr, (size_t)tmp.ld * 4, s->data.ptr, (size_t)s->data.ld * 4, (size_t)p.t_local * 4,
+                              (size_t)p.n_features, cudaMemcpyDeviceToDevice));
+        CMF_TRY(synth_noise(s, tmp.ptr, tmp.ptr, tmp.ld, 1.f));
+      }
+      return dmat_to_host(tmp.ptr, tmp.ld, p.n_features, p.t_local, out, dtype, ld, s->num_sms);
+    }
+    default:
+      CMF_CHECK(false, "unknown item %d", what);
+  }
+  return 0;
+}
+
+int cmf_synth_matrix(cmf_synth_t* s, int what, cmf_dmat_t** out) {
+  CMF_CHECK(s != nullptr && out != nullptr, "null argument");
+  CMF_CHECK(what == CMF_SYNTH_DATA || what == CMF_SYNTH_GENERATE, "only DATA and GENERATE exist as device matrices");
+  DeviceGuard guard(s->p.device);
+  CMF_CHECK(guard.ok, "cannot select CUDA device %d", s->p.device);
+  cmf_dmat_s* m = new cmf_dmat_s();
+  if (what == CMF_SYNTH_DATA) {
+    *m = s->data;                                   // shares the buffer
+  } else {
+    const cmf_synth_params& p = s->p;
+    int rc = new_dmat(m, p.n_features, p.t_local, p.device);
+    if (rc == 0 && cudaMemcpy2D(m->ptr, (size_t)m->ld * 4, s->data.ptr, (size_t)s->data.ld * 4, (size_t)p.t_local * 4,
+                                (size_t)p.n_features, cudaMemcpyDeviceToDevice) != cudaSuccess) {
+      set_error("device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = 1;
+    }
+    if (rc == 0) rc = synth_noise(s, m->ptr, m->ptr, m->ld, 1.f);
+    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_error("generate failed"); rc = 1; }
+    if (rc != 0) { delete m; return rc; }
+  }
+  *out = m;
+  return 0;
+}
+
+int cmf_spectrogram(const void* audio, int dtype, int mem, long long n_samples, double fs, int nperseg, int noverlap,
+                    const double* window, int normalize, int device, cmf_dmat_t** out) {
+  CMF_CHECK(audio != nullptr && window != nullptr && out != nullptr, "null argument");
+  *out = nullptr;
+  CMF_CHECK(dtype == CMF_F32 || dtype == CMF_F64, "unknown dtype %d", dtype);
+  CMF_CHECK(mem == CMF_HOST || (mem == CMF_DEVICE && dtype == CMF_F32), "device audio must be float32");
+  CMF_CHECK(nperseg >= 2 && noverlap >= 0 && noverlap < nperseg, "need 0 <= noverlap < nperseg, nperseg >= 2");
+  CMF_CHECK(n_samples >= nperseg, "fewer samples (%lld) than one segment (%d)", n_samples, nperseg);
+  CMF_CHECK(fs > 0.0, "sampling rate must be positive");
+  int ndev = 0;
+  CMF_CUDA(cudaGetDeviceCount(&ndev));
+  CMF_CHECK(device >= 0 && device < ndev, "device %d out of range (%d visible)", device, ndev);
+  DeviceGuard guard(device);
+  CMF_CHECK(guard.ok, "cannot select CUDA device %d", device);
+  cudaDeviceProp prop;
+  CMF_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int hop = nperseg - noverlap, n_freq = nperseg / 2 + 1;
+  const long long n_seg = (n_samples - noverlap) / hop;
+  const int segld = nperseg | 1;                   // odd row stride: the 32 lanes of a warp read 32 segments
+  const size_t smem = ((size_t)2 * nperseg + (size_t)ds::kSegs * segld + (size_t)n_freq * (ds::kSegs + 1)) * 4;
+  CMF_CHECK(smem <= 227 * 1024, "nperseg=%d is too long for the on-chip DFT (limit about 1400)", nperseg);
+
+  std::vector<float> w((size_t)nperseg);
+  double w2 = 0.0;
+  for (int i = 0; i < nperseg; ++i) { w[i] = (float)window[i]; w2 += window[i] * window[i]; }
+  CMF_CHECK(w2 > 0.0, "the window is identically zero");
+  float *d_audio = nullptr, *d_win = nullptr;
+  double* d_part = nullptr;
+  cmf_dmat_s* m = new cmf_dmat_s();
+  auto body = [&]() -> int {
+    const float* a = (const float*)audio;
+    if (mem == CMF_HOST) {
+      CMF_CUDA(cudaMalloc((void**)&d_audio, (size_t)n_samples * 4));
+      if (dtype == CMF_F32) {
+        CMF_CUDA(cudaMemcpy(d_audio, audio, (size_t)n_samples * 4, cudaMemcpyHostToDevice));
+      } else {
+        std::vector<float> tmp((size_t)n_samples);
+        const double* src = (const double*)audio;
+        for (long long i = 0; i < n_samples; ++i) tmp[(size_t)i] = (float)src[i];
+        CMF_CUDA(cudaMemcpy(d_audio, tmp.data(), (size_t)n_samples * 4, cudaMemcpyHostToDevice));
+      }
+      a = d_audio;
+    }
+    CMF_CUDA(cudaMalloc((void**)&d_win, (size_t)nperseg * 4));
+    CMF_CUDA(cudaMemcpy(d_win, w.data(), (size_t)nperseg * 4, cudaMemcpyHostToDevice));
+    CMF_TRY(new_dmat(m, n_freq, n_seg, device));
+    CMF_CUDA(cudaFuncSetAttribute(ds::spectrogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ds::spectrogram_kernel<<<(unsigned)ceil_div_ll(n_seg, ds::kSegs), 256, smem>>>(
+        a, n_samples, d_win, nperseg, segld, hop, n_seg, n_freq, (float)(1.0 / (fs * w2)), m->ptr, m->ld);
+    CMF_CUDA(cudaGetLastError());
+    if (normalize) {
+      const long long chunk = 1 << 16;
+      const int nchunk = (int)ceil_div_ll(n_seg, chunk);
+      CMF_CUDA(cudaMalloc((void**)&d_part, (size_t)n_freq * nchunk * 2 * 8));
+      ds::row_moments_kernel<<<dim3((unsigned)nchunk, (unsigned)n_freq), 256>>>(m->ptr, m->ld, n_seg, chunk, nchunk, d_part);
+      CMF_CUDA(cudaGetLastError());
+      long long bx = ceil_div_ll(n_seg, 256 * 8);
+      if (bx > 64) bx = 64;
+      ds::row_std_scale_kernel<<<dim3((unsigned)bx, (unsigned)n_freq), 256>>>(m->ptr, m->ld, n_seg, d_part, nchunk);
+      CMF_CUDA(cudaGetLastError());
+    }
+    CMF_CUDA(cudaDeviceSynchronize());
+    return 0;
+  };
+  const int rc = body();
+  cudaFree(d_audio); cudaFree(d_win); cudaFree(d_part);
+  if (rc != 0) { delete m; return rc; }
+  *out = m;
+  return 0;
 }
 
 }  // extern "C"

@@ -74,15 +74,21 @@ class CMF(object):
         around an asynchronous launch would measure nothing).  When `tol == 0`
         the convergence test can never fire (strict `<`, base.py:73), so the
         iterations are submitted in one batch with a single synchronisation."""
-        data = np.asarray(data)
-        if (data < 0).any():
-            raise ValueError('Negative values in data to fit')
+        from .datasets import is_device_matrix
+        on_device = is_device_matrix(data)        # e.g. datasets.Synthetic(...).device_data(): stays on the GPU
+        if not on_device:
+            data = np.asarray(data)
+            if (data < 0).any():
+                raise ValueError('Negative values in data to fit')
 
         dims = ModelDimensions(data, maxlag=self.maxlag, n_components=self.n_components)
         if self.alg_name not in ALGORITHMS:
             raise KeyError("alg_name %r is not provided by cmfpy_b200 (available: %s)"
                            % (self.alg_name, sorted(ALGORITHMS)))
         algorithm = ALGORITHMS[self.alg_name](data, dims, **self.alg_opts)
+        if on_device and algorithm.has_negative:      # the same check (model.py:138-139), reduced on the device
+            algorithm.close()
+            raise ValueError('Negative values in data to fit')
 
         self.loss_hist = [algorithm.loss]
         self.time_hist = [0.0]

@@ -279,6 +279,47 @@ int cmf_tensor_transconv(const void* W, const void* X, void* out, int dtype,
                          int n_features, long long n_timepoints,
                          int n_components, int maxlag, int device, int precision);
 
+/* ---- the step before the solver, on the device ---------- */
+/* A row-major fp32 matrix in device memory, owned by the library: what the
+ * generators below produce and what cmf_mu_set_data accepts with CMF_DEVICE
+ * (ptr, ld from cmf_dmat_info), so a data set never visits the host. */
+typedef struct cmf_dmat_s cmf_dmat_t;
+int cmf_dmat_info(cmf_dmat_t* m, const float** dev_ptr, long long* rows, long long* cols, long long* ld, int* device);
+/* copy to a HOST array (rows x cols, leading dimension ld, CMF_F32 or CMF_F64) */
+int cmf_dmat_get(cmf_dmat_t* m, void* out, int dtype, long long ld);
+int cmf_dmat_destroy(cmf_dmat_t* m);
+
+/* The reference's synthetic data set, Synthetic(...) of cmfpy/datasets/synthetic.py:7-39: H ~ U[0,1) thinned to a
+ * fraction 1 - H_sparsity of non-zeros (:22-25), one Gaussian-bump motif per feature on a random component (:27-30,
+ * :42-46), noise = noise_scale * U[0,1) (:33), data = cmf_predict(W, H) + noise (:36, the reconstruction on the K1
+ * kernel of `precision`).  The reference draws from NumPy's generators (partly the global, unseeded one); here a
+ * counter-based generator keyed by (seed, global element index) makes the data set reproducible and identical for any
+ * time sharding: a handle holds the columns [t_offset, t_offset + t_local) of the n_timebins-column data set. */
+typedef struct cmf_synth_s cmf_synth_t;
+typedef struct {
+  int n_components, n_features, n_lags;
+  long long n_timebins, t_offset, t_local;
+  double H_sparsity, noise_scale;
+  unsigned long long seed;
+  int device, precision;
+} cmf_synth_params;
+enum { CMF_SYNTH_W = 0, CMF_SYNTH_H = 1, CMF_SYNTH_NOISE = 2, CMF_SYNTH_DATA = 3, CMF_SYNTH_GENERATE = 4 };
+int cmf_synth_create(cmf_synth_t** out, const cmf_synth_params* p);
+/* `what` to a HOST array in the reference's layout: W (L x N x K), H (K x t_local, ld), NOISE / DATA / GENERATE
+ * (N x t_local, ld); GENERATE is the reference's generate() = data + noise (synthetic.py:38-39: the noise a 2nd time). */
+int cmf_synth_get(cmf_synth_t* s, int what, void* out, int dtype, long long ld);
+/* DATA (shares the handle's buffer) or GENERATE (a new matrix) as a device matrix */
+int cmf_synth_matrix(cmf_synth_t* s, int what, cmf_dmat_t** out);
+int cmf_synth_destroy(cmf_synth_t* s);
+
+/* The spectrogram step of the audio loader, VoxCeleb.generate of cmfpy/datasets/vox_celeb.py:58-104:
+ * scipy.signal.spectrogram(audio, fs, window, nperseg, noverlap) with its defaults (one-sided power spectral density,
+ * constant detrend) followed, if `normalize`, by StandardScaler(with_mean=False) over time for every frequency bin
+ * (:100-102).  audio: n_samples values (CMF_F32 / CMF_F64, CMF_HOST / CMF_DEVICE); window: nperseg doubles, HOST
+ * (the reference's default is scipy's Tukey(0.25) window).  Result: (nperseg/2 + 1) x n_segments, features x time. */
+int cmf_spectrogram(const void* audio, int dtype, int mem, long long n_samples, double fs, int nperseg, int noverlap,
+                    const double* window, int normalize, int device, cmf_dmat_t** out);
+
 #ifdef __cplusplus
 }
 #endif

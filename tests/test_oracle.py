@@ -182,3 +182,69 @@ def test_model_checkpoint_round_trip(tmp_path):
     except ImportError:
         with pytest.raises(ImportError):
             load_cmfjl_model(path)
+
+
+class _FakeH5File(dict):
+    """A dict-backed stand-in for h5py.File: datasets by name, context manager, `[]` assignment.  The image has no
+    h5py; this executes the cmf.jl loader / saver and pins their axis conventions."""
+    store = {}
+
+    def __init__(self, path, mode="r"):
+        super().__init__()
+        self.path, self.mode = path, mode
+        if "w" not in mode:
+            self.update(_FakeH5File.store[path])
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        if "w" in self.mode:
+            _FakeH5File.store[self.path] = {k: np.array(v) for k, v in self.items()}
+        return False
+
+
+def test_cmfjl_files_round_trip_and_match_reference_loader(monkeypatch):
+    """save_cmfjl_model -> load_cmfjl_model, and (in the build container) the reference's own load_cmfjl_model
+    (model.py:346-363) on the very same file object."""
+    import sys
+    import types
+    from cmfpy_b200.model import CMF, load_cmfjl_model, save_cmfjl_model
+    fake = types.ModuleType("h5py")
+    fake.File = _FakeH5File
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    rng = np.random.default_rng(3)
+    m = CMF(3, 5)
+    m._W, m._H = rng.random((5, 7, 3)), rng.random((3, 40))
+    m.loss_hist, m.time_hist = [0.8, 0.6, 0.55], [0.0, 0.01, 0.02]
+    X = rng.random((7, 40))
+    save_cmfjl_model("mem://model.h5", m, X)
+    raw = _FakeH5File.store["mem://model.h5"]
+    # what a row-major reader sees of Julia's column-major arrays: data T x N, W K x N x L, H T x K
+    assert raw["data"].shape == (40, 7) and raw["W"].shape == (3, 7, 5) and raw["H"].shape == (40, 3)
+    data, m2 = load_cmfjl_model("mem://model.h5")
+    assert np.array_equal(data, X) and np.array_equal(m2.motifs, m.motifs) and np.array_equal(m2.factors, m.factors)
+    assert list(m2.loss_hist) == m.loss_hist and list(m2.time_hist) == m.time_hist
+    assert (m2.n_components, m2.maxlag) == (3, 5)
+    if ref_shim.available():
+        ref_shim.import_reference()
+        import cmfpy.model as ref_model
+        monkeypatch.setattr(ref_model, "h5py", fake)
+        rdata, rm = ref_model.load_cmfjl_model("mem://model.h5")
+        assert np.array_equal(rdata, data) and np.array_equal(rm._W, m2.motifs) and np.array_equal(rm._H, m2.factors)
+        assert np.array_equal(rm.loss_hist, m2.loss_hist)
+
+
+def test_cmfjl_files_with_real_h5py(tmp_path):
+    h5py = pytest.importorskip("h5py")
+    from cmfpy_b200.model import CMF, load_cmfjl_model, save_cmfjl_model
+    rng = np.random.default_rng(4)
+    m = CMF(2, 3)
+    m._W, m._H = rng.random((3, 4, 2)), rng.random((2, 9))
+    m.loss_hist, m.time_hist = [0.5, 0.4], [0.0, 0.1]
+    path = str(tmp_path / "m.h5")
+    save_cmfjl_model(path, m, rng.random((4, 9)))
+    with h5py.File(path, "r") as f:
+        assert f["W"].shape == (2, 4, 3)
+    _, m2 = load_cmfjl_model(path)
+    assert np.array_equal(m2.motifs, m.motifs) and np.array_equal(m2.factors, m.factors)
