@@ -677,7 +677,8 @@ def run_e2e(args, torch, N, T, K, L, Tloc, rank, world, local_rank, precision, d
     if dist:
         dist.barrier()
     sec = time.perf_counter() - t0
-    parts = {"construct_h2d": t1 - t0, "steps": t2 - t1, "read_back": time.perf_counter() - t2}
+    parts = {"construct_h2d": t1 - t0, "steps": t2 - t1, "read_back": time.perf_counter() - t2,
+             "construct_parts": {k: round(v, 4) for k, v in getattr(alg.engine, "timings", {}).items()}}
     if dist:
         t = torch.tensor([sec], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -18,6 +18,7 @@ PRECISIONS = {"fp32": CMF_PREC_FP32, "tf32": CMF_PREC_TF32, "tf32x3": CMF_PREC_T
 CMF_DEN_DIRECT, CMF_DEN_GRAM, CMF_DEN_AUTO = 0, 1, 2
 CMF_PEER_BLOB_BYTES = 512
 DENOMINATORS = {"direct": CMF_DEN_DIRECT, "gram": CMF_DEN_GRAM, "auto": CMF_DEN_AUTO}
+LOSS_MODES = {"auto": 0, "full": 1, "wterms": 2}           # cmf_mu_set_loss_mode
 
 
 class SynthParams(C.Structure):

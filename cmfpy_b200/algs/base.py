@@ -78,9 +78,9 @@ class DeviceOptimizer:
                         t_offset=0, device=device, precision=_lib.PRECISIONS[precision],
                         stream=None, denominators=_lib.DENOMINATORS[denominators])
         _lib.check(self._lib.cmf_mu_create(C.byref(self._h), C.byref(p)))
-        if loss_precision not in ("auto", "full"):
-            raise ValueError("loss_precision must be 'auto' or 'full'")
-        _lib.check(self._lib.cmf_mu_set_loss_mode(self._h, 0 if loss_precision == "auto" else 1))
+        if loss_precision not in _lib.LOSS_MODES:
+            raise ValueError("loss_precision must be one of %s" % sorted(_lib.LOSS_MODES))
+        _lib.check(self._lib.cmf_mu_set_loss_mode(self._h, _lib.LOSS_MODES[loss_precision]))
         _lib.check(self._lib.cmf_mu_set_data(self._h, x_ptr, x_dt, x_mem, x_ld, T))
         if normalize is not None:
             # the reference normalises in its dataset classes, on the host, before the solver sees the data
@@ -146,8 +146,9 @@ class DeviceOptimizer:
         return s * W, s * H
 
     def cache_resids(self):
-        """reference base.py:57-62: refresh est (device) and the residual norm."""
-        _lib.check(self._lib.cmf_mu_recon(self._h))
+        """reference base.py:57-62: refresh the residual norm (and est, where a solver step reads it: with both MU
+        denominators on the Gram route est is only formed when `.est` / `.resids` ask for it)."""
+        _lib.check(self._lib.cmf_mu_recon_loss(self._h))
 
     def converged(self, loss_hist):
         """reference base.py:64-76."""

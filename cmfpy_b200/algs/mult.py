@@ -18,10 +18,11 @@ class MultUpdate(DeviceOptimizer):
                   "tf32" (plain TF32 tensor cores: ~3x faster, loss trajectories within ~1e-3)
       denominators : "direct" (contract est, as the reference does), "gram" (exact identity
                   through the lag Gram operators of W and H; tensor-core modes only) or "auto"
-      loss_precision : "auto" (default) or "full": how tf32x3 computes the loss when nothing else reads the
-                  reconstruction (Gram-route denominators): "auto" runs that reconstruction with one operand pass
-                  instead of three on large problems (a million or more entries in W and in H, K L loss^2 >= 0.2),
-                  where that changes the loss by < 1e-6 relative (cmf_mu_set_loss_mode); W and H are never affected
+      loss_precision : how the loss is formed when both denominators are on the Gram route (cmf_mu_set_loss_mode):
+                  "auto" (default; tf32x3: from the W terms of the updated factors - no reconstruction at all - while
+                  loss^2 >= 0.1, else a one-pass reconstruction on large problems, else the full one; error < 1e-5
+                  relative), "full" (the residual formed explicitly every iteration) or "wterms" (always the
+                  identity, any precision); W and H are never affected
       device    : CUDA device ordinal
       devices   : list of CUDA ordinals: time-sharded solve over several GPUs (algs/multi_gpu.py)
       seed      : seed of the random initialisation when initW/initH are absent

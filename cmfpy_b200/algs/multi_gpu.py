@@ -103,7 +103,7 @@ class MultiGpuMultUpdate:
             self._rand_init(seed)
         else:
             self._set_factors(initW, initH)
-        self._parallel(lambda g: _lib.check(lib.cmf_mu_recon(self._h[g])))
+        self._parallel(lambda g: _lib.check(lib.cmf_mu_recon_loss(self._h[g])))
         self._loss = None
 
     def _set_factors(self, W0, H0):

@@ -80,7 +80,9 @@ struct cmf_mu_s {
 
   long long launches = 0;
   int profiling = 0;
-  int loss_mode = 0;                 // 0: auto (one-pass loss reconstruction where its error bound allows), 1: always full
+  int loss_mode = 0;                 // 0: auto (the cheapest loss evaluation whose error bound allows it), 1: always the
+                                     // full-precision residual, 2: from the W terms whenever the route is full Gram
+  bool loss_gram = false;            // this batch takes the loss from the W terms (decide_loss_mode)
   double last_loss = -1.0;           // the most recent loss the host has seen (< 0: none yet)
   // one MU iteration captured as a CUDA graph (launch-bound small problems; replayed by cmf_mu_step)
   cudaGraphExec_t graph_exec = nullptr;
@@ -966,21 +968,39 @@ int cmf_mu_resid_sumsq_buffer(cmf_mu_t* h, double** dev_ptr) {
 int cmf_mu_loss(cmf_mu_t* h, double* loss) {
   double s = 0.0;
   CMF_TRY(cmf_mu_resid_sumsq(h, &s));
-  *loss = std::sqrt(s) / h->norm_x;
+  *loss = std::sqrt(s > 0.0 ? s : 0.0) / h->norm_x;
   h->last_loss = *loss;
   return 0;
 }
 
 int cmf_mu_set_loss_mode(cmf_mu_t* h, int mode) {
   CMF_CHECK(h != nullptr, "null solver handle");
-  CMF_CHECK(mode == 0 || mode == 1, "loss mode must be 0 (auto) or 1 (full precision)");
+  CMF_CHECK(mode >= 0 && mode <= 2, "loss mode must be 0 (auto), 1 (full precision) or 2 (from the W terms)");
+  if (mode != h->loss_mode) h->graph_dirty = h->sgraph_dirty = true;
   h->loss_mode = mode;
   return 0;
 }
 
-// 3xTF32 + full Gram route: may the loss-only reconstruction of the coming steps run one operand pass?
-// (tc::recon explains the bound; the decision needs a loss the host has already seen)
+// Full Gram route (neither MU step reads est): how the loss of the coming steps is formed.  The decision needs a
+// loss the host has already seen; the step functions take it anew every kLossBatch iterations.
+//
+// (a) from the W terms, no reconstruction at all (ew::wterms_dot_kernel): ||X - est||^2 = ||X||^2 - 2 <W, num_W> +
+//     <W, den_W> with the W terms of the UPDATED factors, which the next iteration's W step needs anyway - the
+//     iteration becomes  W update (cached terms) -> H terms -> H update -> W terms -> loss.  The identity is exact;
+//     what it costs is cancellation: the three terms carry the relative error e of the contractions (3xTF32 with
+//     two-level accumulation: a truncation bias below 1e-6, measured), so the loss moves by about e / (2 loss^2)
+//     relative.  It is used while loss^2 >= 0.1, i.e. e-fold amplification of at most 5 (an error below 1e-5, a tenth
+//     of the parity bar), and re-decided every kLossBatch steps; W and H never see it.
+// (b) 3xTF32 only, otherwise: may the loss-only reconstruction run one operand pass?  (tc::recon explains the bound)
+constexpr int kLossBatch = 8;
 static void decide_loss_mode(cmf_mu_s* h) {
+  const bool full_gram = gram_w(h) && gram_h(h) && h->loss_mode == 0 && h->last_loss > 0.0;
+  static const bool identity_enabled = [] { const char* e = getenv("CMF_LOSS_IDENTITY"); return !e || atoi(e) != 0; }();
+  // auto: the fp32-grade mode only.  Plain TF32 contractions carry the rounding of their operands and a truncation
+  // bias of ~6e-8 per MMA step of a chain (2e-4 on the W terms at config C), which the identity would amplify to
+  // 3e-4 of the loss there and to several 1e-3 on small problems; mode 2 asks for it explicitly.
+  const bool ident = gram_w(h) && gram_h(h) &&
+                     (h->loss_mode == 2 || (full_gram && h->x3 && identity_enabled && h->last_loss * h->last_loss >= 0.1));
   const double kl = (double)h->K * (double)h->L;
   // The omitted cross passes perturb the loss through <resid, W_lo (*) H_hi + W_hi (*) H_lo> = <W_lo, gW> + <H_lo, gH>:
   // sums of L N K and K T rounding residuals with random signs against the current gradients, i.e. a relative
@@ -988,18 +1008,35 @@ static void decide_loss_mode(cmf_mu_s* h) {
   // ~1.9e-8 / (K L loss^2).  Both are far below 1e-6 for a million or more factor entries and K L loss^2 >= 0.2
   // (tests/test_parity_gpu.py::test_one_pass_loss measures it); small problems keep all three passes.
   const double n_w = (double)h->L * h->N * h->K, n_h = (double)h->K * (double)h->p.t_global;
-  const bool fast = h->x3 && h->loss_mode == 0 && gram_w(h) && gram_h(h) && h->last_loss > 0.0 &&
-                    n_w >= 1048576.0 && n_h >= 1048576.0 && kl * h->last_loss * h->last_loss >= 0.2;
-  if (fast != (h->tcs.loss_fast != 0)) {
+  const bool fast = h->x3 && full_gram && n_w >= 1048576.0 && n_h >= 1048576.0 &&
+                    kl * h->last_loss * h->last_loss >= 0.2;
+  if (fast != (h->tcs.loss_fast != 0) || ident != h->loss_gram) {
     h->tcs.loss_fast = fast ? 1 : 0;
+    h->loss_gram = ident;
     h->graph_dirty = h->sgraph_dirty = true;
   }
+}
+static bool loss_batched(const cmf_mu_s* h) { return gram_w(h) && gram_h(h) && h->x3 && h->loss_mode == 0; }
+
+// the loss of the current factors from their W terms: d_sumsq = ||X_local||^2 + sum W (den_W - 2 num_W)
+static int do_loss_identity(cmf_mu_s* h) {
+  CMF_CHECK(h->wterms_valid, "loss identity before w_terms");
+  const long long n4 = h->wcount / 4;
+  const int grid = ew_grid(h, n4);
+  ew::wterms_dot_kernel<<<grid, 256, 0, h->stream>>>((const float4*)h->W, (const float4*)h->numden,
+                                                     (const float4*)(h->numden + h->wcount), n4, h->d_xpart);
+  CMF_TRY(launch_check(h, "loss_identity"));
+  ew::sum_doubles_offset_kernel<<<1, 1024, 0, h->stream>>>(h->d_xpart, grid, h->d_sumsq, h->sumsq_x);
+  CMF_TRY(launch_check(h, "loss_sum"));
+  h->est_valid = true;        // the loss of the current factors is known; est itself is not stored
+  h->est_stored = false;
+  return 0;
 }
 
 // one MU iteration (reference MultUpdate.update, mult.py:15-25) issued on the solver's stream
 static int issue_iteration(cmf_mu_s* h, bool prof, size_t& ne, int slot) {
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-  CMF_TRY(do_w_terms(h));
+  if (!h->loss_gram) CMF_TRY(do_w_terms(h));         // (loss identity: cached by the previous iteration)
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
   CMF_TRY(do_w_apply(h));
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
@@ -1009,7 +1046,12 @@ static int issue_iteration(cmf_mu_s* h, bool prof, size_t& ne, int slot) {
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
   CMF_TRY(do_h_apply(h));
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-  CMF_TRY(do_recon(h, !(gram_w(h) && gram_h(h))));   // full Gram route: est is only needed for the loss
+  if (h->loss_gram) {
+    CMF_TRY(do_w_terms(h));                          // the W terms of the updated factors: loss now, W step next
+    CMF_TRY(do_loss_identity(h));
+  } else {
+    CMF_TRY(do_recon(h, !(gram_w(h) && gram_h(h))));   // full Gram route: est is only needed for the loss
+  }
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
   if (slot >= 0) ew::loss_from_sumsq_kernel<<<1, 1, 0, h->stream>>>(h->d_sumsq, h->norm_x, h->d_ring, slot);
   else ew::loss_from_sumsq_counter_kernel<<<1, 1, 0, h->stream>>>(h->d_sumsq, h->norm_x, h->d_ring, h->d_counter);
@@ -1052,20 +1094,23 @@ int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
   CMF_CHECK(n_steps >= 0, "n_steps must be >= 0");
   CMF_CHECK(h->have_data && h->have_factors, "step before data/factors were set");
   if (n_steps == 0) return 0;
-  if (!h->est_valid) CMF_TRY(do_recon(h));
-  decide_loss_mode(h);
   for (int k = 0; k < 4; ++k) h->kernel_ms[k] = 0.f;
   const bool prof = h->profiling != 0;
   static const bool graphs_enabled = [] { const char* e = getenv("CMF_GRAPH"); return !e || atoi(e) != 0; }();
-  bool use_graph = graphs_enabled && !prof && h->graph_ok;
-  if (use_graph && (h->graph_dirty || !h->graph_exec)) {
-    capture_iteration(h);
-    use_graph = h->graph_ok && h->graph_exec != nullptr;
-    last_error().clear();
-  }
+  const int batch = loss_batched(h) && kLossBatch < h->ring_cap ? kLossBatch : h->ring_cap;
   int done = 0;
   while (done < n_steps) {
-    const int chunk = (n_steps - done < h->ring_cap) ? n_steps - done : h->ring_cap;
+    const int chunk = (n_steps - done < batch) ? n_steps - done : batch;
+    decide_loss_mode(h);
+    const bool ident = h->loss_gram;
+    if (ident) { if (!h->wterms_valid) CMF_TRY(do_w_terms(h)); }
+    else if (!h->est_valid) CMF_TRY(do_recon(h));
+    bool use_graph = graphs_enabled && !prof && h->graph_ok;
+    if (use_graph && (h->graph_dirty || !h->graph_exec)) {
+      capture_iteration(h);
+      use_graph = h->graph_ok && h->graph_exec != nullptr;
+      last_error().clear();
+    }
     size_t ne = 0;
     if (use_graph) CMF_CUDA(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
     launch_log_begin(h);
@@ -1078,7 +1123,7 @@ int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
         CMF_TRY(issue_iteration(h, prof, ne, i));
       }
     }
-    if (use_graph) { h->est_valid = true; h->est_stored = !(gram_w(h) && gram_h(h)); h->wterms_valid = false; }
+    if (use_graph) { h->est_valid = true; h->est_stored = !(gram_w(h) && gram_h(h)); h->wterms_valid = ident; }
     if (ms_out) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
     if (loss_out)
       CMF_CUDA(cudaMemcpyAsync(loss_out + done, h->d_ring, (size_t)chunk * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1098,10 +1143,10 @@ int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
         const size_t e0 = b + (ms_out ? 1 : 0);
         float t[6];
         for (int k = 0; k < 6; ++k) CMF_CUDA(cudaEventElapsedTime(&t[k], h->ev_pool[e0 + k], h->ev_pool[e0 + k + 1]));
-        h->kernel_ms[1] += t[0];            // w_terms
-        h->kernel_ms[3] += t[1] + t[4];     // elementwise updates
-        h->kernel_ms[0] += t[2] + t[5];     // reconstructions (+ loss)
-        h->kernel_ms[2] += t[3];            // h_terms
+        h->kernel_ms[1] += ident ? t[5] : t[0];   // w_terms (loss identity: at the end of the iteration, + the loss)
+        h->kernel_ms[3] += t[1] + t[4];           // elementwise updates
+        h->kernel_ms[0] += ident ? 0.f : t[2] + t[5];   // reconstructions (+ loss)
+        h->kernel_ms[2] += t[3];                  // h_terms
       }
     }
     done += chunk;
@@ -1408,7 +1453,7 @@ static int issue_sharded_iteration(cmf_mu_s* h, bool prof, size_t& ne, int ex_gr
   const long long n4 = h->wcount / 4;
   peer::Control* me = ps.P.ctl[ps.P.rank];
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-  CMF_TRY(do_w_terms(h));
+  if (!h->loss_gram) CMF_TRY(do_w_terms(h));         // (loss identity: cached by the previous iteration)
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
   // reduce-scatter of the partial W terms + W update + all-gather of W: one kernel
   CMF_CHECK(h->wterms_valid, "w exchange before w_terms");
@@ -1432,7 +1477,14 @@ static int issue_sharded_iteration(cmf_mu_s* h, bool prof, size_t& ne, int ex_gr
     CMF_TRY(sync_ops_H(h, h->h + h->Tloc, h->h));
   }
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-  CMF_TRY(do_recon(h, !(gram_w(h) && gram_h(h))));
+  if (h->loss_gram) {
+    // the local W-term partials of the updated factors (with the fresh halos): the loss now (the local values sum
+    // to the global squared residual), the W exchange of the next iteration after it
+    CMF_TRY(do_w_terms(h));
+    CMF_TRY(do_loss_identity(h));
+  } else {
+    CMF_TRY(do_recon(h, !(gram_w(h) && gram_h(h))));
+  }
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
   peer::sumsq_push_kernel<<<1, 32, 0, h->stream>>>(ps.P, h->d_sumsq);
   return launch_check(h, "sumsq_push");
@@ -1476,8 +1528,6 @@ int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out) {
   auto& ps = h->peer;
   CMF_CHECK(ps.attached, "cmf_mu_step_sharded needs cmf_mu_peer_attach");
   if (n_steps == 0) return 0;
-  if (!h->est_valid) CMF_TRY(do_recon(h));
-  decide_loss_mode(h);               // (last_loss is the GLOBAL loss: every rank decides alike)
   for (int k = 0; k < 4; ++k) h->kernel_ms[k] = 0.f;
   const bool prof = h->profiling != 0;
   const long long n4 = h->wcount / 4;
@@ -1487,16 +1537,21 @@ int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out) {
   if (ex_grid > h->num_sms) ex_grid = h->num_sms;       // every block spins: all must be resident
   if (ex_grid < 1) ex_grid = 1;
   static const bool graphs_enabled = [] { const char* e = getenv("CMF_GRAPH"); return !e || atoi(e) != 0; }();
-  bool use_graph = graphs_enabled && !prof && h->sgraph_ok;
-  if (use_graph && (h->sgraph_dirty || !h->sgraph_exec)) {
-    capture_sharded_iteration(h, ex_grid);
-    use_graph = h->sgraph_ok && h->sgraph_exec != nullptr;
-    last_error().clear();
-  }
+  const int batch = loss_batched(h) && kLossBatch < ps.ring_cap ? kLossBatch : ps.ring_cap;
   std::vector<double> ring((size_t)ps.ring_cap * peer::kMaxPeers);
   int done = 0;
   while (done < n_steps) {
-    const int chunk = (n_steps - done < ps.ring_cap) ? n_steps - done : ps.ring_cap;
+    const int chunk = (n_steps - done < batch) ? n_steps - done : batch;
+    decide_loss_mode(h);               // (last_loss is the GLOBAL loss: every rank decides alike)
+    const bool ident = h->loss_gram;
+    if (ident) { if (!h->wterms_valid) CMF_TRY(do_w_terms(h)); }
+    else if (!h->est_valid) CMF_TRY(do_recon(h));
+    bool use_graph = graphs_enabled && !prof && h->sgraph_ok;
+    if (use_graph && (h->sgraph_dirty || !h->sgraph_exec)) {
+      capture_sharded_iteration(h, ex_grid);
+      use_graph = h->sgraph_ok && h->sgraph_exec != nullptr;
+      last_error().clear();
+    }
     size_t ne = 0;
     launch_log_begin(h);
     peer::tick_kernel<<<1, 1, 0, h->stream>>>(ps.P.ctl[ps.P.rank], peer::kTickSlotReset);
@@ -1509,7 +1564,7 @@ int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out) {
         CMF_TRY(issue_sharded_iteration(h, prof, ne, ex_grid));
       }
     }
-    if (use_graph) { h->est_valid = true; h->est_stored = !(gram_w(h) && gram_h(h)); h->wterms_valid = false; }
+    if (use_graph) { h->est_valid = true; h->est_stored = !(gram_w(h) && gram_h(h)); h->wterms_valid = ident; }
     peer::barrier_kernel<<<1, 32, 0, h->stream>>>(ps.P, ++ps.bar_epoch);
     CMF_TRY(launch_check(h, "peer_barrier"));
     CMF_CUDA(cudaMemcpyAsync(ring.data(), ps.P.ring[ps.P.rank], (size_t)chunk * peer::kMaxPeers * 8, cudaMemcpyDeviceToHost,
@@ -1526,7 +1581,7 @@ int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out) {
     for (int i = 0; i < chunk; ++i) {
       double ssum = 0.0;
       for (int p = 0; p < G; ++p) ssum += ring[(size_t)i * peer::kMaxPeers + p];
-      h->last_loss = std::sqrt(ssum) / h->norm_x;
+      h->last_loss = std::sqrt(ssum > 0.0 ? ssum : 0.0) / h->norm_x;
       if (loss_out) loss_out[done + i] = h->last_loss;
     }
     if (prof) {
@@ -1534,10 +1589,10 @@ int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out) {
         const size_t e0 = (size_t)i * 7;
         float t[6];
         for (int k = 0; k < 6; ++k) CMF_CUDA(cudaEventElapsedTime(&t[k], h->ev_pool[e0 + k], h->ev_pool[e0 + k + 1]));
-        h->kernel_ms[1] += t[0];            // w_terms
-        h->kernel_ms[3] += t[1] + t[4];     // exchange + updates, halo exchange
-        h->kernel_ms[0] += t[2] + t[5];     // reconstructions (+ loss)
-        h->kernel_ms[2] += t[3];            // h_terms
+        h->kernel_ms[1] += ident ? t[5] : t[0];         // w_terms (loss identity: at the end, + the loss)
+        h->kernel_ms[3] += t[1] + t[4];                 // exchange + updates, halo exchange
+        h->kernel_ms[0] += ident ? 0.f : t[2] + t[5];   // reconstructions (+ loss)
+        h->kernel_ms[2] += t[3];                        // h_terms
       }
     }
     done += chunk;

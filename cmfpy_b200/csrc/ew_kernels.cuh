@@ -77,15 +77,58 @@ sum_doubles_kernel(const double* __restrict__ in, long long n, double* __restric
   }
 }
 
+// The squared residual through the W terms (the loss identity of the Gram route):
+//   ||X - est||^2 = ||X||^2 - 2 <X, est> + ||est||^2,   <X, est> = sum W (.) num_W,   ||est||^2 = sum W (.) den_W
+// because num_W[l] = X[:, l:] H[:, :T-l]^T and den_W[l] = est[:, l:] H[:, :T-l]^T (mult.py:35-38) are exactly the
+// derivatives of the two inner products with respect to W[l].  partial[b] = sum over block b of W (den - 2 num), in
+// double; sum_doubles_offset_kernel adds ||X||^2.  Time shards: local num / den partials and the local ||X||^2 give
+// local values whose sum over the shards is the global squared residual.
+__global__ void __launch_bounds__(256)
+wterms_dot_kernel(const float4* __restrict__ W, const float4* __restrict__ num, const float4* __restrict__ den,
+                  long long n4, double* __restrict__ partial) {
+  __shared__ double red[8];
+  double s = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 w = W[i], a = num[i], d = den[i];
+    s += (double)w.x * ((double)d.x - 2.0 * (double)a.x) + (double)w.y * ((double)d.y - 2.0 * (double)a.y) +
+         (double)w.z * ((double)d.z - 2.0 * (double)a.z) + (double)w.w * ((double)d.w - 2.0 * (double)a.w);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    partial[blockIdx.x] = v;
+  }
+}
+
+// out[0] = offset + sum_i in[i]   (fixed order: deterministic)
+__global__ void __launch_bounds__(1024)
+sum_doubles_offset_kernel(const double* __restrict__ in, long long n, double* __restrict__ out, double offset) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += in[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = offset + v;
+  }
+}
+
 // loss_out[slot] = sqrt(sumsq[0]) / norm_x    (reference base.py:90-97)
 __global__ void loss_from_sumsq_kernel(const double* sumsq, double norm_x, double* loss_out, int slot) {
-  loss_out[slot] = sqrt(sumsq[0]) / norm_x;
+  loss_out[slot] = sqrt(fmax(sumsq[0], 0.0)) / norm_x;
 }
 
 // same, slot taken from (and advancing) a device counter: the form a captured CUDA graph replays
 __global__ void loss_from_sumsq_counter_kernel(const double* sumsq, double norm_x, double* loss_out, int* counter) {
   const int slot = *counter;
-  loss_out[slot] = sqrt(sumsq[0]) / norm_x;
+  loss_out[slot] = sqrt(fmax(sumsq[0], 0.0)) / norm_x;
   *counter = slot + 1;
 }
 

@@ -47,11 +47,16 @@ class DeviceShard:
         p = _lib.Params(n_features=N, n_components=K, maxlag=L, t_local=t_local, t_global=T,
                         t_offset=t_offset, device=device, precision=_lib.PRECISIONS[precision],
                         stream=stream_ptr, denominators=_lib.DENOMINATORS[denominators])
+        import time
+        t0 = time.perf_counter()
         _lib.check(self._lib.cmf_mu_create(C.byref(self._h), C.byref(p)))
+        t1 = time.perf_counter()
         ptr, dt, mem, ld, ncols = self._describe(X)
         if not (t_local <= ncols <= t_local + L - 1):
             raise ValueError("X must hold t_local .. t_local+L-1 columns, got %d" % ncols)
         _lib.check(self._lib.cmf_mu_set_data(self._h, ptr, dt, mem, ld, ncols))
+        # host seconds of the (synchronous) construction calls: what bench.py's end-to-end figure is made of
+        self.timings = {"create": t1 - t0, "set_data": time.perf_counter() - t1}
         self._keepalive = None
 
     def _describe(self, a):
@@ -277,13 +282,22 @@ class ShardedMultUpdate:
             ss = float(self._to_host(t).item())
         self.normX = float(np.sqrt(ss))
         eng.set_norm_x(self.normX)
+        import time
+        t0 = time.perf_counter()
         eng.set_factors(initW, initH)
+        if hasattr(eng, "timings"):
+            eng.timings["set_factors"] = time.perf_counter() - t0
         if self.world > 1:
             self._sl, self._sr, self._rl, self._rr = eng.halo_buffers()
             if self.torch_stream is not None:       # buffers were zero-filled on torch's current stream
                 torch.cuda.current_stream(self.torch_stream.device).synchronize()
             self._exchange_halos()
-        eng.recon()
+        # the initial loss; est itself is only stored where an MU step will read it (not on the full Gram route)
+        t0 = time.perf_counter()
+        (eng.recon_loss if hasattr(eng, "recon_loss") else eng.recon)()
+        if hasattr(eng, "timings"):
+            self._torch.cuda.synchronize()
+            eng.timings["first_loss"] = time.perf_counter() - t0
         self._loss = None
         # Collectives: "peer" = the library's own kernels over NVLink peer memory (the W-term all-reduce
         # fused with the W update, halo pushes, a loss ring; no host-side collective per iteration);

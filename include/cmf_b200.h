@@ -253,11 +253,21 @@ const char* cmf_mu_path_name(cmf_mu_t* h);
 int cmf_mu_kernel_ms(cmf_mu_t* h, float out[4]);
 /* Toggle per-kernel event timing inside cmf_mu_step (off by default).       */
 int cmf_mu_set_profiling(cmf_mu_t* h, int on);
-/* How the 3xTF32 mode computes the loss of an iteration (reference base.py:90-97) when nothing else reads the
- * reconstruction (both denominators on the Gram route).  0 (default, "auto"): on large problems (L N K and K T of a
- * million entries or more, K L loss^2 >= 0.2) the reconstruction runs its hi x hi operand pass alone - the two
- * cross passes it omits, the rounding residuals of W and H, then change the loss by less than 1e-6 relative;
- * otherwise, and with mode 1 ("full"), all three passes.  W and H are never affected. */
+/* How the loss of an iteration (reference base.py:90-97) is formed when nothing else reads the reconstruction (both
+ * denominators on the Gram route).
+ * 0 (default, "auto"), 3xTF32 mode:
+ *   - while loss^2 >= 0.1, from the W terms of the updated factors and without any reconstruction:
+ *       ||X - est||^2 = ||X||^2 - 2 <W, num_W> + <W, den_W>
+ *     (num_W, den_W of mult.py:35-38 are the derivatives of <X, est> and ||est||^2 / 2 with respect to W, and the next
+ *     iteration's W step needs them anyway).  The identity is exact; its cancellation amplifies the ~1e-6 relative
+ *     error of the contractions by 1 / (2 loss^2) <= 5, hence the bound; re-decided every 8 iterations;
+ *   - otherwise, on large problems (L N K and K T of a million entries or more, K L loss^2 >= 0.2), the
+ *     reconstruction runs its hi x hi operand pass alone - the two cross passes it omits, the rounding residuals of
+ *     W and H, change the loss by less than 1e-6 relative; else all three passes.
+ *   Plain TF32 always reconstructs in auto mode (its contraction errors are too large to amplify).
+ * 1 ("full"): the residual is formed explicitly with every operand pass, every iteration.
+ * 2 ("wterms"): the identity whenever both denominators are on the Gram route, any precision, any loss.
+ * W and H are never affected by this choice. */
 int cmf_mu_set_loss_mode(cmf_mu_t* h, int mode);
 /* on = 2: additionally one CUDA event after EVERY kernel launch of the following steps; cmf_mu_launch_table then
  * returns one text line "label launches total_ms" per kernel label (a measurement aid of bench.py: the per-kernel

@@ -371,3 +371,45 @@ def test_one_pass_loss(built_lib, kind):
     print("one-pass loss vs full (%s): max rel diff %.2e" % (kind, (np.abs(a - f) / f).max()))
     assert (np.abs(a - f) / f).max() <= 1e-6
     assert np.array_equal(out["auto"][1], out["full"][1]) and np.array_equal(out["auto"][2], out["full"][2])
+
+
+@pytest.mark.parametrize("precision,tol", [("tf32x3", 1e-5), ("tf32", 1e-3)])
+@pytest.mark.parametrize("kind", ["uniform", "planted"])
+def test_loss_from_w_terms(built_lib, precision, kind, tol):
+    """Full Gram route, loss_precision="auto": while loss^2 >= 0.1 the loss comes from the W terms of the updated
+    factors (||X||^2 - 2 <W, num_W> + <W, den_W>, cmf_abi.cu decide_loss_mode) and no reconstruction runs; below that
+    the residual is reconstructed again.  The losses must agree with loss_precision="full" (every iteration's
+    residual formed explicitly, all operand passes) - 1e-5 relative for the fp32-grade mode, a tenth of the parity
+    bar - and W, H must be bit-identical: the loss evaluation never feeds the factors.  'uniform' keeps the loss
+    near 0.5 (identity throughout), 'planted' falls through the threshold (the switch back is exercised)."""
+    from cmfpy_b200.algs.mult import MultUpdate
+    from cmfpy_b200.model import ModelDimensions
+    N, T, K, L = 256, 1 << 14, 8, 32
+    X, W0, H0 = make_inputs(N, T, K, L, kind, seed=23)
+    dims = ModelDimensions(X, maxlag=L, n_components=K)
+    out = {}
+    for mode in ("auto", "full"):
+        # (plain TF32 never takes the identity on its own: its W terms are too coarse to amplify; asked for explicitly)
+        lp = "wterms" if (mode == "auto" and precision == "tf32") else mode
+        alg = MultUpdate(X, dims, initW=W0, initH=H0, tol=0, precision=precision, denominators="gram", loss_precision=lp)
+        assert alg.path_name.endswith("+gram")
+        l0 = alg.loss
+        hist = alg.update_many(5) + [alg.update() for _ in range(3)] + alg.update_many(40)
+        alg.set_profiling(2)
+        hist += alg.update_many(2)
+        table = alg.launch_table()
+        alg.set_profiling(0)
+        out[mode] = (np.array([l0] + hist), alg.W, alg.H, table)
+        alg.close()
+    a, f = out["auto"][0], out["full"][0]
+    rel = np.abs(a - f) / f
+    print("loss from W terms vs residual (%s, %s): loss %.3f -> %.3f, max rel diff %.2e" % (precision, kind, f[0], f[-1], rel.max()))
+    assert rel.max() <= tol
+    assert np.array_equal(out["auto"][1], out["full"][1]) and np.array_equal(out["auto"][2], out["full"][2])
+    assert "loss_identity" not in out["full"][3]
+    if f[-3] ** 2 >= 0.1 or precision == "tf32":
+        assert "loss_identity" in out["auto"][3] and not any(k.startswith("tc_recon") for k in out["auto"][3])
+    else:
+        assert "loss_identity" not in out["auto"][3]
+    if kind == "uniform":
+        assert f[-1] ** 2 >= 0.1              # (the identity was active from the second batch on)
