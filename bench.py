@@ -321,17 +321,24 @@ def resolve_precision(lib, _lib, precision, N, K, L):
     return "tf32x3" if lib.cmf_precision_supported(_lib.CMF_PREC_TF32X3, N, K, L) else "fp32"
 
 
-def device_inputs(torch, dev, N, T, K, L, rank, world):
-    """Synthetic inputs generated on the device, identical for any world size: global column t of X / H0 depends
+def shard_bounds(N, T, K, L, world, precision, denominators):
+    """[t0, t1) of every rank: equal shards, the last one shorter by the estimated cost of the end-of-data
+    corrections that only it computes on the Gram route (cmfpy_b200.algs.multi_gpu.tail_handicap)."""
+    from cmfpy_b200.algs.multi_gpu import shard_ranges, tail_handicap
+    gram = denominators == "gram" or (denominators == "auto" and precision != "fp32" and
+                                      2.0 * N * K * L * (T / world) >= 2e11 and N >= 4 * K)
+    return shard_ranges(T, world, tail_handicap(N, K, L, T, world, gram))
+
+
+def device_inputs(torch, dev, N, T, K, L, t_begin, Tloc):
+    """Synthetic inputs generated on the device, identical for any sharding: global column t of X / H0 depends
     only on (seed, t).  Returns (X with its static right halo, W0, H0, t_begin, ncols_x)."""
-    Tloc = T // world
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234)
     W0 = torch.rand((L, N, K), generator=gen, device=dev, dtype=torch.float32)
     chunk = 1 << 14
     X = torch.empty((N, Tloc + L - 1), device=dev, dtype=torch.float32)
     H0 = torch.empty((K, Tloc), device=dev, dtype=torch.float32)
-    t_begin = rank * Tloc
     ncols_x = min(Tloc + L - 1, T - t_begin)
     for c0 in range(0, T, chunk):
         # every rank walks the same global stream so that shards agree
@@ -489,39 +496,52 @@ def run_mode(torch, dist, dev, lib, _lib, args, cfg, precision, X, ncols_x, W0, 
     return info
 
 
-def quick_config(torch, dev, lib, _lib, args, letter, peaks, tf32_peak, steps, warmup):
-    """One of the other BASELINE configs on one GPU (device-timed, graph replay), with the roofline that bounds it."""
+def quick_config(torch, dev, lib, _lib, args, letter, steps, warmup):
+    """One of the other BASELINE configs on one GPU (device-timed, graph replay); `quick_rooflines` adds the roofline
+    that bounds it once the peaks are known (they are measured last: 4 s of back-to-back cuBLAS heats the GPU)."""
     from cmfpy_b200.dist import ShardedMultUpdate
     N, T, K, L = FULL[letter]
     out = {}
-    X, W0, H0, t_begin, ncols_x = device_inputs(torch, dev, N, T, K, L, 0, 1)
+    X, W0, H0, t_begin, ncols_x = device_inputs(torch, dev, N, T, K, L, 0, T)
     for name, prec in (("parity_grade", resolve_precision(lib, _lib, "auto", N, K, L)), ("tf32", "tf32")):
         if not lib.cmf_precision_supported(_lib.PRECISIONS[prec], N, K, L):
             continue
         alg = ShardedMultUpdate(X[:, :ncols_x], N, T, K, L, t_offset=0, t_local=T, initW=W0, initH=H0,
                                 precision=prec, device=dev.index, group=None, denominators="auto")
         torch.cuda.synchronize()
-        ms, losses, launches = timed_steps(torch, None, dev, alg, steps, warmup)
-        per = ms / steps
+        sampler = ClockSampler(dev.index)
+        sampler.start()
+        ms, losses, launches = timed_steps(torch, None, dev, alg, steps, warmup, sampler)
+        clocks = sampler.stop()
+        out[name] = {"precision": prec, "path": alg.path_name, "value": steps / (ms * 1e-3), "unit": UNIT,
+                     "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
+                     "final_loss": losses[-1], "clocks": clocks}
+        alg.close()
+    del X, W0, H0
+    torch.cuda.empty_cache()
+    return {"workload": "config %s: N=%d T=%d K=%d L=%d MU" % (letter, N, T, K, L), **out}
+
+
+def quick_rooflines(other, peaks, tf32_peak):
+    for letter, entry in other.items():
+        N, T, K, L = FULL[letter]
         flops = algorithmic_flops(N, T, K, L)
         bytes_iter = 28.0 * N * T + 36.0 * K * T                    # SURVEY 8d: whole-iteration lower bound
         peak_tf = tf32_peak.get("sustained") or peaks["bf16_tflops_sustained"] / 2.0
         t_tensor, t_hbm = flops / (peak_tf * 1e12), bytes_iter / (peaks["hbm_gbs"] * 1e9)
         bound = "tensor" if t_tensor >= t_hbm else "hbm"
-        ach = flops / (per * 1e-3) / 1e12 if bound == "tensor" else bytes_iter / (per * 1e-3) / 1e9
-        pk = peak_tf if bound == "tensor" else peaks["hbm_gbs"]
-        out[name] = {"precision": prec, "path": alg.path_name, "value": steps / (ms * 1e-3), "unit": UNIT,
-                     "ms_per_step": per, "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
-                     "final_loss": losses[-1],
-                     "roofline": {"bound": bound, "achieved": ach, "peak": pk,
-                                  "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": ach / pk,
-                                  "what": "whole iteration: 12 N K L T reference-equivalent flops (tensor) or "
-                                          "28 N T + 36 K T bytes (hbm), whichever bound is the longer, over the "
-                                          "measured time"}}
-        alg.close()
-    del X, W0, H0
-    torch.cuda.empty_cache()
-    return {"workload": "config %s: N=%d T=%d K=%d L=%d MU" % (letter, N, T, K, L), **out}
+        for name in ("parity_grade", "tf32"):
+            if name not in entry:
+                continue
+            per = entry[name]["ms_per_step"]
+            ach = flops / (per * 1e-3) / 1e12 if bound == "tensor" else bytes_iter / (per * 1e-3) / 1e9
+            pk = peak_tf if bound == "tensor" else peaks["hbm_gbs"]
+            entry[name]["roofline"] = {
+                "bound": bound, "achieved": ach, "peak": pk, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                "frac": ach / pk,
+                "what": "whole iteration: 12 N K L T reference-equivalent flops (tensor) or 28 N T + 36 K T bytes (hbm), "
+                        "whichever bound is the longer, over the measured time"}
+    return other
 
 
 def run_b200(args):
@@ -548,11 +568,11 @@ def run_b200(args):
     N, T, K, L = cfg = FULL[args.config]
     T = int(T * args.t_scale)
     cfg = (N, T, K, L)
-    assert T % world == 0
-    Tloc = T // world
     precision = resolve_precision(lib, _lib, args.precision, N, K, L)
+    bounds = shard_bounds(N, T, K, L, world, precision, args.denominators)
+    t_begin, Tloc = bounds[rank][0], bounds[rank][1] - bounds[rank][0]
 
-    X, W0, H0, t_begin, ncols_x = device_inputs(torch, dev, N, T, K, L, rank, world)
+    X, W0, H0, t_begin, ncols_x = device_inputs(torch, dev, N, T, K, L, t_begin, Tloc)
 
     # ---- the headline: the mode CMF(...).fit uses (parity-grade) ------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -575,16 +595,32 @@ def run_b200(args):
     # ---- end-to-end through the public host API (pinned host buffers) ---------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, torch, N, T, K, L, Tloc, rank, world, local_rank, precision, dist)
+        e2e = run_e2e(args, torch, N, T, K, L, t_begin, Tloc, rank, world, local_rank, precision, dist)
     del X, H0, W0
     torch.cuda.empty_cache()
+    # ---- the other BASELINE configs, quick lines on one GPU (A, B, D; E = 32 GiB of X fits one 180 GB GPU) -------
+    other = None
+    if world == 1 and not args.no_other_configs and args.config == "C" and args.t_scale == 1.0:
+        other = {}
+        for c in ("A", "B", "D", "E"):
+            try:
+                other[c] = quick_config(torch, dev, lib, _lib, args, c, steps=5 if c == "E" else max(10, args.steps),
+                                        warmup=3)
+            except Exception as e:          # noqa: BLE001 - (config E needs ~110 GiB; reported, not fatal)
+                other[c] = {"workload": "config %s" % c, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+                torch.cuda.empty_cache()
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
 
     peaks, peaks_src = measured_peaks()
-    tf32_peak = measure_tf32_peak(torch, dev) if not args.no_peak else {"burst": None, "sustained": None, "how": "skipped"}
+    tf32_peak = {"burst": None, "sustained": None, "how": "skipped"}
+    if not args.no_peak:
+        try:
+            tf32_peak = measure_tf32_peak(torch, dev)
+        except Exception as e:              # noqa: BLE001
+            tf32_peak = {"burst": None, "sustained": None, "how": "failed: %s" % str(e)[:100]}
     roofline = roofline_report(N, Tloc, K, L, main["path"], precision, main["table"], main["phases"], main["clocks"],
                                tf32_peak, peaks, peaks_src, world)
     tf32_line = None
@@ -598,10 +634,8 @@ def run_b200(args):
                      "parity": "plain TF32 operands (10-bit mantissa): loss trajectories within 4e-8 .. 2.1e-3 of the "
                                "float64 reference on the golden cases (profiles/r02_trajectory_errors.log), not held to "
                                "the 1e-4 bar; reported separately as north_star asks"}
-    other = None
-    if world == 1 and not args.no_other_configs and args.config == "C" and args.t_scale == 1.0:
-        other = {c: quick_config(torch, dev, lib, _lib, args, c, peaks, tf32_peak, steps=max(10, args.steps), warmup=3)
-                 for c in ("B", "D")}
+    if other:
+        quick_rooflines(other, peaks, tf32_peak)
     cb = None
     if not args.no_cpu_baseline and world == 1:          # the CPU baseline is a 1-GPU-run item (rank 0, N = 1 only)
         cb = cpu_baseline(N, T, K, L)
@@ -612,7 +646,11 @@ def run_b200(args):
         "dtype": DTYPE_NAMES.get(precision, precision), "data": "synthetic",
         "config": {"workload": "config %s: N=%d T=%d K=%d L=%d MU%s" %
                    (args.config, N, T, K, L, "" if args.t_scale == 1.0 else " (T reduced: debug)"),
-                   "sharding": "time axis, %d x %d columns, halo %d" % (world, Tloc, L - 1),
+                   "sharding": ("time axis, %d x %d columns, halo %d" % (world, Tloc, L - 1)
+                                if len({b[1] - b[0] for b in bounds}) == 1 else
+                                "time axis, %d x %d + 1 x %d columns (the last shard also computes the end-of-data "
+                                "corrections of the Gram route), halo %d"
+                                % (world - 1, bounds[0][1] - bounds[0][0], bounds[-1][1] - bounds[-1][0], L - 1)),
                    "l2": "inputs_exceed_l2 (X is %.1f GiB per GPU)" % (N * Tloc * 4 * (2 if precision == "tf32x3" else 1) / 2**30),
                    "precision": precision, "precision_requested": args.precision,
                    "parity": "loss trajectory within 1e-4 of the float64 reference on every golden case "
@@ -634,13 +672,12 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, torch, N, T, K, L, Tloc, rank, world, local_rank, precision, dist):
+def run_e2e(args, torch, N, T, K, L, t_begin, Tloc, rank, world, local_rank, precision, dist):
     """The call a user makes: solver built from HOST arrays (pinned), every
     update() returns its loss to the host, W and H read back at the end.  The
     timed region holds all host<->device traffic."""
     from cmfpy_b200.dist import ShardedMultUpdate
     dev = torch.device("cuda", local_rank)
-    t_begin = rank * Tloc
     ncols_x = min(Tloc + L - 1, T - t_begin)
     gen = torch.Generator(device=dev)
     gen.manual_seed(99 + rank)

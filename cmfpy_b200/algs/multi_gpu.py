@@ -21,15 +21,36 @@ from .. import _lib
 from .base import _as_host_matrix, resolve_precision
 
 
-def shard_ranges(T, G):
-    """Contiguous column ranges [t0, t1) of G shards, sizes differing by at most one."""
+def shard_ranges(T, G, tail_columns=0, align=256):
+    """Contiguous column ranges [t0, t1) of G shards.  `tail_columns` = 0: sizes differing by at most one.
+    Otherwise the LAST shard ends up about that many columns shorter than the others (which share what it gives up,
+    in multiples of `align`): with the Gram-route denominators only the shard that sees the end of the data computes
+    the end-of-data corrections - a few small kernels per iteration while every other rank waits at the next
+    exchange; `tail_handicap` estimates their cost in columns."""
     base, rem = divmod(T, G)
+    sizes = [base + (1 if g < rem else 0) for g in range(G)]
+    if G > 1 and tail_columns > 0:
+        per = int(round(tail_columns / G / align)) * align          # what each of the other shards takes over
+        if per > 0 and per * (G - 1) <= sizes[-1] // 4:
+            for g in range(G - 1):
+                sizes[g] += per
+            sizes[-1] -= per * (G - 1)
     out, t0 = [], 0
-    for g in range(G):
-        t1 = t0 + base + (1 if g < rem else 0)
-        out.append((t0, t1))
-        t0 = t1
+    for n in sizes:
+        out.append((t0, t0 + n))
+        t0 += n
     return out
+
+
+def tail_handicap(N, K, L, T, G, gram, num_sms=148):
+    """Columns of MU work that the end-of-data corrections of the Gram route cost the last of G time shards per
+    iteration (see shard_ranges).  They are dominated by two reconstructions of ONE 256-column time tile, which
+    occupy ceil(N / 128) SMs where an iteration's two full contractions use all of them - 256 * num_sms /
+    ceil(N / 128) column-equivalents - plus about half as much again for the small FFMA contractions after them
+    (measured at config C: 0.26 ms of the last rank per iteration = 7 800 columns; the estimate gives 7 104)."""
+    if G < 2 or not gram:
+        return 0
+    return int(1.5 * 256 * num_sms / -(-N // 128))
 
 
 class MultiGpuMultUpdate:
@@ -63,7 +84,9 @@ class MultiGpuMultUpdate:
         if X.shape != (N, T):
             raise ValueError("data has shape %s, dimensions say %s" % (X.shape, (N, T)))
         self._X = X
-        self.ranges = shard_ranges(T, self.G)
+        gram = denominators == "gram" or (denominators == "auto" and self.precision != "fp32" and
+                                          2.0 * N * K * L * (T / self.G) >= 2e11 and N >= 4 * K)
+        self.ranges = shard_ranges(T, self.G, tail_handicap(N, K, L, T, self.G, gram))
         if self.G > 1 and min(t1 - t0 for t0, t1 in self.ranges) < max(L - 1, 1):
             raise ValueError("each of the %d time shards needs at least L-1 = %d columns (T = %d)" % (self.G, L - 1, T))
         self._h = [C.c_void_p() for _ in devices]

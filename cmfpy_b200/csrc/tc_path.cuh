@@ -37,9 +37,25 @@ struct Fold {
   int recon_LB = 0;                               // K1: lags per window (0: all of them in one window)
   int h_hd = 0;                                   // H terms: columns before a time tile that its lag groups reach
   int h_stages = 0;                               // H terms: W ring depth that fits shared memory (0: none does)
+  int h_staged = 0;                               // H terms: folded lags reduced through the staged gather
 };
 
 constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
+
+// W ring depth and reduction form of the H-terms kernel: the staged gather (folded lags, K < 32) is taken when it
+// costs no ring stage
+inline void choose_hterms_ring(Fold& f, bool direct) {
+  f.h_stages = 0;
+  f.h_staged = 0;
+  static const bool staging_enabled = [] { const char* e = getenv("CMF_HT_STAGED"); return !e || atoi(e) != 0; }();
+  for (int st = 3; st >= 2 && !f.h_stages; --st) {
+    if (f.s > 1 && staging_enabled && hterms_smem_bytes(st, f.hterms_wrows, f.Kp, f.h_hd, direct, true) <= kMaxSmem) {
+      f.h_stages = st; f.h_staged = 1;
+    } else if (hterms_smem_bytes(st, f.hterms_wrows, f.Kp, f.h_hd, direct, false) <= kMaxSmem) {
+      f.h_stages = st;
+    }
+  }
+}
 
 inline Fold make_fold(int Kp, int L) {
   Fold f;
@@ -60,9 +76,7 @@ inline Fold make_fold(int Kp, int L) {
   f.hterms_wrows = round_up(256 + f.s * (f.J - 1), 32);
   f.h_hd = (f.n_glag - 1) * f.s * f.J + f.s - 1;
   const bool direct = f.n_glag == 1 && f.s == 1;
-  f.h_stages = 0;
-  for (int st = 3; st >= 2 && !f.h_stages; --st)
-    if (hterms_smem_bytes(st, f.hterms_wrows, Kp, f.h_hd, direct) <= kMaxSmem) f.h_stages = st;
+  choose_hterms_ring(f, direct);
   return f;
 }
 
@@ -478,7 +492,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   s.tmXlo_k3 = s.tmX_k3;
   if (s.x3) CMF_TRY(make_map(&s.tmXlo_k3, Xlo, d.RT, d.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
   CMF_CUDA(cudaFuncSetAttribute(tc_hterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)hterms_smem_bytes(f.h_stages, f.hterms_wrows, d.Kp, f.h_hd, f.n_glag == 1 && f.s == 1)));
+                                (int)hterms_smem_bytes(f.h_stages, f.hterms_wrows, d.Kp, f.h_hd, f.n_glag == 1 && f.s == 1, f.h_staged != 0)));
 
   // ---- Gram route ---------------------------------------------------------
   s.gram = s.gram_request;
@@ -494,9 +508,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     s.fr.J = (s.Lrv + f.n_glag - 1) / f.n_glag;
     s.fr.hterms_wrows = round_up(256 + f.s * (s.fr.J - 1), 32);
     s.fr.h_hd = (f.n_glag - 1) * f.s * s.fr.J + f.s - 1;
-    s.fr.h_stages = 0;
-    for (int st = 3; st >= 2 && !s.fr.h_stages; --st)
-      if (hterms_smem_bytes(st, s.fr.hterms_wrows, d.Kp, s.fr.h_hd, f.n_glag == 1 && f.s == 1) <= kMaxSmem) s.fr.h_stages = st;
+    choose_hterms_ring(s.fr, f.n_glag == 1 && f.s == 1);
     if (!s.fr.h_stages) s.gram &= ~1;
   }
   if ((long long)s.g_rows * s.LK * 4 > (1ll << 30)) s.gram &= ~1;
@@ -522,8 +534,8 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     if (s.fr.h_hd > 0) CMF_CUDA(cudaMalloc((void**)&s.hcarry_r, (size_t)(d.TO / 256 + 1) * s.fr.h_hd * d.Kp * 4));
     // one attribute for both uses of the H-terms kernel
     const bool direct = f.n_glag == 1 && f.s == 1;
-    const size_t a = hterms_smem_bytes(f.h_stages, f.hterms_wrows, d.Kp, f.h_hd, direct);
-    const size_t b = hterms_smem_bytes(s.fr.h_stages, s.fr.hterms_wrows, d.Kp, s.fr.h_hd, direct);
+    const size_t a = hterms_smem_bytes(f.h_stages, f.hterms_wrows, d.Kp, f.h_hd, direct, f.h_staged != 0);
+    const size_t b = hterms_smem_bytes(s.fr.h_stages, s.fr.hterms_wrows, d.Kp, s.fr.h_hd, direct, s.fr.h_staged != 0);
     CMF_CUDA(cudaFuncSetAttribute(tc_hterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(a > b ? a : b)));
   }
   // H terms.  3xTF32: short tensor-memory sub-chunks folded in fp32 registers (no truncation bias to speak of).
@@ -734,11 +746,11 @@ inline int den_h_gram(TcState& s, cudaStream_t stream) {
     p.n_time_tiles = d.TO / 256 + 1;
     p.n_items = p.n_time_tiles;
     p.TO = d.TO; p.out = den; p.carry = s.hcarry_r; p.hd = r.h_hd;
-    p.sub_units = s.x3 ? strict_sub_units() : 0; p.n_stages = r.h_stages;
+    p.sub_units = s.x3 ? strict_sub_units() : 0; p.n_stages = r.h_stages; p.staged = r.h_staged;
     p.x3 = s.x3; p.lo_off = f.KW; p.err = s.d_err;
     const bool direct = f.n_glag == 1 && f.s == 1;
     const int grid = (int)(p.n_items < d.num_sms ? p.n_items : d.num_sms);
-    tc_hterms_kernel<<<grid, kSThreads, hterms_smem_bytes(r.h_stages, r.hterms_wrows, d.Kp, r.h_hd, direct), stream>>>(
+    tc_hterms_kernel<<<grid, kSThreads, hterms_smem_bytes(r.h_stages, r.hterms_wrows, d.Kp, r.h_hd, direct, r.h_staged != 0), stream>>>(
         s.tmRw_k3, s.tmHs_k3, s.tmHs_k3, s.tmHslo_k3, s.tmHslo_k3, p);
     CMF_TRY(launch_ok("gram_den_h"));
     if (r.h_hd > 0) {
@@ -798,10 +810,10 @@ inline int h_terms(TcState& s, cudaStream_t stream) {
   p.n_time_tiles = d.TO / 256 + 1;
   p.n_items = p.n_time_tiles * p.n_src;
   p.TO = d.TO; p.out = s.hterms; p.carry = s.hcarry; p.hd = f.h_hd;
-  p.sub_units = s.h_sub; p.n_stages = f.h_stages;
+  p.sub_units = s.h_sub; p.n_stages = f.h_stages; p.staged = f.h_staged;
   p.x3 = s.x3; p.lo_off = f.KW; p.err = s.d_err;
   const bool direct = f.n_glag == 1 && f.s == 1;
-  tc_hterms_kernel<<<s.hterms_grid, kSThreads, hterms_smem_bytes(f.h_stages, f.hterms_wrows, d.Kp, f.h_hd, direct), stream>>>(
+  tc_hterms_kernel<<<s.hterms_grid, kSThreads, hterms_smem_bytes(f.h_stages, f.hterms_wrows, d.Kp, f.h_hd, direct, f.h_staged != 0), stream>>>(
       s.tmW_k3, s.tmX_k3, s.tmE_k3, s.tmXlo_k3, s.tmElo_k3, p);
   CMF_TRY(launch_ok("tc_hterms"));
   if (f.h_hd > 0) {

@@ -589,6 +589,7 @@ struct HTermsParams {
   int hd;                          // columns before the tile that its lag groups reach: (4/CB - 1) s J + s - 1
   int sub_units;                   // units per sub-chunk (0: the whole item in one tensor-memory chain)
   int n_stages;                    // W ring depth (2 lags per stage)
+  int staged;                      // folded lags: reduce through a staged gather (needs hterms_stage_bytes of shared memory)
   int x3, lo_off;                  // 3xTF32: the feature chunks of an item are walked three times - (W lo, S hi),
                                    // (W hi, S lo), (W hi, S hi)
   int* err;
@@ -599,11 +600,15 @@ constexpr int kHtABytes = 4 * 32 * 128;            // 4 regions x 32 n x 32 k
 constexpr int kHtStageBytes = kHtLagsPerStage * kHtABytes;
 constexpr int kHtMaxStages = 4;
 
-__host__ __device__ inline size_t hterms_r_bytes(int Kp, int hd, bool direct) {
-  return direct ? 0 : (size_t)(256 + hd) * Kp * 4;
+constexpr int kHtStageLd = 33;                     // staging row stride in floats (odd: conflict-free both ways)
+__host__ __device__ inline size_t hterms_stage_bytes(bool staged) {
+  return staged ? (size_t)2 * 128 * kHtStageLd * 4 : 0;       // folded lags: [column half][128 rows][32 columns]
 }
-__host__ __device__ inline size_t hterms_smem_bytes(int n_stages, int wrows, int Kp, int hd, bool direct) {
-  return 1024 + (size_t)n_stages * kHtStageBytes + 2 * (size_t)wrows * 128 + hterms_r_bytes(Kp, hd, direct) + 256;
+__host__ __device__ inline size_t hterms_r_bytes(int Kp, int hd, bool direct, bool staged) {
+  return direct ? 0 : (size_t)(256 + hd) * Kp * 4 + hterms_stage_bytes(staged);
+}
+__host__ __device__ inline size_t hterms_smem_bytes(int n_stages, int wrows, int Kp, int hd, bool direct, bool staged) {
+  return 1024 + (size_t)n_stages * kHtStageBytes + 2 * (size_t)wrows * 128 + hterms_r_bytes(Kp, hd, direct, staged) + 256;
 }
 
 __global__ void __launch_bounds__(kSThreads, 1)
@@ -619,7 +624,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   const uint32_t wbytes = (uint32_t)p.wrows * 128;                // one 32-feature chunk of the window
   uint8_t* Ws = As + (size_t)n_stages * kHtStageBytes;            // [2][wbytes]
   float* R = (float*)(Ws + 2 * (size_t)wbytes);                   // [256 + hd][Kp]
-  uint64_t* bars = (uint64_t*)((uint8_t*)R + hterms_r_bytes(p.Kp, p.hd, direct));
+  uint64_t* bars = (uint64_t*)((uint8_t*)R + hterms_r_bytes(p.Kp, p.hd, direct, p.staged != 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + kHtMaxStages;
   uint64_t* wfull = bars + 2 * kHtMaxStages;                      // [2]
@@ -806,6 +811,40 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         for (int i = etid; i < n4; i += kSEpiThreads) R4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       epi_bar();
+      if (p.staged) {
+        // Folded lags (K < 32): the 128 accumulator rows are (lag group, lag inside a virtual lag, k) and every one of
+        // them lands on its own row offset of R.  Letting the eight warps add their rows one after the other made this
+        // reduction - not the MMAs - the length of a work item on small problems (config B: 64 k cycles against 25 k).
+        // Instead all warps stage 32 columns at a time, row-major, and the 256 threads gather: R row u, component k
+        // is owned by ONE thread, which adds its sources in a fixed order (deterministic, no atomics).
+        float* St = R + (size_t)U * p.Kp;                         // [2][128][kHtStageLd]
+        float* mine = St + ((size_t)half * 128 + q * 32 + lane) * kHtStageLd;
+        const int n_src_rows = n_glag * p.s;                      // (lag group, folded lag) pairs
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mine[i] = m[i];
+          rotate32(m);
+          epi_bar();
+          // this column block reaches R rows [32 c, 32 c + 160 + hd)
+          const int u_lo = c * 32;
+          int n_u = 160 + p.hd;
+          if (u_lo + n_u > U) n_u = U - u_lo;
+          for (int idx = etid; idx < n_u * p.Kp; idx += kSEpiThreads) {
+            const int k = idx / n_u, u = u_lo + idx % n_u;       // u fastest: a warp reads consecutive staging columns
+            float acc = R[(size_t)u * p.Kp + k];
+            for (int sr = 0; sr < n_src_rows; ++sr) {
+              const int g = sr / p.s, d = sr % p.s;
+              const int j0 = u - ((n_glag - 1 - g) * p.s * J + (p.s - 1 - d)) - c * 32;      // column in half 0
+              const float* srow = St + (size_t)(g * 32 + d * p.Kp + k) * kHtStageLd;
+              if (j0 >= 0 && j0 < 32) acc += srow[j0];
+              const int j1 = j0 - 128;                                                       // column in half 1
+              if (j1 >= 0 && j1 < 32) acc += srow[128 * kHtStageLd + j1];
+            }
+            R[(size_t)u * p.Kp + k] = acc;
+          }
+          epi_bar();
+        }
+      } else {
       for (int w = 0; w < 8; ++w) {
         if (w == e) {
 #pragma unroll 1
@@ -827,6 +866,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           }
         }
         epi_bar();
+      }
       }
       // ---- R -> carry (the hd columns before the tile) and out (the tile's own 256 columns) ----
       {
