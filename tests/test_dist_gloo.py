@@ -216,3 +216,28 @@ def test_peer_transport_host_logic(fail_attach_on):
         np.testing.assert_allclose(W, ref.W, rtol=1e-5, atol=1e-7)
     assert attached_after_close is False
     np.testing.assert_allclose(np.concatenate([g[0] for g in gathered], axis=1), ref.H, rtol=1e-5, atol=1e-7)
+
+
+def test_tail_aware_shard_ranges():
+    """shard_ranges / tail_handicap (algs/multi_gpu.py): contiguous cover of [0, T), the last shard shorter by about
+    the estimated cost of the end-of-data corrections, every shard a multiple of 256 when T / G is, and no change
+    where the estimate does not apply (direct denominators, one shard, shards too short to give anything up)."""
+    from cmfpy_b200.algs.multi_gpu import shard_ranges, tail_handicap
+    T = 1 << 20
+    for G in (1, 2, 3, 4, 8):
+        h = tail_handicap(1024, 32, 64, T, G, gram=True)
+        r = shard_ranges(T, G, h)
+        assert r[0][0] == 0 and r[-1][1] == T and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        sizes = [b - a for a, b in r]
+        if G == 1:
+            assert h == 0 and sizes == [T]
+            continue
+        assert h == 7104                                   # 1.5 * 256 * 148 / 8 feature tiles
+        assert len(set(sizes[:-1])) <= 2 and sizes[-1] < min(sizes[:-1])
+        assert abs((sizes[0] - sizes[-1]) - h) <= 256 * G  # the others are `h` columns longer, up to the alignment
+        if T % (G * 256) == 0:
+            assert all(s % 256 == 0 for s in sizes)
+    assert tail_handicap(1024, 32, 64, T, 8, gram=False) == 0
+    assert shard_ranges(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert shard_ranges(1000, 4, 300) == [(0, 250), (250, 500), (500, 750), (750, 1000)]        # 300 / 4 < 256: none
+    assert shard_ranges(4096, 2, 4096) == [(0, 2048), (2048, 4096)]                              # would take > 1/4
