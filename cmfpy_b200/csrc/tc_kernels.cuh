@@ -732,6 +732,39 @@ toeplitz_kernel(const float* __restrict__ P, float* __restrict__ Mt, int L, int 
   }
 }
 
+// The same operator as a SHIFT operand (round 2): den_W is itself a convolution over lags,
+//   den_W[(l,k)][n] = sum_{l'v} sum_c Wv[l'v][n][c] * Pw[(l,k) + s_rows (Lv-1-l'v)][c],
+//   Pw[rho][(dl,k')] = A[rho / Kp - s (Lv-1) - dl][k'][rho % Kp]   (zero outside |d| <= L-1),
+// i.e. exactly the reconstruction est = sum_l W_l shift(H, l) with the lag autocorrelation in the place of H^T, (l,k)
+// in the place of time and a lag stride of s_rows = max(32, Kp) rows: K1 reads every lag as a shifted window of ONE
+// small operand ((L + s Lv) Kp rows x KW columns) instead of streaming a 2048 x 2048 block-Toeplitz matrix of which
+// each 32 KB window fed 4 MMAs (0.245 -> see DESIGN.md 4).  x3: rows are [hi (KW) | lo (KW)].
+__global__ void __launch_bounds__(256)
+autocorr_shift_operand_kernel(const float* __restrict__ P, float* __restrict__ Pw, int L, int Lv, int Kp, int s, int KW,
+                              long long rows_alloc, int x3) {
+  const long long total = rows_alloc * KW;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int ld = (x3 ? 2 : 1) * KW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long rho = i / KW;
+    const int c = (int)(i % KW);
+    const int dl = (s > 1) ? c / Kp : 0;
+    const int kq = (s > 1) ? c % Kp : c;
+    const int k = (int)(rho % Kp);
+    const long long d = rho / Kp - (long long)s * (Lv - 1) - dl;
+    float v = 0.f;
+    if (kq < Kp && d > -(long long)L && d < (long long)L)
+      v = (d >= 0) ? P[((size_t)d * Kp + kq) * Kp + k] : P[((size_t)(-d) * Kp + k) * Kp + kq];
+    if (x3) {
+      const float hi = round_tf32(v);
+      Pw[rho * ld + c] = hi;
+      Pw[rho * ld + KW + c] = round_tf32(v - hi);
+    } else {
+      Pw[rho * ld + c] = round_tf32(v);
+    }
+  }
+}
+
 // Wt[(l*Kp + k)][n] = round_tf32(W[l][n][k])      (32x32 tiles through smem)
 // x3: rows are [hi (lo_off columns) | lo]
 __global__ void __launch_bounds__(256)

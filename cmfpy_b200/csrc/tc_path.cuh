@@ -126,6 +126,10 @@ struct TcState {
   CUtensorMap tmWt_a, tmWt_b;
   // W step
   float *P = nullptr, *Ppart = nullptr, *Mt = nullptr;
+  float* Pw = nullptr;             // the lag autocorrelation of H as the shift operand of den_W (see den_w_gram)
+  long long pw_rows = 0;
+  int pw_LB = 0, pw_wrows = 0, pw_srows = 32;
+  CUtensorMap tmPw_b;
   int p_chunks = 1, p_grid = 1;
   CUtensorMap tmHx_k2, tmHxlo_k2, tmMt_b;
   int p_quad = 0, p_lag_groups = 1;     // autocorrelation pass: quad mode (Kp <= 32), its lag groups
@@ -202,8 +206,8 @@ inline int make_map_k3w(CUtensorMap* m, const float* Wv, const Fold& f, long lon
 inline void destroy(TcState& s) {
   cudaFree(s.wpart); cudaFree(s.hcarry); cudaFree(s.d_err); cudaFree(s.Wv); cudaFree(s.Hv);
   cudaFree(s.Wt); cudaFree(s.G); cudaFree(s.Rw); cudaFree(s.Rwv); cudaFree(s.Etail); cudaFree(s.hcarry_r);
-  cudaFree(s.P); cudaFree(s.Ppart); cudaFree(s.Mt);
-  s.Wt = s.G = s.Rw = s.Rwv = s.Etail = s.P = s.Ppart = s.Mt = s.hcarry_r = nullptr;
+  cudaFree(s.P); cudaFree(s.Ppart); cudaFree(s.Mt); cudaFree(s.Pw);
+  s.Wt = s.G = s.Rw = s.Rwv = s.Etail = s.P = s.Ppart = s.Mt = s.hcarry_r = s.Pw = nullptr;
   s.wpart = s.hcarry = s.Wv = s.Hv = nullptr;
   s.d_err = nullptr;
   s.ready = false;
@@ -556,8 +560,31 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   if (s.gram && s.ntail > 0) CMF_CUDA(cudaMalloc((void**)&s.Etail, (size_t)round_up_ll(s.ntail, 256) * d.Np * 4));
   if (s.gram & 2) {
     CMF_TRY(ensure_autocorr(s));
-    CMF_CUDA(cudaMalloc((void**)&s.Mt, (size_t)s.g_rows * f.Lv * f.KW * halves * 4));
-    CMF_TRY(make_map(&s.tmMt_b, s.Mt, s.g_rows, (long long)f.Lv * f.KW * halves, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
+    static const bool shift_form = [] { const char* e = getenv("CMF_DENW_SHIFT"); return !e || atoi(e) != 0; }();
+    if (shift_form) {
+      // den_W as a shift-GEMM (autocorr_shift_operand_kernel): lag stride s_rows rows, lags walked in blocks of pw_LB
+      s.pw_srows = d.Kp > 32 ? d.Kp : 32;
+      const int max_rows = (int)((kMaxSmem - recon_smem_bytes(0)) / (2 * kKp * 4) / 64) * 64;
+      int LB = (max_rows - 256) / s.pw_srows + 1;    // lags whose shifted windows fit one shared-memory window
+      const bool fits = LB >= 2 || LB >= f.Lv;
+      if (LB >= f.Lv) LB = 0;                        // every lag in one window
+      else LB &= ~1;                                 // (two lags per pipeline stage)
+      s.pw_LB = LB;
+      s.pw_wrows = round_up(256 + s.pw_srows * ((LB > 0 ? LB : f.Lv) - 1), 64);
+      s.pw_rows = round_up_ll(s.g_rows + (long long)s.pw_srows * f.Lv + s.pw_wrows, 64);
+      if (!fits || recon_smem_bytes(s.pw_wrows) > kMaxSmem) {
+        s.pw_rows = 0;                               // (no room for two lags per window: keep the Toeplitz GEMM)
+      } else {
+        CMF_CUDA(cudaMalloc((void**)&s.Pw, (size_t)s.pw_rows * s.KWs * 4));
+        CMF_TRY(make_map(&s.tmPw_b, s.Pw, s.pw_rows, s.KWs, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
+        const size_t a = recon_smem_bytes(f.recon_wrows), b = recon_smem_bytes(s.pw_wrows);
+        CMF_TRY(set_recon_smem(a > b ? a : b));
+      }
+    }
+    if (s.pw_rows == 0) {
+      CMF_CUDA(cudaMalloc((void**)&s.Mt, (size_t)s.g_rows * f.Lv * f.KW * halves * 4));
+      CMF_TRY(make_map(&s.tmMt_b, s.Mt, s.g_rows, (long long)f.Lv * f.KW * halves, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
+    }
   }
   s.ready = true;
   return 0;
@@ -609,12 +636,30 @@ inline int den_w_gram(TcState& s, cudaStream_t stream) {
   const Fold& f = s.f;
   // (a) P[d][k'][k] = sum_t H[k'][t] H[k][t-d] over the owned columns: the W-terms kernel on H^T
   CMF_TRY(autocorr(s, stream));
-  // (b) block-Toeplitz operand
-  toeplitz_kernel<<<ew_blocks(s, s.g_rows * f.Lv * f.KW), 256, 0, stream>>>(s.P, s.Mt, d.L, f.Lv, d.Kp, f.s, f.KW, s.g_rows, s.x3);
-  CMF_TRY(launch_ok("toeplitz"));
-  // (c) den_W[n][(l,k)] = sum_{(l'v,c)} Wv[l'v][n][c] Mt[(l,k)][(l'v,c)]  (plain GEMM on the recon kernel)
   float* den = s.numden + s.wcount;
-  {
+  if (s.pw_rows > 0) {
+    // (b) the autocorrelation as a shift operand, (c) den_W = W (*) A as a shift-GEMM on the recon kernel:
+    //     "time" = (l,k), lag stride pw_srows rows, output in the W layout (store mode 2)
+    autocorr_shift_operand_kernel<<<ew_blocks(s, s.pw_rows * f.KW), 256, 0, stream>>>(s.P, s.Pw, d.L, f.Lv, d.Kp, f.s, f.KW,
+                                                                                   s.pw_rows, s.x3);
+    CMF_TRY(launch_ok("autocorr_operand"));
+    ReconParams p{};
+    p.Np = d.Np; p.L = f.Lv; p.n_tiles_n = (int)ceil_div_ll(d.Np, 128); p.wrows = s.pw_wrows;
+    p.s = s.pw_srows; p.CB = f.CB; p.cb_cols = f.CB; p.h_shift = 0;
+    p.n_rows = d.Np; p.ld_out = d.Np; p.store_mode = 2; p.w_kp = d.Kp; p.w_np = d.Np;
+    p.n_tiles = (long long)p.n_tiles_n * (s.g_rows / 256);
+    p.t_own = 0; p.t_valid = s.LK;
+    p.Et = den; p.Xt = nullptr; p.loss_partials = s.loss_partials + d.num_sms; p.round_out = 0; p.err = s.d_err;
+    p.LB = s.pw_LB;
+    const int grid = (int)(p.n_tiles < d.num_sms ? p.n_tiles : d.num_sms);
+    set_x3(s, p, f.KW, f.KW);
+    launch_recon(s, grid, recon_smem_bytes(s.pw_wrows), stream, s.tmW_k1, s.tmPw_b, p);
+    CMF_TRY(launch_ok("gram_den_w"));
+  } else {
+    // (b) block-Toeplitz operand
+    toeplitz_kernel<<<ew_blocks(s, s.g_rows * f.Lv * f.KW), 256, 0, stream>>>(s.P, s.Mt, d.L, f.Lv, d.Kp, f.s, f.KW, s.g_rows, s.x3);
+    CMF_TRY(launch_ok("toeplitz"));
+    // (c) den_W[n][(l,k)] = sum_{(l'v,c)} Wv[l'v][n][c] Mt[(l,k)][(l'v,c)]  (plain GEMM on the recon kernel)
     ReconParams p{};
     p.Np = d.Np; p.L = 1; p.n_tiles_n = (int)ceil_div_ll(d.Np, 128); p.wrows = 256;
     p.s = 0; p.CB = f.Lv * f.CB; p.cb_cols = f.CB; p.h_shift = 0;
