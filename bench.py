@@ -399,28 +399,31 @@ def kernel_breakdown(alg, steps):
     return {k: (n / steps, ms / max(n, 1)) for k, (n, ms) in table.items()}, phases
 
 
-def ncu_traffic(kernel_name, path_name):
-    """DRAM bytes per launch of `kernel_name` from the committed `ncu --set full` summary of this round (the largest
-    launch of that kernel), or (None, None) when no capture is on file."""
-    import glob
+def ncu_traffic(kernel_name, path_name, config):
+    """DRAM bytes per launch of `kernel_name` from the committed `ncu --set full` summary of this round for this
+    config and path (profiles/r02_ncu_kernels_<config>_<path>.txt; the largest launch of that kernel), or
+    (None, None) when no capture is on file."""
     import re
     tag = path_name.replace("tcgen05-", "").replace("+", "_")
+    f = os.path.join(ROOT, "profiles", "r02_ncu_kernels_%s_%s.txt" % (config, tag))
     best = (None, None)
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_ncu_kernels_%s*.txt" % tag))):
-        for line in open(f):
-            if not line.startswith("kernel=") or ("::" + kernel_name + "(") not in line.replace("kernel=", "kernel=::", 1):
-                continue
-            tot = 0.0
-            for key in ("dram_rd", "dram_wr"):
-                m = re.search(key + r"=([0-9.]+)([GMK]?)byte", line)
-                if m:
-                    tot += float(m.group(1)) * {"G": 1e9, "M": 1e6, "K": 1e3, "": 1.0}[m.group(2)]
-            if best[0] is None or tot > best[0]:
-                best = (tot, os.path.relpath(f, ROOT))
+    if not os.path.exists(f):
+        return best
+    for line in open(f):
+        if not line.startswith("kernel=" + kernel_name + "("):
+            continue
+        tot = 0.0
+        for key in ("dram_rd", "dram_wr"):
+            m = re.search(key + r"=([0-9.]+)([GMK]?)byte", line)
+            if m:
+                tot += float(m.group(1)) * {"G": 1e9, "M": 1e6, "K": 1e3, "": 1.0}[m.group(2)]
+        if best[0] is None or tot > best[0]:
+            best = (tot, os.path.relpath(f, ROOT))
     return best
 
 
-def roofline_report(N, Tloc, K, L, path_name, precision, table, phases, clocks, tf32_peak, peaks, peaks_src, world):
+def roofline_report(N, Tloc, K, L, path_name, precision, table, phases, clocks, tf32_peak, peaks, peaks_src, world,
+                    config="C"):
     """Per-kernel roofline table of one iteration and the headline entry for the dominant kernel."""
     gram = path_name.endswith("+gram")
     x3 = precision == "tf32x3"
@@ -455,7 +458,7 @@ def roofline_report(N, Tloc, K, L, path_name, precision, table, phases, clocks, 
         kname = {"tc_recon": "tc_recon_x3_kernel" if x3 else "tc_recon_kernel",
                  "tc_wterms": "tc_wterms_x3_kernel" if x3 else "tc_wterms_kernel",
                  "tc_hterms": "tc_hterms_kernel"}.get(dominant["kernel"], dominant["kernel"])
-        traffic, traffic_file = ncu_traffic(kname, path_name) if world == 1 else (None, None)
+        traffic, traffic_file = ncu_traffic(kname, path_name, config) if world == 1 else (None, None)
         out.update(kernel="%s (%s, %s)" % (dominant["kernel"], kname, path_name),
                    achieved=dominant["algorithmic_tflops"], frac=dominant["frac_of_measured_tf32"],
                    traffic=traffic, traffic_source=traffic_file,
@@ -622,11 +625,11 @@ def run_b200(args):
         except Exception as e:              # noqa: BLE001
             tf32_peak = {"burst": None, "sustained": None, "how": "failed: %s" % str(e)[:100]}
     roofline = roofline_report(N, Tloc, K, L, main["path"], precision, main["table"], main["phases"], main["clocks"],
-                               tf32_peak, peaks, peaks_src, world)
+                               tf32_peak, peaks, peaks_src, world, args.config)
     tf32_line = None
     if tf32:
         r2 = roofline_report(N, Tloc, K, L, tf32["path"], "tf32", tf32["table"], tf32["phases"], tf32["clocks"],
-                             tf32_peak, peaks, peaks_src, world)
+                             tf32_peak, peaks, peaks_src, world, args.config)
         tf32_line = {"precision": "tf32", "path": tf32["path"], "value": args.steps / (tf32["ms"] * 1e-3), "unit": UNIT,
                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": tf32["ms"] / args.steps,
                      "gpu_launches": int(tf32["launches"]), "final_loss": tf32["losses"][-1], "clocks": tf32["clocks"],

@@ -7,6 +7,7 @@
 """
 from .model import CMF, ModelDimensions
 from .algs import ALGORITHMS
+from ._lib import release_cached_memory
 
 __version__ = "0.1.0"
-__all__ = ["CMF", "ModelDimensions", "ALGORITHMS"]
+__all__ = ["CMF", "ModelDimensions", "ALGORITHMS", "release_cached_memory"]

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "cmf_abi_version": (C.c_int, []),
     "cmf_last_error": (C.c_char_p, []),
     "cmf_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "cmf_release_cached_memory": (C.c_int, []),
     "cmf_precision_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "cmf_mu_create": (C.c_int, [C.POINTER(_H), C.POINTER(Params)]),
     "cmf_mu_destroy": (C.c_int, [_H]),
@@ -169,6 +170,11 @@ def np_dtype_code(a):
     if a.dtype == np.float64:
         return CMF_F64
     raise TypeError("expected float32 or float64, got %s" % a.dtype)
+
+
+def release_cached_memory():
+    """Returns the library's cached N x T device buffers (kept across solvers of the same shape) to the driver."""
+    load().cmf_release_cached_memory()
 
 
 def device_count():

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -171,6 +172,57 @@ inline int ew_grid(const cmf_mu_s* h, long long n_items) {
   return (int)blocks;
 }
 
+// The N x T buffers (X^T, est^T and their lo halves) come from a small process-wide cache of freed blocks: cudaMalloc
+// of a few GiB costs anywhere from 10 ms to 0.4 s on these virtualised boxes (the end-to-end figure of bench.py moved
+// between 19 and 25 it/s with identical code for that reason alone), and a process that fits model after model -
+// a sweep over K or L, CMF.fit in a loop - asks for the same sizes again and again.  A block is reused only for the
+// same device and exactly the same size; at most CMF_CACHE_GB GiB stay cached (default 16, 0 disables);
+// cmf_release_cached_memory() returns them to the driver.
+struct BigCache {
+  struct Block { int dev; void* p; size_t bytes; };
+  std::mutex mu;
+  std::vector<Block> free_blocks;
+  size_t cached = 0;
+  size_t cap() {
+    static const size_t c = [] { const char* e = getenv("CMF_CACHE_GB"); return (size_t)((e ? atof(e) : 16.0) * (1ull << 30)); }();
+    return c;
+  }
+};
+BigCache& big_cache() { static BigCache* c = new BigCache(); return *c; }     // (never destroyed: outlives the runtime)
+
+int big_alloc(void** p, size_t bytes, int dev) {
+  {
+    BigCache& c = big_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    for (size_t i = 0; i < c.free_blocks.size(); ++i)
+      if (c.free_blocks[i].dev == dev && c.free_blocks[i].bytes == bytes) {
+        *p = c.free_blocks[i].p;
+        c.cached -= bytes;
+        c.free_blocks.erase(c.free_blocks.begin() + (long)i);
+        return 0;
+      }
+  }
+  if (cudaMalloc(p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    cmf_release_cached_memory();                      // make room and try once more
+    CMF_CUDA(cudaMalloc(p, bytes));
+  }
+  return 0;
+}
+void big_free(void* p, size_t bytes, int dev) {
+  if (!p) return;
+  BigCache& c = big_cache();
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (bytes >= (64u << 20) && c.cached + bytes <= c.cap()) {
+      c.free_blocks.push_back({dev, p, bytes});
+      c.cached += bytes;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+
 template <class T> int dmalloc(T** p, long long count) {
   CMF_CUDA(cudaMalloc((void**)p, (size_t)(count > 0 ? count : 1) * sizeof(T)));
   return 0;
@@ -267,10 +319,10 @@ bool gram_h(const cmf_mu_s* h) { return h->use_tc && (h->tcs.mask & 4) && (h->tc
 
 int ensure_est_buffer(cmf_mu_s* h) {
   if (h->Et) return 0;
-  CMF_CUDA(cudaMalloc((void**)&h->Et, ((size_t)h->RT * h->Np + 128) * 4));   // + slack: see make_map_k2src
+  CMF_TRY(big_alloc((void**)&h->Et, ((size_t)h->RT * h->Np + 128) * 4, h->dev));   // + slack: see make_map_k2src
   CMF_CUDA(cudaMemsetAsync(h->Et, 0, (size_t)h->RT * h->Np * 4, h->stream));
   if (h->x3) {
-    CMF_CUDA(cudaMalloc((void**)&h->Elo, ((size_t)h->RT * h->Np + 128) * 4));
+    CMF_TRY(big_alloc((void**)&h->Elo, ((size_t)h->RT * h->Np + 128) * 4, h->dev));
     CMF_CUDA(cudaMemsetAsync(h->Elo, 0, (size_t)h->RT * h->Np * 4, h->stream));
   }
   if (h->use_tc) CMF_TRY(tc::attach_est(h->tcs, h->Et, h->Elo));
@@ -513,7 +565,12 @@ void free_all(cmf_mu_s* h) {
   cudaFree(h->halsst.Rt); cudaFree(h->halsst.part); cudaFree(h->halsst.part_h); cudaFree(h->halsst.delta);
   cudaFree(h->halsst.Wk); cudaFree(h->halsst.prev); cudaFree(h->halsst.w2); cudaFree(h->halsst.d_diff);
   tc::destroy(h->tcs);
-  cudaFree(h->Xt); cudaFree(h->Et); cudaFree(h->Ht); cudaFree(h->W); cudaFree(h->Xlo); cudaFree(h->Elo);
+  {
+    const size_t nt_bytes = ((size_t)h->RT * h->Np + 128) * 4;
+    big_free(h->Xt, nt_bytes, h->dev); big_free(h->Et, nt_bytes, h->dev);
+    big_free(h->Xlo, nt_bytes, h->dev); big_free(h->Elo, nt_bytes, h->dev);
+  }
+  cudaFree(h->Ht); cudaFree(h->W);
   cudaFree(h->numden); cudaFree(h->wpart); cudaFree(h->hterms);
   cudaFree(h->loss_partials); cudaFree(h->d_sumsq); cudaFree(h->d_ring); cudaFree(h->d_xpart);
   cudaFree(h->d_neg);
@@ -531,6 +588,24 @@ void free_all(cmf_mu_s* h) {
 extern "C" {
 
 int cmf_abi_version(void) { return CMF_B200_ABI_VERSION; }
+
+int cmf_release_cached_memory(void) {
+  BigCache& c = big_cache();
+  std::vector<BigCache::Block> blocks;
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    blocks.swap(c.free_blocks);
+    c.cached = 0;
+  }
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (auto& b : blocks) {
+    cudaSetDevice(b.dev);
+    cudaFree(b.p);
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  return 0;
+}
 
 const char* cmf_last_error(void) { return last_error().c_str(); }
 
@@ -635,8 +710,8 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
 
   int rc = 0;
   auto A = [&](int r) { if (rc == 0) rc = r; };
-  A(dmalloc(&h->Xt, h->RT * h->Np + 128));        // + slack: the K2 box of a ragged feature count reads on
-  if (h->x3) A(dmalloc(&h->Xlo, h->RT * h->Np + 128));
+  A(big_alloc((void**)&h->Xt, ((size_t)h->RT * h->Np + 128) * 4, h->dev));   // + slack: the K2 box of a ragged feature count reads on
+  if (h->x3) A(big_alloc((void**)&h->Xlo, ((size_t)h->RT * h->Np + 128) * 4, h->dev));
   A(dmalloc(&h->Ht, h->RH * h->Kp));
   A(dmalloc(&h->W, h->wcount));
   A(dmalloc(&h->numden, 2 * h->wcount));

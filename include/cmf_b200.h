@@ -81,6 +81,10 @@ typedef struct cmf_mu_params {
 int         cmf_abi_version(void);
 const char* cmf_last_error(void);
 int         cmf_device_count(int* count);
+/* The N x T device buffers of a destroyed solver stay in a small process-wide cache (same device, same size; at
+ * most CMF_CACHE_GB GiB, default 16) so that the next solver of the same shape does not pay cudaMalloc again - tens
+ * to hundreds of ms for a few GiB.  This returns the cached blocks to the driver.                                    */
+int         cmf_release_cached_memory(void);
 /* 1 if `precision` has a kernel path for this shape on this build.         */
 int         cmf_precision_supported(int precision, int n_features,
                                     int n_components, int maxlag);

@@ -413,3 +413,22 @@ def test_loss_from_w_terms(built_lib, precision, kind, tol):
         assert "loss_identity" not in out["auto"][3]
     if kind == "uniform":
         assert f[-1] ** 2 >= 0.1              # (the identity was active from the second batch on)
+
+
+def test_device_buffer_cache(built_lib):
+    """The N x T buffers of a closed solver are reused by the next solver of the same shape (cmf_abi.cu BigCache):
+    results must not depend on what the previous owner left in them, and release_cached_memory() must leave the
+    library usable."""
+    import cmfpy_b200
+    N, T, K, L = 512, 1 << 16, 8, 16                  # 128 MiB per buffer: above the 64 MiB caching threshold
+    hists = []
+    for seed, release in ((1, False), (2, False), (1, True), (1, False)):
+        X, W0, H0 = make_inputs(N, T, K, L, "uniform", seed=seed)
+        alg = _solver(X, W0, H0, L, K, "tf32x3")
+        hists.append((seed, [alg.loss] + alg.update_many(3)))
+        alg.close()
+        if release:
+            cmfpy_b200.release_cached_memory()
+    same = [h for s, h in hists if s == 1]
+    assert same[0] == same[1] == same[2]              # bit-identical whatever the buffers held before
+    assert hists[1][1] != same[0]
