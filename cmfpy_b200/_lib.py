@@ -85,6 +85,7 @@ _SIGNATURES = {
     "cmf_hals_end": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "cmf_gd_cache": (C.c_int, [_H]),
     "cmf_gd_lipschitz_w": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "cmf_gd_lipschitz_state": (C.c_int, [_H, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cmf_gd_step": (C.c_int, [_H, C.c_int, C.c_double, C.POINTER(C.c_double)]),
     "cmf_mu_get_W": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
     "cmf_mu_get_H": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_longlong]),

@@ -10,6 +10,7 @@ SciPy that still accepts `eigh(eigvals=...)`; this one has no such dependency.
 """
 import ctypes as C
 import time
+import warnings
 
 import numpy as np
 
@@ -28,6 +29,7 @@ class GradDescent(DeviceOptimizer):
         super().__init__(data, dims, patience=patience, tol=tol, **kwargs)
         self.step_size = 1e-4                       # gradient_descent.py:29
         self.step_decrement = step_decrement
+        self._warned_unsettled = False
         _lib.check(self._lib.cmf_gd_cache(self._h))  # cache_gW, cache_gH (:37-38)
 
     # -- gradients (gradient_descent.py:40-52), read back on demand ------------
@@ -57,6 +59,13 @@ class GradDescent(DeviceOptimizer):
         _lib.check(self._lib.cmf_gd_lipschitz_w(self._h, C.byref(lam)))
         return float(lam.value)
 
+    def lipschitz_state(self):
+        """(settled, iterations) of the last power iteration: the reference's `eigh` is exact, a Rayleigh quotient that
+        has not settled is a lower bound of lambda_max (a W step that is too long)."""
+        ok, it = C.c_int(0), C.c_int(0)
+        _lib.check(self._lib.cmf_gd_lipschitz_state(self._h, C.byref(ok), C.byref(it)))
+        return bool(ok.value), int(it.value)
+
     def lipschitz_H(self):
         raise NotImplementedError()                 # as in the reference (:71-79)
 
@@ -64,6 +73,12 @@ class GradDescent(DeviceOptimizer):
         """One update (:81-92; BlockDescent: :132-147); returns the loss."""
         loss = C.c_double(0)
         _lib.check(self._lib.cmf_gd_step(self._h, int(self.block_descent), float(self.step_size), C.byref(loss)))
+        if not self._warned_unsettled:
+            settled, iters = self.lipschitz_state()
+            if not settled:
+                self._warned_unsettled = True
+                warnings.warn("lipschitz_W: the power iteration had not settled after %d iterations; the W step "
+                              "may be longer than the reference's 1 / lambda_max" % iters, RuntimeWarning)
         return float(loss.value)
 
     def update_many(self, n_steps, return_times=False):

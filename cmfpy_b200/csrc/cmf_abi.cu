@@ -111,7 +111,9 @@ struct cmf_mu_s {
     float *P = nullptr, *Ppart = nullptr, *Pt = nullptr, *v = nullptr, *y = nullptr, *d_inv = nullptr;
     double* d_lam = nullptr;
     gd::PowerState* st = nullptr;
-    int max_iter = 64;
+    int batch_iter = 64, max_batches = 16;   // power iteration: batches of launches, `done` read back in between
+    int iters = 0;                           // iterations issued by the last lipschitz_W
+    bool settled = true;                     // ... and whether its Rayleigh quotient settled (2 x rel. change <= 1e-7)
   } gdst;
 
   // ---- HALS (hals_kernels.cuh) ----
@@ -1731,13 +1733,26 @@ int gd_lipschitz(cmf_mu_s* h) {
   gd::power_reset_kernel<<<1, 1024, 0, h->stream>>>(g.st, g.v, n);
   CMF_TRY(launch_check(h, "power_reset"));
   const int mv_blocks = (int)ceil_div_ll((long long)n * 32, 256);
-  for (int it = 0; it < g.max_iter; ++it) {
-    gd::toeplitz_matvec_kernel<<<mv_blocks, 256, 0, h->stream>>>(P, g.Pt, g.v, g.y, h->L, h->Kp, g.st);
-    gd::power_normalize_kernel<<<1, 1024, 0, h->stream>>>(g.v, g.y, n, g.st, 1e-7, g.d_lam, g.d_inv);
-    h->launches += 2;
+  // A Rayleigh quotient is a LOWER bound of lambda_max (the W step 1 / lambda would be too long), so the iteration is
+  // not cut off at a fixed count: after every batch the `done` flag comes back (8 bytes; the solver step is
+  // synchronous anyway) and unsettled iterations go on, warm-started, for up to max_batches batches.  What is left
+  // unsettled after that is reported through cmf_gd_lipschitz_state.
+  g.iters = 0;
+  g.settled = false;
+  for (int b = 0; b < g.max_batches && !g.settled; ++b) {
+    for (int it = 0; it < g.batch_iter; ++it) {
+      gd::toeplitz_matvec_kernel<<<mv_blocks, 256, 0, h->stream>>>(P, g.Pt, g.v, g.y, h->L, h->Kp, g.st);
+      gd::power_normalize_kernel<<<1, 1024, 0, h->stream>>>(g.v, g.y, n, g.st, 1e-7, g.d_lam, g.d_inv);
+      h->launches += 2;
+    }
+    g.iters += g.batch_iter;
+    cudaError_t e = cudaGetLastError();
+    CMF_CHECK(e == cudaSuccess, "power iteration launch failed: %s", cudaGetErrorString(e));
+    double done = 0.0;
+    CMF_CUDA(cudaMemcpyAsync(&done, &g.st->done, 8, cudaMemcpyDeviceToHost, h->stream));
+    CMF_CUDA(cudaStreamSynchronize(h->stream));
+    g.settled = done != 0.0;
   }
-  cudaError_t e = cudaGetLastError();
-  CMF_CHECK(e == cudaSuccess, "power iteration launch failed: %s", cudaGetErrorString(e));
   return 0;
 }
 
@@ -1798,6 +1813,14 @@ int cmf_gd_lipschitz_w(cmf_mu_t* h, double* lam) {
   CMF_CUDA(cudaMemcpyAsync(lam, h->gdst.d_lam, 8, cudaMemcpyDeviceToHost, h->stream));
   CMF_CUDA(cudaStreamSynchronize(h->stream));
   if (h->use_tc) CMF_TRY(tc::check(h->tcs, h->stream));
+  return 0;
+}
+
+int cmf_gd_lipschitz_state(cmf_mu_t* h, int* settled, int* iterations) {
+  CMF_ENTER(h);
+  CMF_CHECK(settled != nullptr && iterations != nullptr, "null argument");
+  *settled = h->gdst.settled ? 1 : 0;
+  *iterations = h->gdst.iters;
   return 0;
 }
 

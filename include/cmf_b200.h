@@ -212,12 +212,16 @@ int cmf_mu_halo_exchange_peer(cmf_mu_t* h);
  *   cmf_mu_get_w_terms / cmf_mu_h_terms return num and den of the current factors.
  * cmf_gd_lipschitz_w: lambda_max of the (K L) x (K L) block-Toeplitz matrix of the
  *   lag autocorrelations of H (:54-69), by power iteration on the device.
+ * cmf_gd_lipschitz_state: whether the last power iteration (of cmf_gd_lipschitz_w or
+ *   cmf_gd_step) settled (two consecutive relative changes <= 1e-7) and how many
+ *   iterations it issued (batches of 64, up to 1024); the reference's eigh() is exact.
  * cmf_gd_step: one update(); block_descent = 0: W and H steps from the cached
  *   gradients, then residuals and both gradients (:81-92); 1: W step, residuals,
  *   gH, H step, residuals, gW (:132-147).  x <- max(x - ss g, 0) (:148-159) with
  *   ss = 1 / lipschitz_W for W and step_size_h for H.  Returns the loss (:120-123). */
 int cmf_gd_cache(cmf_mu_t* h);
 int cmf_gd_lipschitz_w(cmf_mu_t* h, double* lambda_max);
+int cmf_gd_lipschitz_state(cmf_mu_t* h, int* settled, int* iterations);
 int cmf_gd_step(cmf_mu_t* h, int block_descent, double step_size_h, double* loss_out);
 
 /* ---- HALS: HALSUpdate, algs/hals.py on algs/accelerated.py ----------------- */

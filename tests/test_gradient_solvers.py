@@ -125,6 +125,8 @@ def test_device_trajectory_against_reference_golden(built_lib, name, key, precis
     lam = alg.lipschitz_W()
     ref_lam = float(g[key + "_lipschitz0"])
     assert abs(lam - ref_lam) <= (1e-5 if precision != "tf32" else 2e-3) * ref_lam
+    settled, iters = alg.lipschitz_state()
+    assert settled and 64 <= iters <= 1024 and iters % 64 == 0
     if precision == "fp32" and key + "_gW0" in g.files:
         gW, gH = alg.gW, alg.gH
         assert np.abs(gW - g[key + "_gW0"]).max() <= 2e-5 * np.abs(g[key + "_gW0"]).max()
