@@ -77,6 +77,7 @@ struct cmf_mu_s {
   double sumsq_x = 0.0, norm_x = 0.0;
   int has_neg = 0;
   bool have_data = false, have_factors = false, est_valid = false, wterms_valid = false;
+  bool sumsq_current = true;         // d_sumsq is the residual of the factors est_valid refers to (do_recon)
   bool est_stored = false;           // the est buffer holds the reconstruction (est_valid alone: only its loss is current)
 
   long long launches = 0;
@@ -333,17 +334,21 @@ int ensure_est_buffer(cmf_mu_s* h) {
 }
 
 // store_est = false: only the loss is wanted (legal when neither MU step reads est)
-int do_recon(cmf_mu_s* h, bool store_est = true) {
+// need_loss = false (the reconstruction between the W and the H step of one iteration): the residual is not formed
+// (tc::recon); d_sumsq then belongs to older factors until the next full reconstruction (sumsq_current).
+int do_recon(cmf_mu_s* h, bool store_est = true, bool need_loss = true) {
   CMF_CHECK(h->have_data && h->have_factors, "recon before data/factors were set");
   if (store_est || !(h->use_tc && (h->tcs.mask & 1))) CMF_TRY(ensure_est_buffer(h));
   if (h->use_tc && (h->tcs.mask & 1)) {
     const long long n0 = tc::launch_counter();
-    CMF_TRY(tc::recon(h->tcs, h->stream, store_est));
+    CMF_TRY(tc::recon(h->tcs, h->stream, store_est, need_loss));
     h->launches += tc::launch_counter() - n0;
     h->est_stored = store_est;
+    h->sumsq_current = need_loss;
   } else {
     CMF_TRY(simt_recon(h));
     h->est_stored = true;
+    h->sumsq_current = true;
   }
   h->est_valid = true;
   return 0;
@@ -1030,6 +1035,7 @@ int cmf_mu_resid_sumsq(cmf_mu_t* h, double* sumsq) {
   CMF_ENTER(h);
   CMF_CHECK(sumsq != nullptr, "null argument");
   CMF_CHECK(h->est_valid, "Residuals not initialized.");                // base.py:95-96
+  if (!h->sumsq_current) CMF_TRY(do_recon(h, h->est_stored));           // (only after an iteration that failed half-way)
   CMF_CUDA(cudaMemcpyAsync(sumsq, h->d_sumsq, 8, cudaMemcpyDeviceToHost, h->stream));
   CMF_CUDA(cudaStreamSynchronize(h->stream));
   if (h->use_tc) CMF_TRY(tc::check(h->tcs, h->stream));
@@ -1107,6 +1113,7 @@ static int do_loss_identity(cmf_mu_s* h) {
   CMF_TRY(launch_check(h, "loss_sum"));
   h->est_valid = true;        // the loss of the current factors is known; est itself is not stored
   h->est_stored = false;
+  h->sumsq_current = true;
   return 0;
 }
 
@@ -1117,7 +1124,7 @@ static int issue_iteration(cmf_mu_s* h, bool prof, size_t& ne, int slot) {
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
   CMF_TRY(do_w_apply(h));
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-  if (!gram_h(h)) CMF_TRY(do_recon(h));       // the Gram H step does not read est
+  if (!gram_h(h)) CMF_TRY(do_recon(h, true, false));       // the Gram H step does not read est
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
   CMF_TRY(do_h_terms(h));
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
@@ -1148,11 +1155,13 @@ static void capture_iteration(cmf_mu_s* h) {
   // issue_iteration walks the host-side state flags although nothing executes during capture: put them back, so
   // that a capture that fails half-way leaves the plain-launch fallback a consistent state
   const bool est_valid = h->est_valid, est_stored = h->est_stored, wterms_valid = h->wterms_valid;
+  const bool sumsq_current = h->sumsq_current;
   size_t ne = 0;
   const int rc = issue_iteration(h, false, ne, -1);
   cudaGraph_t graph = nullptr;
   const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
   h->est_valid = est_valid; h->est_stored = est_stored; h->wterms_valid = wterms_valid;
+  h->sumsq_current = sumsq_current;
   h->graph_launches = h->launches - l0;
   h->launches = l0;                       // nothing ran yet; replays add graph_launches each
   if (rc != 0 || e != cudaSuccess || graph == nullptr ||
@@ -1200,7 +1209,7 @@ int cmf_mu_step(cmf_mu_t* h, int n_steps, double* loss_out, float* ms_out) {
         CMF_TRY(issue_iteration(h, prof, ne, i));
       }
     }
-    if (use_graph) { h->est_valid = true; h->est_stored = !(gram_w(h) && gram_h(h)); h->wterms_valid = ident; }
+    if (use_graph) { h->est_valid = true; h->est_stored = !(gram_w(h) && gram_h(h)); h->wterms_valid = ident; h->sumsq_current = true; }
     if (ms_out) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
     if (loss_out)
       CMF_CUDA(cudaMemcpyAsync(loss_out + done, h->d_ring, (size_t)chunk * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1542,7 +1551,7 @@ static int issue_sharded_iteration(cmf_mu_s* h, bool prof, size_t& ne, int ex_gr
   h->est_valid = false;
   CMF_TRY(sync_ops_W(h));
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
-  if (!gram_h(h)) CMF_TRY(do_recon(h));
+  if (!gram_h(h)) CMF_TRY(do_recon(h, true, false));
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
   CMF_TRY(do_h_terms(h));
   if (prof) CMF_CUDA(cudaEventRecord(get_event(h, ne++), h->stream));
@@ -1578,11 +1587,13 @@ static void capture_sharded_iteration(cmf_mu_s* h, int ex_grid) {
   }
   const long long l0 = h->launches;
   const bool est_valid = h->est_valid, est_stored = h->est_stored, wterms_valid = h->wterms_valid;
+  const bool sumsq_current = h->sumsq_current;
   size_t ne = 0;
   const int rc = issue_sharded_iteration(h, false, ne, ex_grid);
   cudaGraph_t graph = nullptr;
   const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
   h->est_valid = est_valid; h->est_stored = est_stored; h->wterms_valid = wterms_valid;
+  h->sumsq_current = sumsq_current;
   h->sgraph_launches = h->launches - l0;
   h->launches = l0;
   if (rc != 0 || e != cudaSuccess || graph == nullptr ||
@@ -1641,7 +1652,7 @@ int cmf_mu_step_sharded(cmf_mu_t* h, int n_steps, double* loss_out) {
         CMF_TRY(issue_sharded_iteration(h, prof, ne, ex_grid));
       }
     }
-    if (use_graph) { h->est_valid = true; h->est_stored = !(gram_w(h) && gram_h(h)); h->wterms_valid = ident; }
+    if (use_graph) { h->est_valid = true; h->est_stored = !(gram_w(h) && gram_h(h)); h->wterms_valid = ident; h->sumsq_current = true; }
     peer::barrier_kernel<<<1, 32, 0, h->stream>>>(ps.P, ++ps.bar_epoch);
     CMF_TRY(launch_check(h, "peer_barrier"));
     CMF_CUDA(cudaMemcpyAsync(ring.data(), ps.P.ring[ps.P.rank], (size_t)chunk * peer::kMaxPeers * 8, cudaMemcpyDeviceToHost,
@@ -1837,7 +1848,7 @@ int cmf_gd_step(cmf_mu_t* h, int block_descent, double step_size_h, double* loss
     CMF_TRY(do_w_terms(h));
     CMF_TRY(do_h_terms(h));
   } else {
-    CMF_TRY(do_recon(h));                                // residuals with the new W
+    CMF_TRY(do_recon(h, true, false));                   // est with the new W (its loss is not read)
     CMF_TRY(do_h_terms(h));
     CMF_TRY(gd_projected_step_H(h, step_size_h));
     CMF_TRY(do_recon(h));

@@ -86,6 +86,72 @@ __device__ __forceinline__ void wait_uniform(const Abort& ab, uint64_t* bar, uin
   __syncwarp();            // the lanes may leave the spin loop apart: converge before the uniform code goes on
 }
 
+// ---- the element-wise tail of the K1 epilogues: 32 consecutive est^T rows of one lane's feature column ----------
+// Row tests are 32-bit compares against per-block counts (nv rows below t_valid hold values, the others zeros; the
+// no rows below t_own enter the residual) and addresses are running pointers.  Written per element with 64-bit
+// `tau < t_own` tests, `off0 + j * np` products and the store-mode branches inside, this tail was ~55 instructions per
+// element, and on short reconstructions (config B: 96 MMAs per tile) the epilogue warps' instruction stream - not the
+// MMAs, not memory - was the length of K1 (ncu: 8 % tensor-active, the epilogue warps never idle).
+__device__ __forceinline__ int rows_below(long long limit, long long tau0) {
+  const long long d = limit - tau0;
+  return d <= 0 ? 0 : (d >= 32 ? 32 : (int)d);
+}
+// (volatile: the loads keep their program order, so all of them are in flight before the first use - left to itself
+// the compiler interleaved loads and uses under the register pressure of the epilogues and serialised the latencies)
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+// no >= 1.  Rows >= no are not read: the running pointer stops at row no - 1 (always valid memory) and their
+// values are zeroed afterwards - one code path for every block, no per-row branches.
+__device__ __forceinline__ void recon_load_x(float (&x)[32], int no, const float* __restrict__ xp,
+                                             const float* __restrict__ xlop, size_t np) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { x[j] = ld_stream(xp); xp += (j + 1 < no) ? np : 0; }
+  if (xlop) {
+    float xl[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { xl[j] = ld_stream(xlop); xlop += (j + 1 < no) ? np : 0; }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] += xl[j];
+  }
+  if (no < 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = j < no ? x[j] : 0.f;
+  }
+}
+__device__ __forceinline__ void recon_finish(const float* v, const float (&x)[32], int nv, int no, float* __restrict__ ep,
+                                             float* __restrict__ elop, size_t np, bool store, bool round_out,
+                                             float& tile_loss) {
+  if (no > 0) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = (j < nv ? v[j] : 0.f) - x[j];
+      if (j < no) tile_loss = fmaf(d, d, tile_loss);
+    }
+  }
+  if (!store) return;
+  if (elop) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float vv = j < nv ? v[j] : 0.f;
+      const float hi = round_tf32(vv);
+      *ep = hi;
+      *elop = round_tf32(vv - hi);
+      ep += np; elop += np;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float vv = j < nv ? v[j] : 0.f;
+      if (round_out) vv = round_tf32(vv);
+      *ep = vv;
+      ep += np;
+    }
+  }
+}
+
 struct PipeState {
   int stage = 0;
   uint32_t phase = 0;
@@ -336,11 +402,9 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + c * 32), r);
         const long long tau0 = tt * 256 + c * 32;
         const size_t off0 = (size_t)tau0 * np + n;
+        const int nv = rows_below(p.t_valid, tau0), no = rows_below(p.t_own, tau0);
         // all 32 X loads are issued before anything depends on them
-        if (n_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = (tau0 + j < p.t_own) ? __ldcs(Xt + off0 + (size_t)j * np) : 0.f;
-        }
+        if (n_ok && no > 0) recon_load_x(x, no, Xt + off0, nullptr, np);
         tmem_ld_wait();
         if (p.store_mode == 2) {
           // tau = l*Kp + k: 32 consecutive tau are whole groups of 4 components of one lag
@@ -357,20 +421,10 @@ tc_recon_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             }
           }
         } else if (n_ok) {
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long long tau = tau0 + j;
-            float v = __uint_as_float(r[j]);
-            if (tau >= p.t_valid) v = 0.f;
-            if (tau < p.t_own) {
-              const float d = v - x[j];
-              tile_loss = fmaf(d, d, tile_loss);
-            }
-            if (!p.skip_store) {
-              if (p.round_out) v = round_tf32(v);
-              Et[off0 + (size_t)j * np] = v;
-            }
-          }
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          recon_finish(v, x, nv, no, Et + off0, nullptr, np, !p.skip_store, p.round_out != 0, tile_loss);
         }
       }
       loss_acc += (double)tile_loss;

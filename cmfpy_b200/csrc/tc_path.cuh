@@ -685,7 +685,10 @@ inline int den_w_gram(TcState& s, cudaStream_t stream) {
   return 0;
 }
 
-inline int recon(TcState& s, cudaStream_t stream, bool store_est = true) {
+// need_loss = false: the reconstruction in the middle of an iteration (between the W and the H step) - nobody reads
+// its residual, so the epilogue does not load X (hi and lo halves: half of the launch's HBM traffic on problems whose
+// K1 is bound by its epilogue, config B) and the partial sums are not added up.
+inline int recon(TcState& s, cudaStream_t stream, bool store_est = true, bool need_loss = true) {
   const Dims& d = s.d;
   const Fold& f = s.f;
   ReconParams p{};
@@ -710,9 +713,11 @@ inline int recon(TcState& s, cudaStream_t stream, bool store_est = true) {
     set_x3(s, p, f.KW, 0);
     p.Elo = s.Elo; p.Xlo = s.Xlo;
   }
+  if (!need_loss) { p.t_own = 0; p.Xlo = nullptr; }
   const int grid = s.recon_grid;
   launch_recon(s, grid, recon_smem_bytes(f.recon_wrows), stream, s.tmW_k1, s.tmH_k1, p);
   CMF_TRY(launch_ok(loss_only_fast ? "tc_recon_loss_1pass" : "tc_recon"));
+  if (!need_loss) return 0;
   ew::sum_doubles_kernel<<<1, 1024, 0, stream>>>(s.loss_partials, grid, s.d_sumsq);
   return launch_ok("loss_sum");
 }

@@ -306,6 +306,19 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       float* __restrict__ Et = p.Et;
       float* __restrict__ Elo = p.Elo;
       const size_t np = (size_t)p.ld_out;
+      // The X rows of this CTA's NEXT tile go to L2 now (one bulk prefetch of a 512-byte row segment per thread and
+      // array): the loads of the residual below are issued in bursts between the folds and the stores, so on problems
+      // whose reconstruction is short (config B: 96 MMAs per tile) their DRAM latency was part of the epilogue.
+      if (p.t_own > 0 && tile + gridDim.x < p.n_tiles) {
+        const long long ntile = tile + gridDim.x;
+        const int col = (int)(ntile % p.n_tiles_n) * 128;
+        const long long ptau = (ntile / p.n_tiles_n) * 256 + (tid - 128);
+        if (ptau < p.t_own && col < p.n_rows) {
+          const uint32_t bytes = (uint32_t)min(128, p.n_rows - col) * 4;
+          prefetch_l2_bulk(Xt + (size_t)ptau * np + col, bytes);
+          if (Xlo) prefetch_l2_bulk(Xlo + (size_t)ptau * np + col, bytes);
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const long long tau0 = tt * 256 + half * 128 + c * 32;
@@ -324,34 +337,12 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             }
           }
         } else if (n_ok) {
+          // (t_own is 0 whenever there is no X: the plain GEMMs of the Gram route, the reconstruction between the W and
+          // the H step)
+          const int nv = rows_below(p.t_valid, tau0), no = rows_below(p.t_own, tau0);
           float x[32];
-          // (t_own is 0 whenever there is no X: the plain GEMMs of the Gram route)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = (tau0 + j < p.t_own) ? __ldcs(Xt + off0 + (size_t)j * np) : 0.f;
-          if (Xlo) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] += (tau0 + j < p.t_own) ? __ldcs(Xlo + off0 + (size_t)j * np) : 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long long tau = tau0 + j;
-            float v = m[j];
-            if (tau >= p.t_valid) v = 0.f;
-            if (tau < p.t_own) {
-              const float d = v - x[j];
-              tile_loss = fmaf(d, d, tile_loss);
-            }
-            if (!p.skip_store) {
-              if (Elo) {
-                const float hi = round_tf32(v);
-                Et[off0 + (size_t)j * np] = hi;
-                Elo[off0 + (size_t)j * np] = round_tf32(v - hi);
-              } else {
-                if (p.round_out) v = round_tf32(v);
-                Et[off0 + (size_t)j * np] = v;
-              }
-            }
-          }
+          if (no > 0) recon_load_x(x, no, Xt + off0, Xlo ? Xlo + off0 : nullptr, np);
+          recon_finish(m, x, nv, no, Et + off0, Elo ? Elo + off0 : nullptr, np, !p.skip_store, p.round_out != 0, tile_loss);
         }
         rotate32(m);
       }
@@ -819,7 +810,6 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         // is owned by ONE thread, which adds its sources in a fixed order (deterministic, no atomics).
         float* St = R + (size_t)U * p.Kp;                         // [2][128][kHtStageLd]
         float* mine = St + ((size_t)half * 128 + q * 32 + lane) * kHtStageLd;
-        const int n_src_rows = n_glag * p.s;                      // (lag group, folded lag) pairs
         for (int c = 0; c < 4; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) mine[i] = m[i];
@@ -829,18 +819,27 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           const int u_lo = c * 32;
           int n_u = 160 + p.hd;
           if (u_lo + n_u > U) n_u = U - u_lo;
-          for (int idx = etid; idx < n_u * p.Kp; idx += kSEpiThreads) {
-            const int k = idx / n_u, u = u_lo + idx % n_u;       // u fastest: a warp reads consecutive staging columns
-            float acc = R[(size_t)u * p.Kp + k];
-            for (int sr = 0; sr < n_src_rows; ++sr) {
-              const int g = sr / p.s, d = sr % p.s;
-              const int j0 = u - ((n_glag - 1 - g) * p.s * J + (p.s - 1 - d)) - c * 32;      // column in half 0
-              const float* srow = St + (size_t)(g * 32 + d * p.Kp + k) * kHtStageLd;
-              if (j0 >= 0 && j0 < 32) acc += srow[j0];
-              const int j1 = j0 - 128;                                                       // column in half 1
-              if (j1 >= 0 && j1 < 32) acc += srow[128 * kHtStageLd + j1];
+          // warp e takes components e, e + 8, ..., its lanes consecutive R rows: consecutive staging columns (no bank
+          // conflicts), no integer division, and the sources in the order (lag group, folded lag, column half) - with
+          // run-time divisions per source this gather was ~20 k cycles per column block, the length of the work item
+          // on small problems (config B)
+          const int sJ = p.s * J;
+          for (int k = e; k < p.Kp; k += 8) {
+            for (int v = lane; v < n_u; v += 32) {               // v = u - 32 c
+              float* rp = R + (size_t)(u_lo + v) * p.Kp + k;
+              float acc = *rp;
+              const float* srow_g = St + (size_t)k * kHtStageLd;
+              int j_g = v - (n_glag - 1) * sJ - (p.s - 1);       // column (half 0) of source (g = 0, d = 0)
+              for (int g = 0; g < n_glag; ++g, j_g += sJ, srow_g += 32 * kHtStageLd) {
+                const float* srow = srow_g;
+                int j0 = j_g;
+                for (int d = 0; d < p.s; ++d, ++j0, srow += p.Kp * kHtStageLd) {
+                  if ((unsigned)j0 < 32u) acc += srow[j0];
+                  if ((unsigned)(j0 - 128) < 32u) acc += srow[128 * kHtStageLd + j0 - 128];
+                }
+              }
+              *rp = acc;
             }
-            R[(size_t)u * p.Kp + k] = acc;
           }
           epi_bar();
         }
