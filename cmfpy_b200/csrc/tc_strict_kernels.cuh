@@ -288,6 +288,33 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     for (long long tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
       const int nt = (int)(tile % p.n_tiles_n);
       const long long tt = tile / p.n_tiles_n;
+      const float* __restrict__ Xt = p.Xt;
+      const float* __restrict__ Xlo = p.Xlo;
+      const size_t np = (size_t)p.ld_out;
+      // The X rows of this CTA's NEXT tile go to L2 now (one bulk prefetch of a 512-byte row segment per thread and
+      // array): the loads of the residual below are issued in bursts between the folds and the stores, so on problems
+      // whose reconstruction is short (config B: 96 MMAs per tile) their DRAM latency was part of the epilogue.
+      // (warp-uniform addresses, one elected lane: the instruction takes uniform registers, per-lane addresses would be
+      // issued one lane at a time)
+      if (p.t_own > 0 && tile + gridDim.x < p.n_tiles) {
+        const long long ntile = tile + gridDim.x;
+        const int col = (int)(ntile % p.n_tiles_n) * 128;
+        const long long row0 = (ntile / p.n_tiles_n) * 256 + (warp - 4) * 32;
+        if (col < p.n_rows) {
+          const uint32_t bytes = (uint32_t)min(128, p.n_rows - col) * 4;
+          const float* px = Xt + (size_t)row0 * np + col;
+          const float* pl = Xlo ? Xlo + (size_t)row0 * np + col : nullptr;
+#pragma unroll 1
+          for (int r = 0; r < 32; ++r) {
+            if (row0 + r < p.t_own && elect_one()) {
+              prefetch_l2_bulk(px, bytes);
+              if (pl) prefetch_l2_bulk(pl, bytes);
+            }
+            px += np;
+            if (pl) pl += np;
+          }
+        }
+      }
       for (int sub = 0; sub < n_sub; ++sub, sd.next()) {
         if (!wait_relaxed(ab, &sfull[sd.b], sd.ph)) { ok = false; break; }
         tc_fence_after();
@@ -301,24 +328,8 @@ tc_recon_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       const int n = nt * 128 + q * 32 + lane;
       const bool n_ok = n < p.n_rows;
       float tile_loss = 0.f;
-      const float* __restrict__ Xt = p.Xt;
-      const float* __restrict__ Xlo = p.Xlo;
       float* __restrict__ Et = p.Et;
       float* __restrict__ Elo = p.Elo;
-      const size_t np = (size_t)p.ld_out;
-      // The X rows of this CTA's NEXT tile go to L2 now (one bulk prefetch of a 512-byte row segment per thread and
-      // array): the loads of the residual below are issued in bursts between the folds and the stores, so on problems
-      // whose reconstruction is short (config B: 96 MMAs per tile) their DRAM latency was part of the epilogue.
-      if (p.t_own > 0 && tile + gridDim.x < p.n_tiles) {
-        const long long ntile = tile + gridDim.x;
-        const int col = (int)(ntile % p.n_tiles_n) * 128;
-        const long long ptau = (ntile / p.n_tiles_n) * 256 + (tid - 128);
-        if (ptau < p.t_own && col < p.n_rows) {
-          const uint32_t bytes = (uint32_t)min(128, p.n_rows - col) * 4;
-          prefetch_l2_bulk(Xt + (size_t)ptau * np + col, bytes);
-          if (Xlo) prefetch_l2_bulk(Xlo + (size_t)ptau * np + col, bytes);
-        }
-      }
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const long long tau0 = tt * 256 + half * 128 + c * 32;
@@ -596,7 +607,8 @@ __host__ __device__ inline size_t hterms_stage_bytes(bool staged) {
   return staged ? (size_t)2 * 128 * kHtStageLd * 4 : 0;       // folded lags: [column half][128 rows][32 columns]
 }
 __host__ __device__ inline size_t hterms_r_bytes(int Kp, int hd, bool direct, bool staged) {
-  return direct ? 0 : (size_t)(256 + hd) * Kp * 4 + hterms_stage_bytes(staged);
+  // (staged: R is component-major with an odd row length, at most 256 + hd + 1)
+  return direct ? 0 : (size_t)(256 + hd + (staged ? 1 : 0)) * Kp * 4 + hterms_stage_bytes(staged);
 }
 __host__ __device__ inline size_t hterms_smem_bytes(int n_stages, int wrows, int Kp, int hd, bool direct, bool staged) {
   return 1024 + (size_t)n_stages * kHtStageBytes + 2 * (size_t)wrows * 128 + hterms_r_bytes(Kp, hd, direct, staged) + 256;
@@ -796,49 +808,44 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         continue;
       }
       // ---- reduce the lag groups through R ----
+      const int Up = U | 1;                        // staged: R is [Kp][Up] (component-major, odd row length)
       {
         float4* R4 = reinterpret_cast<float4*>(R);
-        const int n4 = U * p.Kp / 4;
+        const int n4 = (p.staged ? Up : U) * p.Kp / 4;
         for (int i = etid; i < n4; i += kSEpiThreads) R4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       epi_bar();
       if (p.staged) {
         // Folded lags (K < 32): the 128 accumulator rows are (lag group, lag inside a virtual lag, k) and every one of
-        // them lands on its own row offset of R.  Letting the eight warps add their rows one after the other made this
-        // reduction - not the MMAs - the length of a work item on small problems (config B: 64 k cycles against 25 k).
-        // Instead all warps stage 32 columns at a time, row-major, and the 256 threads gather: R row u, component k
-        // is owned by ONE thread, which adds its sources in a fixed order (deterministic, no atomics).
-        float* St = R + (size_t)U * p.Kp;                         // [2][128][kHtStageLd]
+        // them lands on its own row offset (`shift`) of R.  All warps stage 32 accumulator columns at a time, row-major;
+        // then warp e owns components e, e + 8, ... and lane r the R rows u = r (mod 32): staged column j of source row
+        // (g, d) belongs to u = 32 c + j + shift, so for every source the lane reads column (r - shift) mod 32 and adds
+        // it to the row 32 c + r + 32 ceil((shift - r) / 32) - two real adds per source (one per column half), no
+        // predicates, staging reads and R accesses conflict-free, one owner per R element (fixed order: deterministic,
+        // no atomics).  Its predecessors - the warps adding their rows one after the other, then a gather over (u, k)
+        // with sixteen predicated sources per output - made this reduction, not the MMAs, the length of a work item on
+        // small problems (config B: 44 k cycles per item against 25 k of MMAs).
+        float* St = R + (size_t)Up * p.Kp;                        // [2][128][kHtStageLd]
         float* mine = St + ((size_t)half * 128 + q * 32 + lane) * kHtStageLd;
+        const int sJ = p.s * J;
         for (int c = 0; c < 4; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) mine[i] = m[i];
           rotate32(m);
           epi_bar();
-          // this column block reaches R rows [32 c, 32 c + 160 + hd)
-          const int u_lo = c * 32;
-          int n_u = 160 + p.hd;
-          if (u_lo + n_u > U) n_u = U - u_lo;
-          // warp e takes components e, e + 8, ..., its lanes consecutive R rows: consecutive staging columns (no bank
-          // conflicts), no integer division, and the sources in the order (lag group, folded lag, column half) - with
-          // run-time divisions per source this gather was ~20 k cycles per column block, the length of the work item
-          // on small problems (config B)
-          const int sJ = p.s * J;
           for (int k = e; k < p.Kp; k += 8) {
-            for (int v = lane; v < n_u; v += 32) {               // v = u - 32 c
-              float* rp = R + (size_t)(u_lo + v) * p.Kp + k;
-              float acc = *rp;
-              const float* srow_g = St + (size_t)k * kHtStageLd;
-              int j_g = v - (n_glag - 1) * sJ - (p.s - 1);       // column (half 0) of source (g = 0, d = 0)
-              for (int g = 0; g < n_glag; ++g, j_g += sJ, srow_g += 32 * kHtStageLd) {
-                const float* srow = srow_g;
-                int j0 = j_g;
-                for (int d = 0; d < p.s; ++d, ++j0, srow += p.Kp * kHtStageLd) {
-                  if ((unsigned)j0 < 32u) acc += srow[j0];
-                  if ((unsigned)(j0 - 128) < 32u) acc += srow[128 * kHtStageLd + j0 - 128];
-                }
+            float* rk = R + (size_t)k * Up + c * 32 + lane;
+            const float* srow_g = St + (size_t)k * kHtStageLd;
+            int shift_g = (n_glag - 1) * sJ + (p.s - 1);         // shift of source (g = 0, d = 0)
+            for (int g = 0; g < n_glag; ++g, shift_g -= sJ, srow_g += 32 * kHtStageLd) {
+              const float* srow = srow_g;
+              int shift = shift_g;
+              for (int d = 0; d < p.s; ++d, --shift, srow += p.Kp * kHtStageLd) {
+                const int j0 = (lane - shift) & 31;
+                float* ru = rk + ((shift - lane + 31) & ~31);
+                ru[0] += srow[j0];
+                ru[128] += srow[128 * kHtStageLd + j0];
               }
-              *rp = acc;
             }
           }
           epi_bar();
@@ -877,8 +884,19 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         long long rows_left = p.TO - base;
         if (rows_left > 256) rows_left = 256;
         const int main4 = rows_left > 0 ? (int)rows_left * kp4 : 0;
-        for (int i = etid; i < head4; i += kSEpiThreads) c4[i] = R4[i];
-        for (int i = etid; i < main4; i += kSEpiThreads) o4[i] = R4[head4 + i];
+        if (p.staged) {
+          // component-major R: element (u, 4 k4 .. 4 k4 + 3) -> one float4 of the row-major output (Kp is 8 or 16)
+          const int sh = kp4 == 2 ? 1 : 2;
+          for (int i = etid; i < head4 + main4; i += kSEpiThreads) {
+            const int u = i >> sh, k0 = (i & (kp4 - 1)) * 4;
+            const float* r = R + (size_t)k0 * Up + u;
+            const float4 v = make_float4(r[0], r[Up], r[2 * Up], r[3 * Up]);
+            if (i < head4) c4[i] = v; else o4[i - head4] = v;
+          }
+        } else {
+          for (int i = etid; i < head4; i += kSEpiThreads) c4[i] = R4[i];
+          for (int i = etid; i < main4; i += kSEpiThreads) o4[i] = R4[head4 + i];
+        }
       }
       epi_bar();                                   // R is zeroed again by the next item
     }
