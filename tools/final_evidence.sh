@@ -1,7 +1,7 @@
 # Round-end evidence on one B200 (run through gpurun; everything lands in gpurun_out/, the big .ncu-rep files are
 # summarised on the box and removed: gpurun copies back at most 64 MiB).
 set -x
-python -m pytest tests -m gpu -q > gpurun_out/f_pytest.log 2>&1; tail -3 gpurun_out/f_pytest.log
+if [ -z "$SKIP_PYTEST" ]; then python -m pytest tests -m gpu -q > gpurun_out/f_pytest.log 2>&1; tail -3 gpurun_out/f_pytest.log; fi
 python bench.py > gpurun_out/f_bench_default.json 2> gpurun_out/f_bench_default.err; tail -c 300 gpurun_out/f_bench_default.err
 python tools/trajectory_errors.py fp32,tf32x3,tf32x3g,tf32,tf32g > gpurun_out/f_traj.log 2>&1; tail -3 gpurun_out/f_traj.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/f_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-peak --no-other-configs > gpurun_out/f_ncu_list.log 2>&1
