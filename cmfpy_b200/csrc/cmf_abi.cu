@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "dev_cache.cuh"
 #include "ew_kernels.cuh"
 #include "simt_gemm.cuh"
 #include "tc_path.cuh"
@@ -175,58 +176,11 @@ inline int ew_grid(const cmf_mu_s* h, long long n_items) {
   return (int)blocks;
 }
 
-// The N x T buffers (X^T, est^T and their lo halves) come from a small process-wide cache of freed blocks: cudaMalloc
-// of a few GiB costs anywhere from 10 ms to 0.4 s on these virtualised boxes (the end-to-end figure of bench.py moved
-// between 19 and 25 it/s with identical code for that reason alone), and a process that fits model after model -
-// a sweep over K or L, CMF.fit in a loop - asks for the same sizes again and again.  A block is reused only for the
-// same device and exactly the same size; at most CMF_CACHE_GB GiB stay cached (default 16, 0 disables);
-// cmf_release_cached_memory() returns them to the driver.
-struct BigCache {
-  struct Block { int dev; void* p; size_t bytes; };
-  std::mutex mu;
-  std::vector<Block> free_blocks;
-  size_t cached = 0;
-  size_t cap() {
-    static const size_t c = [] { const char* e = getenv("CMF_CACHE_GB"); return (size_t)((e ? atof(e) : 16.0) * (1ull << 30)); }();
-    return c;
-  }
-};
-BigCache& big_cache() { static BigCache* c = new BigCache(); return *c; }     // (never destroyed: outlives the runtime)
-
-int big_alloc(void** p, size_t bytes, int dev) {
-  {
-    BigCache& c = big_cache();
-    std::lock_guard<std::mutex> lock(c.mu);
-    for (size_t i = 0; i < c.free_blocks.size(); ++i)
-      if (c.free_blocks[i].dev == dev && c.free_blocks[i].bytes == bytes) {
-        *p = c.free_blocks[i].p;
-        c.cached -= bytes;
-        c.free_blocks.erase(c.free_blocks.begin() + (long)i);
-        return 0;
-      }
-  }
-  if (cudaMalloc(p, bytes) != cudaSuccess) {
-    cudaGetLastError();
-    cmf_release_cached_memory();                      // make room and try once more
-    CMF_CUDA(cudaMalloc(p, bytes));
-  }
-  return 0;
-}
-void big_free(void* p, size_t bytes, int dev) {
-  if (!p) return;
-  BigCache& c = big_cache();
-  {
-    std::lock_guard<std::mutex> lock(c.mu);
-    if (bytes >= (64u << 20) && c.cached + bytes <= c.cap()) {
-      c.free_blocks.push_back({dev, p, bytes});
-      c.cached += bytes;
-      return;
-    }
-  }
-  cudaFree(p);
-}
-
 template <class T> int dmalloc(T** p, long long count) {
+  return cached_malloc((void**)p, (size_t)(count > 0 ? count : 1) * sizeof(T));
+}
+// (W and the W-term buffer: their CUDA-IPC handles go to the peer processes of a sharded solve)
+template <class T> int dmalloc_plain(T** p, long long count) {
   CMF_CUDA(cudaMalloc((void**)p, (size_t)(count > 0 ? count : 1) * sizeof(T)));
   return 0;
 }
@@ -235,7 +189,7 @@ template <class T> int dmalloc(T** p, long long count) {
 int stage_get(cmf_mu_s* h, size_t bytes, void** out) {
   if (h->stage_bytes < bytes) {
     CMF_CUDA(cudaStreamSynchronize(h->stream));
-    cudaFree(h->stage_buf);
+    cached_free(h->stage_buf);
     h->stage_buf = nullptr;
     h->stage_bytes = 0;
     CMF_CUDA(cudaMalloc(&h->stage_buf, bytes));
@@ -564,24 +518,27 @@ int peer_detach(cmf_mu_s* h) {
 }
 
 void free_all(cmf_mu_s* h) {
+  // nothing of this solver may still run when its blocks go back to the cache (cudaFree would have waited; the
+  // cache does not)
+  if (h->stream) cudaStreamSynchronize(h->stream);
   peer_detach(h);
-  cudaFree(h->peer.shared);
-  cudaFree(h->stage_buf);
-  cudaFree(h->gdst.P); cudaFree(h->gdst.Ppart); cudaFree(h->gdst.Pt); cudaFree(h->gdst.v); cudaFree(h->gdst.y);
-  cudaFree(h->gdst.d_inv); cudaFree(h->gdst.d_lam); cudaFree(h->gdst.st);
-  cudaFree(h->halsst.Rt); cudaFree(h->halsst.part); cudaFree(h->halsst.part_h); cudaFree(h->halsst.delta);
-  cudaFree(h->halsst.Wk); cudaFree(h->halsst.prev); cudaFree(h->halsst.w2); cudaFree(h->halsst.d_diff);
+  cached_free(h->peer.shared);
+  cached_free(h->stage_buf);
+  cached_free(h->gdst.P); cached_free(h->gdst.Ppart); cached_free(h->gdst.Pt); cached_free(h->gdst.v); cached_free(h->gdst.y);
+  cached_free(h->gdst.d_inv); cached_free(h->gdst.d_lam); cached_free(h->gdst.st);
+  cached_free(h->halsst.Rt); cached_free(h->halsst.part); cached_free(h->halsst.part_h); cached_free(h->halsst.delta);
+  cached_free(h->halsst.Wk); cached_free(h->halsst.prev); cached_free(h->halsst.w2); cached_free(h->halsst.d_diff);
   tc::destroy(h->tcs);
   {
     const size_t nt_bytes = ((size_t)h->RT * h->Np + 128) * 4;
     big_free(h->Xt, nt_bytes, h->dev); big_free(h->Et, nt_bytes, h->dev);
     big_free(h->Xlo, nt_bytes, h->dev); big_free(h->Elo, nt_bytes, h->dev);
   }
-  cudaFree(h->Ht); cudaFree(h->W);
-  cudaFree(h->numden); cudaFree(h->wpart); cudaFree(h->hterms);
-  cudaFree(h->loss_partials); cudaFree(h->d_sumsq); cudaFree(h->d_ring); cudaFree(h->d_xpart);
-  cudaFree(h->d_neg);
-  cudaFree(h->d_counter);
+  cached_free(h->Ht); cached_free(h->W);
+  cached_free(h->numden); cached_free(h->wpart); cached_free(h->hterms);
+  cached_free(h->loss_partials); cached_free(h->d_sumsq); cached_free(h->d_ring); cached_free(h->d_xpart);
+  cached_free(h->d_neg);
+  cached_free(h->d_counter);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->sgraph_exec) cudaGraphExecDestroy(h->sgraph_exec);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
@@ -597,20 +554,7 @@ extern "C" {
 int cmf_abi_version(void) { return CMF_B200_ABI_VERSION; }
 
 int cmf_release_cached_memory(void) {
-  BigCache& c = big_cache();
-  std::vector<BigCache::Block> blocks;
-  {
-    std::lock_guard<std::mutex> lock(c.mu);
-    blocks.swap(c.free_blocks);
-    c.cached = 0;
-  }
-  int prev = -1;
-  cudaGetDevice(&prev);
-  for (auto& b : blocks) {
-    cudaSetDevice(b.dev);
-    cudaFree(b.p);
-  }
-  if (prev >= 0) cudaSetDevice(prev);
+  release_cached_blocks();
   return 0;
 }
 
@@ -720,8 +664,8 @@ int cmf_mu_create(cmf_mu_t** out, const cmf_mu_params* p) {
   A(big_alloc((void**)&h->Xt, ((size_t)h->RT * h->Np + 128) * 4, h->dev));   // + slack: the K2 box of a ragged feature count reads on
   if (h->x3) A(big_alloc((void**)&h->Xlo, ((size_t)h->RT * h->Np + 128) * 4, h->dev));
   A(dmalloc(&h->Ht, h->RH * h->Kp));
-  A(dmalloc(&h->W, h->wcount));
-  A(dmalloc(&h->numden, 2 * h->wcount));
+  A(dmalloc_plain(&h->W, h->wcount));
+  A(dmalloc_plain(&h->numden, 2 * h->wcount));
   if (h->wsplits > 1) A(dmalloc(&h->wpart, 2 * h->wcount * h->wsplits));
   A(dmalloc(&h->hterms, 2 * h->TO * h->Kp));
   h->n_loss_partials = (h->RT / 128) * ceil_div_ll(h->Np, 64) + 1024;
@@ -828,7 +772,7 @@ int cmf_mu_row_stats(cmf_mu_t* h, double* s1, double* s2, double* sabs) {
   }
   if (rc == 0 && (cudaMemcpyAsync(host.data(), out, host.size() * 8, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
                   cudaStreamSynchronize(h->stream) != cudaSuccess)) { set_error("row stats read-back failed"); rc = 1; }
-  cudaFree(part); cudaFree(out);
+  cached_free(part); cached_free(out);
   if (rc) return rc;
   for (int n = 0; n < h->N; ++n) {
     if (s1) s1[n] = host[n];
@@ -856,7 +800,7 @@ int cmf_mu_scale_rows(cmf_mu_t* h, const double* scale) {
     rc = launch_check(h, "scale_rows");
   }
   if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) { set_error("sync failed in scale_rows"); rc = 1; }
-  cudaFree(d_sc);
+  cached_free(d_sc);
   if (rc) return rc;
   return finish_data(h);
 }
@@ -2050,7 +1994,7 @@ struct DevBuf {
   float* p = nullptr;
   int dev = 0;
   ~DevBuf() {
-    if (p) { DeviceGuard g(dev); cudaFree(p); }
+    if (p) { DeviceGuard g(dev); cached_free(p); }
   }
 };
 struct cmf_dmat_s {
@@ -2110,7 +2054,7 @@ int dmat_to_host(const float* src, long long lds, long long rows, long long cols
       rc = 1;
     }
   }
-  cudaFree(tmp);
+  cached_free(tmp);
   return rc;
 }
 
@@ -2155,8 +2099,8 @@ int cmf_synth_destroy(cmf_synth_t* s) {
   if (!s) return 0;
   {
     DeviceGuard guard(s->p.device);
-    cudaFree(s->W);
-    cudaFree(s->H);
+    cached_free(s->W);
+    cached_free(s->H);
   }
   delete s;
   return 0;
@@ -2340,7 +2284,7 @@ int cmf_spectrogram(const void* audio, int dtype, int mem, long long n_samples, 
     return 0;
   };
   const int rc = body();
-  cudaFree(d_audio); cudaFree(d_win); cudaFree(d_part);
+  cached_free(d_audio); cached_free(d_win); cached_free(d_part);
   if (rc != 0) { delete m; return rc; }
   *out = m;
   return 0;

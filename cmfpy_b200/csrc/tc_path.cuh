@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "dev_cache.cuh"
 #include "ew_kernels.cuh"
 #include "simt_gemm.cuh"
 #include "tc_strict_kernels.cuh"
@@ -204,9 +205,9 @@ inline int make_map_k3w(CUtensorMap* m, const float* Wv, const Fold& f, long lon
 }
 
 inline void destroy(TcState& s) {
-  cudaFree(s.wpart); cudaFree(s.hcarry); cudaFree(s.d_err); cudaFree(s.Wv); cudaFree(s.Hv);
-  cudaFree(s.Wt); cudaFree(s.G); cudaFree(s.Rw); cudaFree(s.Rwv); cudaFree(s.Etail); cudaFree(s.hcarry_r);
-  cudaFree(s.P); cudaFree(s.Ppart); cudaFree(s.Mt); cudaFree(s.Pw);
+  cached_free(s.wpart); cached_free(s.hcarry); cached_free(s.d_err); cached_free(s.Wv); cached_free(s.Hv);
+  cached_free(s.Wt); cached_free(s.G); cached_free(s.Rw); cached_free(s.Rwv); cached_free(s.Etail); cached_free(s.hcarry_r);
+  cached_free(s.P); cached_free(s.Ppart); cached_free(s.Mt); cached_free(s.Pw);
   s.Wt = s.G = s.Rw = s.Rwv = s.Etail = s.P = s.Ppart = s.Mt = s.hcarry_r = s.Pw = nullptr;
   s.wpart = s.hcarry = s.Wv = s.Hv = nullptr;
   s.d_err = nullptr;
@@ -361,8 +362,8 @@ inline int ensure_autocorr(TcState& s) {
     const long long items = units * c;
     s.p_grid = (int)(items < d.num_sms ? items : d.num_sms);
   }
-  CMF_CUDA(cudaMalloc((void**)&s.P, (size_t)pcount * 4));
-  CMF_CUDA(cudaMalloc((void**)&s.Ppart, (size_t)pcount * s.p_chunks * 4));
+  CMF_TRY(cached_malloc((void**)&s.P, (size_t)pcount * 4));
+  CMF_TRY(cached_malloc((void**)&s.Ppart, (size_t)pcount * s.p_chunks * 4));
   // H^T itself as the "data" operand: the first Kp columns of Hv are the unfolded, rounded H^T
   const float* base = s.Hv + (long long)d.h * s.KWs;
   if (s.p_quad) {
@@ -422,13 +423,13 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
   CMF_CHECK(d.Kp == padded_k(d.K) && shape_supported(d.N, d.K, d.L), "shape not supported by the tensor-core path");
   CMF_CHECK(n_loss_partials >= d.num_sms, "loss partial buffer too small");
 
-  CMF_CUDA(cudaMalloc((void**)&s.d_err, 4));
+  CMF_TRY(cached_malloc((void**)&s.d_err, 4));
   CMF_CUDA(cudaMemsetAsync(s.d_err, 0, 4, stream));
   // (K3 addresses Wv as n_glag x J lags: the lags past Lv exist and stay zero)
   const long long lv_alloc = (long long)f.n_glag * f.J > f.Lv ? (long long)f.n_glag * f.J : f.Lv;
   const size_t wv_bytes = (size_t)lv_alloc * d.Np * f.KW * halves * 4;
-  CMF_CUDA(cudaMalloc((void**)&s.Wv, wv_bytes));
-  CMF_CUDA(cudaMalloc((void**)&s.Hv, (size_t)s.hv_count * halves * 4));
+  CMF_TRY(cached_malloc((void**)&s.Wv, wv_bytes));
+  CMF_TRY(cached_malloc((void**)&s.Hv, (size_t)s.hv_count * halves * 4));
   CMF_CUDA(cudaMemsetAsync(s.Wv, 0, wv_bytes, stream));
   CMF_CUDA(cudaMemsetAsync(s.Hv, 0, (size_t)s.hv_count * halves * 4, stream));
 
@@ -520,13 +521,13 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     // 3xTF32: Wt rows are [hi (NpA) | lo (NpA)], Rwv rows [hi (KW) | lo (KW)]
     s.NpA = s.x3 ? round_up(d.Np, 32) : d.Np;
     const long long wt_ld = (long long)halves * s.NpA;
-    CMF_CUDA(cudaMalloc((void**)&s.Wt, (size_t)s.LK * wt_ld * 4));
+    CMF_TRY(cached_malloc((void**)&s.Wt, (size_t)s.LK * wt_ld * 4));
     CMF_CUDA(cudaMemsetAsync(s.Wt, 0, (size_t)s.LK * wt_ld * 4, stream));
-    CMF_CUDA(cudaMalloc((void**)&s.G, (size_t)s.g_rows * s.LK * 4));
-    CMF_CUDA(cudaMalloc((void**)&s.Rw, (size_t)s.Lr * d.Kp * d.Kp * 4));
+    CMF_TRY(cached_malloc((void**)&s.G, (size_t)s.g_rows * s.LK * 4));
+    CMF_TRY(cached_malloc((void**)&s.Rw, (size_t)s.Lr * d.Kp * d.Kp * 4));
     // Rwv: R as a W-like operand [lag][k' (feature)][k], folded like Wv; allocated for n_glag * J lags (zeros past Lrv)
     const long long lr_alloc = (long long)f.n_glag * s.fr.J > s.Lrv ? (long long)f.n_glag * s.fr.J : s.Lrv;
-    CMF_CUDA(cudaMalloc((void**)&s.Rwv, (size_t)lr_alloc * d.Kp * s.KWs * 4));
+    CMF_TRY(cached_malloc((void**)&s.Rwv, (size_t)lr_alloc * d.Kp * s.KWs * 4));
     CMF_CUDA(cudaMemsetAsync(s.Rwv, 0, (size_t)lr_alloc * d.Kp * s.KWs * 4, stream));
     CMF_TRY(make_map(&s.tmWt_a, s.Wt, s.LK, wt_ld, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B));
     CMF_TRY(make_map(&s.tmWt_b, s.Wt, s.LK, wt_ld, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
@@ -535,7 +536,7 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     CMF_TRY(make_map(&s.tmHs_k3, s.Hv, d.RH, d.Kp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B, s.KWs));
     s.tmHslo_k3 = s.tmHs_k3;
     if (s.x3) CMF_TRY(make_map(&s.tmHslo_k3, s.Hv + f.KW, d.RH, d.Kp, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B, s.KWs));
-    if (s.fr.h_hd > 0) CMF_CUDA(cudaMalloc((void**)&s.hcarry_r, (size_t)(d.TO / 256 + 1) * s.fr.h_hd * d.Kp * 4));
+    if (s.fr.h_hd > 0) CMF_TRY(cached_malloc((void**)&s.hcarry_r, (size_t)(d.TO / 256 + 1) * s.fr.h_hd * d.Kp * 4));
     // one attribute for both uses of the H-terms kernel
     const bool direct = f.n_glag == 1 && f.s == 1;
     const size_t a = hterms_smem_bytes(f.h_stages, f.hterms_wrows, d.Kp, f.h_hd, direct, f.h_staged != 0);
@@ -551,13 +552,13 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     s.h_sub = s.x3 ? strict_sub_units() : ((s.gram & 1) ? (int)ceil_div_ll(d.Kp, 32) * s.fr.J : 0);
     if (const char* e = getenv("CMF_HSUB")) s.h_sub = atoi(e);
     const long long tt = d.TO / 256 + 1;
-    if (f.h_hd > 0) CMF_CUDA(cudaMalloc((void**)&s.hcarry, (size_t)2 * tt * f.h_hd * d.Kp * 4));
+    if (f.h_hd > 0) CMF_TRY(cached_malloc((void**)&s.hcarry, (size_t)2 * tt * f.h_hd * d.Kp * 4));
     const long long items = tt * ((s.gram & 1) ? 1 : 2);
     s.hterms_grid = (int)(items < d.num_sms ? items : d.num_sms);
   }
   if ((long long)s.g_rows * f.Lv * f.KW * halves * 4 > (1ll << 30)) s.gram &= ~2;
-  CMF_CUDA(cudaMalloc((void**)&s.wpart, (size_t)s.n_chunks * ((s.gram & 2) ? 1 : 2) * s.wcount * 4));
-  if (s.gram && s.ntail > 0) CMF_CUDA(cudaMalloc((void**)&s.Etail, (size_t)round_up_ll(s.ntail, 256) * d.Np * 4));
+  CMF_TRY(cached_malloc((void**)&s.wpart, (size_t)s.n_chunks * ((s.gram & 2) ? 1 : 2) * s.wcount * 4));
+  if (s.gram && s.ntail > 0) CMF_TRY(cached_malloc((void**)&s.Etail, (size_t)round_up_ll(s.ntail, 256) * d.Np * 4));
   if (s.gram & 2) {
     CMF_TRY(ensure_autocorr(s));
     static const bool shift_form = [] { const char* e = getenv("CMF_DENW_SHIFT"); return !e || atoi(e) != 0; }();
@@ -575,14 +576,14 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
       if (!fits || recon_smem_bytes(s.pw_wrows) > kMaxSmem) {
         s.pw_rows = 0;                               // (no room for two lags per window: keep the Toeplitz GEMM)
       } else {
-        CMF_CUDA(cudaMalloc((void**)&s.Pw, (size_t)s.pw_rows * s.KWs * 4));
+        CMF_TRY(cached_malloc((void**)&s.Pw, (size_t)s.pw_rows * s.KWs * 4));
         CMF_TRY(make_map(&s.tmPw_b, s.Pw, s.pw_rows, s.KWs, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
         const size_t a = recon_smem_bytes(f.recon_wrows), b = recon_smem_bytes(s.pw_wrows);
         CMF_TRY(set_recon_smem(a > b ? a : b));
       }
     }
     if (s.pw_rows == 0) {
-      CMF_CUDA(cudaMalloc((void**)&s.Mt, (size_t)s.g_rows * f.Lv * f.KW * halves * 4));
+      CMF_TRY(cached_malloc((void**)&s.Mt, (size_t)s.g_rows * f.Lv * f.KW * halves * 4));
       CMF_TRY(make_map(&s.tmMt_b, s.Mt, s.g_rows, (long long)f.Lv * f.KW * halves, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
     }
   }
