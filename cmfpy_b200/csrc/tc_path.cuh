@@ -104,6 +104,8 @@ struct TcState {
   double *loss_partials = nullptr, *d_sumsq = nullptr;
   float* wpart = nullptr;
   float* hcarry = nullptr;         // [2][time tiles][h_hd][Kp]: the part of each K3 tile that belongs to the tile before it
+  float* hparts = nullptr;         // K3 with split items: [n_src][h_split][TO][Kp] partial outputs
+  int h_split = 1;                 // K3: items per (time tile, source) (HTermsParams::n_split)
   int* d_err = nullptr;
   int n_chunks = 1, n_lag_groups = 1;    // K2: time chunks; lag groups of 16 (tf32) or 8 (3xTF32) virtual lags
   int h_sub = 0;                         // K3: units per tensor-memory sub-chunk (0: one chain per item)
@@ -205,11 +207,11 @@ inline int make_map_k3w(CUtensorMap* m, const float* Wv, const Fold& f, long lon
 }
 
 inline void destroy(TcState& s) {
-  cached_free(s.wpart); cached_free(s.hcarry); cached_free(s.d_err); cached_free(s.Wv); cached_free(s.Hv);
+  cached_free(s.wpart); cached_free(s.hcarry); cached_free(s.hparts); cached_free(s.d_err); cached_free(s.Wv); cached_free(s.Hv);
   cached_free(s.Wt); cached_free(s.G); cached_free(s.Rw); cached_free(s.Rwv); cached_free(s.Etail); cached_free(s.hcarry_r);
   cached_free(s.P); cached_free(s.Ppart); cached_free(s.Mt); cached_free(s.Pw);
   s.Wt = s.G = s.Rw = s.Rwv = s.Etail = s.P = s.Ppart = s.Mt = s.hcarry_r = s.Pw = nullptr;
-  s.wpart = s.hcarry = s.Wv = s.Hv = nullptr;
+  s.wpart = s.hcarry = s.hparts = s.Wv = s.Hv = nullptr;
   s.d_err = nullptr;
   s.ready = false;
 }
@@ -552,8 +554,28 @@ inline int init(TcState& s, const Dims& d, float* Xt, float* Et, float* Ht, floa
     s.h_sub = s.x3 ? strict_sub_units() : ((s.gram & 1) ? (int)ceil_div_ll(d.Kp, 32) * s.fr.J : 0);
     if (const char* e = getenv("CMF_HSUB")) s.h_sub = atoi(e);
     const long long tt = d.TO / 256 + 1;
-    if (f.h_hd > 0) CMF_TRY(cached_malloc((void**)&s.hcarry, (size_t)2 * tt * f.h_hd * d.Kp * 4));
-    const long long items = tt * ((s.gram & 1) ? 1 : 2);
+    const int n_src = (s.gram & 1) ? 1 : 2;
+    long long items = tt * n_src;
+    // Work items are whole time tiles.  On a short shard (config C on 8 GPUs: 513 tiles = 3.47 rounds of 148 CTAs, so
+    // 4) the last round runs half empty; when halving the items (two CTAs share a tile's feature chunks and write
+    // partial outputs, summed afterwards) fills the rounds better by 4 % or more, do that.
+    s.h_split = 1;
+    {
+      const long long cn = ceil_div_ll(d.Np, 32);
+      const auto eff = [&](long long n) { return (double)n / (double)(ceil_div_ll(n, d.num_sms) * d.num_sms); };
+      // (only where an item is long enough to pay for the partial-sum pass and the extra carry launches)
+      // 3xTF32 only: its two-level accumulation makes the truncation bias of a result independent of the chain length;
+      // in plain TF32 the half chains of a split numerator would no longer carry the bias of the Gram denominator's
+      // chain and the W / H scale split would drift (measured: 1e-3 of sum(W) after 100 iterations of `mid`)
+      if (s.x3 && cn % 2 == 0 && cn * f.J >= 128 && items > d.num_sms && eff(2 * items) > eff(items) + 0.04) s.h_split = 2;
+      if (const char* e = getenv("CMF_HT_SPLIT")) {
+        const int v = atoi(e);
+        s.h_split = (v >= 1 && v <= 4 && cn % v == 0) ? v : 1;
+      }
+    }
+    if (f.h_hd > 0) CMF_TRY(cached_malloc((void**)&s.hcarry, (size_t)2 * s.h_split * tt * f.h_hd * d.Kp * 4));
+    if (s.h_split > 1) CMF_TRY(cached_malloc((void**)&s.hparts, (size_t)2 * s.h_split * d.TO * d.Kp * 4));
+    items *= s.h_split;
     s.hterms_grid = (int)(items < d.num_sms ? items : d.num_sms);
   }
   if ((long long)s.g_rows * f.Lv * f.KW * halves * 4 > (1ll << 30)) s.gram &= ~2;
@@ -859,20 +881,42 @@ inline int h_terms(TcState& s, cudaStream_t stream) {
   p.s = f.s; p.CB = f.CB; p.Kp = d.Kp;
   p.n_src = (s.gram & 1) ? 1 : 2;                 // the Gram route contracts X only
   p.n_time_tiles = d.TO / 256 + 1;
-  p.n_items = p.n_time_tiles * p.n_src;
-  p.TO = d.TO; p.out = s.hterms; p.carry = s.hcarry; p.hd = f.h_hd;
+  p.n_split = s.h_split;
+  p.n_items = p.n_time_tiles * p.n_src * p.n_split;
+  p.TO = d.TO; p.out = s.h_split > 1 ? s.hparts : s.hterms; p.carry = s.hcarry; p.hd = f.h_hd;
   p.sub_units = s.h_sub; p.n_stages = f.h_stages; p.staged = f.h_staged;
   p.x3 = s.x3; p.lo_off = f.KW; p.err = s.d_err;
   const bool direct = f.n_glag == 1 && f.s == 1;
   tc_hterms_kernel<<<s.hterms_grid, kSThreads, hterms_smem_bytes(f.h_stages, f.hterms_wrows, d.Kp, f.h_hd, direct, f.h_staged != 0), stream>>>(
       s.tmW_k3, s.tmX_k3, s.tmE_k3, s.tmXlo_k3, s.tmElo_k3, p);
   CMF_TRY(launch_ok("tc_hterms"));
+  if (s.h_split > 1) {
+    // out[src] = sum of the partial outputs of its items (fixed order)
+    const long long n4 = d.TO * d.Kp / 4;
+    for (int src = 0; src < p.n_src; ++src) {
+      ew::sum_splits_kernel<<<ew_blocks(s, n4), 256, 0, stream>>>((float4*)(s.hterms + (size_t)src * d.TO * d.Kp),
+                                                                 (const float4*)(s.hparts + (size_t)src * s.h_split * d.TO * d.Kp),
+                                                                 n4, n4, s.h_split);
+      CMF_TRY(launch_ok("h_terms_sum"));
+    }
+  }
   if (f.h_hd > 0) {
     const long long wmax = f.h_hd < 256 ? f.h_hd : 256;
-    const long long total = (p.n_time_tiles - 1) * wmax * (d.Kp / 4) * p.n_src;
-    if (total > 0) {
-      hterms_carry_kernel<<<ew_blocks(s, total), 256, 0, stream>>>(s.hterms, s.hcarry, d.TO, p.n_time_tiles, f.h_hd, d.Kp, p.n_src);
-      CMF_TRY(launch_ok("hterms_carry"));
+    const long long per_src = (p.n_time_tiles - 1) * wmax * (d.Kp / 4);
+    if (per_src > 0) {
+      if (s.h_split == 1) {
+        hterms_carry_kernel<<<ew_blocks(s, per_src * p.n_src), 256, 0, stream>>>(s.hterms, s.hcarry, d.TO, p.n_time_tiles, f.h_hd, d.Kp, p.n_src);
+        CMF_TRY(launch_ok("hterms_carry"));
+      } else {
+        const size_t per_carry = (size_t)p.n_time_tiles * f.h_hd * d.Kp;
+        for (int src = 0; src < p.n_src; ++src)
+          for (int sp = 0; sp < s.h_split; ++sp) {
+            hterms_carry_kernel<<<ew_blocks(s, per_src), 256, 0, stream>>>(s.hterms + (size_t)src * d.TO * d.Kp,
+                                                                          s.hcarry + (size_t)(src * s.h_split + sp) * per_carry,
+                                                                          d.TO, p.n_time_tiles, f.h_hd, d.Kp, 1);
+            CMF_TRY(launch_ok("hterms_carry"));
+          }
+      }
     }
   }
   if (s.gram & 1) CMF_TRY(den_h_gram(s, stream));

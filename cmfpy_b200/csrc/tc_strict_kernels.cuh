@@ -584,10 +584,13 @@ struct HTermsParams {
   int s, CB, Kp;                   // lag stride in rows; column blocks (regions = (4/CB lag groups) x CB); padded K
   int n_src;                       // 2: X and est (numerator, denominator); 1: X only (denominator via Gram)
   long long n_time_tiles;          // TO / 256 + 1 (the last tile only feeds the carry of the final columns)
-  long long n_items;               // n_time_tiles * n_src
+  long long n_items;               // n_time_tiles * n_src * n_split
+  int n_split;                     // > 1: the feature chunks of a (time tile, source) are shared out over n_split items
+                                   // (short shards, where whole tiles leave the last round of CTAs half empty); n_chunks_n
+                                   // is a multiple of it; the items write partial outputs that the host sums
   long long TO;                    // output rows per source
-  float* out;                      // [n_src][TO][Kp]
-  float* carry;                    // [n_src][n_time_tiles][hd][Kp]
+  float* out;                      // [n_src][TO][Kp]  (n_split > 1: [n_src][n_split][TO][Kp] partials)
+  float* carry;                    // [n_src][n_split][n_time_tiles][hd][Kp]
   int hd;                          // columns before the tile that its lag groups reach: (4/CB - 1) s J + s - 1
   int sub_units;                   // units per sub-chunk (0: the whole item in one tensor-memory chain)
   int n_stages;                    // W ring depth (2 lags per stage)
@@ -657,7 +660,10 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   const Abort ab{abort_flag, p.err};
   const int J = p.J, wrows = p.wrows;
   const int n_pass = p.x3 ? 3 : 1;
-  const SubPlan plan((long long)n_pass * p.n_chunks_n * J, p.x3 ? 2ll * p.n_chunks_n * J : 0, p.sub_units);   // units per item
+  const int n_split = p.n_split > 1 ? p.n_split : 1;
+  const int cpi = p.n_chunks_n / n_split;                        // feature chunks per item
+  const int per_tile = p.n_src * n_split;                        // item = (time tile, source, split)
+  const SubPlan plan((long long)n_pass * cpi * J, p.x3 ? 2ll * cpi * J : 0, p.sub_units);   // units per item
 
   if (warp == 0) {
     reg_dec<kSCtlRegs>();
@@ -667,7 +673,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       struct Chunk { long long item; int nc, combo; bool valid; };
       auto make_chunk = [&](long long item) { return Chunk{item, 0, p.x3 ? 0 : 2, item < p.n_items}; };
       auto next_chunk = [&](Chunk c) {
-        if (++c.nc >= p.n_chunks_n) {
+        if (++c.nc >= cpi) {
           if (c.combo < 2) { ++c.combo; c.nc = 0; }
           else c = make_chunk(c.item + gridDim.x);
         }
@@ -676,14 +682,15 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       // window of chunk number wc (its buffer is known to be free)
       auto issue_window = [&](const Chunk& c, long long wc) {
         const int wb = (int)(wc & 1);
-        const long long tile = c.item / p.n_src;
-        const int src = (int)(c.item % p.n_src);
+        const long long tile = c.item / per_tile;
+        const int rem = (int)(c.item % per_tile);
+        const int src = rem / n_split, nc0 = (rem % n_split) * cpi;
         uint8_t* wdst = Ws + (size_t)wb * wbytes;
         const CUtensorMap* tmS = src ? (c.combo == 1 ? &tmElo : &tmE) : (c.combo == 1 ? &tmXlo : &tmX);
         if (elect_one()) {
           mbar_arrive_expect_tx(&wfull[wb], wbytes);
           for (int rb = 0; rb < wrows / 32; ++rb)
-            tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], c.nc * 32, (int)(tile * 256 + rb * 32));
+            tma_load_2d(wdst + (size_t)rb * 32 * 128, tmS, &wfull[wb], (nc0 + c.nc) * 32, (int)(tile * 256 + rb * 32));
         }
       };
       Chunk cur = make_chunk(blockIdx.x);
@@ -700,7 +707,8 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           // and features >= Np arrive as zeros)
           if (elect_one()) {
             mbar_arrive_expect_tx(&full[ps.stage], kHtStageBytes);
-            tma_load_5d(As + (size_t)ps.stage * kHtStageBytes, &tmW, &full[ps.stage], 0, cur.nc * 32,
+            tma_load_5d(As + (size_t)ps.stage * kHtStageBytes, &tmW, &full[ps.stage], 0,
+                        ((int)(cur.item % n_split) * cpi + cur.nc) * 32,
                         cur.combo == 0 ? p.lo_off / 32 : 0, 0, j);
           }
           ps.advance(n_stages);
@@ -729,7 +737,7 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       uint32_t wb = 0, wph = 0;
       for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int unit = 0;
-        for (int chunk = 0; chunk < n_pass * p.n_chunks_n; ++chunk) {
+        for (int chunk = 0; chunk < n_pass * cpi; ++chunk) {
           wait_uniform(ab, &wfull[wb], wph);
           tc_fence_after();
           uint64_t bd = bdesc0 + (uint64_t)((wb * wbytes) >> 4);             // lag j: row shift s * j
@@ -777,8 +785,8 @@ tc_hterms_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     SubDrain sd;
     bool ok = true;
     for (long long item = blockIdx.x; item < p.n_items && ok; item += gridDim.x) {
-      const long long tile = item / p.n_src;
-      const int src = (int)(item % p.n_src);
+      const long long tile = item / per_tile;
+      const int src = (int)(item % per_tile);       // source * n_split + split: the index of this item's (partial) output
       for (int sub = 0; sub < n_sub; ++sub, sd.next()) {
         if (!wait_relaxed(ab, &sfull[sd.b], sd.ph)) { ok = false; break; }
         tc_fence_after();
