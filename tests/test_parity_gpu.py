@@ -416,11 +416,11 @@ def test_loss_from_w_terms(built_lib, precision, kind, tol):
 
 
 def test_device_buffer_cache(built_lib):
-    """The N x T buffers of a closed solver are reused by the next solver of the same shape (cmf_abi.cu BigCache):
-    results must not depend on what the previous owner left in them, and release_cached_memory() must leave the
-    library usable."""
+    """The device buffers of a closed solver (1 MiB and more) are reused by the next solver that asks for the same
+    sizes (csrc/dev_cache.cuh): results must not depend on what the previous owner left in them, and
+    release_cached_memory() must leave the library usable."""
     import cmfpy_b200
-    N, T, K, L = 512, 1 << 16, 8, 16                  # 128 MiB per buffer: above the 64 MiB caching threshold
+    N, T, K, L = 512, 1 << 16, 8, 16                  # 128 MiB per N x T buffer
     hists = []
     for seed, release in ((1, False), (2, False), (1, True), (1, False)):
         X, W0, H0 = make_inputs(N, T, K, L, "uniform", seed=seed)
