@@ -69,3 +69,28 @@ def test_clamped_row_walk_reads_only_valid_rows(no):
         rows.append(row)
         row += 1 if j + 1 < no else 0
     assert max(rows) == no - 1 and rows[:no] == list(range(no)) and all(r == no - 1 for r in rows[no:])
+
+
+@pytest.mark.parametrize("n_src,n_split,n_chunks_n,n_tiles", [(1, 1, 8, 5), (2, 1, 32, 3), (1, 2, 32, 7), (2, 2, 16, 4),
+                                                              (2, 4, 16, 3)])
+def test_hterms_item_split_covers_every_chunk_once(n_src, n_split, n_chunks_n, n_tiles):
+    """Work items of tc_hterms_kernel with HTermsParams::n_split (short shards): item -> (time tile, source, split);
+    the producer's feature chunk is (item % n_split) * cpi + nc, the epilogue's output slot source * n_split + split.
+    Every (tile, source, chunk) must be contracted exactly once, and the slots of one source must be the n_split
+    consecutive partial outputs that the host sums (tc_path.cuh h_terms)."""
+    cpi = n_chunks_n // n_split
+    per_tile = n_src * n_split
+    seen = {}
+    for item in range(n_tiles * per_tile):
+        tile, rem = divmod(item, per_tile)
+        src_w, nc0_w = rem // n_split, (rem % n_split) * cpi          # window loads
+        nc0_a = (item % n_split) * cpi                                # W stage loads
+        slot = item % per_tile                                        # epilogue
+        assert nc0_w == nc0_a and slot // n_split == src_w
+        for nc in range(cpi):
+            key = (tile, src_w, nc0_w + nc)
+            assert key not in seen
+            seen[key] = slot
+    assert len(seen) == n_tiles * n_src * n_chunks_n
+    for (tile, src, chunk), slot in seen.items():
+        assert src * n_split <= slot < (src + 1) * n_split and slot - src * n_split == chunk // cpi
